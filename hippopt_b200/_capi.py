@@ -1,0 +1,108 @@
+"""ctypes binding of the C ABI declared in include/hippopt_b200.h.
+
+The header is the single source of truth for the configuration-table indices: its enums and
+integer ``#define``s are parsed here rather than duplicated.  Loading fails loudly when the CUDA
+library has not been built -- there is no CPU fallback (``__graft_entry__.build()`` builds it).
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import re
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+HEADER = os.path.join(os.path.dirname(_HERE), "include", "hippopt_b200.h")
+LIB_PATH = os.path.join(_HERE, "libhippopt_b200.so")
+
+
+def parse_header(path: str = HEADER) -> dict[str, int]:
+    text = open(path).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    text = re.sub(r"//[^\n]*", "", text)
+    env: dict[str, int] = {}
+    # process #defines and enums in file order (later ones reference earlier ones)
+    pattern = re.compile(r"#define\s+(\w+)\s+([^\n]+)|enum\s*\{([^}]*)\}", re.S)
+    for mt in pattern.finditer(text):
+        if mt.group(1):
+            name, expr = mt.group(1), mt.group(2).strip()
+            if not expr or name.endswith("_H"):
+                continue
+            try:
+                env[name] = int(eval(expr, {"__builtins__": {}}, env))
+            except Exception:
+                pass
+        else:
+            nxt = 0
+            for item in mt.group(3).split(","):
+                item = item.strip()
+                if not item:
+                    continue
+                if "=" in item:
+                    name, expr = (s.strip() for s in item.split("=", 1))
+                    nxt = int(eval(expr, {"__builtins__": {}}, env))
+                else:
+                    name = item
+                env[name] = nxt
+                nxt += 1
+    return env
+
+
+H = parse_header()
+
+
+class LibraryNotBuilt(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def lib() -> ctypes.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise LibraryNotBuilt(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a). hippopt_b200 has no CPU fallback."
+        )
+    L = ctypes.CDLL(LIB_PATH)
+    vp, i32p, i16p, f64p, i64p = (ctypes.c_void_p, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int16),
+                                  ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int64))
+    L.hb_kino_create.restype = ctypes.c_int
+    L.hb_kino_create.argtypes = [i32p, f64p, i32p, i32p, i16p, i32p, i32p, i32p, ctypes.POINTER(vp)]
+    L.hb_toy_create.restype = ctypes.c_int
+    L.hb_toy_create.argtypes = [ctypes.c_int32, ctypes.c_int32, ctypes.c_double, ctypes.POINTER(vp)]
+    L.hb_destroy.restype = ctypes.c_int
+    L.hb_destroy.argtypes = [vp]
+    L.hb_dims.restype = ctypes.c_int
+    L.hb_dims.argtypes = [vp, i64p, i64p, i64p, i64p, i64p]
+    L.hb_pattern_jac.restype = ctypes.c_int
+    L.hb_pattern_jac.argtypes = [vp, i64p, i64p]
+    L.hb_pattern_hess.restype = ctypes.c_int
+    L.hb_pattern_hess.argtypes = [vp, i64p, i64p]
+    L.hb_eval.restype = ctypes.c_int
+    L.hb_eval.argtypes = [vp, ctypes.c_uint32, vp, vp, ctypes.c_int64, vp, vp, vp, vp, vp, vp, vp, ctypes.c_int64, vp]
+    L.hb_last_launch_count.restype = ctypes.c_int
+    L.hb_last_launch_count.argtypes = [vp]
+    L.hb_last_error.restype = ctypes.c_char_p
+    L.hb_last_error.argtypes = []
+    L.hb_probe_fp64_tflops.restype = ctypes.c_int
+    L.hb_probe_fp64_tflops.argtypes = [f64p, vp]
+    _lib = L
+    return L
+
+
+EXPORTED_SYMBOLS = [
+    "hb_kino_create", "hb_toy_create", "hb_destroy", "hb_dims", "hb_pattern_jac", "hb_pattern_hess", "hb_eval",
+    "hb_last_launch_count", "hb_last_error", "hb_probe_fp64_tflops",
+]
+
+
+class EvaluationError(RuntimeError):
+    pass
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        raise EvaluationError(f"{what} failed with code {rc}: {lib().hb_last_error().decode()}")

@@ -1,0 +1,385 @@
+// api.cu -- C ABI (include/hippopt_b200.h): handle management, launches, fp64 probe.
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "kino_const.cuh"
+// single translation unit: the kernels are included by hippopt_b200.cu before this file
+
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+#define CUDA_TRY(expr)                                                                      \
+  do {                                                                                      \
+    cudaError_t e__ = (expr);                                                               \
+    if (e__ != cudaSuccess) return fail(HB_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__)); \
+  } while (0)
+
+enum { KIND_KINO = 1, KIND_TOY = 2 };
+
+struct hb_problem_s {
+  int kind = 0;
+  int launches = 0;
+  // kinodynamic
+  hb::KinoConst host{};
+  hb::KinoConst* dev = nullptr;
+  int *d_jc = nullptr, *d_jk = nullptr, *d_hc = nullptr, *d_hk = nullptr, *d_hk2 = nullptr;
+  short* d_hci = nullptr;
+  double* d_fpart = nullptr;
+  int64_t fpart_cap = 0;
+  // toy
+  hb::ToyProblem* toy = nullptr;
+};
+
+__global__ void reduce_f_kernel(const double* __restrict__ fpart, double* __restrict__ f, int n_terms, long batch) {
+  const long b = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= batch) return;
+  const double* fp = fpart + b * n_terms;
+  double acc = 0.0;
+  for (int i = 0; i < n_terms; ++i) acc += fp[i];
+  f[b] = acc;
+}
+
+template <class T>
+static cudaError_t upload(T** dst, const T* src, size_t n) {
+  cudaError_t e = cudaMalloc(dst, n * sizeof(T) + 16);
+  if (e != cudaSuccess) return e;
+  return cudaMemcpy(*dst, src, n * sizeof(T), cudaMemcpyHostToDevice);
+}
+
+extern "C" int hb_kino_create(const int32_t* icfg, const double* dcfg, const int32_t* jc_map, const int32_t* jk_map,
+                              const int16_t* hc_index, const int32_t* hc_map, const int32_t* hk_map,
+                              const int32_t* hk2_map, hb_handle* out) {
+  if (!icfg || !dcfg || !jc_map || !jk_map || !hc_index || !hc_map || !hk_map || !hk2_map || !out)
+    return fail(HB_ERR_INVALID, "hb_kino_create: null argument");
+  hb_problem_s* h = new hb_problem_s();
+  h->kind = KIND_KINO;
+  hb::KinoConst& C = h->host;
+  C.N = icfg[HB_KI_HORIZON];
+  C.n_x = icfg[HB_KI_N_X];
+  C.n_p = icfg[HB_KI_N_P];
+  C.m = icfg[HB_KI_M];
+  C.nnz_j = icfg[HB_KI_NNZ_J];
+  C.nnz_h = icfg[HB_KI_NNZ_H];
+  C.n_jc = icfg[HB_KI_N_JC];
+  C.n_jk = icfg[HB_KI_N_JK];
+  C.n_hc = icfg[HB_KI_N_HC];
+  C.terrain = icfg[HB_KI_TERRAIN];
+  C.has_final = icfg[HB_KI_HAS_FINAL];
+  C.has_per = icfg[HB_KI_HAS_PERIODICITY];
+  C.h_init = icfg[HB_KI_H_INIT];
+  C.po_desc0 = icfg[HB_KI_PO_DESC0];
+  C.po_mass = icfg[HB_KI_PO_MASS];
+  C.po_init = icfg[HB_KI_PO_INIT];
+  C.po_final = icfg[HB_KI_PO_FINAL];
+  C.po_dt = icfg[HB_KI_PO_DT];
+  C.po_gravity = icfg[HB_KI_PO_GRAVITY];
+  C.po_kt = icfg[HB_KI_PO_KT];
+  C.po_kbs = icfg[HB_KI_PO_KBS];
+  C.po_eps = icfg[HB_KI_PO_EPS];
+  C.po_mu = icfg[HB_KI_PO_MU];
+  C.po_max_u = icfg[HB_KI_PO_MAX_U];
+  C.po_max_fd = icfg[HB_KI_PO_MAX_FD];
+  C.po_max_L = icfg[HB_KI_PO_MAX_L];
+  C.po_min_com_h = icfg[HB_KI_PO_MIN_COM_H];
+  C.po_min_feet_d = icfg[HB_KI_PO_MIN_FEET_D];
+  C.po_max_feet_h = icfg[HB_KI_PO_MAX_FEET_H];
+  C.po_max_s = icfg[HB_KI_PO_MAX_S];
+  C.po_min_s = icfg[HB_KI_PO_MIN_S];
+  C.po_max_sd = icfg[HB_KI_PO_MAX_SD];
+  C.po_min_sd = icfg[HB_KI_PO_MIN_SD];
+  C.po_refs0 = icfg[HB_KI_PO_REFS0];
+  C.po_terrain = icfg[HB_KI_PO_TERRAIN];
+  C.yaw[0] = icfg[HB_KI_YAW_BR];
+  C.yaw[1] = icfg[HB_KI_YAW_TR];
+  C.yaw[2] = icfg[HB_KI_YAW_TL];
+  C.nb = icfg[HB_KI_N_BODIES];
+  C.foot_body[0] = icfg[HB_KI_FOOT_BODY_L];
+  C.foot_body[1] = icfg[HB_KI_FOOT_BODY_R];
+  C.chest_body = icfg[HB_KI_CHEST_BODY];
+  if (C.terrain != 0) {
+    delete h;
+    return fail(HB_ERR_UNSUPPORTED, "hb_kino_create: only the planar terrain is implemented on the device");
+  }
+  if (C.nb < 2 || C.nb > HB_MAX_BODIES || C.nb - 1 != HB_N_JOINTS) {
+    delete h;
+    return fail(HB_ERR_INVALID, "hb_kino_create: the kernels are laid out for 23 joints / <= 32 bodies");
+  }
+  for (int f = 0; f < HB_KF_COUNT; ++f)
+    for (int i = 0; i < 4; ++i) C.fam[f][i] = icfg[HB_KI_FAM0 + 4 * f + i];
+  C.w_swing = dcfg[HB_KD_W_SWING];
+  C.w_u = dcfg[HB_KD_W_U];
+  C.w_fd = dcfg[HB_KD_W_FD];
+  C.w_centroid = dcfg[HB_KD_W_CENTROID];
+  for (int i = 0; i < 3; ++i) C.w_comvel[i] = dcfg[HB_KD_W_COMVEL0 + i];
+  C.w_frame = dcfg[HB_KD_W_FRAME];
+  C.w_bq = dcfg[HB_KD_W_BQ];
+  C.w_bqv = dcfg[HB_KD_W_BQV];
+  C.w_joint = dcfg[HB_KD_W_JOINT];
+  C.w_ratio = dcfg[HB_KD_W_RATIO];
+  C.w_yaw = dcfg[HB_KD_W_YAW];
+  for (int i = 0; i < HB_N_JOINTS; ++i) C.wj[i] = dcfg[HB_KD_WJ0 + i];
+  C.total_mass = dcfg[HB_KD_TOTAL_MASS];
+  for (int f = 0; f < 2; ++f) {
+    for (int i = 0; i < 9; ++i) C.foot_R[f][i] = dcfg[HB_KD_FOOT_R0 + 9 * f + i];
+    for (int i = 0; i < 3; ++i) C.foot_t[f][i] = dcfg[HB_KD_FOOT_T0 + 3 * f + i];
+  }
+  for (int i = 0; i < 9; ++i) C.chest_R[i] = dcfg[HB_KD_CHEST_R0 + i];
+  C.max_depth = 0;
+  C.n_slots = 0;
+  for (int l = 0; l < C.nb; ++l) {
+    hb::BodyC& B = C.body[l];
+    const double* d = dcfg + HB_KD_BODY0 + HB_KD_BODY_STRIDE * l;
+    for (int i = 0; i < 9; ++i) B.E[i] = d[i];
+    for (int i = 0; i < 3; ++i) B.r[i] = d[9 + i];
+    for (int i = 0; i < 3; ++i) B.axis[i] = d[12 + i];
+    B.mass = d[15];
+    for (int i = 0; i < 3; ++i) B.com[i] = d[16 + i];
+    const double* I = d + 19;
+    B.inertia[0] = I[0];
+    B.inertia[1] = I[1];
+    B.inertia[2] = I[2];
+    B.inertia[3] = I[4];
+    B.inertia[4] = I[5];
+    B.inertia[5] = I[8];
+    const double a[3] = {B.axis[0], B.axis[1], B.axis[2]};
+    const double A[9] = {0, -a[2], a[1], a[2], 0, -a[0], -a[1], a[0], 0};
+    double A2[9];
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j) A2[3 * i + j] = A[3 * i] * A[j] + A[3 * i + 1] * A[3 + j] + A[3 * i + 2] * A[6 + j];
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j) {
+        B.EA[3 * i + j] = B.E[3 * i] * A[j] + B.E[3 * i + 1] * A[3 + j] + B.E[3 * i + 2] * A[6 + j];
+        B.EA2[3 * i + j] = B.E[3 * i] * A2[j] + B.E[3 * i + 1] * A2[3 + j] + B.E[3 * i + 2] * A2[6 + j];
+      }
+    B.parent = l == 0 ? -1 : icfg[HB_KI_PARENT0 + l];
+    if (l > 0 && (B.parent < 0 || B.parent >= l)) {
+      delete h;
+      return fail(HB_ERR_INVALID, "hb_kino_create: bodies must be ordered parent-before-child");
+    }
+    B.depth = l == 0 ? 0 : C.body[B.parent].depth + 1;
+    if (B.depth > C.max_depth) C.max_depth = B.depth;
+    B.slot = -1;
+    B.carry = 0;
+  }
+  for (int l = 1; l < C.nb; ++l) {
+    const int p = C.body[l].parent;
+    if (p == l - 1) C.body[p].carry = 1;
+    else if (p != 0 && C.body[p].slot < 0) C.body[p].slot = C.n_slots++;
+  }
+  for (int j = 0; j < HB_MAX_BODIES; ++j) C.sub_mask[j] = 0u;
+  for (int l = 0; l < C.nb; ++l) {
+    int bdy = l;
+    while (bdy >= 0) {
+      C.sub_mask[bdy] |= (1u << l);
+      bdy = C.body[bdy].parent;
+    }
+  }
+  const size_t N = C.N;
+  cudaError_t e = cudaSuccess;
+  if (e == cudaSuccess) e = upload(&h->d_jc, jc_map, N * C.n_jc);
+  if (e == cudaSuccess) e = upload(&h->d_jk, jk_map, N * C.n_jk);
+  if (e == cudaSuccess) e = upload(&h->d_hci, hc_index, (size_t)129 * 129);
+  if (e == cudaSuccess) e = upload(&h->d_hc, hc_map, N * C.n_hc);
+  if (e == cudaSuccess) e = upload(&h->d_hk, hk_map, N * 27 * 57);
+  if (e == cudaSuccess) e = upload(&h->d_hk2, hk2_map, N * 27);
+  C.jc_map = h->d_jc;
+  C.jk_map = h->d_jk;
+  C.hc_index = h->d_hci;
+  C.hc_map = h->d_hc;
+  C.hk_map = h->d_hk;
+  C.hk2_map = h->d_hk2;
+  if (e == cudaSuccess) e = upload(&h->dev, &C, 1);
+  if (e != cudaSuccess) {
+    hb_destroy(h);
+    return fail(HB_ERR_CUDA, std::string("hb_kino_create: ") + cudaGetErrorString(e));
+  }
+  *out = h;
+  return HB_OK;
+}
+
+extern "C" int hb_toy_create(int32_t horizon, int32_t integrator, double dt, hb_handle* out) {
+  if (!out || horizon < 2 || (integrator != 0 && integrator != 1)) return fail(HB_ERR_INVALID, "hb_toy_create: bad argument");
+  hb_problem_s* h = new hb_problem_s();
+  h->kind = KIND_TOY;
+  h->toy = hb::toy_create(horizon, integrator, dt);
+  if (!h->toy) {
+    delete h;
+    return fail(HB_ERR_CUDA, "hb_toy_create: device allocation failed");
+  }
+  *out = h;
+  return HB_OK;
+}
+
+extern "C" int hb_destroy(hb_handle h) {
+  if (!h) return HB_OK;
+  cudaFree(h->d_jc);
+  cudaFree(h->d_jk);
+  cudaFree(h->d_hci);
+  cudaFree(h->d_hc);
+  cudaFree(h->d_hk);
+  cudaFree(h->d_hk2);
+  cudaFree(h->dev);
+  cudaFree(h->d_fpart);
+  if (h->toy) hb::toy_destroy(h->toy);
+  delete h;
+  return HB_OK;
+}
+
+extern "C" int hb_dims(hb_handle h, int64_t* n_x, int64_t* n_p, int64_t* m, int64_t* nnz_j, int64_t* nnz_h) {
+  if (!h) return fail(HB_ERR_INVALID, "hb_dims: null handle");
+  if (h->kind == KIND_TOY) {
+    hb::toy_dims(h->toy, n_x, n_p, m, nnz_j, nnz_h);
+    return HB_OK;
+  }
+  if (n_x) *n_x = h->host.n_x;
+  if (n_p) *n_p = h->host.n_p;
+  if (m) *m = h->host.m;
+  if (nnz_j) *nnz_j = h->host.nnz_j;
+  if (nnz_h) *nnz_h = h->host.nnz_h;
+  return HB_OK;
+}
+
+extern "C" int hb_pattern_jac(hb_handle h, int64_t* colind, int64_t* row) {
+  if (!h || !colind || !row) return fail(HB_ERR_INVALID, "hb_pattern_jac: null argument");
+  if (h->kind != KIND_TOY) return fail(HB_ERR_UNSUPPORTED, "hb_pattern_jac: pattern is owned by the layout compiler");
+  hb::toy_pattern_jac(h->toy, colind, row);
+  return HB_OK;
+}
+
+extern "C" int hb_pattern_hess(hb_handle h, int64_t* colind, int64_t* row) {
+  if (!h || !colind || !row) return fail(HB_ERR_INVALID, "hb_pattern_hess: null argument");
+  if (h->kind != KIND_TOY) return fail(HB_ERR_UNSUPPORTED, "hb_pattern_hess: pattern is owned by the layout compiler");
+  hb::toy_pattern_hess(h->toy, colind, row);
+  return HB_OK;
+}
+
+extern "C" int hb_eval(hb_handle h, uint32_t mask, const double* x, const double* p, int64_t p_stride,
+                       const double* lam_g, const double* sigma, double* f, double* grad_f, double* g,
+                       double* jac_vals, double* hess_vals, int64_t batch, void* stream) {
+  if (!h) return fail(HB_ERR_INVALID, "hb_eval: null handle");
+  if (batch <= 0) return fail(HB_ERR_INVALID, "hb_eval: batch must be positive");
+  if (!x || !p) return fail(HB_ERR_INVALID, "hb_eval: x and p are required");
+  if ((mask & HB_EVAL_F) && !f) return fail(HB_ERR_INVALID, "hb_eval: f requested but NULL");
+  if ((mask & HB_EVAL_GRAD_F) && !grad_f) return fail(HB_ERR_INVALID, "hb_eval: grad_f requested but NULL");
+  if ((mask & HB_EVAL_G) && !g) return fail(HB_ERR_INVALID, "hb_eval: g requested but NULL");
+  if ((mask & HB_EVAL_JAC_G) && !jac_vals) return fail(HB_ERR_INVALID, "hb_eval: jac_vals requested but NULL");
+  if ((mask & HB_EVAL_HESS_L) && (!hess_vals || !lam_g || !sigma))
+    return fail(HB_ERR_INVALID, "hb_eval: hess_vals, lam_g and sigma are required for HB_EVAL_HESS_L");
+  if (!(mask & 31u)) return fail(HB_ERR_INVALID, "hb_eval: empty mask");
+  cudaStream_t st = (cudaStream_t)stream;
+  h->launches = 0;
+  if (h->kind == KIND_TOY) {
+    const int rc = hb::toy_eval(h->toy, mask, x, p, p_stride, lam_g, sigma, f, grad_f, g, jac_vals, hess_vals, batch, st);
+    if (rc < 0) return fail(HB_ERR_CUDA, "hb_eval(toy): launch failed");
+    h->launches = rc;
+    return HB_OK;
+  }
+  const hb::KinoConst& C = h->host;
+  if (p_stride != 0 && p_stride != C.n_p) return fail(HB_ERR_INVALID, "hb_eval: p_stride must be 0 or n_p");
+  if (mask & HB_EVAL_F) {
+    const int64_t need = batch * C.N * 2;
+    if (need > h->fpart_cap) {
+      cudaFree(h->d_fpart);
+      h->d_fpart = nullptr;
+      CUDA_TRY(cudaMalloc(&h->d_fpart, need * sizeof(double)));
+      h->fpart_cap = need;
+    }
+  }
+  const int warps_per_block = 4;
+  const long total_warps = (long)batch * C.N;
+  const unsigned grid = (unsigned)((total_warps + warps_per_block - 1) / warps_per_block);
+  const bool with_hess = (mask & HB_EVAL_HESS_L) != 0;
+  {
+    const size_t smem = (size_t)hb::contact_smem_layout(C.n_hc).total * sizeof(double) * warps_per_block;
+    static bool attr_set = false;
+    if (!attr_set) {
+      CUDA_TRY(cudaFuncSetAttribute(hb::kino_contact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      CUDA_TRY(cudaFuncSetAttribute(hb::kino_kin_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      CUDA_TRY(cudaFuncSetAttribute(hb::kino_kin_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      attr_set = true;
+    }
+    hb::kino_contact_kernel<<<grid, 32 * warps_per_block, smem, st>>>(h->dev, mask, x, p, (long)p_stride, lam_g, sigma,
+                                                                     h->d_fpart, grad_f, g, jac_vals, hess_vals,
+                                                                     (long)batch);
+    CUDA_TRY(cudaGetLastError());
+    h->launches++;
+  }
+  {
+    const size_t smem = (size_t)hb::kin_smem_layout(C.nb, C.n_slots, with_hess).total * sizeof(double) * warps_per_block;
+    if (with_hess)
+      hb::kino_kin_kernel<true><<<grid, 32 * warps_per_block, smem, st>>>(h->dev, mask, x, p, (long)p_stride, lam_g, sigma,
+                                                                         h->d_fpart, grad_f, g, jac_vals, hess_vals,
+                                                                         (long)batch);
+    else
+      hb::kino_kin_kernel<false><<<grid, 32 * warps_per_block, smem, st>>>(h->dev, mask, x, p, (long)p_stride, lam_g,
+                                                                          sigma, h->d_fpart, grad_f, g, jac_vals,
+                                                                          hess_vals, (long)batch);
+    CUDA_TRY(cudaGetLastError());
+    h->launches++;
+  }
+  if (mask & HB_EVAL_F) {
+    reduce_f_kernel<<<(unsigned)((batch + 127) / 128), 128, 0, st>>>(h->d_fpart, f, 2 * C.N, (long)batch);
+    CUDA_TRY(cudaGetLastError());
+    h->launches++;
+  }
+  return HB_OK;
+}
+
+extern "C" int hb_last_launch_count(hb_handle h) { return h ? h->launches : 0; }
+
+extern "C" const char* hb_last_error(void) { return g_err.c_str(); }
+
+// ---------------------------------------------------------------------------------------------
+// fp64 FMA throughput probe: 8 independent FMA chains per thread, enough CTAs to fill the chip.
+__global__ void __launch_bounds__(256) fp64_probe_kernel(double* out, int iters) {
+  double a0 = threadIdx.x * 1e-3, a1 = a0 + 1.0, a2 = a0 + 2.0, a3 = a0 + 3.0, a4 = a0 + 4.0, a5 = a0 + 5.0,
+         a6 = a0 + 6.0, a7 = a0 + 7.0;
+  const double m = 1.0000001, c = 1e-9;
+  for (int i = 0; i < iters; ++i) {
+    a0 = fma(a0, m, c);
+    a1 = fma(a1, m, c);
+    a2 = fma(a2, m, c);
+    a3 = fma(a3, m, c);
+    a4 = fma(a4, m, c);
+    a5 = fma(a5, m, c);
+    a6 = fma(a6, m, c);
+    a7 = fma(a7, m, c);
+  }
+  out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+}
+
+extern "C" int hb_probe_fp64_tflops(double* tflops, void* stream) {
+  if (!tflops) return fail(HB_ERR_INVALID, "hb_probe_fp64_tflops: null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  int dev = 0, sms = 0;
+  CUDA_TRY(cudaGetDevice(&dev));
+  CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int blocks = sms * 8, threads = 256, iters = 1 << 14;
+  double* buf = nullptr;
+  CUDA_TRY(cudaMalloc(&buf, (size_t)blocks * threads * sizeof(double)));
+  cudaEvent_t e0, e1;
+  CUDA_TRY(cudaEventCreate(&e0));
+  CUDA_TRY(cudaEventCreate(&e1));
+  double best = 0.0;
+  for (int rep = 0; rep < 5; ++rep) {
+    CUDA_TRY(cudaEventRecord(e0, st));
+    fp64_probe_kernel<<<blocks, threads, 0, st>>>(buf, iters);
+    CUDA_TRY(cudaEventRecord(e1, st));
+    CUDA_TRY(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+    const double flops = 2.0 * 8.0 * (double)iters * blocks * threads;
+    const double tf = flops / (ms * 1e-3) / 1e12;
+    if (rep > 0 && tf > best) best = tf;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(buf);
+  *tflops = best;
+  return HB_OK;
+}

@@ -1,0 +1,63 @@
+// kino_const.cuh -- device-resident constant block of one kinodynamic problem handle.
+#pragma once
+#include "../../include/hippopt_b200.h"
+#include "hb_math.cuh"
+
+namespace hb {
+
+struct BodyC {
+  double E[9];    // parent <- joint frame rotation
+  double EA[9];   // E [a]x
+  double EA2[9];  // E [a]x^2
+  double r[3];    // joint origin in the parent frame
+  double axis[3];
+  double mass;
+  double com[3];
+  double inertia[6];  // about the CoM, body frame, (xx, xy, xz, yy, yz, zz)
+  int parent;
+  int depth;
+  int slot;   // >= 0: this body owns a shared-memory branch accumulator
+  int carry;  // 1: the contribution of body index+1 continues into this body (parent[index+1] == index)
+};
+
+struct KinoConst {
+  int N, n_x, n_p, m, nnz_j, nnz_h, n_jc, n_jk, n_hc, terrain, has_final, has_per, h_init;
+  int po_desc0, po_mass, po_init, po_final, po_dt, po_gravity, po_kt, po_kbs, po_eps, po_mu, po_max_u, po_max_fd,
+      po_max_L, po_min_com_h, po_min_feet_d, po_max_feet_h, po_max_s, po_min_s, po_max_sd, po_min_sd, po_refs0,
+      po_terrain;
+  int yaw[3];
+  int nb, foot_body[2], chest_body, max_depth, n_slots;
+  int fam[HB_KF_COUNT][4];
+  unsigned sub_mask[HB_MAX_BODIES];  // bit l: body l is in the subtree rooted at this body
+  double w_swing, w_u, w_fd, w_centroid, w_comvel[3], w_frame, w_bq, w_bqv, w_joint, w_ratio, w_yaw;
+  double wj[HB_N_JOINTS];
+  double total_mass;
+  double foot_R[2][9], foot_t[2][3], chest_R[9];
+  BodyC body[HB_MAX_BODIES];
+  const int* jc_map;
+  const int* jk_map;
+  const short* hc_index;
+  const int* hc_map;
+  const int* hk_map;
+  const int* hk2_map;
+};
+
+// global g index of local row r of family `fam` at knot k, or -1 when the row does not exist
+__device__ __forceinline__ int grow(const KinoConst& C, int fam, int k, int r) {
+  const int base = C.fam[fam][0];
+  if (base < 0 || k < C.fam[fam][2] || k > C.fam[fam][3]) return -1;
+  return base + (k - C.fam[fam][2]) * C.fam[fam][1] + r;
+}
+
+// reference sub-offsets (variables.py:13-116)
+enum {
+  R_RATIO_L = 0, R_YAW_L = 4, R_RATIO_R = 5, R_YAW_R = 9, R_SWING = 10, R_CW = 11, R_CC = 14, R_COMV = 17,
+  R_FQ = 20, R_BQ = 24, R_BQV = 28, R_JR = 32, R_COUNT = 55
+};
+// offsets inside one knot of x
+enum {
+  Z_V = 0, Z_FD = 3, Z_P = 6, Z_F = 9, Z_U = 12, Z_VB = 120, Z_QD = 123, Z_PB = 127, Z_Q = 130, Z_SD = 134,
+  Z_S = 157, Z_COM = 180, Z_H = 183, NZ = 189
+};
+
+}  // namespace hb

@@ -1,0 +1,564 @@
+// kino_contact.cu -- integrator defects, contact-point constraints, bounds and contact-space costs of the
+// kinodynamic NLP: one warp per (instance, knot); planar terrain.
+//
+// Rows / costs evaluated here (reference file:line restated):
+//   ImplicitTrapezoid defects + initial conditions   integrators/implicit_trapezoid.py:31-37,
+//                                                    base/multiple_shooting_solver.py:703-742
+//     for f_i, p_i (planner.py:721-744), pb, qb, s, com (planner.py:522-564)
+//   centroidal momentum dynamics                     planner.py:566-588, expressions/centroidal.py:62-64
+//   planar DCC complementarity                       planner.py:646-654, expressions/complementarity.py:24-32
+//   DCC margin                                       planner.py:656-669, complementarity.py:68-89
+//   height / normal force / friction cone            planner.py:671-697, expressions/contacts.py:24,54-66
+//   control bounds                                   planner.py:699-719
+//   angular momentum / CoM height / joint bounds     planner.py:341-358, 385-405
+//   feet relative height, centroid cost              planner.py:215-264
+//   final state / periodicity                        planner.py:407-425, 897-930
+//   swing heuristic, control regularisations         planner.py:855-895, contacts.py:158-166
+//   force ratio and foot yaw costs                   planner.py:746-853, contacts.py:132
+//   CoM velocity cost                                planner.py:432-447
+// Terrain: PlanarTerrain (utilities/planar_terrain.py:13,25,37): h = p_z, n = e_z, R = I.
+//
+// Local Jacobian order: hippopt_b200/kino_layout.py::_enumerate_jc.  Hessian contributions are routed
+// through the (variable, variable) -> local entry table hc_index and accumulated per warp in shared
+// memory in a fixed order (deterministic), then scattered once.
+#include "kino_const.cuh"
+
+namespace hb {
+
+enum { NCV = 129, CV_COM = 120, CV_H = 123, LS_ROWS = 31, LS_MAXV = 8 };
+
+struct ContactSmem {
+  int z, zp, hbuf, gbuf, ls_coef, ls_w, ls_r, ls_var, ls_n, total;
+};
+__host__ __device__ inline ContactSmem contact_smem_layout(int n_hc) {
+  ContactSmem s;
+  int o = 0;
+  s.z = o;
+  o += NZ + 1;
+  s.zp = o;
+  o += NZ + 1;
+  s.hbuf = o;
+  o += (n_hc + 1) & ~1;
+  s.gbuf = o;
+  o += NCV + 1;
+  s.ls_coef = o;
+  o += LS_ROWS * LS_MAXV;
+  s.ls_w = o;
+  o += LS_ROWS + 1;
+  s.ls_r = o;
+  o += LS_ROWS + 1;
+  s.ls_var = o;  // ints, two per double slot
+  o += (LS_ROWS * LS_MAXV) / 2 + 1;
+  s.ls_n = o;
+  o += LS_ROWS / 2 + 1;
+  s.total = o;
+  return s;
+}
+
+__device__ __forceinline__ double eps3(int a, int b) { return ((b - a + 3) % 3 == 1) ? 1.0 : -1.0; }
+
+// state scalars with linear dynamics, in family emission order (kino_layout.py::linear_states)
+__device__ __forceinline__ void linear_state(int j, int& so, int& ro, int& fam_dyn, int& fam_ic, int& comp) {
+  if (j < 48) {
+    const int i = j / 6, w = (j % 6) / 3;
+    comp = j % 3;
+    so = 15 * i + (w == 0 ? Z_F : Z_P) + comp;
+    ro = 15 * i + (w == 0 ? Z_FD : Z_V) + comp;
+    fam_dyn = i * HB_KF_PT_COUNT + (w == 0 ? HB_KF_PT_F_DYN : HB_KF_PT_P_DYN);
+    fam_ic = i * HB_KF_PT_COUNT + (w == 0 ? HB_KF_PT_F_IC : HB_KF_PT_P_IC);
+  } else if (j < 51) {
+    comp = j - 48;
+    so = Z_PB + comp;
+    ro = Z_VB + comp;
+    fam_dyn = HB_KF_PB_DYN;
+    fam_ic = HB_KF_PB_IC;
+  } else if (j < 55) {
+    comp = j - 51;
+    so = Z_Q + comp;
+    ro = Z_QD + comp;
+    fam_dyn = HB_KF_Q_DYN;
+    fam_ic = HB_KF_Q_IC;
+  } else if (j < 78) {
+    comp = j - 55;
+    so = Z_S + comp;
+    ro = Z_SD + comp;
+    fam_dyn = HB_KF_S_DYN;
+    fam_ic = HB_KF_S_IC;
+  } else {
+    comp = j - 78;
+    so = Z_COM + comp;
+    ro = Z_H + comp;
+    fam_dyn = HB_KF_COM_DYN;
+    fam_ic = HB_KF_COM_IC;
+  }
+}
+
+__global__ void __launch_bounds__(128) kino_contact_kernel(const KinoConst* __restrict__ Cp, unsigned mask,
+                                                           const double* __restrict__ x, const double* __restrict__ p,
+                                                           long p_stride, const double* __restrict__ lam,
+                                                           const double* __restrict__ sigma, double* __restrict__ fpart,
+                                                           double* __restrict__ grad_f, double* __restrict__ g,
+                                                           double* __restrict__ jac, double* __restrict__ hess,
+                                                           long batch) {
+  extern __shared__ double smem[];
+  const KinoConst& C = *Cp;
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const long wid = (long)blockIdx.x * (blockDim.x >> 5) + warp;
+  const int N = C.N;
+  if (wid >= batch * N) return;
+  const long b = wid / N;
+  const int k = (int)(wid % N);
+  const ContactSmem L = contact_smem_layout(C.n_hc);
+  double* sm = smem + (size_t)warp * L.total;
+  double* zs = sm + L.z;
+  double* zp = sm + L.zp;
+  double* hbuf = sm + L.hbuf;
+  double* gbuf = sm + L.gbuf;
+  double* ls_coef = sm + L.ls_coef;
+  double* ls_w = sm + L.ls_w;
+  double* ls_r = sm + L.ls_r;
+  int* ls_var = reinterpret_cast<int*>(sm + L.ls_var);
+  int* ls_n = reinterpret_cast<int*>(sm + L.ls_n);
+  const double* xinst = x + b * C.n_x;
+  const double* xb = xinst + (long)k * NZ;
+  const double* pp = p + b * p_stride;
+  const bool k1 = k >= 1;
+  const bool want_f = mask & HB_EVAL_F, want_grad = mask & HB_EVAL_GRAD_F, want_g = mask & HB_EVAL_G;
+  const bool want_jac = mask & HB_EVAL_JAC_G, want_hess = mask & HB_EVAL_HESS_L;
+
+  for (int i = lane; i < NZ; i += 32) {
+    zs[i] = xb[i];
+    zp[i] = k1 ? xb[i - NZ] : 0.0;
+  }
+  for (int i = lane; i < C.n_hc; i += 32) hbuf[i] = 0.0;
+  for (int i = lane; i < NCV; i += 32) gbuf[i] = 0.0;
+  if (lane < LS_ROWS) ls_n[lane] = 0;
+  __syncwarp();
+
+  const double dt = pp[C.po_dt];
+  const double hdt = 0.5 * dt;
+  const double mass = pp[C.po_mass];
+  const double kt = pp[C.po_kt], kbs = pp[C.po_kbs], eps = pp[C.po_eps], mu = pp[C.po_mu];
+  const double* ref = pp + C.po_refs0 + R_COUNT * k;
+  double* gb = g + b * C.m;
+  const double* lb = lam + b * C.m;
+  const double sg = want_hess ? sigma[b] : 0.0;
+  const int* jmap = C.jc_map + (size_t)k * C.n_jc;
+  double* jb = jac + b * C.nnz_j;
+  auto jput = [&](int e, double v) {
+    const int slot = jmap[e];
+    if (slot >= 0) jb[slot] = v;
+  };
+  auto hadd = [&](int vi, int vj, double v) {
+    const int e = C.hc_index[vi * NCV + vj];
+    if (e >= 0) hbuf[e] += v;
+  };
+  auto lamrow = [&](int fam, int kk, int r) -> double {
+    const int row = grow(C, fam, kk, r);
+    return row >= 0 ? lb[row] : 0.0;
+  };
+
+  // ------------------------------------------------------------------ per-point quantities (lanes 0..7)
+  const int pi_ = lane & 7;
+  const double* zpt = zs + 15 * pi_;
+  const D3 pv = ld3(zpt + Z_V), pfd = ld3(zpt + Z_FD), ppos = ld3(zpt + Z_P), pf = ld3(zpt + Z_F), pu = ld3(zpt + Z_U);
+  const double tau = tanh(kt * ppos.z);
+  const double dtau = kt * (1.0 - tau * tau);          // d tau / d p_z
+  const double ddtau = -2.0 * kt * tau * dtau;         // d2 tau / d p_z2
+  double cost = 0.0;
+
+  // ------------------------------------------------------------------ g rows
+  if (want_g) {
+    // linear defects / initial conditions
+    for (int j = lane; j < 81; j += 32) {
+      int so, ro, fd, fi, comp;
+      linear_state(j, so, ro, fd, fi, comp);
+      if (k1) {
+        const int r = grow(C, fd, k, comp);
+        if (r >= 0) gb[r] = zs[so] - (zp[so] + hdt * (zp[ro] + zs[ro]));
+      } else {
+        const int r = grow(C, fi, 0, comp);
+        if (r >= 0) gb[r] = zs[so];
+      }
+    }
+    if (!k1 && lane < 6) {
+      const int r = grow(C, HB_KF_H_IC, 0, lane);
+      if (r >= 0) gb[r] = zs[Z_H + lane] - xinst[C.h_init + lane];
+    }
+  }
+  // centroidal momentum dynamics: F(z) = g + sum_i [f_i; (p_i - x) x f_i] at knots k (lanes 0..7) and k-1 (8..15)
+  {
+    const double* zz = (lane & 8) ? zp : zs;
+    const D3 pos = ld3(zz + 15 * pi_ + Z_P), frc = ld3(zz + 15 * pi_ + Z_F), com = ld3(zz + Z_COM);
+    D3 lin = frc, ang = cross(pos - com, frc);
+    if (lane >= 16) lin = ang = v3<double>(0.0, 0.0, 0.0);
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) {
+      lin.x += __shfl_xor_sync(0xffffffffu, lin.x, o);
+      lin.y += __shfl_xor_sync(0xffffffffu, lin.y, o);
+      lin.z += __shfl_xor_sync(0xffffffffu, lin.z, o);
+      ang.x += __shfl_xor_sync(0xffffffffu, ang.x, o);
+      ang.y += __shfl_xor_sync(0xffffffffu, ang.y, o);
+      ang.z += __shfl_xor_sync(0xffffffffu, ang.z, o);
+    }
+    // lanes 0..7 hold F(z_k) sums, lanes 8..15 F(z_{k-1}); bring both to lanes 0..5
+    const double Fk[6] = {lin.x, lin.y, lin.z, ang.x, ang.y, ang.z};
+    double fa = 0.0, fb = 0.0;
+#pragma unroll
+    for (int c = 0; c < 6; ++c) {
+      const double vb_ = __shfl_sync(0xffffffffu, Fk[c], 0);
+      const double va_ = __shfl_sync(0xffffffffu, Fk[c], 8);
+      if (lane == c) {
+        fb = vb_;
+        fa = va_;
+      }
+    }
+    if (want_g && k1 && lane < 6) {
+      const double gr = pp[C.po_gravity + lane];
+      const int r = grow(C, HB_KF_H_DYN, k, lane);
+      if (r >= 0) gb[r] = zs[Z_H + lane] - (zp[Z_H + lane] + hdt * ((gr + fa) + (gr + fb)));
+    }
+  }
+  const D3 fsum = v3<double>(
+      zs[Z_F] + zs[15 + Z_F] + zs[30 + Z_F] + zs[45 + Z_F] + zs[60 + Z_F] + zs[75 + Z_F] + zs[90 + Z_F] + zs[105 + Z_F],
+      zs[Z_F + 1] + zs[16 + Z_F] + zs[31 + Z_F] + zs[46 + Z_F] + zs[61 + Z_F] + zs[76 + Z_F] + zs[91 + Z_F] + zs[106 + Z_F],
+      zs[Z_F + 2] + zs[17 + Z_F] + zs[32 + Z_F] + zs[47 + Z_F] + zs[62 + Z_F] + zs[77 + Z_F] + zs[92 + Z_F] + zs[107 + Z_F]);
+  const D3 comv = ld3(zs + Z_COM);
+
+  if (lane < 8) {
+    const int fb_ = lane * HB_KF_PT_COUNT;
+    if (want_g) {
+      int r = grow(C, fb_ + HB_KF_PT_PLANAR, k, 0);
+      if (r >= 0) {
+        gb[r] = pv.x - tau * pu.x;
+        gb[r + 1] = pv.y - tau * pu.y;
+        gb[r + 2] = pv.z - pu.z;
+      }
+      r = grow(C, fb_ + HB_KF_PT_DCC, k, 0);
+      if (r >= 0) gb[r] = eps - kbs * (ppos.z * pf.z) - (pv.z * pf.z + ppos.z * pfd.z);
+      r = grow(C, fb_ + HB_KF_PT_HEIGHT, k, 0);
+      if (r >= 0) gb[r] = ppos.z;
+      r = grow(C, fb_ + HB_KF_PT_NORMAL, k, 0);
+      if (r >= 0) gb[r] = pf.z;
+      r = grow(C, fb_ + HB_KF_PT_FRICTION, k, 0);
+      if (r >= 0) gb[r] = -(pf.x * pf.x) - pf.y * pf.y + mu * mu * (pf.z * pf.z);
+      r = grow(C, fb_ + HB_KF_PT_U_BOUNDS, k, 0);
+      if (r >= 0) {
+        gb[r] = pu.x;
+        gb[r + 1] = pu.y;
+        gb[r + 2] = pu.z;
+      }
+      r = grow(C, fb_ + HB_KF_PT_FD_BOUNDS, k, 0);
+      if (r >= 0) {
+        gb[r] = pfd.x * mass;
+        gb[r + 1] = pfd.y * mass;
+        gb[r + 2] = pfd.z * mass;
+      }
+    }
+    // per-point costs (k >= 1): swing heuristic, control regularisations
+    if (k1) {
+      const double hd = ref[R_SWING];
+      const double dh = ppos.z - hd;
+      cost += C.w_swing * 0.5 * (dh * dh + (pv.x * pv.x + pv.y * pv.y));
+      cost += C.w_u * (pu.x * pu.x + pu.y * pu.y + pu.z * pu.z);
+      cost += C.w_fd * (pfd.x * pfd.x + pfd.y * pfd.y + pfd.z * pfd.z);
+      double* gp = gbuf + 15 * lane;
+      gp[Z_P + 2] += C.w_swing * dh;
+      gp[Z_V] += C.w_swing * pv.x;
+      gp[Z_V + 1] += C.w_swing * pv.y;
+      gp[Z_U] += 2.0 * C.w_u * pu.x;
+      gp[Z_U + 1] += 2.0 * C.w_u * pu.y;
+      gp[Z_U + 2] += 2.0 * C.w_u * pu.z;
+      gp[Z_FD] += 2.0 * C.w_fd * pfd.x;
+      gp[Z_FD + 1] += 2.0 * C.w_fd * pfd.y;
+      gp[Z_FD + 2] += 2.0 * C.w_fd * pfd.z;
+    }
+  }
+  // CoM velocity cost (all knots): sum_c w_c (h_c - ref_c)^2
+  if (lane < 3) {
+    const double e = zs[Z_H + lane] - ref[R_COMV + lane];
+    cost += C.w_comvel[lane] * e * e;
+    gbuf[CV_H + lane] += 2.0 * C.w_comvel[lane] * e;
+    if (want_hess) hadd(CV_H + lane, CV_H + lane, 2.0 * sg * C.w_comvel[lane]);
+  }
+  if (want_g) {
+    if (lane < 3) {
+      const int r = grow(C, HB_KF_L_BOUNDS, k, lane);
+      if (r >= 0) gb[r] = zs[Z_H + 3 + lane] * mass;
+    }
+    if (lane == 3) {
+      int r = grow(C, HB_KF_COM_HEIGHT, k, 0);
+      if (r >= 0) gb[r] = comv.z;
+      r = grow(C, HB_KF_FEET_RELH, k, 0);
+      if (r >= 0) {
+        const double lc = (((zs[Z_P + 2] + zs[15 + Z_P + 2]) + zs[30 + Z_P + 2]) + zs[45 + Z_P + 2]) / 4.0;
+        const double rc = (((zs[60 + Z_P + 2] + zs[75 + Z_P + 2]) + zs[90 + Z_P + 2]) + zs[105 + Z_P + 2]) / 4.0;
+        gb[r] = lc - rc;
+      }
+    }
+    if (lane < HB_N_JOINTS) {
+      int r = grow(C, HB_KF_S_BOUNDS, k, lane);
+      if (r >= 0) gb[r] = zs[Z_S + lane];
+      r = grow(C, HB_KF_SD_BOUNDS, k, lane);
+      if (r >= 0) gb[r] = zs[Z_SD + lane];
+    }
+    // final state rows (alphabetical leaf order, optimization_object.py:305-306) / periodicity
+    if (C.has_final && k == N - 1) {
+      const int r0 = grow(C, HB_KF_FINAL, k, 0);
+      for (int r = lane; r < 105; r += 32) {
+        double v;
+        if (r < 3) v = zs[Z_COM + r];
+        else if (r < 75) {
+          const int i = (r - 3) / 9, w = ((r - 3) % 9) / 3, c = (r - 3) % 3;
+          v = w == 0 ? pp[C.po_desc0 + 24 * k + 3 * i + c] : (w == 1 ? zs[15 * i + Z_F + c] : zs[15 * i + Z_P + c]);
+        } else if (r < 78) v = zs[Z_PB + r - 75];
+        else if (r < 82) v = zs[Z_Q + r - 78];
+        else v = zs[Z_S + r - 82];
+        gb[r0 + r] = v;
+      }
+    }
+    if (C.has_per && k == 0) {
+      const int r0 = grow(C, HB_KF_PERIODICITY, 0, 0);
+      const double* xl = xinst + (long)(N - 1) * NZ;
+      for (int r = lane; r < 84; r += 32) {
+        int off;
+        if (r < 48) off = 15 * (r / 6) + ((r % 6) < 3 ? Z_U + r % 3 : Z_FD + r % 3);
+        else if (r < 54) off = Z_H + r - 48;
+        else if (r < 57) off = Z_VB + r - 54;
+        else if (r < 61) off = Z_QD + r - 57;
+        else off = Z_SD + r - 61;
+        gb[r0 + r] = zs[off] - xl[off];
+      }
+    }
+  }
+
+  // ------------------------------------------------------------------ least-squares cost rows (k >= 1)
+  if (k1 && (want_f || want_grad || want_hess)) {
+    if (lane < LS_ROWS) {
+      int n = 0;
+      int* var = ls_var + lane * LS_MAXV;
+      double* cf = ls_coef + lane * LS_MAXV;
+      double w = 0.0, r = 0.0;
+      if (lane < 3) {  // contacts centroid cost, component `lane`
+        n = 8;
+        double acc = 0.0;
+        for (int i = 0; i < 8; ++i) {
+          var[i] = 15 * i + Z_P + lane;
+          cf[i] = -0.125;
+          acc += zs[15 * i + Z_P + lane];
+        }
+        r = ref[R_CC + lane] - 0.125 * acc;
+        w = C.w_centroid * ref[R_CW + lane];
+      } else if (lane < 7) {  // foot yaw task
+        const int foot = (lane - 3) >> 1, side = (lane - 3) & 1;
+        const double yaw = ref[foot == 0 ? R_YAW_L : R_YAW_R] + (side ? 1.5707963267948966 : 0.0);
+        double sn, cs;
+        sincos(yaw, &sn, &cs);
+        const int pa = 15 * (4 * foot + C.yaw[side ? 1 : 0]) + Z_P, pb2 = 15 * (4 * foot + C.yaw[side ? 2 : 1]) + Z_P;
+        n = 4;
+        var[0] = pa;
+        var[1] = pa + 1;
+        var[2] = pb2;
+        var[3] = pb2 + 1;
+        cf[0] = sn;
+        cf[1] = -cs;
+        cf[2] = -sn;
+        cf[3] = cs;
+        r = -sn * (zs[pb2] - zs[pa]) + cs * (zs[pb2 + 1] - zs[pa + 1]);
+        w = 0.5 * C.w_yaw;
+      } else {  // force ratio
+        const int t = lane - 7;
+        const int foot = t / 12, i = (t % 12) / 3, c = t % 3;
+        const double alpha = ref[(foot == 0 ? R_RATIO_L : R_RATIO_R) + i];
+        n = 4;
+        double ssum = 0.0;
+        for (int j = 0; j < 4; ++j) {
+          var[j] = 15 * (4 * foot + j) + Z_F + c;
+          cf[j] = (j == i ? 1.0 : 0.0) - alpha;
+          ssum += zs[var[j]];
+        }
+        r = zs[var[i]] - alpha * ssum;
+        w = C.w_ratio;
+      }
+      ls_n[lane] = n;
+      ls_w[lane] = w;
+      ls_r[lane] = r;
+      cost += w * r * r;
+    }
+    __syncwarp();
+    for (int row = 0; row < LS_ROWS; ++row) {
+      const int n = ls_n[row];
+      const double w = ls_w[row];
+      const int* var = ls_var + row * LS_MAXV;
+      const double* cf = ls_coef + row * LS_MAXV;
+      if (lane < n) gbuf[var[lane]] += 2.0 * w * ls_r[row] * cf[lane];
+      if (want_hess) {
+        const int npairs = n * (n + 1) / 2;
+        for (int t = lane; t < npairs; t += 32) {
+          int a = 0, tt = t;
+          while (tt >= n - a) {
+            tt -= n - a;
+            ++a;
+          }
+          const int c = a + tt;
+          hadd(var[a], var[c], 2.0 * sg * w * cf[a] * cf[c]);
+        }
+      }
+      __syncwarp();
+    }
+  }
+
+  // ------------------------------------------------------------------ f partial + grad_f
+  if (want_f || want_grad) {
+    const double total = warp_sum(cost);
+    if (lane == 0 && want_f) fpart[(b * N + k) * 2] = total;
+  }
+  __syncwarp();
+  if (want_grad) {
+    double* gf = grad_f + b * C.n_x + (long)k * NZ;
+    for (int i = lane; i < NCV; i += 32) {
+      const int off = i < 120 ? i : (i < CV_H ? Z_COM + i - CV_COM : Z_H + i - CV_H);
+      gf[off] = gbuf[i];
+    }
+    if (k == 0 && lane < 6) grad_f[b * C.n_x + C.h_init + lane] = 0.0;
+  }
+
+  // ------------------------------------------------------------------ Jacobian values
+  if (want_jac) {
+    int base = 0;
+    for (int e = lane; e < 324; e += 32) {
+      const int t = e & 3;
+      jput(e, t == 0 ? 1.0 : (t == 2 ? -1.0 : -hdt));
+    }
+    base = 324;
+    for (int e = lane; e < 93; e += 32) jput(base + e, e < 87 ? 1.0 : -1.0);
+    base += 93;
+    for (int e = lane; e < 81; e += 32) jput(base + e, 1.0);
+    base += 81;
+    for (int e = lane; e < 84; e += 32) jput(base + e, k == 0 ? 1.0 : -1.0);
+    base += 84;
+    for (int side = 0; side < 2; ++side) {
+      const int sbase = base + side * 132;
+      for (int e = lane; e < 132; e += 32) {
+        double v;
+        if (e < 6) v = side == 0 ? 1.0 : -1.0;
+        else if (e < 30) v = -hdt;
+        else if (e < 78) {
+          const int i = (e - 30) / 6, pr = (e - 30) % 6;
+          const int a = pr >> 1, bb = (a + 1 + (pr & 1) + ((a == 1 && (pr & 1) == 0) ? -2 : 0));
+          // pair order (0,1),(0,2),(1,0),(1,2),(2,0),(2,1)
+          const int bcol = a == 0 ? (pr & 1) + 1 : (a == 1 ? ((pr & 1) ? 2 : 0) : (pr & 1));
+          (void)bb;
+          const int c = 3 - a - bcol;
+          v = -hdt * eps3(a, bcol) * zs[15 * i + Z_F + c];
+        } else if (e < 126) {
+          const int i = (e - 78) / 6, pr = (e - 78) % 6;
+          const int a = pr >> 1;
+          const int bcol = a == 0 ? (pr & 1) + 1 : (a == 1 ? ((pr & 1) ? 2 : 0) : (pr & 1));
+          const int c = 3 - a - bcol;
+          v = hdt * eps3(a, bcol) * (zs[15 * i + Z_P + c] - zs[Z_COM + c]);
+        } else {
+          const int pr = e - 126;
+          const int a = pr >> 1;
+          const int bcol = a == 0 ? (pr & 1) + 1 : (a == 1 ? ((pr & 1) ? 2 : 0) : (pr & 1));
+          const int c = 3 - a - bcol;
+          const double fs = c == 0 ? fsum.x : (c == 1 ? fsum.y : fsum.z);
+          v = hdt * eps3(a, bcol) * fs;
+        }
+        jput(sbase + e, v);
+      }
+    }
+    base += 264;
+    if (lane < 8) {
+      const int pb0 = base + 29 * lane;
+      jput(pb0 + 0, 1.0);
+      jput(pb0 + 1, 1.0);
+      jput(pb0 + 2, 1.0);
+      jput(pb0 + 3, -tau);
+      jput(pb0 + 4, -tau);
+      jput(pb0 + 5, -1.0);
+      jput(pb0 + 6, -dtau * pu.x);
+      jput(pb0 + 7, -dtau * pu.y);
+      jput(pb0 + 8, -pf.z);                      // dcc wrt v_z
+      jput(pb0 + 9, -ppos.z);                    // wrt f_dot_z
+      jput(pb0 + 10, -kbs * pf.z - pfd.z);       // wrt p_z
+      jput(pb0 + 11, -kbs * ppos.z - pv.z);      // wrt f_z
+      jput(pb0 + 12, 1.0);                       // height
+      jput(pb0 + 13, 1.0);                       // normal force
+      jput(pb0 + 14, -2.0 * pf.x);
+      jput(pb0 + 15, -2.0 * pf.y);
+      jput(pb0 + 16, 2.0 * mu * mu * pf.z);
+      jput(pb0 + 17, 1.0);
+      jput(pb0 + 18, 1.0);
+      jput(pb0 + 19, 1.0);
+      jput(pb0 + 20, mass);
+      jput(pb0 + 21, mass);
+      jput(pb0 + 22, mass);
+      jput(pb0 + 23, 1.0);
+      jput(pb0 + 24, 1.0);
+      jput(pb0 + 25, 1.0);
+      jput(pb0 + 26, -1.0);
+      jput(pb0 + 27, -1.0);
+      jput(pb0 + 28, -1.0);
+    }
+    base += 232;
+    for (int e = lane; e < 67; e += 32) {
+      double v;
+      if (e < 3) v = 1.0;
+      else if (e < 6) v = -1.0;
+      else if (e < 9) v = 1.0;
+      else if (e < 12) v = mass;
+      else if (e < 59) v = 1.0;
+      else v = (e - 59) < 4 ? 0.25 : -0.25;
+      jput(base + e, v);
+    }
+  }
+
+  // ------------------------------------------------------------------ Hessian of the Lagrangian, contact block
+  if (want_hess) {
+    if (lane < 8) {
+      const int fb_ = lane * HB_KF_PT_COUNT;
+      const int o = 15 * lane;
+      const double l0 = lamrow(fb_ + HB_KF_PT_PLANAR, k, 0), l1 = lamrow(fb_ + HB_KF_PT_PLANAR, k, 1);
+      const double ld = lamrow(fb_ + HB_KF_PT_DCC, k, 0), lf = lamrow(fb_ + HB_KF_PT_FRICTION, k, 0);
+      hadd(o + Z_P + 2, o + Z_P + 2, -(l0 * pu.x + l1 * pu.y) * ddtau + (k1 ? sg * C.w_swing : 0.0));
+      hadd(o + Z_P + 2, o + Z_U, -l0 * dtau);
+      hadd(o + Z_P + 2, o + Z_U + 1, -l1 * dtau);
+      hadd(o + Z_P + 2, o + Z_F + 2, -ld * kbs);
+      hadd(o + Z_V + 2, o + Z_F + 2, -ld);
+      hadd(o + Z_FD + 2, o + Z_P + 2, -ld);
+      if (k1) {
+        hadd(o + Z_V, o + Z_V, sg * C.w_swing);
+        hadd(o + Z_V + 1, o + Z_V + 1, sg * C.w_swing);
+        hadd(o + Z_F, o + Z_F, -2.0 * lf);
+        hadd(o + Z_F + 1, o + Z_F + 1, -2.0 * lf);
+        hadd(o + Z_F + 2, o + Z_F + 2, 2.0 * mu * mu * lf);
+        for (int c = 0; c < 3; ++c) {
+          hadd(o + Z_U + c, o + Z_U + c, 2.0 * sg * C.w_u);
+          hadd(o + Z_FD + c, o + Z_FD + c, 2.0 * sg * C.w_fd);
+        }
+      }
+      // centroidal momentum dynamics: -(dt/2) (lam_k + lam_{k+1})_ang . ((p - x) x f)
+      double La[3];
+      for (int c = 0; c < 3; ++c) La[c] = lamrow(HB_KF_H_DYN, k, 3 + c) + lamrow(HB_KF_H_DYN, k + 1, 3 + c);
+      for (int a = 0; a < 3; ++a)
+        for (int bb = 0; bb < 3; ++bb) {
+          if (a == bb) continue;
+          const int c = 3 - a - bb;
+          const double v = -hdt * eps3(a, bb) * La[c];
+          hadd(o + Z_P + a, o + Z_F + bb, v);
+          hadd(CV_COM + a, o + Z_F + bb, -v);
+        }
+    }
+    __syncwarp();
+    const int* hmap = C.hc_map + (size_t)k * C.n_hc;
+    double* hb_ = hess + b * C.nnz_h;
+    for (int e = lane; e < C.n_hc; e += 32) {
+      const int slot = hmap[e];
+      if (slot >= 0) hb_[slot] = hbuf[e];
+    }
+  }
+}
+
+}  // namespace hb

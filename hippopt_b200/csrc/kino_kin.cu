@@ -1,0 +1,798 @@
+// kino_kin.cu -- floating-base kinematics block of the kinodynamic NLP: one warp per (instance, knot).
+//
+// Rows evaluated here (reference file:line of the expression each one restates):
+//   unit quaternion            planner.py:276-282
+//   contact FK consistency     planner.py:590-632  (expressions/kinematics.py:217-308)
+//   CoM consistency            planner.py:284-306  (expressions/kinematics.py:134-214)
+//   angular momentum consist.  planner.py:308-339  (expressions/kinematics.py:11-131, quaternion.py:25-51)
+//   minimum feet distance      planner.py:360-383  (expressions/kinematics.py:311-394)
+// Costs: frame orientation (planner.py:449-477, kinematics.py:397-491), base quaternion (:479-491,
+// quaternion.py:54-85), quaternion velocity (:493-503), joint regularisation (:505-520).
+//
+// Algorithm (not the reference's: CasADi differentiates an expression graph; here the tree structure
+// is used directly).
+//   1. primal forward kinematics by depth level (lane = body), world transforms, twists, world
+//      inertias staged in shared memory; CoM / momentum sums by warp shuffles;
+//   2. one adjoint sweep over the tree per lane in fp64: lane r carries the seed of g-row r, so the
+//      sweep returns row r of the Jacobian (32 rows: 24 FK, 3 CoM, 3 momentum, feet distance and
+//      the frame-orientation trace whose gradient feeds grad_f);
+//   3. the same adjoint sweep in dual arithmetic: lane j carries the unit tangent of variable j
+//      (4 quaternion + 23 joint directions; tangents of every link state are closed-form in the
+//      staged primal state), seeds are the true multipliers, so the tangent part of the sweep is
+//      column j of the Lagrangian Hessian (q, s, and velocity rows).
+#include "kino_const.cuh"
+
+namespace hb {
+
+enum { SB_O = 0, SB_D = 3, SB_W = 6, SB_V = 9, SB_AX = 12, SB_I = 15, SB_R = 21, SB_STRIDE = 30 };
+
+struct KinSmem {
+  int bodies, arms, fdu, fdal, fdar, G, z, gbuf, slot, total;
+};
+__host__ __device__ inline KinSmem kin_smem_layout(int nb, int n_slots, bool with_hess) {
+  KinSmem s;
+  int o = 0;
+  s.bodies = o;
+  o += nb * SB_STRIDE;
+  s.arms = o;
+  o += 24;
+  s.fdu = o;
+  o += 3;
+  s.fdal = o;
+  o += 3;
+  s.fdar = o;
+  o += 3;
+  s.G = o;
+  o += 9;
+  s.z = o;
+  o += NZ + 1;
+  s.gbuf = o;
+  o += 58;
+  s.slot = o;
+  o += n_slots * 32 * (with_hess ? 24 : 12);
+  s.total = o;
+  return s;
+}
+
+// direction data of one Hessian lane: every link state tangent is closed-form in these
+struct Dir {
+  D3 alpha, pi, wpi, vpi, u;
+  unsigned mask;
+};
+
+template <class T>
+struct St {
+  V3<T> o, d, w, v, ax;
+};
+
+__device__ __forceinline__ St<double> load_state(const double* sb, int l, const Dir&, double) {
+  const double* b = sb + l * SB_STRIDE;
+  St<double> s;
+  s.o = ld3(b + SB_O);
+  s.d = ld3(b + SB_D);
+  s.w = ld3(b + SB_W);
+  s.v = ld3(b + SB_V);
+  s.ax = ld3(b + SB_AX);
+  return s;
+}
+__device__ __forceinline__ St<Dual> load_state(const double* sb, int l, const Dir& dir, Dual) {
+  const double* b = sb + l * SB_STRIDE;
+  const D3 o = ld3(b + SB_O), d = ld3(b + SB_D), w = ld3(b + SB_W), v = ld3(b + SB_V), ax = ld3(b + SB_AX);
+  const double in = ((dir.mask >> l) & 1u) ? 1.0 : 0.0;
+  const D3 a = scale(in, dir.alpha);
+  const D3 uu = scale(in, dir.u);
+  const D3 r = o - dir.pi;
+  const D3 to = cross(a, r);
+  const D3 tw = cross(a, w - dir.wpi) + uu;
+  const D3 tv = cross(dir.wpi, to) + cross(a, (v - dir.vpi) - cross(dir.wpi, r)) + cross(uu, r);
+  St<Dual> s;
+  s.o = lift<Dual>(o, to);
+  s.d = lift<Dual>(d, cross(a, d));
+  s.w = lift<Dual>(w, tw);
+  s.v = lift<Dual>(v, tv);
+  s.ax = lift<Dual>(ax, cross(a, ax));
+  return s;
+}
+
+// world inertia of body l applied to x
+__device__ __forceinline__ D3 iapply(const double* sb, int l, const Dir&, D3 x) {
+  return symmul(sb + l * SB_STRIDE + SB_I, x);
+}
+__device__ __forceinline__ V3<Dual> iapply(const double* sb, int l, const Dir& dir, V3<Dual> x) {
+  const double* I = sb + l * SB_STRIDE + SB_I;
+  const D3 xv = v3<double>(x.x.v, x.y.v, x.z.v), xd = v3<double>(x.x.d, x.y.d, x.z.d);
+  const double in = ((dir.mask >> l) & 1u) ? 1.0 : 0.0;
+  const D3 a = scale(in, dir.alpha);
+  const D3 Ix = symmul(I, xv);
+  // d(I^w) x = [a]x I x - I [a]x x
+  const D3 t = symmul(I, xd) + cross(a, Ix) - symmul(I, cross(a, xv));
+  return lift<Dual>(Ix, t);
+}
+
+template <class T>
+struct Seeds {
+  V3<T> wc;         // d Phi / d (sum_l m_l c_l)
+  V3<T> hb;         // d Phi / d h_ang
+  V3<T> footF[2];   // force / torque (about the foot body origin) applied on the two foot bodies
+  V3<T> footN[2];
+  V3<T> chestN;     // torque on the frame-orientation body
+};
+
+// Right-trivialised angular velocity map Omega(a, b) = 2(-b_w a_v + a_w b_v - b_v x a_v)
+// (expressions/quaternion.py:42), bilinear in (quaternion a, its rate b).
+template <class A, class B>
+__device__ __forceinline__ V3<typename Prom<A, B>::type> omega_map(const A* a, const B* b) {
+  typedef typename Prom<A, B>::type T;
+  V3<A> av = v3<A>(a[0], a[1], a[2]);
+  V3<B> bv = v3<B>(b[0], b[1], b[2]);
+  V3<T> c = cross(bv, av);
+  return v3<T>(2.0 * (a[3] * b[0] - b[3] * a[0] - c.x), 2.0 * (a[3] * b[1] - b[3] * a[1] - c.y),
+               2.0 * (a[3] * b[2] - b[3] * a[2] - c.z));
+}
+
+// One adjoint sweep over the tree.  `emit.joint(l, sbar, sdbar)` receives d Phi / d s_{l-1} and
+// d Phi / d s_dot_{l-1}; the totals at the root are returned for the base chain rule.
+template <class T, class Emit>
+__device__ __forceinline__ void kin_backward(const KinoConst& C, const double* sb, const double* zs, const Dir& dir,
+                                             const Seeds<T>& S, const V3<T>& xc, const V3<T>& xd, double* slot,
+                                             Emit& emit, V3<T>& n0, V3<T>& w0, V3<T>& v0) {
+  const int nb = C.nb;
+  const int lane = threadIdx.x & 31;
+  constexpr int SW = sizeof(T) / sizeof(double);  // doubles per T
+  for (int i = 0; i < C.n_slots * 12 * SW; ++i) slot[i * 32 + lane] = 0.0;
+  V3<T> cn = vzero<T>(), cF = vzero<T>(), cw = vzero<T>(), cv = vzero<T>();
+  V3<T> An = vzero<T>(), AF = vzero<T>(), Aw = vzero<T>(), Av = vzero<T>();
+  for (int l = nb - 1; l >= 0; --l) {
+    const BodyC& bc = C.body[l];
+    if (!bc.carry) {
+      cn = vzero<T>();
+      cF = vzero<T>();
+      cw = vzero<T>();
+      cv = vzero<T>();
+    }
+    if (l == 0) {
+      cn = cn + An;
+      cF = cF + AF;
+      cw = cw + Aw;
+      cv = cv + Av;
+    }
+    const St<T> s = load_state(sb, l, dir, T());
+    // ---- local adjoints of body l
+    {
+      const double m = bc.mass;
+      const V3<T> c = s.o + s.d;
+      const V3<T> cd = s.v + cross(s.w, s.d);
+      const V3<T> cbar = scale(m, cross(cd - xd, S.hb) + S.wc);
+      const V3<T> cdbar = scale(m, cross(S.hb, c - xc));
+      const V3<T> Iw = iapply(sb, l, dir, s.w);
+      const V3<T> Ih = iapply(sb, l, dir, S.hb);
+      cF = cF + cbar;
+      cn = cn + cross(s.d, cbar) + cross(s.d, cross(cdbar, s.w)) + cross(Iw, S.hb) + cross(Ih, s.w);
+      cv = cv + cdbar;
+      cw = cw + cross(s.d, cdbar) + Ih;
+      if (l == C.foot_body[0]) {
+        cF = cF + S.footF[0];
+        cn = cn + S.footN[0];
+      }
+      if (l == C.foot_body[1]) {
+        cF = cF + S.footF[1];
+        cn = cn + S.footN[1];
+      }
+      if (l == C.chest_body) cn = cn + S.chestN;
+    }
+    if (bc.slot >= 0) {
+      double* sl = slot + bc.slot * 12 * SW * 32 + lane;
+      T* cc[12] = {&cn.x, &cn.y, &cn.z, &cF.x, &cF.y, &cF.z, &cw.x, &cw.y, &cw.z, &cv.x, &cv.y, &cv.z};
+#pragma unroll
+      for (int i = 0; i < 12; ++i) {
+        if (SW == 2)
+          *cc[i] = *cc[i] + mk<T>(sl[(2 * i) * 32], sl[(2 * i + 1) * 32]);
+        else
+          *cc[i] = *cc[i] + mk<T>(sl[i * 32], 0.0);
+      }
+    }
+    if (l == 0) break;
+    // ---- joint outputs
+    emit.joint(l, dot(s.ax, cn), dot(s.ax, cw));
+    // ---- contribution to the parent
+    const int p = bc.parent;
+    const St<T> sp = load_state(sb, p, dir, T());
+    const V3<T> rho = s.o - sp.o;
+    const double sd = zs[Z_SD + l - 1];
+    const V3<T> pn = cn + cross(rho, cF) + scale(sd, cross(s.ax, cw)) + cross(rho, cross(cv, sp.w));
+    const V3<T> pw = cw + cross(rho, cv);
+    if (p == l - 1) {
+      cn = pn;
+      cw = pw;  // cF, cv carry unchanged
+    } else if (p == 0) {
+      An = An + pn;
+      AF = AF + cF;
+      Aw = Aw + pw;
+      Av = Av + cv;
+    } else {
+      double* sl = slot + C.body[p].slot * 12 * SW * 32 + lane;
+      const T vals[12] = {pn.x, pn.y, pn.z, cF.x, cF.y, cF.z, pw.x, pw.y, pw.z, cv.x, cv.y, cv.z};
+#pragma unroll
+      for (int i = 0; i < 12; ++i) {
+        if (SW == 2) {
+          sl[(2 * i) * 32] += prim(vals[i]);
+          sl[(2 * i + 1) * 32] += tang(vals[i]);
+        } else {
+          sl[i * 32] += prim(vals[i]);
+        }
+      }
+    }
+  }
+  n0 = cn;
+  w0 = cw;
+  v0 = cv;
+}
+
+// quaternion maps: g_a (rotation tangent of R(q/|q|) along q_a), u_a = d omega_0 / d q_a,
+// w_a = d omega_0 / d q_dot_a.
+template <class T>
+__device__ __forceinline__ void quat_maps(const T* q, const double* qd, V3<T>* g, V3<T>* u, V3<T>* w) {
+  const T r2 = q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3];
+  const T r = dsqrt(r2);
+  const T ir = 1.0 / r;
+  T qh[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) qh[i] = q[i] * ir;
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    T t[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) t[i] = ((i == a ? 1.0 : 0.0) - qh[i] * qh[a]) * ir;
+    g[a] = omega_map(qh, t);
+    u[a] = omega_map(t, qd);
+    double e[4] = {0.0, 0.0, 0.0, 0.0};
+    e[a] = 1.0;
+    w[a] = omega_map(qh, e);
+  }
+}
+
+struct JacEmit {
+  const KinoConst* C;
+  const int* map;  // jk_map row of this knot
+  double* jac;     // instance base
+  double* gbuf;    // shared: grad_f accumulation for the kinematic variables
+  int lane, k;
+  double gscale;   // chest lane: 2 w_frame (phi - 3)
+  bool write;
+  // local bases inside JK (kino_layout.py::_enumerate_jk)
+  __device__ __forceinline__ int base_q() const {
+    if (lane < 24) return 4 + lane * 27;
+    if (lane < 27) return 4 + 648 + (lane - 24) * 27;
+    if (lane < 30) return 4 + 648 + 81 + (lane - 27) * 57 + 7;  // after vb(3), qd(4)
+    return -1;
+  }
+  __device__ __forceinline__ void put(int e, double v) const {
+    const int slot = map[e];
+    if (slot >= 0) jac[slot] = v;
+  }
+  __device__ __forceinline__ void joint(int l, double sbar, double sdbar) const {
+    const int j = l - 1;
+    if (lane == 31) {
+      gbuf[34 + j] += gscale * sbar;  // gbuf order: vb3 qd4 q4 sd23 s23 -> s at 34
+      return;
+    }
+    if (!write) return;
+    if (lane < 27) {
+      put(base_q() + 4 + j, sbar);
+    } else if (lane < 30) {
+      const int b = 4 + 648 + 81 + (lane - 27) * 57;
+      put(b + 11 + j, sdbar);
+      put(b + 34 + j, sbar);
+    } else if (lane == 30) {
+      put(4 + 648 + 81 + 171 + j, sbar);
+    }
+  }
+};
+
+struct HessEmit {
+  const int* map;  // hk_map row of this knot
+  double* hess;    // instance base
+  int dirj;        // direction index 0..26, or -1 (idle lane)
+  double add_sd, add_s;  // joint-regularisation terms on (sd_j, s_j), (s_j, s_j) for joint lanes
+  __device__ __forceinline__ void put(int row, double v) const {
+    const int slot = map[dirj * 57 + row];
+    if (slot >= 0) hess[slot] = v;
+  }
+  __device__ __forceinline__ void joint(int l, Dual sbar, Dual sdbar) const {
+    if (dirj < 0) return;
+    const int j = l - 1;
+    const bool own = (dirj - 4 == j);
+    put(7 + j, sdbar.d + (own ? add_sd : 0.0));   // rows: vb3 qd4 sd23 q4 s23
+    put(34 + j, sbar.d + (own ? add_s : 0.0));
+  }
+};
+
+template <bool WITH_HESS>
+__global__ void __launch_bounds__(128) kino_kin_kernel(const KinoConst* __restrict__ Cp, unsigned mask,
+                                                       const double* __restrict__ x, const double* __restrict__ p,
+                                                       long p_stride, const double* __restrict__ lam,
+                                                       const double* __restrict__ sigma, double* __restrict__ fpart,
+                                                       double* __restrict__ grad_f, double* __restrict__ g,
+                                                       double* __restrict__ jac, double* __restrict__ hess,
+                                                       long batch) {
+  extern __shared__ double smem[];
+  const KinoConst& C = *Cp;
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const long wid = (long)blockIdx.x * (blockDim.x >> 5) + warp;
+  const int N = C.N;
+  if (wid >= batch * N) return;
+  const long b = wid / N;
+  const int k = (int)(wid % N);
+  const KinSmem L = kin_smem_layout(C.nb, C.n_slots, WITH_HESS);
+  double* sm = smem + (size_t)warp * L.total;
+  double* sb = sm + L.bodies;
+  double* zs = sm + L.z;
+  double* gbuf = sm + L.gbuf;
+  const double* xb = x + b * C.n_x + (long)k * NZ;
+  const double* pb_ = p + b * p_stride;
+  const int nb = C.nb;
+  const bool k1 = k >= 1;
+
+  for (int i = lane; i < NZ; i += 32) zs[i] = xb[i];
+  for (int i = lane; i < 58; i += 32) gbuf[i] = 0.0;
+  __syncwarp();
+
+  // ------------------------------------------------------------------ base
+  const double q0 = zs[Z_Q], q1 = zs[Z_Q + 1], q2 = zs[Z_Q + 2], q3 = zs[Z_Q + 3];
+  const double qq = q0 * q0 + q1 * q1 + q2 * q2 + q3 * q3;
+  const double qn = sqrt(qq);
+  const double qh[4] = {q0 / qn, q1 / qn, q2 / qn, q3 / qn};
+  const double qdv[4] = {zs[Z_QD], zs[Z_QD + 1], zs[Z_QD + 2], zs[Z_QD + 3]};
+  if (lane == 0) {
+    // R = I + 2 w [v]x + 2 [v]x^2 (liecasadi SO3.from_quat().as_matrix() [ext])
+    const double vx = qh[0], vy = qh[1], vz = qh[2], w = qh[3];
+    double* R = sb + SB_R;
+    R[0] = 1.0 - 2.0 * (vy * vy + vz * vz);
+    R[1] = 2.0 * (vx * vy - w * vz);
+    R[2] = 2.0 * (vx * vz + w * vy);
+    R[3] = 2.0 * (vx * vy + w * vz);
+    R[4] = 1.0 - 2.0 * (vx * vx + vz * vz);
+    R[5] = 2.0 * (vy * vz - w * vx);
+    R[6] = 2.0 * (vx * vz - w * vy);
+    R[7] = 2.0 * (vy * vz + w * vx);
+    R[8] = 1.0 - 2.0 * (vx * vx + vy * vy);
+    st3(sb + SB_O, v3<double>(0.0, 0.0, 0.0));  // positions are relative to the base origin
+    st3(sb + SB_W, omega_map(qh, qdv));
+    st3(sb + SB_V, ld3(zs + Z_VB));
+    st3(sb + SB_AX, v3<double>(0.0, 0.0, 0.0));
+  }
+  __syncwarp();
+  // ------------------------------------------------------------------ forward kinematics by depth
+  for (int d = 1; d <= C.max_depth; ++d) {
+    if (lane < nb && lane > 0 && C.body[lane].depth == d) {
+      const BodyC& bc = C.body[lane];
+      const double* bp = sb + bc.parent * SB_STRIDE;
+      double* bl = sb + lane * SB_STRIDE;
+      const double s = zs[Z_S + lane - 1], sd = zs[Z_SD + lane - 1];
+      double sn, cs;
+      sincos(s, &sn, &cs);
+      const double oc = 1.0 - cs;
+      double Rl[9];
+#pragma unroll
+      for (int i = 0; i < 9; ++i) Rl[i] = bc.E[i] + sn * bc.EA[i] + oc * bc.EA2[i];
+      const double* Rp = bp + SB_R;
+      double R[9];
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) R[3 * i + j] = Rp[3 * i] * Rl[j] + Rp[3 * i + 1] * Rl[3 + j] + Rp[3 * i + 2] * Rl[6 + j];
+#pragma unroll
+      for (int i = 0; i < 9; ++i) bl[SB_R + i] = R[i];
+      const D3 op = ld3(bp + SB_O), wp = ld3(bp + SB_W), vp = ld3(bp + SB_V);
+      const D3 rho = matvec(Rp, ld3(bc.r));
+      const D3 ax = matvec(R, ld3(bc.axis));
+      st3(bl + SB_O, op + rho);
+      st3(bl + SB_AX, ax);
+      st3(bl + SB_W, wp + scale(sd, ax));
+      st3(bl + SB_V, vp + cross(wp, rho));
+    }
+    __syncwarp();
+  }
+  // ------------------------------------------------------------------ per-body derived quantities + sums
+  D3 mc = v3<double>(0.0, 0.0, 0.0), mcd = mc, hl = mc;
+  if (lane < nb) {
+    const BodyC& bc = C.body[lane];
+    double* bl = sb + lane * SB_STRIDE;
+    const double* R = bl + SB_R;
+    const D3 d = matvec(R, ld3(bc.com));
+    st3(bl + SB_D, d);
+    // I^w = R I R^T
+    double RI[9];
+    const double* I = bc.inertia;
+    const double Im[9] = {I[0], I[1], I[2], I[1], I[3], I[4], I[2], I[4], I[5]};
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) RI[3 * i + j] = R[3 * i] * Im[j] + R[3 * i + 1] * Im[3 + j] + R[3 * i + 2] * Im[6 + j];
+    double Iw[6];
+    const int ii[6] = {0, 0, 0, 1, 1, 2}, jj[6] = {0, 1, 2, 1, 2, 2};
+#pragma unroll
+    for (int e = 0; e < 6; ++e)
+      Iw[e] = RI[3 * ii[e]] * R[3 * jj[e]] + RI[3 * ii[e] + 1] * R[3 * jj[e] + 1] + RI[3 * ii[e] + 2] * R[3 * jj[e] + 2];
+#pragma unroll
+    for (int e = 0; e < 6; ++e) bl[SB_I + e] = Iw[e];
+    const D3 o = ld3(bl + SB_O), w = ld3(bl + SB_W), v = ld3(bl + SB_V);
+    const D3 c = o + d;
+    const D3 cd = v + cross(w, d);
+    mc = scale(bc.mass, c);
+    mcd = scale(bc.mass, cd);
+    hl = cross(mc, cd) + symmul(Iw, w);
+  }
+  const double M = C.total_mass;
+  const D3 Pm = v3<double>(warp_sum(mc.x), warp_sum(mc.y), warp_sum(mc.z));
+  const D3 Pd = v3<double>(warp_sum(mcd.x), warp_sum(mcd.y), warp_sum(mcd.z));
+  D3 hang = v3<double>(warp_sum(hl.x), warp_sum(hl.y), warp_sum(hl.z));
+  hang = hang - scale(1.0 / M, cross(Pm, Pd));
+  const D3 xc = scale(1.0 / M, Pm), xcd = scale(1.0 / M, Pd);
+  // ------------------------------------------------------------------ frames
+  const int po_desc = C.po_desc0 + 24 * k;
+  if (lane < 8) {
+    const int f = lane >> 2;
+    const double* Rf = C.foot_R[f];
+    const D3 r = ld3(pb_ + po_desc + 3 * lane);
+    const D3 bf = matvec(Rf, r) + ld3(C.foot_t[f]);
+    const D3 a = matvec(sb + C.foot_body[f] * SB_STRIDE + SB_R, bf);
+    st3(sm + L.arms + 3 * lane, a);
+  }
+  const double* ref = pb_ + C.po_refs0 + R_COUNT * k;
+  if (lane == 8) {
+    // G = R_chest_body * (R_c * R(qd)^T), qd = desired frame quaternion (not normalised, kinematics.py:447)
+    const double vx = ref[R_FQ], vy = ref[R_FQ + 1], vz = ref[R_FQ + 2], w = ref[R_FQ + 3];
+    double Rd[9];
+    Rd[0] = 1.0 - 2.0 * (vy * vy + vz * vz);
+    Rd[1] = 2.0 * (vx * vy - w * vz);
+    Rd[2] = 2.0 * (vx * vz + w * vy);
+    Rd[3] = 2.0 * (vx * vy + w * vz);
+    Rd[4] = 1.0 - 2.0 * (vx * vx + vz * vz);
+    Rd[5] = 2.0 * (vy * vz - w * vx);
+    Rd[6] = 2.0 * (vx * vz - w * vy);
+    Rd[7] = 2.0 * (vy * vz + w * vx);
+    Rd[8] = 1.0 - 2.0 * (vx * vx + vy * vy);
+    double Kc[9];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 3; ++j)
+        Kc[3 * i + j] = C.chest_R[3 * i] * Rd[3 * j] + C.chest_R[3 * i + 1] * Rd[3 * j + 1] + C.chest_R[3 * i + 2] * Rd[3 * j + 2];
+    const double* Rb = sb + C.chest_body * SB_STRIDE + SB_R;
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) sm[L.G + 3 * i + j] = Rb[3 * i] * Kc[j] + Rb[3 * i + 1] * Kc[3 + j] + Rb[3 * i + 2] * Kc[6 + j];
+  }
+  if (lane == 9) {
+    const double* RR = sb + C.foot_body[1] * SB_STRIDE + SB_R;
+    const double* RL = sb + C.foot_body[0] * SB_STRIDE + SB_R;
+    const double* Rf = C.foot_R[1];
+    st3(sm + L.fdu, matvec(RR, v3<double>(Rf[1], Rf[4], Rf[7])));  // y axis of the reference sole frame
+    st3(sm + L.fdal, matvec(RL, ld3(C.foot_t[0])));
+    st3(sm + L.fdar, matvec(RR, ld3(C.foot_t[1])));
+  }
+  __syncwarp();
+  const double* G = sm + L.G;
+  const double phi = G[0] + G[4] + G[8];
+  const D3 mG = v3<double>(G[5] - G[7], G[6] - G[2], G[1] - G[3]);
+  const D3 fdu = ld3(sm + L.fdu), fdal = ld3(sm + L.fdal), fdar = ld3(sm + L.fdar);
+  const D3 oL = ld3(sb + C.foot_body[0] * SB_STRIDE + SB_O), oR = ld3(sb + C.foot_body[1] * SB_STRIDE + SB_O);
+  const D3 fdDelta = (oL + fdal) - (oR + fdar);
+  const double feet_y = dot(fdu, fdDelta);
+  const double mass_p = pb_[C.po_mass];
+
+  // ------------------------------------------------------------------ values: g rows, costs, grad_f (simple terms)
+  const bool want_g = (mask & HB_EVAL_G) != 0;
+  double* gb = g + b * C.m;
+  if (want_g) {
+    if (lane < 8 && k1) {
+      const int f = lane >> 2;
+      const D3 a = ld3(sm + L.arms + 3 * lane);
+      const D3 o = ld3(sb + C.foot_body[f] * SB_STRIDE + SB_O);
+      const int r0 = grow(C, lane * HB_KF_PT_COUNT + HB_KF_PT_FK, k, 0);
+      const double* pp = zs + 15 * lane + Z_P;
+      if (r0 >= 0) {
+        gb[r0] = pp[0] - (zs[Z_PB] + o.x + a.x);
+        gb[r0 + 1] = pp[1] - (zs[Z_PB + 1] + o.y + a.y);
+        gb[r0 + 2] = pp[2] - (zs[Z_PB + 2] + o.z + a.z);
+      }
+    }
+    if (lane == 8) {
+      int r0 = grow(C, HB_KF_UNIT_QUAT, k, 0);
+      if (r0 >= 0) gb[r0] = qq;
+      r0 = grow(C, HB_KF_COM_KIN, k, 0);
+      if (r0 >= 0) {
+        gb[r0] = zs[Z_COM] - (zs[Z_PB] + xc.x);
+        gb[r0 + 1] = zs[Z_COM + 1] - (zs[Z_PB + 1] + xc.y);
+        gb[r0 + 2] = zs[Z_COM + 2] - (zs[Z_PB + 2] + xc.z);
+      }
+      r0 = grow(C, HB_KF_MOM_KIN, k, 0);
+      if (r0 >= 0) {
+        gb[r0] = zs[Z_H + 3] - hang.x / mass_p;
+        gb[r0 + 1] = zs[Z_H + 4] - hang.y / mass_p;
+        gb[r0 + 2] = zs[Z_H + 5] - hang.z / mass_p;
+      }
+      r0 = grow(C, HB_KF_FEET_DIST, k, 0);
+      if (r0 >= 0) gb[r0] = feet_y;
+    }
+  }
+  // base-quaternion error e = qd^-1 (x) q - (0,0,0,1) = A q - e4 (quaternion.py:64-70); columns of A
+  double Aq[4][4];
+  {
+    const double dx = -ref[R_BQ], dy = -ref[R_BQ + 1], dz = -ref[R_BQ + 2], dw = ref[R_BQ + 3];
+    // (dw, dv) (x) (bw, bv): v = dw bv + bw dv + dv x bv ; w = dw bw - dv.bv ; column a: b = e_a
+    // b = e_x
+    Aq[0][0] = dw; Aq[1][0] = dz; Aq[2][0] = -dy; Aq[3][0] = -dx;
+    Aq[0][1] = -dz; Aq[1][1] = dw; Aq[2][1] = dx; Aq[3][1] = -dy;
+    Aq[0][2] = dy; Aq[1][2] = -dx; Aq[2][2] = dw; Aq[3][2] = -dz;
+    Aq[0][3] = dx; Aq[1][3] = dy; Aq[2][3] = dz; Aq[3][3] = dw;
+  }
+  double eq[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) eq[i] = Aq[i][0] * q0 + Aq[i][1] * q1 + Aq[i][2] * q2 + Aq[i][3] * q3 - (i == 3 ? 1.0 : 0.0);
+  const double frame_cost = (phi - 3.0) * (phi - 3.0);
+  if (mask & (HB_EVAL_F | HB_EVAL_GRAD_F)) {
+    double cost = 0.0;
+    // quaternion-velocity cost (all knots) and, for k >= 1, base quaternion / joint / frame costs
+    if (lane < 4) {
+      const double e = qdv[lane] - ref[R_BQV + lane];
+      cost += C.w_bqv * e * e;
+      gbuf[3 + lane] += 2.0 * C.w_bqv * e;
+      if (k1) {
+        cost += C.w_bq * eq[lane] * eq[lane];
+        double gq = 0.0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) gq += Aq[i][lane] * eq[i];
+        gbuf[7 + lane] += 2.0 * C.w_bq * gq;
+      }
+    }
+    if (lane < HB_N_JOINTS && k1) {
+      const double sd = zs[Z_SD + lane], e = zs[Z_S + lane] - ref[R_JR + lane];
+      const double t = sd + C.wj[lane] * e;
+      cost += C.w_joint * ((HB_N_JOINTS - 1) * sd * sd + t * t);
+      gbuf[11 + lane] += C.w_joint * (2.0 * (HB_N_JOINTS - 1) * sd + 2.0 * t);
+      gbuf[34 + lane] += C.w_joint * 2.0 * C.wj[lane] * t;
+    }
+    if (lane == 31 && k1) cost += C.w_frame * frame_cost;
+    cost = warp_sum(cost);
+    if (lane == 0 && (mask & HB_EVAL_F)) fpart[(b * N + k) * 2 + 1] = cost;
+  }
+  __syncwarp();
+
+  const bool want_jac = (mask & HB_EVAL_JAC_G) != 0, want_grad = (mask & HB_EVAL_GRAD_F) != 0;
+  double* slot = sm + L.slot;
+  Dir nodir;
+  nodir.mask = 0u;
+  // ------------------------------------------------------------------ adjoint sweep, fp64: Jacobian rows
+  if (want_jac || want_grad) {
+    Seeds<double> S;
+    S.wc = S.hb = S.footF[0] = S.footF[1] = S.footN[0] = S.footN[1] = S.chestN = v3<double>(0.0, 0.0, 0.0);
+    if (lane < 24) {
+      const int pt = lane / 3, a = lane % 3, f = pt >> 2;
+      const D3 frc = v3<double>(a == 0 ? -1.0 : 0.0, a == 1 ? -1.0 : 0.0, a == 2 ? -1.0 : 0.0);
+      S.footF[f] = frc;
+      S.footN[f] = cross(ld3(sm + L.arms + 3 * pt), frc);
+    } else if (lane < 27) {
+      const int a = lane - 24;
+      S.wc = v3<double>(a == 0 ? -1.0 / M : 0.0, a == 1 ? -1.0 / M : 0.0, a == 2 ? -1.0 / M : 0.0);
+    } else if (lane < 30) {
+      const int a = lane - 27;
+      const double sc = -1.0 / mass_p;
+      S.hb = v3<double>(a == 0 ? sc : 0.0, a == 1 ? sc : 0.0, a == 2 ? sc : 0.0);
+    } else if (lane == 30) {
+      S.footF[0] = fdu;
+      S.footN[0] = cross(fdal, fdu);
+      S.footF[1] = -fdu;
+      S.footN[1] = cross(fdu, fdDelta) - cross(fdar, fdu);
+    } else {
+      S.chestN = mG;
+    }
+    JacEmit em;
+    em.C = Cp;
+    em.map = C.jk_map + (size_t)k * C.n_jk;
+    em.jac = jac + b * C.nnz_j;
+    em.gbuf = gbuf;
+    em.lane = lane;
+    em.k = k;
+    em.gscale = k1 ? 2.0 * C.w_frame * (phi - 3.0) : 0.0;
+    em.write = want_jac;
+    D3 n0, w0, v0;
+    kin_backward<double>(C, sb, zs, nodir, S, xc, xcd, slot, em, n0, w0, v0);
+    // base chain rule
+    D3 gq[4], uq[4], wq[4];
+    const double qraw[4] = {q0, q1, q2, q3};
+    quat_maps<double>(qraw, qdv, gq, uq, wq);
+    double dq[4], dqd[4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      dq[a] = dot(n0, gq[a]) + dot(w0, uq[a]);
+      dqd[a] = dot(w0, wq[a]);
+    }
+    if (lane == 31) {
+#pragma unroll
+      for (int a = 0; a < 4; ++a) gbuf[7 + a] += em.gscale * dq[a];
+    } else if (want_jac) {
+      if (lane < 27) {
+        const int bq = em.base_q();
+#pragma unroll
+        for (int a = 0; a < 4; ++a) em.put(bq + a, dq[a]);
+      } else if (lane < 30) {
+        const int bm = 4 + 648 + 81 + (lane - 27) * 57;
+        em.put(bm + 0, v0.x);
+        em.put(bm + 1, v0.y);
+        em.put(bm + 2, v0.z);
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+          em.put(bm + 3 + a, dqd[a]);
+          em.put(bm + 7 + a, dq[a]);
+        }
+      }
+      if (lane < 4) em.put(lane, 2.0 * qraw[lane]);  // unit quaternion row
+    }
+    __syncwarp();
+    if (want_grad) {
+      // gbuf order vb3 qd4 q4 sd23 s23 -> x offsets
+      double* gf = grad_f + b * C.n_x + (long)k * NZ;
+      for (int i = lane; i < 57; i += 32) {
+        int off;
+        if (i < 3) off = Z_VB + i;
+        else if (i < 7) off = Z_QD + i - 3;
+        else if (i < 11) off = Z_Q + i - 7;
+        else if (i < 34) off = Z_SD + i - 11;
+        else off = Z_S + i - 34;
+        gf[off] = gbuf[i];
+      }
+      if (lane < 3) gf[Z_PB + lane] = 0.0;
+    }
+  }
+  if (!WITH_HESS) return;
+  if (!(mask & HB_EVAL_HESS_L)) return;
+  // ------------------------------------------------------------------ adjoint sweep, dual: Hessian columns
+  {
+    const double sg = sigma[b];
+    const double* lb = lam + b * C.m;
+    const int dirj = lane < 27 ? lane : -1;
+    Dir dir;
+    dir.mask = 0u;
+    dir.alpha = dir.pi = dir.wpi = dir.vpi = dir.u = v3<double>(0.0, 0.0, 0.0);
+    Dual qD[4] = {mkdual(q0, 0.0), mkdual(q1, 0.0), mkdual(q2, 0.0), mkdual(q3, 0.0)};
+    if (lane < 4) qD[lane].d = 1.0;
+    V3<Dual> gq[4], uq[4], wq[4];
+    quat_maps<Dual>(qD, qdv, gq, uq, wq);
+    if (lane < 4) {
+      dir.mask = 0xffffffffu;
+      dir.alpha = v3<double>(gq[lane].x.v, gq[lane].y.v, gq[lane].z.v);
+      dir.u = v3<double>(uq[lane].x.v, uq[lane].y.v, uq[lane].z.v);
+      dir.wpi = ld3(sb + SB_W);
+      dir.vpi = ld3(sb + SB_V);
+    } else if (lane < 27) {
+      const int l = lane - 4 + 1;
+      dir.mask = C.sub_mask[l];
+      const double* bl = sb + l * SB_STRIDE;
+      dir.alpha = ld3(bl + SB_AX);
+      dir.pi = ld3(bl + SB_O);
+      dir.wpi = ld3(bl + SB_W);
+      dir.vpi = ld3(bl + SB_V);
+    }
+    // tangents of the CoM position / velocity along this direction
+    D3 tP = v3<double>(0.0, 0.0, 0.0), tPd = tP;
+    for (int l = 0; l < nb; ++l) {
+      const St<Dual> s = load_state(sb, l, dir, Dual());
+      const V3<Dual> c = s.o + s.d;
+      const V3<Dual> cd = s.v + cross(s.w, s.d);
+      const double m = C.body[l].mass;
+      tP = tP + scale(m, v3<double>(c.x.d, c.y.d, c.z.d));
+      tPd = tPd + scale(m, v3<double>(cd.x.d, cd.y.d, cd.z.d));
+    }
+    const V3<Dual> xcD = lift<Dual>(xc, scale(1.0 / M, tP));
+    const V3<Dual> xdD = lift<Dual>(xcd, scale(1.0 / M, tPd));
+    const double inL = ((dir.mask >> C.foot_body[0]) & 1u) ? 1.0 : 0.0;
+    const double inR = ((dir.mask >> C.foot_body[1]) & 1u) ? 1.0 : 0.0;
+    const double inC = ((dir.mask >> C.chest_body) & 1u) ? 1.0 : 0.0;
+    Seeds<Dual> S;
+    S.footF[0] = S.footF[1] = S.footN[0] = S.footN[1] = vzero<Dual>();
+    {
+      const int r0 = grow(C, HB_KF_COM_KIN, k, 0);
+      const D3 lc = r0 >= 0 ? v3<double>(lb[r0], lb[r0 + 1], lb[r0 + 2]) : v3<double>(0.0, 0.0, 0.0);
+      S.wc = lift<Dual>(scale(-1.0 / M, lc), v3<double>(0.0, 0.0, 0.0));
+      const int r1 = grow(C, HB_KF_MOM_KIN, k, 0);
+      const D3 lh = r1 >= 0 ? v3<double>(lb[r1], lb[r1 + 1], lb[r1 + 2]) : v3<double>(0.0, 0.0, 0.0);
+      S.hb = lift<Dual>(scale(-1.0 / mass_p, lh), v3<double>(0.0, 0.0, 0.0));
+    }
+    for (int pt = 0; pt < 8; ++pt) {
+      const int f = pt >> 2;
+      const int r0 = grow(C, pt * HB_KF_PT_COUNT + HB_KF_PT_FK, k, 0);
+      if (r0 < 0) continue;
+      const D3 frc = v3<double>(-lb[r0], -lb[r0 + 1], -lb[r0 + 2]);
+      const D3 a = ld3(sm + L.arms + 3 * pt);
+      const double in = f == 0 ? inL : inR;
+      const V3<Dual> aD = lift<Dual>(a, scale(in, cross(dir.alpha, a)));
+      S.footF[f] = S.footF[f] + lift<Dual>(frc, v3<double>(0.0, 0.0, 0.0));
+      S.footN[f] = S.footN[f] + cross(aD, frc);
+    }
+    {
+      const int r0 = grow(C, HB_KF_FEET_DIST, k, 0);
+      const double kd = r0 >= 0 ? lb[r0] : 0.0;
+      const St<Dual> sL = load_state(sb, C.foot_body[0], dir, Dual());
+      const St<Dual> sR = load_state(sb, C.foot_body[1], dir, Dual());
+      const V3<Dual> uD = lift<Dual>(fdu, scale(inR, cross(dir.alpha, fdu)));
+      const V3<Dual> alD = lift<Dual>(fdal, scale(inL, cross(dir.alpha, fdal)));
+      const V3<Dual> arD = lift<Dual>(fdar, scale(inR, cross(dir.alpha, fdar)));
+      const V3<Dual> dD = (sL.o + alD) - (sR.o + arD);
+      const V3<Dual> ku = scale(kd, uD);
+      S.footF[0] = S.footF[0] + ku;
+      S.footN[0] = S.footN[0] + cross(alD, ku);
+      S.footF[1] = S.footF[1] - ku;
+      S.footN[1] = S.footN[1] + scale(kd, cross(uD, dD)) - cross(arD, ku);
+    }
+    {
+      // kappa = 2 sigma w (phi - 3) with its tangent; m(G) with its tangent (columns of G rotate with alpha)
+      const D3 a = scale(inC, dir.alpha);
+      double tG[9];
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        const D3 col = v3<double>(G[j], G[3 + j], G[6 + j]);
+        const D3 t = cross(a, col);
+        tG[j] = t.x;
+        tG[3 + j] = t.y;
+        tG[6 + j] = t.z;
+      }
+      const double tphi = tG[0] + tG[4] + tG[8];
+      const double cw = k1 ? 2.0 * sg * C.w_frame : 0.0;
+      const Dual kappa = mkdual(cw * (phi - 3.0), cw * tphi);
+      const V3<Dual> mGD = lift<Dual>(mG, v3<double>(tG[5] - tG[7], tG[6] - tG[2], tG[1] - tG[3]));
+      S.chestN = scale(kappa, mGD);
+    }
+    HessEmit em;
+    em.map = C.hk_map + (size_t)k * (27 * 57);
+    em.hess = hess + b * C.nnz_h;
+    em.dirj = dirj;
+    em.add_sd = em.add_s = 0.0;
+    if (lane >= 4 && lane < 27 && k1) {
+      const double wjl = C.wj[lane - 4];
+      em.add_sd = sg * C.w_joint * 2.0 * wjl;
+      em.add_s = sg * C.w_joint * 2.0 * wjl * wjl;
+    }
+    V3<Dual> n0, w0, v0;
+    kin_backward<Dual>(C, sb, zs, dir, S, xcD, xdD, slot, em, n0, w0, v0);
+    if (dirj >= 0) {
+      em.put(0, v0.x.d);
+      em.put(1, v0.y.d);
+      em.put(2, v0.z.d);
+      const int ru = grow(C, HB_KF_UNIT_QUAT, k, 0);
+      const double lu = ru >= 0 ? lb[ru] : 0.0;
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        const Dual dq = dot(n0, gq[a]) + dot(w0, uq[a]);
+        const Dual dqd = dot(w0, wq[a]);
+        double extra = 0.0;
+        if (lane < 4 && k1) {
+          double ata = 0.0;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) ata += Aq[i][a] * Aq[i][lane];
+          extra = 2.0 * sg * C.w_bq * ata + (a == lane ? 2.0 * lu : 0.0);
+        }
+        em.put(3 + a, dqd.d);
+        em.put(30 + a, dq.d + extra);
+      }
+    }
+    // velocity-diagonal entries (HK2): quaternion-velocity cost, joint regularisation
+    if (lane < 27) {
+      const int slot2 = C.hk2_map[(size_t)k * 27 + lane];
+      if (slot2 >= 0)
+        em.hess[slot2] = lane < 4 ? 2.0 * sg * C.w_bqv : sg * C.w_joint * 2.0 * HB_N_JOINTS;
+    }
+  }
+}
+
+template __global__ void kino_kin_kernel<true>(const KinoConst*, unsigned, const double*, const double*, long,
+                                               const double*, const double*, double*, double*, double*, double*,
+                                               double*, long);
+template __global__ void kino_kin_kernel<false>(const KinoConst*, unsigned, const double*, const double*, long,
+                                                const double*, const double*, double*, double*, double*, double*,
+                                                double*, long);
+
+}  // namespace hb

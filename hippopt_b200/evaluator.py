@@ -1,0 +1,264 @@
+"""Batched NLP evaluators: thin Python owners of device buffers around the C ABI.
+
+PyTorch is used only for device memory and streams; every number is produced by the CUDA
+kernels behind ``hb_eval`` (include/hippopt_b200.h).  ``eval`` mirrors the five CasADi nlpsol
+oracle functions IPOPT calls inside ``opti.solve()``
+(`/root/reference/src/hippopt/base/opti_solver.py:479`): f, grad_f, g, jac_g, hess_l.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _capi
+from ._capi import H
+from .kino_layout import NJ, KinoLayout, KinoSettings
+from .robot_model import RobotModel
+
+F, GRAD_F, G, JAC_G, HESS_L = (H["HB_EVAL_F"], H["HB_EVAL_GRAD_F"], H["HB_EVAL_G"], H["HB_EVAL_JAC_G"],
+                               H["HB_EVAL_HESS_L"])
+ALL = F | GRAD_F | G | JAC_G | HESS_L
+
+
+def _ptr(t):
+    return ctypes.c_void_p(0 if t is None else t.data_ptr())
+
+
+class _Evaluator:
+    """Common part: dims, output buffer ownership, the hb_eval call."""
+
+    def __init__(self):
+        self._h = ctypes.c_void_p()
+        self._bufs: dict = {}
+
+    def _read_dims(self):
+        v = [ctypes.c_int64() for _ in range(5)]
+        _capi.check(_capi.lib().hb_dims(self._h, *[ctypes.byref(a) for a in v]), "hb_dims")
+        self.n_x, self.n_p, self.m, self.nnz_j, self.nnz_h = (int(a.value) for a in v)
+
+    def close(self):
+        if self._h:
+            _capi.lib().hb_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _out(self, name, shape, device):
+        key = (name, tuple(shape), str(device))
+        buf = self._bufs.get(key)
+        if buf is None:
+            buf = torch.empty(shape, dtype=torch.float64, device=device)
+            self._bufs[key] = buf
+        return buf
+
+    def eval(self, mask: int, x: torch.Tensor, p: torch.Tensor, lam_g: torch.Tensor | None = None,
+             sigma: torch.Tensor | None = None, stream: torch.cuda.Stream | None = None) -> dict:
+        """x: (B, n_x) cuda float64; p: (B, n_p) or (n_p,); lam_g: (B, m); sigma: (B,).
+        Returns a dict with the requested outputs (buffers are reused between calls)."""
+        if not x.is_cuda or x.dtype != torch.float64 or not x.is_contiguous():
+            raise ValueError("x must be a contiguous float64 CUDA tensor")
+        if x.dim() != 2 or x.shape[1] != self.n_x:
+            raise ValueError(f"x must have shape (B, {self.n_x})")
+        B = x.shape[0]
+        if not p.is_cuda or p.dtype != torch.float64 or not p.is_contiguous():
+            raise ValueError("p must be a contiguous float64 CUDA tensor")
+        if p.dim() == 1:
+            if p.shape[0] != self.n_p:
+                raise ValueError(f"p must have {self.n_p} entries")
+            p_stride = 0
+        else:
+            if tuple(p.shape) != (B, self.n_p):
+                raise ValueError(f"p must have shape ({B}, {self.n_p})")
+            p_stride = self.n_p
+        if mask & HESS_L:
+            if lam_g is None or sigma is None:
+                raise ValueError("lam_g and sigma are required for the Hessian")
+            if tuple(lam_g.shape) != (B, self.m) or tuple(sigma.shape) != (B,):
+                raise ValueError("lam_g must be (B, m) and sigma (B,)")
+            for t in (lam_g, sigma):
+                if not t.is_cuda or t.dtype != torch.float64 or not t.is_contiguous():
+                    raise ValueError("lam_g / sigma must be contiguous float64 CUDA tensors")
+        dev = x.device
+        out = {}
+        if mask & F:
+            out["f"] = self._out("f", (B,), dev)
+        if mask & GRAD_F:
+            out["grad_f"] = self._out("grad_f", (B, self.n_x), dev)
+        if mask & G:
+            out["g"] = self._out("g", (B, self.m), dev)
+        if mask & JAC_G:
+            out["jac"] = self._out("jac", (B, self.nnz_j), dev)
+        if mask & HESS_L:
+            out["hess"] = self._out("hess", (B, self.nnz_h), dev)
+        st = stream if stream is not None else torch.cuda.current_stream(dev)
+        rc = _capi.lib().hb_eval(self._h, mask, _ptr(x), _ptr(p), p_stride, _ptr(lam_g), _ptr(sigma),
+                                 _ptr(out.get("f")), _ptr(out.get("grad_f")), _ptr(out.get("g")),
+                                 _ptr(out.get("jac")), _ptr(out.get("hess")), B, ctypes.c_void_p(st.cuda_stream))
+        _capi.check(rc, "hb_eval")
+        return out
+
+    def last_launch_count(self) -> int:
+        return int(_capi.lib().hb_last_launch_count(self._h))
+
+
+def _i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+class KinoEvaluator(_Evaluator):
+    """Evaluator of the humanoid kinodynamic OCP
+    (`/root/reference/src/hippopt/turnkey_planners/humanoid_kinodynamic/planner.py:27-176`)."""
+
+    def __init__(self, model: RobotModel, settings: KinoSettings, layout: KinoLayout | None = None):
+        super().__init__()
+        self.model = model
+        self.settings = settings
+        self.layout = lay = layout if layout is not None else KinoLayout(model, settings)
+        icfg = np.zeros(H["HB_KI_COUNT"], dtype=np.int32)
+        po = lay.po
+        ints = {
+            "HORIZON": lay.N, "N_X": lay.n_x, "N_P": lay.n_p, "M": lay.m, "NNZ_J": lay.nnz_j, "NNZ_H": lay.nnz_h,
+            "N_JC": lay.n_jc, "N_JK": lay.n_jk, "N_HC": lay.n_hc, "TERRAIN": 0 if settings.terrain == "planar" else 1,
+            "HAS_FINAL": int(settings.final_state_constraint), "HAS_PERIODICITY": int(settings.periodicity_constraint),
+            "H_INIT": lay.h_init, "PO_DESC0": po.desc0, "PO_MASS": po.mass, "PO_INIT": po.init, "PO_FINAL": po.final,
+            "PO_DT": po.dt, "PO_GRAVITY": po.gravity, "PO_KT": po.kt, "PO_KBS": po.k_bs, "PO_EPS": po.eps,
+            "PO_MU": po.mu, "PO_MAX_U": po.max_u, "PO_MAX_FD": po.max_fd, "PO_MAX_L": po.max_L,
+            "PO_MIN_COM_H": po.min_com_h, "PO_MIN_FEET_D": po.min_feet_d, "PO_MAX_FEET_H": po.max_feet_h,
+            "PO_MAX_S": po.max_s, "PO_MIN_S": po.min_s, "PO_MAX_SD": po.max_sd, "PO_MIN_SD": po.min_sd,
+            "PO_REFS0": po.refs0, "PO_TERRAIN": po.terrain, "YAW_BR": settings.yaw_points[0],
+            "YAW_TR": settings.yaw_points[1], "YAW_TL": settings.yaw_points[2], "N_BODIES": model.n_bodies,
+            "FOOT_BODY_L": model.frames[settings.foot_frames[0]][0],
+            "FOOT_BODY_R": model.frames[settings.foot_frames[1]][0],
+            "CHEST_BODY": model.frames[settings.frame_quaternion_cost_frame][0],
+        }
+        for k, v in ints.items():
+            icfg[H["HB_KI_" + k]] = v
+        icfg[H["HB_KI_PARENT0"]:H["HB_KI_PARENT0"] + model.n_bodies] = model.parent
+        pt_names = ["f_ic", "f_dyn", "p_ic", "p_dyn", "planar", "dcc", "height", "normal", "friction", "u_bounds",
+                    "fd_bounds", "fk"]
+        robot = {"PB_IC": "pb_ic", "PB_DYN": "pb_dyn", "Q_IC": "q_ic", "Q_DYN": "q_dyn", "S_IC": "s_ic",
+                 "S_DYN": "s_dyn", "COM_IC": "com_ic", "COM_DYN": "com_dyn", "H_IC": "h_ic", "H_DYN": "h_dyn",
+                 "UNIT_QUAT": "unit_quat", "COM_KIN": "com_kin", "MOM_KIN": "mom_kin", "L_BOUNDS": "L_bounds",
+                 "COM_HEIGHT": "com_height", "FEET_DIST": "feet_dist", "S_BOUNDS": "s_bounds",
+                 "SD_BOUNDS": "sd_bounds", "FINAL": "final", "FEET_RELH": "feet_relh", "PERIODICITY": "periodicity"}
+
+        def put_fam(fid, name):
+            base, rows, k0, k1 = lay.fam.get(name, (-1, 0, 1, 0))
+            icfg[H["HB_KI_FAM0"] + 4 * fid:H["HB_KI_FAM0"] + 4 * fid + 4] = (base, rows, k0, k1)
+
+        assert H["HB_KF_PT_COUNT"] == len(pt_names)
+        for i in range(8):
+            for j, nm in enumerate(pt_names):
+                put_fam(i * H["HB_KF_PT_COUNT"] + j, f"pt{i}.{nm}")
+        for cname, nm in robot.items():
+            put_fam(H["HB_KF_" + cname], nm)
+
+        dcfg = np.zeros(H["HB_KD_COUNT"], dtype=np.float64)
+        s = settings
+        dcfg[H["HB_KD_W_SWING"]] = s.swing_foot_height_cost_multiplier
+        dcfg[H["HB_KD_W_U"]] = s.contact_velocity_control_cost_multiplier
+        dcfg[H["HB_KD_W_FD"]] = s.contact_force_control_cost_multiplier
+        dcfg[H["HB_KD_W_CENTROID"]] = s.contacts_centroid_cost_multiplier
+        dcfg[H["HB_KD_W_COMVEL0"]:H["HB_KD_W_COMVEL0"] + 3] = (
+            s.com_linear_velocity_cost_multiplier * np.asarray(s.com_linear_velocity_cost_weights, dtype=np.float64))
+        dcfg[H["HB_KD_W_FRAME"]] = s.desired_frame_quaternion_cost_multiplier
+        dcfg[H["HB_KD_W_BQ"]] = s.base_quaternion_cost_multiplier
+        dcfg[H["HB_KD_W_BQV"]] = s.base_quaternion_velocity_cost_multiplier
+        dcfg[H["HB_KD_W_JOINT"]] = s.joint_regularization_cost_multiplier
+        dcfg[H["HB_KD_W_RATIO"]] = s.force_regularization_cost_multiplier
+        dcfg[H["HB_KD_W_YAW"]] = s.foot_yaw_regularization_cost_multiplier
+        dcfg[H["HB_KD_WJ0"]:H["HB_KD_WJ0"] + NJ] = s.joint_regularization_cost_weights
+        dcfg[H["HB_KD_TOTAL_MASS"]] = model.total_mass()
+        for f, fr in enumerate(s.foot_frames):
+            _, R, t = model.frames[fr]
+            dcfg[H["HB_KD_FOOT_R0"] + 9 * f:H["HB_KD_FOOT_R0"] + 9 * f + 9] = R.ravel()
+            dcfg[H["HB_KD_FOOT_T0"] + 3 * f:H["HB_KD_FOOT_T0"] + 3 * f + 3] = t
+        dcfg[H["HB_KD_CHEST_R0"]:H["HB_KD_CHEST_R0"] + 9] = model.frames[s.frame_quaternion_cost_frame][1].ravel()
+        st = H["HB_KD_BODY_STRIDE"]
+        for b in range(model.n_bodies):
+            o = H["HB_KD_BODY0"] + st * b
+            dcfg[o:o + 9] = model.joint_rot[b].ravel()
+            dcfg[o + 9:o + 12] = model.joint_xyz[b]
+            dcfg[o + 12:o + 15] = model.joint_axis[b]
+            dcfg[o + 15] = model.mass[b]
+            dcfg[o + 16:o + 19] = model.com[b]
+            dcfg[o + 19:o + 28] = model.inertia[b].ravel()
+        self._keep = (icfg, dcfg, _i32(lay.jc_map), _i32(lay.jk_map), np.ascontiguousarray(lay.hc_index, dtype=np.int16),
+                      _i32(lay.hc_map), _i32(lay.hk_map), _i32(lay.hk2_map))
+        i32p, i16p, f64p = (ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int16),
+                            ctypes.POINTER(ctypes.c_double))
+        a = self._keep
+        rc = _capi.lib().hb_kino_create(
+            a[0].ctypes.data_as(i32p), a[1].ctypes.data_as(f64p), a[2].ctypes.data_as(i32p), a[3].ctypes.data_as(i32p),
+            a[4].ctypes.data_as(i16p), a[5].ctypes.data_as(i32p), a[6].ctypes.data_as(i32p), a[7].ctypes.data_as(i32p),
+            ctypes.byref(self._h))
+        _capi.check(rc, "hb_kino_create")
+        self._read_dims()
+        assert (self.n_x, self.n_p, self.m) == (lay.n_x, lay.n_p, lay.m)
+
+    # patterns (CasADi-style compressed-column)
+    def jac_sparsity(self):
+        return self.layout.jac_colind, self.layout.jac_row
+
+    def hess_sparsity(self):
+        return self.layout.hess_colind, self.layout.hess_row
+
+    def bounds(self, p):
+        return self.layout.bounds(np.asarray(p))
+
+
+class ToyEvaluator(_Evaluator):
+    """Mass-falling OCP of `/root/reference/test/test_multiple_shooting.py:253-353`; p = [g, x0, v0]."""
+
+    def __init__(self, horizon: int = 100, integrator: str = "euler", dt: float = 0.01):
+        super().__init__()
+        kind = {"euler": 0, "trapezoid": 1}[integrator]
+        _capi.check(_capi.lib().hb_toy_create(horizon, kind, dt, ctypes.byref(self._h)), "hb_toy_create")
+        self.horizon, self.dt = horizon, dt
+        self._read_dims()
+
+    def _pattern(self, fn, nnz):
+        colind = np.zeros(self.n_x + 1, dtype=np.int64)
+        row = np.zeros(nnz, dtype=np.int64)
+        i64p = ctypes.POINTER(ctypes.c_int64)
+        _capi.check(fn(self._h, colind.ctypes.data_as(i64p), row.ctypes.data_as(i64p)), "hb_pattern")
+        return colind, row
+
+    def jac_sparsity(self):
+        return self._pattern(_capi.lib().hb_pattern_jac, self.nnz_j)
+
+    def hess_sparsity(self):
+        return self._pattern(_capi.lib().hb_pattern_hess, self.nnz_h)
+
+    def bounds(self, p):
+        """(lbg, ubg) in the row order of the test's subject_to calls."""
+        p = np.atleast_2d(np.asarray(p, dtype=np.float64))
+        N = self.horizon
+        B = p.shape[0]
+        lb = np.zeros((B, self.m))
+        ub = np.zeros((B, self.m))
+        o = 2 * (N - 1)
+        lb[:, o] = ub[:, o] = p[:, 1]
+        lb[:, o + 1] = ub[:, o + 1] = p[:, 2]
+        o += 2
+        lb[:, o] = ub[:, o] = p[:, 1]
+        o += N
+        lb[:, o] = ub[:, o] = p[:, 2]
+        o += N
+        lb[:, o:o + 3 * (N - 1)] = 5.0
+        ub[:, o:o + 3 * (N - 1)] = np.inf
+        o += 3 * (N - 1)
+        lb[:, o + 3:o + 6] = ub[:, o + 3:o + 6] = 6.0
+        return lb, ub
+
+
+def probe_fp64_tflops() -> float:
+    v = ctypes.c_double()
+    _capi.check(_capi.lib().hb_probe_fp64_tflops(ctypes.byref(v), None), "hb_probe_fp64_tflops")
+    return float(v.value)

@@ -1,0 +1,214 @@
+/* hippopt_b200.h -- C ABI of the B200-native NLP evaluator for hippopt's multiple-shooting OCPs.
+ *
+ * What this boundary replaces.  hippopt has no FFI of its own: the numerical hot path is the set of
+ * NLP oracle functions CasADi builds and IPOPT calls at every iteration of ``opti.solve()``
+ *   /root/reference/src/hippopt/base/opti_solver.py:479   (single blocking call into CasADi)
+ *   [ext] nlpsol oracle functions nlp_f, nlp_grad_f, nlp_g, nlp_jac_g, nlp_hess_l
+ * for the problem that
+ *   /root/reference/src/hippopt/turnkey_planners/humanoid_kinodynamic/planner.py:27-176
+ * assembles.  A CasADi ``Callback`` / ``external`` shim forwards exactly those five
+ * evaluations to hb_eval(); the sparsity queries replace ``Function.sparsity_out`` of nlp_jac_g /
+ * nlp_hess_l (compressed-column, Hessian upper triangle).
+ *
+ * Conventions
+ *   - plain C types only; every pointer marked "device" is a CUDA device pointer owned by the caller
+ *     (fp64, contiguous, instance-major: x[b*n_x + i]); the library never allocates or frees caller
+ *     buffers and keeps no reference to them after the call returns (work is enqueued on `stream`).
+ *   - return 0 on success, non-zero error code otherwise (CasADi external-function convention);
+ *     hb_last_error() gives a message.  NaN/Inf in outputs are passed through, not trapped.
+ *   - the layout tables (row offsets, scatter maps) are computed by the host-side layout compiler
+ *     (hippopt_b200/kino_layout.py) and copied into the handle at creation.
+ */
+#ifndef HIPPOPT_B200_H
+#define HIPPOPT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct hb_problem_s* hb_handle;
+
+/* evaluation mask bits for hb_eval (any combination) */
+enum {
+  HB_EVAL_F = 1,      /* nlp_f       : f[b]                         */
+  HB_EVAL_GRAD_F = 2, /* nlp_grad_f  : grad_f[b*n_x + i]            */
+  HB_EVAL_G = 4,      /* nlp_g       : g[b*m + r]                   */
+  HB_EVAL_JAC_G = 8,  /* nlp_jac_g   : jac_vals[b*nnz_j + slot]     */
+  HB_EVAL_HESS_L = 16 /* nlp_hess_l  : hess_vals[b*nnz_h + slot]    */
+};
+
+enum { HB_OK = 0, HB_ERR_INVALID = 1, HB_ERR_CUDA = 2, HB_ERR_UNSUPPORTED = 3 };
+
+#define HB_MAX_BODIES 32
+#define HB_N_JOINTS 23
+#define HB_N_POINTS 8
+
+/* ---- integer configuration table of the kinodynamic problem (indices into icfg[]) ---- */
+enum {
+  HB_KI_HORIZON = 0,
+  HB_KI_N_X,
+  HB_KI_N_P,
+  HB_KI_M,
+  HB_KI_NNZ_J,
+  HB_KI_NNZ_H,
+  HB_KI_N_JC,
+  HB_KI_N_JK,
+  HB_KI_N_HC,
+  HB_KI_TERRAIN,          /* 0 planar (planar_terrain.py), 1 sum of two smooth steps */
+  HB_KI_HAS_FINAL,
+  HB_KI_HAS_PERIODICITY,
+  HB_KI_H_INIT,           /* x offset of initial_state.centroidal_momentum */
+  /* parameter offsets inside p */
+  HB_KI_PO_DESC0,
+  HB_KI_PO_MASS,
+  HB_KI_PO_INIT,
+  HB_KI_PO_FINAL,
+  HB_KI_PO_DT,
+  HB_KI_PO_GRAVITY,
+  HB_KI_PO_KT,
+  HB_KI_PO_KBS,
+  HB_KI_PO_EPS,
+  HB_KI_PO_MU,
+  HB_KI_PO_MAX_U,
+  HB_KI_PO_MAX_FD,
+  HB_KI_PO_MAX_L,
+  HB_KI_PO_MIN_COM_H,
+  HB_KI_PO_MIN_FEET_D,
+  HB_KI_PO_MAX_FEET_H,
+  HB_KI_PO_MAX_S,
+  HB_KI_PO_MIN_S,
+  HB_KI_PO_MAX_SD,
+  HB_KI_PO_MIN_SD,
+  HB_KI_PO_REFS0,
+  HB_KI_PO_TERRAIN,
+  /* yaw task corner indices inside a foot (planner.py:780-828) */
+  HB_KI_YAW_BR,
+  HB_KI_YAW_TR,
+  HB_KI_YAW_TL,
+  /* model topology */
+  HB_KI_N_BODIES,
+  HB_KI_FOOT_BODY_L,
+  HB_KI_FOOT_BODY_R,
+  HB_KI_CHEST_BODY,
+  HB_KI_PARENT0,                                   /* HB_MAX_BODIES entries */
+  HB_KI_FAM0 = HB_KI_PARENT0 + HB_MAX_BODIES,      /* HB_KF_COUNT x 4 entries: base, rows, k0, k1 */
+  HB_KI_COUNT_BASE = HB_KI_FAM0
+};
+
+/* constraint families in the reference's subject_to order (planner.py:124-176); the first
+ * HB_KF_PT_COUNT ids repeat per contact point: family id = point * HB_KF_PT_COUNT + local id */
+enum {
+  HB_KF_PT_F_IC = 0,
+  HB_KF_PT_F_DYN,
+  HB_KF_PT_P_IC,
+  HB_KF_PT_P_DYN,
+  HB_KF_PT_PLANAR,
+  HB_KF_PT_DCC,
+  HB_KF_PT_HEIGHT,
+  HB_KF_PT_NORMAL,
+  HB_KF_PT_FRICTION,
+  HB_KF_PT_U_BOUNDS,
+  HB_KF_PT_FD_BOUNDS,
+  HB_KF_PT_FK,
+  HB_KF_PT_COUNT
+};
+enum {
+  HB_KF_PB_IC = HB_KF_PT_COUNT * HB_N_POINTS,
+  HB_KF_PB_DYN,
+  HB_KF_Q_IC,
+  HB_KF_Q_DYN,
+  HB_KF_S_IC,
+  HB_KF_S_DYN,
+  HB_KF_COM_IC,
+  HB_KF_COM_DYN,
+  HB_KF_H_IC,
+  HB_KF_H_DYN,
+  HB_KF_UNIT_QUAT,
+  HB_KF_COM_KIN,
+  HB_KF_MOM_KIN,
+  HB_KF_L_BOUNDS,
+  HB_KF_COM_HEIGHT,
+  HB_KF_FEET_DIST,
+  HB_KF_S_BOUNDS,
+  HB_KF_SD_BOUNDS,
+  HB_KF_FINAL,
+  HB_KF_FEET_RELH,
+  HB_KF_PERIODICITY,
+  HB_KF_COUNT
+};
+#define HB_KI_COUNT (HB_KI_COUNT_BASE + 4 * HB_KF_COUNT)
+
+/* ---- double configuration table (indices into dcfg[]) ---- */
+enum {
+  HB_KD_W_SWING = 0,     /* swing_foot_height_cost_multiplier                      */
+  HB_KD_W_U,             /* contact_velocity_control_cost_multiplier               */
+  HB_KD_W_FD,            /* contact_force_control_cost_multiplier                  */
+  HB_KD_W_CENTROID,      /* contacts_centroid_cost_multiplier                      */
+  HB_KD_W_COMVEL0,       /* 3: com_linear_velocity multiplier * weights            */
+  HB_KD_W_FRAME = HB_KD_W_COMVEL0 + 3,
+  HB_KD_W_BQ,
+  HB_KD_W_BQV,
+  HB_KD_W_JOINT,
+  HB_KD_W_RATIO,
+  HB_KD_W_YAW,
+  HB_KD_WJ0,             /* 23: joint_regularization_cost_weights                  */
+  HB_KD_TOTAL_MASS = HB_KD_WJ0 + HB_N_JOINTS,
+  HB_KD_FOOT_R0,         /* 2 x 9 : sole frame rotation in its body                */
+  HB_KD_FOOT_T0 = HB_KD_FOOT_R0 + 18, /* 2 x 3                                     */
+  HB_KD_CHEST_R0 = HB_KD_FOOT_T0 + 6, /* 9                                         */
+  HB_KD_BODY0 = HB_KD_CHEST_R0 + 9    /* per body 31 doubles: E(9) r(3) axis(3) mass(1) com(3) inertia(9) pad(3) */
+};
+#define HB_KD_BODY_STRIDE 31
+#define HB_KD_COUNT (HB_KD_BODY0 + HB_KD_BODY_STRIDE * HB_MAX_BODIES)
+
+/* Create an evaluator for the humanoid kinodynamic OCP.  All arrays are HOST pointers and are copied.
+ *   icfg[HB_KI_COUNT], dcfg[HB_KD_COUNT]          configuration tables (enums above)
+ *   jc_map[N*n_jc], jk_map[N*n_jk]                local Jacobian entry -> CCS slot (-1: absent)
+ *   hc_index[129*129]                             contact-block variable pair -> local Hessian entry
+ *   hc_map[N*n_hc], hk_map[N*27*57], hk2_map[N*27] local Hessian entry -> CCS slot (-1: absent)
+ * replaces: graph construction in planner.py:27-176 + nlpsol init [ext]. */
+int hb_kino_create(const int32_t* icfg, const double* dcfg, const int32_t* jc_map, const int32_t* jk_map,
+                   const int16_t* hc_index, const int32_t* hc_map, const int32_t* hk_map,
+                   const int32_t* hk2_map, hb_handle* out);
+
+/* Create an evaluator for the mass-falling toy OCP of /root/reference/test/test_multiple_shooting.py:
+ * 210-353 (3 masses, ForwardEuler or ImplicitTrapezoid defects, horizon N).  integrator: 0 Euler, 1 trapezoid. */
+int hb_toy_create(int32_t horizon, int32_t integrator, double dt, hb_handle* out);
+
+int hb_destroy(hb_handle h);
+
+/* problem dimensions: n_x, n_p, m, nnz(jac_g), nnz(hess_l upper) */
+int hb_dims(hb_handle h, int64_t* n_x, int64_t* n_p, int64_t* m, int64_t* nnz_j, int64_t* nnz_h);
+
+/* Sparsity of jac_g (m x n_x) and hess_l (n_x x n_x, upper triangle) in compressed-column form,
+ * written to HOST arrays colind[n_x+1], row[nnz].  Only available for problems whose layout lives in
+ * the library (toy OCP); the kinodynamic pattern is owned by the layout compiler. */
+int hb_pattern_jac(hb_handle h, int64_t* colind, int64_t* row);
+int hb_pattern_hess(hb_handle h, int64_t* colind, int64_t* row);
+
+/* Evaluate the requested NLP functions for `batch` independent instances.
+ *   x      device [batch*n_x]          decision vectors
+ *   p      device [batch*n_p] or [n_p] parameters (p_stride = n_p, or 0 to share one vector)
+ *   lam_g  device [batch*m]            constraint multipliers (HB_EVAL_HESS_L only)
+ *   sigma  device [batch]              objective factor       (HB_EVAL_HESS_L only)
+ *   outputs may be NULL when their bit is not in `mask`.
+ *   stream: cudaStream_t (NULL = default stream).
+ * replaces: nlp_f / nlp_grad_f / nlp_g / nlp_jac_g / nlp_hess_l calls inside opti_solver.py:479. */
+int hb_eval(hb_handle h, uint32_t mask, const double* x, const double* p, int64_t p_stride,
+            const double* lam_g, const double* sigma, double* f, double* grad_f, double* g,
+            double* jac_vals, double* hess_vals, int64_t batch, void* stream);
+
+/* number of kernel launches the last hb_eval enqueued (for bench.py's gpu_launches claim) */
+int hb_last_launch_count(hb_handle h);
+
+const char* hb_last_error(void);
+
+/* fp64 FMA throughput probe (TFLOP/s) used as roofline denominator when none is published */
+int hb_probe_fp64_tflops(double* tflops, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HIPPOPT_B200_H */
