@@ -87,6 +87,10 @@ def lib() -> ctypes.CDLL:
     L.hb_last_launch_count.argtypes = [vp]
     L.hb_last_error.restype = ctypes.c_char_p
     L.hb_last_error.argtypes = []
+    L.hb_profile_enable.restype = ctypes.c_int
+    L.hb_profile_enable.argtypes = [vp, ctypes.c_int]
+    L.hb_profile_read.restype = ctypes.c_int
+    L.hb_profile_read.argtypes = [vp, f64p, i64p]
     L.hb_probe_fp64_tflops.restype = ctypes.c_int
     L.hb_probe_fp64_tflops.argtypes = [f64p, vp]
     _lib = L
@@ -95,7 +99,7 @@ def lib() -> ctypes.CDLL:
 
 EXPORTED_SYMBOLS = [
     "hb_kino_create", "hb_toy_create", "hb_destroy", "hb_dims", "hb_pattern_jac", "hb_pattern_hess", "hb_eval",
-    "hb_last_launch_count", "hb_last_error", "hb_probe_fp64_tflops",
+    "hb_last_launch_count", "hb_last_error", "hb_probe_fp64_tflops", "hb_profile_enable", "hb_profile_read",
 ]
 
 

@@ -1,6 +1,7 @@
 // api.cu -- C ABI (include/hippopt_b200.h): handle management, launches, fp64 probe.
 #include <cstdio>
 #include <cstring>
+#include <map>
 #include <string>
 #include <vector>
 
@@ -29,8 +30,12 @@ struct hb_problem_s {
   hb::KinoConst* dev = nullptr;
   int *d_jc = nullptr, *d_jk = nullptr, *d_hc = nullptr, *d_hk = nullptr, *d_hk2 = nullptr;
   short* d_hci = nullptr;
-  double* d_fpart = nullptr;
-  int64_t fpart_cap = 0;
+  // per-knot cost partial sums, one scratch buffer per stream so that evaluations enqueued on
+  // different streams (HostPipeline) do not share scratch
+  std::map<cudaStream_t, std::pair<double*, int64_t>> fpart;
+  // optional per-kernel timing (CUDA events on the launching stream)
+  bool prof = false;
+  std::vector<cudaEvent_t> prof_ev;  // 4 events per hb_eval: start, after contact, after kin, after reduce
   // toy
   hb::ToyProblem* toy = nullptr;
 };
@@ -224,7 +229,8 @@ extern "C" int hb_destroy(hb_handle h) {
   cudaFree(h->d_hk);
   cudaFree(h->d_hk2);
   cudaFree(h->dev);
-  cudaFree(h->d_fpart);
+  for (auto& kv : h->fpart) cudaFree(kv.second.first);
+  for (cudaEvent_t e : h->prof_ev) cudaEventDestroy(e);
   if (h->toy) hb::toy_destroy(h->toy);
   delete h;
   return HB_OK;
@@ -281,19 +287,32 @@ extern "C" int hb_eval(hb_handle h, uint32_t mask, const double* x, const double
   }
   const hb::KinoConst& C = h->host;
   if (p_stride != 0 && p_stride != C.n_p) return fail(HB_ERR_INVALID, "hb_eval: p_stride must be 0 or n_p");
+  double* d_fpart = nullptr;
   if (mask & HB_EVAL_F) {
     const int64_t need = batch * C.N * 2;
-    if (need > h->fpart_cap) {
-      cudaFree(h->d_fpart);
-      h->d_fpart = nullptr;
-      CUDA_TRY(cudaMalloc(&h->d_fpart, need * sizeof(double)));
-      h->fpart_cap = need;
+    auto& slot = h->fpart[st];
+    if (need > slot.second) {
+      cudaFree(slot.first);
+      slot.first = nullptr;
+      slot.second = 0;
+      CUDA_TRY(cudaMalloc(&slot.first, need * sizeof(double)));
+      slot.second = need;
     }
+    d_fpart = slot.first;
   }
   const int warps_per_block = 4;
   const long total_warps = (long)batch * C.N;
   const unsigned grid = (unsigned)((total_warps + warps_per_block - 1) / warps_per_block);
   const bool with_hess = (mask & HB_EVAL_HESS_L) != 0;
+  auto mark = [&]() -> int {
+    if (!h->prof) return HB_OK;
+    cudaEvent_t e;
+    CUDA_TRY(cudaEventCreate(&e));
+    h->prof_ev.push_back(e);
+    CUDA_TRY(cudaEventRecord(e, st));
+    return HB_OK;
+  };
+  if (mark() != HB_OK) return HB_ERR_CUDA;
   {
     const size_t smem = (size_t)hb::contact_smem_layout(C.n_hc).total * sizeof(double) * warps_per_block;
     static bool attr_set = false;
@@ -304,29 +323,55 @@ extern "C" int hb_eval(hb_handle h, uint32_t mask, const double* x, const double
       attr_set = true;
     }
     hb::kino_contact_kernel<<<grid, 32 * warps_per_block, smem, st>>>(h->dev, mask, x, p, (long)p_stride, lam_g, sigma,
-                                                                     h->d_fpart, grad_f, g, jac_vals, hess_vals,
+                                                                     d_fpart, grad_f, g, jac_vals, hess_vals,
                                                                      (long)batch);
     CUDA_TRY(cudaGetLastError());
     h->launches++;
   }
+  if (mark() != HB_OK) return HB_ERR_CUDA;
   {
     const size_t smem = (size_t)hb::kin_smem_layout(C.nb, C.n_slots, with_hess).total * sizeof(double) * warps_per_block;
     if (with_hess)
       hb::kino_kin_kernel<true><<<grid, 32 * warps_per_block, smem, st>>>(h->dev, mask, x, p, (long)p_stride, lam_g, sigma,
-                                                                         h->d_fpart, grad_f, g, jac_vals, hess_vals,
+                                                                         d_fpart, grad_f, g, jac_vals, hess_vals,
                                                                          (long)batch);
     else
       hb::kino_kin_kernel<false><<<grid, 32 * warps_per_block, smem, st>>>(h->dev, mask, x, p, (long)p_stride, lam_g,
-                                                                          sigma, h->d_fpart, grad_f, g, jac_vals,
+                                                                          sigma, d_fpart, grad_f, g, jac_vals,
                                                                           hess_vals, (long)batch);
     CUDA_TRY(cudaGetLastError());
     h->launches++;
   }
+  if (mark() != HB_OK) return HB_ERR_CUDA;
   if (mask & HB_EVAL_F) {
-    reduce_f_kernel<<<(unsigned)((batch + 127) / 128), 128, 0, st>>>(h->d_fpart, f, 2 * C.N, (long)batch);
+    reduce_f_kernel<<<(unsigned)((batch + 127) / 128), 128, 0, st>>>(d_fpart, f, 2 * C.N, (long)batch);
     CUDA_TRY(cudaGetLastError());
     h->launches++;
   }
+  if (mark() != HB_OK) return HB_ERR_CUDA;
+  return HB_OK;
+}
+
+extern "C" int hb_profile_enable(hb_handle h, int enable) {
+  if (!h) return fail(HB_ERR_INVALID, "hb_profile_enable: null handle");
+  for (cudaEvent_t e : h->prof_ev) cudaEventDestroy(e);
+  h->prof_ev.clear();
+  h->prof = enable != 0;
+  return HB_OK;
+}
+
+extern "C" int hb_profile_read(hb_handle h, double* ms, int64_t* n_evals) {
+  if (!h || !ms || !n_evals) return fail(HB_ERR_INVALID, "hb_profile_read: null argument");
+  ms[0] = ms[1] = ms[2] = 0.0;
+  const size_t n = h->prof_ev.size() / 4;
+  if (n) CUDA_TRY(cudaEventSynchronize(h->prof_ev[4 * n - 1]));
+  for (size_t i = 0; i < n; ++i)
+    for (int j = 0; j < 3; ++j) {
+      float t = 0.f;
+      CUDA_TRY(cudaEventElapsedTime(&t, h->prof_ev[4 * i + j], h->prof_ev[4 * i + j + 1]));
+      ms[j] += t;
+    }
+  *n_evals = (int64_t)n;
   return HB_OK;
 }
 

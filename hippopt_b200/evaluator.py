@@ -58,9 +58,11 @@ class _Evaluator:
         return buf
 
     def eval(self, mask: int, x: torch.Tensor, p: torch.Tensor, lam_g: torch.Tensor | None = None,
-             sigma: torch.Tensor | None = None, stream: torch.cuda.Stream | None = None) -> dict:
+             sigma: torch.Tensor | None = None, stream: torch.cuda.Stream | None = None,
+             out: dict | None = None) -> dict:
         """x: (B, n_x) cuda float64; p: (B, n_p) or (n_p,); lam_g: (B, m); sigma: (B,).
-        Returns a dict with the requested outputs (buffers are reused between calls)."""
+        Returns a dict with the requested outputs; ``out`` supplies caller-owned output tensors,
+        otherwise internal buffers are reused between calls."""
         if not x.is_cuda or x.dtype != torch.float64 or not x.is_contiguous():
             raise ValueError("x must be a contiguous float64 CUDA tensor")
         if x.dim() != 2 or x.shape[1] != self.n_x:
@@ -85,17 +87,18 @@ class _Evaluator:
                 if not t.is_cuda or t.dtype != torch.float64 or not t.is_contiguous():
                     raise ValueError("lam_g / sigma must be contiguous float64 CUDA tensors")
         dev = x.device
+        given = out if out is not None else {}
         out = {}
-        if mask & F:
-            out["f"] = self._out("f", (B,), dev)
-        if mask & GRAD_F:
-            out["grad_f"] = self._out("grad_f", (B, self.n_x), dev)
-        if mask & G:
-            out["g"] = self._out("g", (B, self.m), dev)
-        if mask & JAC_G:
-            out["jac"] = self._out("jac", (B, self.nnz_j), dev)
-        if mask & HESS_L:
-            out["hess"] = self._out("hess", (B, self.nnz_h), dev)
+        for bit, name, shape in ((F, "f", (B,)), (GRAD_F, "grad_f", (B, self.n_x)), (G, "g", (B, self.m)),
+                                 (JAC_G, "jac", (B, self.nnz_j)), (HESS_L, "hess", (B, self.nnz_h))):
+            if not mask & bit:
+                continue
+            t = given.get(name)
+            if t is None:
+                t = self._out(name, shape, dev)
+            elif tuple(t.shape) != shape or not t.is_cuda or t.dtype != torch.float64 or not t.is_contiguous():
+                raise ValueError(f"out[{name!r}] must be a contiguous float64 CUDA tensor of shape {shape}")
+            out[name] = t
         st = stream if stream is not None else torch.cuda.current_stream(dev)
         rc = _capi.lib().hb_eval(self._h, mask, _ptr(x), _ptr(p), p_stride, _ptr(lam_g), _ptr(sigma),
                                  _ptr(out.get("f")), _ptr(out.get("grad_f")), _ptr(out.get("g")),
@@ -105,6 +108,82 @@ class _Evaluator:
 
     def last_launch_count(self) -> int:
         return int(_capi.lib().hb_last_launch_count(self._h))
+
+    def profile(self, enable: bool) -> None:
+        _capi.check(_capi.lib().hb_profile_enable(self._h, int(enable)), "hb_profile_enable")
+
+    def profile_read(self):
+        """({kernel: summed ms}, number of hb_eval calls) since profile(True)."""
+        ms = (ctypes.c_double * 3)()
+        n = ctypes.c_int64()
+        _capi.check(_capi.lib().hb_profile_read(self._h, ms, ctypes.byref(n)), "hb_profile_read")
+        return {"contact": ms[0], "kinematics": ms[1], "reduce_f": ms[2]}, int(n.value)
+
+
+class HostPipeline:
+    """The call a CPU-side solver makes: host buffers in, host buffers out.
+
+    IPOPT lives on the host, so every evaluation needs x (and lam_g, sigma) copied
+    to the device and the values copied back.  The batch is cut into chunks that are pipelined over a
+    few CUDA streams so that H2D copies, the kernels and D2H copies of different chunks overlap; all
+    host buffers are pinned.  Parameters are uploaded once per solve (``set_parameters``), as they do
+    not change between IPOPT iterations."""
+
+    def __init__(self, ev: _Evaluator, batch: int, mask: int = ALL, chunk: int = 128, n_streams: int = 3,
+                 device: torch.device | None = None):
+        self.ev, self.B, self.mask = ev, batch, mask
+        self.dev = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self.chunk = min(chunk, batch)
+        self.streams = [torch.cuda.Stream(self.dev) for _ in range(n_streams)]
+        c = self.chunk
+
+        def dbuf(*shape):
+            return torch.empty(shape, dtype=torch.float64, device=self.dev)
+
+        def hbuf(*shape):
+            return torch.empty(shape, dtype=torch.float64).pin_memory()
+
+        shapes = {"f": (), "grad_f": (ev.n_x,), "g": (ev.m,), "jac": (ev.nnz_j,), "hess": (ev.nnz_h,)}
+        bits = {"f": F, "grad_f": GRAD_F, "g": G, "jac": JAC_G, "hess": HESS_L}
+        self.names = [n for n in shapes if mask & bits[n]]
+        self.slots = []
+        for _ in self.streams:
+            self.slots.append({
+                "x": dbuf(c, ev.n_x), "lam": dbuf(c, ev.m), "sigma": dbuf(c),
+                "out": {n: dbuf(c, *shapes[n]) for n in self.names},
+            })
+        self.p_dev = dbuf(batch, ev.n_p)
+        self.host_out = {n: hbuf(batch, *shapes[n]) for n in self.names}
+        self.h2d_bytes = 8 * batch * (ev.n_x + (ev.m + 1 if mask & HESS_L else 0))
+        self.d2h_bytes = 8 * sum(self.host_out[n].numel() for n in self.names)
+
+    def set_parameters(self, p_host: torch.Tensor) -> None:
+        self.p_dev.copy_(p_host, non_blocking=True)
+        torch.cuda.current_stream(self.dev).synchronize()
+
+    def run(self, x_host: torch.Tensor, lam_host: torch.Tensor | None = None,
+            sigma_host: torch.Tensor | None = None) -> dict:
+        """x_host (B, n_x), lam_host (B, m), sigma_host (B,): pinned float64 host tensors."""
+        need_l = bool(self.mask & HESS_L)
+        n_chunks = -(-self.B // self.chunk)
+        for ci in range(n_chunks):
+            lo, hi = ci * self.chunk, min(self.B, (ci + 1) * self.chunk)
+            n = hi - lo
+            st = self.streams[ci % len(self.streams)]
+            sl = self.slots[ci % len(self.streams)]
+            with torch.cuda.stream(st):
+                sl["x"][:n].copy_(x_host[lo:hi], non_blocking=True)
+                if need_l:
+                    sl["lam"][:n].copy_(lam_host[lo:hi], non_blocking=True)
+                    sl["sigma"][:n].copy_(sigma_host[lo:hi], non_blocking=True)
+                self.ev.eval(self.mask, sl["x"][:n], self.p_dev[lo:hi], sl["lam"][:n] if need_l else None,
+                             sl["sigma"][:n] if need_l else None, stream=st,
+                             out={k: v[:n] for k, v in sl["out"].items()})
+                for k in self.names:
+                    self.host_out[k][lo:hi].copy_(sl["out"][k][:n], non_blocking=True)
+        for st in self.streams:
+            st.synchronize()
+        return self.host_out
 
 
 def _i32(a):

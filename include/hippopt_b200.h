@@ -203,6 +203,13 @@ int hb_eval(hb_handle h, uint32_t mask, const double* x, const double* p, int64_
 /* number of kernel launches the last hb_eval enqueued (for bench.py's gpu_launches claim) */
 int hb_last_launch_count(hb_handle h);
 
+/* Per-kernel device timing of the kinodynamic evaluator.  While enabled, every hb_eval records CUDA
+ * events on its stream around the contact kernel, the kinematics kernel and the f reduction.
+ * hb_profile_read sums the elapsed milliseconds {contact, kinematics, reduce} over the hb_eval calls
+ * made since hb_profile_enable(h, 1) and returns their number. */
+int hb_profile_enable(hb_handle h, int enable);
+int hb_profile_read(hb_handle h, double* ms3, int64_t* n_evals);
+
 const char* hb_last_error(void);
 
 /* fp64 FMA throughput probe (TFLOP/s) used as roofline denominator when none is published */

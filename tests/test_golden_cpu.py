@@ -1,0 +1,36 @@
+"""The oracle reproduces the committed golden fixtures (guards the fixtures against oracle drift) and
+the product layout's pattern equals the fixtures' pattern.  CPU only."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from hippopt_b200.kino_layout import KinoLayout, KinoSettings
+from oracle import kinodynamic as kd
+from oracle import toy
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLD, "kino_*.npz"))))
+def test_kino_fixture(model, path):
+    d = np.load(path)
+    N, fin, per = int(d["horizon"]), bool(d["final"]), bool(d["periodicity"])
+    nlp, _ = kd.build(model, kd.Settings(horizon=N, final_state_constraint=fin, periodicity_constraint=per))
+    assert nlp.eval_g(d["x"], d["p"]) == pytest.approx(d["g"], rel=1e-13, abs=1e-13)
+    assert nlp.eval_f(d["x"], d["p"]) == pytest.approx(d["f"], rel=1e-13)
+    lay = KinoLayout(model, KinoSettings(horizon=N, final_state_constraint=fin, periodicity_constraint=per))
+    assert np.array_equal(lay.jac_colind, d["jac_colind"]) and np.array_equal(lay.jac_row, d["jac_row"])
+    assert np.array_equal(lay.hess_colind, d["hess_colind"]) and np.array_equal(lay.hess_row, d["hess_row"])
+    lb, ub = lay.bounds(d["p"])
+    assert np.array_equal(lb, d["lbg"]) and np.array_equal(ub, d["ubg"])
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLD, "toy_*.npz"))))
+def test_toy_fixture(path):
+    d = np.load(path)
+    integrator = "euler" if "euler" in path else "trapezoid"
+    nlp = toy.build(int(d["horizon"]), integrator, float(d["dt"]))
+    assert nlp.eval_g(d["x"], d["p"]) == pytest.approx(d["g"], rel=1e-14, abs=1e-14)
+    assert nlp.eval_hess(d["x"], d["p"], d["lam"], d["sigma"]) == pytest.approx(d["hess"], rel=1e-14)

@@ -1,0 +1,210 @@
+"""Parity tests proper: the CUDA path, called through the C ABI, against the committed golden
+fixtures, against the CPU oracle on seeded inputs, and -- at BASELINE.json's full sizes -- through
+size-independent properties.  Tolerance: 1e-10 relative (north_star), with the scale floor below."""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+RTOL = 1e-10
+
+
+def close(got, ref, rtol=RTOL):
+    """|got - ref| <= rtol * max(1, |ref|): relative for O(1)+ entries, absolute floor for entries that
+    are structurally present but numerically ~0 (e.g. d h_ang / d pb_dot)."""
+    got, ref = np.asarray(got), np.asarray(ref)
+    err = np.abs(got - ref) / np.maximum(1.0, np.abs(ref))
+    assert err.max() <= rtol, f"max scaled error {err.max():.3e} at {np.unravel_index(err.argmax(), err.shape)}"
+
+
+def dev():
+    return torch.device("cuda:0")
+
+
+def run(ev, x, p, lam, sigma, mask=None):
+    from hippopt_b200.evaluator import ALL
+
+    t = [torch.tensor(np.ascontiguousarray(a), device=dev()) for a in (x, p, lam, sigma)]
+    out = ev.eval(ALL if mask is None else mask, *t)
+    torch.cuda.synchronize()
+    return {k: v.cpu().numpy().copy() for k, v in out.items()}
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLD, "kino_*.npz"))))
+def test_kino_golden(model, built_library, path):
+    from hippopt_b200.evaluator import KinoEvaluator
+    from hippopt_b200.kino_layout import KinoSettings
+
+    d = np.load(path)
+    ev = KinoEvaluator(model, KinoSettings(horizon=int(d["horizon"]), final_state_constraint=bool(d["final"]),
+                                           periodicity_constraint=bool(d["periodicity"])))
+    assert np.array_equal(ev.jac_sparsity()[1], d["jac_row"]) and np.array_equal(ev.hess_sparsity()[1], d["hess_row"])
+    out = run(ev, d["x"], d["p"], d["lam"], d["sigma"])
+    for k in ("f", "grad_f", "g", "jac", "hess"):
+        close(out[k], d[k])
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLD, "toy_*.npz"))))
+def test_toy_golden(built_library, path):
+    from hippopt_b200.evaluator import ToyEvaluator
+
+    d = np.load(path)
+    ev = ToyEvaluator(int(d["horizon"]), "euler" if "euler" in path else "trapezoid", float(d["dt"]))
+    jc, jr = ev.jac_sparsity()
+    hc, hr = ev.hess_sparsity()
+    assert np.array_equal(jc, d["jac_colind"]) and np.array_equal(jr, d["jac_row"])
+    assert np.array_equal(hc, d["hess_colind"]) and np.array_equal(hr, d["hess_row"])
+    lb, ub = ev.bounds(d["p"])
+    assert np.array_equal(lb, d["lbg"]) and np.array_equal(ub, d["ubg"])
+    out = run(ev, d["x"], d["p"], d["lam"], d["sigma"])
+    for k in ("f", "grad_f", "g", "jac", "hess"):
+        close(out[k], d[k])
+
+
+def test_toy_reference_solution(built_library):
+    """/root/reference/test/test_multiple_shooting.py:336-353 at the test's own size (N = 100)."""
+    from hippopt_b200.evaluator import F, G, GRAD_F, ToyEvaluator
+    from oracle import toy
+
+    N, dt, g, x0, v0 = 100, 0.01, -9.81, 1.0, 0.0
+    ev = ToyEvaluator(N, "euler", dt)
+    assert (ev.n_x, ev.m) == (900, 703)
+    x = toy.closed_form_solution(N, dt, g, x0, v0)[None]
+    p = np.array([[g, x0, v0]])
+    out = run(ev, x, p, np.zeros((1, ev.m)), np.ones(1), F | G | GRAD_F)
+    lb, ub = ev.bounds(p)
+    assert np.all(out["g"] >= lb - 1e-12) and np.all(out["g"] <= ub + 1e-12)
+    assert out["f"][0] == pytest.approx(3 * (98 * 25.0 + 36.0), rel=1e-14)
+    assert np.abs(out["grad_f"][0, :600]).max() < 1e-12
+
+
+@pytest.mark.parametrize("N,fin,per,noise", [(2, False, False, 0.3), (6, True, True, 0.05), (3, True, False, 1.0)])
+def test_kino_against_oracle(model, built_library, N, fin, per, noise):
+    from hippopt_b200.evaluator import KinoEvaluator
+    from hippopt_b200.kino_layout import KinoSettings
+    from hippopt_b200.workloads import kino_batch
+    from oracle import kinodynamic as kd
+
+    ev = KinoEvaluator(model, KinoSettings(horizon=N, final_state_constraint=fin, periodicity_constraint=per))
+    x, p, lam, sigma = kino_batch(ev.layout, model, 3, seed=100 + N, noise=noise, spread=2.0)
+    sigma = np.array([0.0, 1.0, 3.5])
+    nlp, _ = kd.build(model, kd.Settings(horizon=N, final_state_constraint=fin, periodicity_constraint=per))
+    out = run(ev, x, p, lam, sigma)
+    close(out["f"], nlp.eval_f(x, p))
+    close(out["g"], nlp.eval_g(x, p))
+    close(out["grad_f"], nlp.eval_grad_f(x, p))
+    close(out["jac"], nlp.eval_jac(x, p))
+    close(out["hess"], nlp.eval_hess(x, p, lam, sigma))
+
+
+def test_kino_edge_cases(model, built_library):
+    """Single instance, shared parameter vector, zero multipliers, partial masks, argument errors."""
+    from hippopt_b200 import _capi
+    from hippopt_b200.evaluator import ALL, F, G, HESS_L, JAC_G, KinoEvaluator
+    from hippopt_b200.kino_layout import KinoSettings
+    from hippopt_b200.workloads import kino_batch
+
+    ev = KinoEvaluator(model, KinoSettings(horizon=4))
+    x, p, lam, sigma = kino_batch(ev.layout, model, 5, seed=7, noise=0.1)
+    p[:] = p[0]
+    full = run(ev, x, p, lam, sigma)
+    X, P1, L, S = (torch.tensor(a, device=dev()) for a in (x, p[0].copy(), lam, sigma))
+    shared = ev.eval(ALL, X, P1, L, S)
+    torch.cuda.synchronize()
+    for k in full:
+        assert np.array_equal(shared[k].cpu().numpy(), full[k]), k  # bit-identical
+    one = run(ev, x[2:3], p[2:3], lam[2:3], sigma[2:3])
+    for k in full:
+        assert np.array_equal(one[k][0], full[k][2]), k  # batching does not change results
+    part = run(ev, x, p, lam, sigma, F | G)
+    assert set(part) == {"f", "g"} and np.array_equal(part["g"], full["g"]) and np.array_equal(part["f"], full["f"])
+    jac_only = run(ev, x, p, lam, sigma, JAC_G)
+    assert np.array_equal(jac_only["jac"], full["jac"])
+    zero = run(ev, x, p, np.zeros_like(lam), np.zeros_like(sigma), HESS_L)
+    assert np.abs(zero["hess"]).max() == 0.0
+    with pytest.raises(ValueError):
+        ev.eval(ALL, X[:, :-1].contiguous(), P1, L, S)
+    with pytest.raises(ValueError):
+        ev.eval(HESS_L, X, P1)
+    with pytest.raises(_capi.EvaluationError):
+        ev.eval(0, X, P1)
+
+
+@pytest.fixture(scope="module")
+def config3(model):
+    """BASELINE.json config 3: single step on flat ground, N = 30, batch of 1024."""
+    from hippopt_b200.evaluator import KinoEvaluator
+    from hippopt_b200.kino_layout import KinoSettings
+    from hippopt_b200.workloads import kino_batch
+
+    ev = KinoEvaluator(model, KinoSettings(horizon=30))
+    x, p, lam, sigma = kino_batch(ev.layout, model, 1024, seed=2)
+    return ev, x, p, lam, sigma
+
+
+def _spmv_ccs(colind, row, vals, d, n_rows, transpose=False):
+    """y = A d (or A^T d) for a batch of CCS value arrays sharing one pattern."""
+    col = np.repeat(np.arange(len(colind) - 1), np.diff(colind))
+    y = np.zeros((vals.shape[0], n_rows if not transpose else len(colind) - 1))
+    if not transpose:
+        np.add.at(y, (slice(None), row), vals * d[:, col])
+    else:
+        np.add.at(y, (slice(None), col), vals * d[:, row])
+    return y
+
+
+def test_config3_full_size_properties(config3):
+    """Full-size checks that need no oracle: directional derivatives of g / of the Lagrangian gradient
+    reproduce J d and H d; results are deterministic and independent of the batch order."""
+    from hippopt_b200.evaluator import G, GRAD_F, JAC_G
+
+    ev, x, p, lam, sigma = config3
+    lay = ev.layout
+    out = run(ev, x, p, lam, sigma)
+    again = run(ev, x, p, lam, sigma)
+    for k in out:
+        assert np.array_equal(out[k], again[k]), f"{k} is not deterministic"
+    perm = np.random.default_rng(0).permutation(x.shape[0])
+    shuffled = run(ev, x[perm], p[perm], lam[perm], sigma[perm])
+    for k in out:
+        assert np.array_equal(shuffled[k], out[k][perm]), f"{k} depends on the batch order"
+    assert np.isfinite(out["jac"]).all() and np.isfinite(out["hess"]).all()
+    rng = np.random.default_rng(1)
+    d = rng.normal(size=x.shape)
+    eps = 1e-6
+    plus = run(ev, x + eps * d, p, lam, sigma, G | GRAD_F | JAC_G)
+    minus = run(ev, x - eps * d, p, lam, sigma, G | GRAD_F | JAC_G)
+    Jd = _spmv_ccs(lay.jac_colind, lay.jac_row, out["jac"], d, lay.m)
+    fd = (plus["g"] - minus["g"]) / (2 * eps)
+    assert np.abs(fd - Jd).max() <= 1e-5 * max(1.0, np.abs(Jd).max())
+
+    def lag_grad(o):
+        return sigma[:, None] * o["grad_f"] + _spmv_ccs(lay.jac_colind, lay.jac_row, o["jac"], lam, lay.m, transpose=True)
+
+    fdh = (lag_grad(plus) - lag_grad(minus)) / (2 * eps)
+    col = np.repeat(np.arange(lay.n_x), np.diff(lay.hess_colind))
+    Hd = _spmv_ccs(lay.hess_colind, lay.hess_row, out["hess"], d, lay.n_x)
+    off = lay.hess_row != col
+    strict = out["hess"] * off  # mirror the strictly-upper part
+    np.add.at(Hd, (slice(None), col), strict * d[:, lay.hess_row])
+    assert np.abs(fdh - Hd).max() <= 2e-5 * max(1.0, np.abs(Hd).max())
+
+
+def test_config3_samples_against_oracle(model, config3):
+    """Two instances of the full-size batch against the CPU oracle (finishes in seconds)."""
+    from oracle import kinodynamic as kd
+
+    ev, x, p, lam, sigma = config3
+    idx = np.array([0, 517])
+    out = run(ev, x[idx], p[idx], lam[idx], sigma[idx])
+    nlp, _ = kd.build(model, kd.Settings(horizon=30))
+    close(out["g"], nlp.eval_g(x[idx], p[idx]))
+    close(out["f"], nlp.eval_f(x[idx], p[idx]))
+    close(out["grad_f"], nlp.eval_grad_f(x[idx], p[idx]))
+    close(out["jac"], nlp.eval_jac(x[idx], p[idx]))
+    close(out["hess"], nlp.eval_hess(x[idx], p[idx], lam[idx], sigma[idx]))
