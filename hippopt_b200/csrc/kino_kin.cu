@@ -24,7 +24,7 @@
 
 namespace hb {
 
-enum { SB_O = 0, SB_D = 3, SB_W = 6, SB_V = 9, SB_AX = 12, SB_I = 15, SB_R = 21, SB_STRIDE = 30 };
+enum { SB_O = 0, SB_D = 3, SB_W = 6, SB_V = 9, SB_AX = 12, SB_I = 15, SB_R = 21, SB_L = 30, SB_IH = 33, SB_RHO = 36, SB_STRIDE = 39 };
 
 struct KinSmem {
   int bodies, arms, fdu, fdal, fdar, G, z, gbuf, slot, total;
@@ -109,10 +109,70 @@ __device__ __forceinline__ V3<Dual> iapply(const double* sb, int l, const Dir& d
   return lift<Dual>(Ix, t);
 }
 
+// I^w w_l and I^w hbar with the primal products staged in shared memory (SB_L, SB_IH)
+__device__ __forceinline__ D3 iw_omega(const double* sb, int l, const Dir&, const St<double>&) {
+  return ld3(sb + l * SB_STRIDE + SB_L);
+}
+__device__ __forceinline__ V3<Dual> iw_omega(const double* sb, int l, const Dir& dir, const St<Dual>& s) {
+  const double* I = sb + l * SB_STRIDE + SB_I;
+  const D3 Lw = ld3(sb + l * SB_STRIDE + SB_L);
+  const D3 wv = v3<double>(s.w.x.v, s.w.y.v, s.w.z.v), wd = v3<double>(s.w.x.d, s.w.y.d, s.w.z.d);
+  const double in = ((dir.mask >> l) & 1u) ? 1.0 : 0.0;
+  const D3 a = scale(in, dir.alpha);
+  return lift<Dual>(Lw, symmul(I, wd - cross(a, wv)) + cross(a, Lw));
+}
+__device__ __forceinline__ D3 iw_hbar(const double* sb, int l, const Dir&, D3 hb, double) {
+  return symmul(sb + l * SB_STRIDE + SB_I, hb);  // seeds differ per lane in the fp64 sweep
+}
+// rho_l = o_l - o_parent and the parent's angular velocity, without rebuilding the parent state
+__device__ __forceinline__ void parent_link(const double* sb, int l, int p, const Dir&, D3& rho, D3& wp) {
+  rho = ld3(sb + l * SB_STRIDE + SB_RHO);
+  wp = ld3(sb + p * SB_STRIDE + SB_W);
+}
+__device__ __forceinline__ void parent_link(const double* sb, int l, int p, const Dir& dir, V3<Dual>& rho,
+                                            V3<Dual>& wp) {
+  const D3 r = ld3(sb + l * SB_STRIDE + SB_RHO), w = ld3(sb + p * SB_STRIDE + SB_W);
+  const double in = ((dir.mask >> p) & 1u) ? 1.0 : 0.0;
+  const D3 a = scale(in, dir.alpha);
+  rho = lift<Dual>(r, cross(a, r));
+  wp = lift<Dual>(w, cross(a, w - dir.wpi) + scale(in, dir.u));
+}
+// branch accumulators in shared memory, component-major and lane-minor
+__device__ __forceinline__ void slot_get(D3& v, const double* sl, int c) {
+  v.x += sl[(c)*32];
+  v.y += sl[(c + 1) * 32];
+  v.z += sl[(c + 2) * 32];
+}
+__device__ __forceinline__ void slot_get(V3<Dual>& v, const double* sl, int c) {
+  v.x = v.x + mkdual(sl[(2 * c) * 32], sl[(2 * c + 1) * 32]);
+  v.y = v.y + mkdual(sl[(2 * c + 2) * 32], sl[(2 * c + 3) * 32]);
+  v.z = v.z + mkdual(sl[(2 * c + 4) * 32], sl[(2 * c + 5) * 32]);
+}
+__device__ __forceinline__ void slot_add(double* sl, int c, D3 v) {
+  sl[(c)*32] += v.x;
+  sl[(c + 1) * 32] += v.y;
+  sl[(c + 2) * 32] += v.z;
+}
+__device__ __forceinline__ void slot_add(double* sl, int c, V3<Dual> v) {
+  sl[(2 * c) * 32] += v.x.v;
+  sl[(2 * c + 1) * 32] += v.x.d;
+  sl[(2 * c + 2) * 32] += v.y.v;
+  sl[(2 * c + 3) * 32] += v.y.d;
+  sl[(2 * c + 4) * 32] += v.z.v;
+  sl[(2 * c + 5) * 32] += v.z.d;
+}
+__device__ __forceinline__ V3<Dual> iw_hbar(const double* sb, int l, const Dir& dir, D3 hb, Dual) {
+  const double* I = sb + l * SB_STRIDE + SB_I;
+  const D3 Ih = ld3(sb + l * SB_STRIDE + SB_IH);
+  const double in = ((dir.mask >> l) & 1u) ? 1.0 : 0.0;
+  const D3 a = scale(in, dir.alpha);
+  return lift<Dual>(Ih, cross(a, Ih) - symmul(I, cross(a, hb)));
+}
+
 template <class T>
 struct Seeds {
-  V3<T> wc;         // d Phi / d (sum_l m_l c_l)
-  V3<T> hb;         // d Phi / d h_ang
+  D3 wc;            // d Phi / d (sum_l m_l c_l)   (constant along every direction)
+  D3 hb;            // d Phi / d h_ang             (constant along every direction)
   V3<T> footF[2];   // force / torque (about the foot body origin) applied on the two foot bodies
   V3<T> footN[2];
   V3<T> chestN;     // torque on the frame-orientation body
@@ -164,8 +224,8 @@ __device__ __forceinline__ void kin_backward(const KinoConst& C, const double* s
       const V3<T> cd = s.v + cross(s.w, s.d);
       const V3<T> cbar = scale(m, cross(cd - xd, S.hb) + S.wc);
       const V3<T> cdbar = scale(m, cross(S.hb, c - xc));
-      const V3<T> Iw = iapply(sb, l, dir, s.w);
-      const V3<T> Ih = iapply(sb, l, dir, S.hb);
+      const V3<T> Iw = iw_omega(sb, l, dir, s);
+      const V3<T> Ih = iw_hbar(sb, l, dir, S.hb, T());
       cF = cF + cbar;
       cn = cn + cross(s.d, cbar) + cross(s.d, cross(cdbar, s.w)) + cross(Iw, S.hb) + cross(Ih, s.w);
       cv = cv + cdbar;
@@ -181,25 +241,21 @@ __device__ __forceinline__ void kin_backward(const KinoConst& C, const double* s
       if (l == C.chest_body) cn = cn + S.chestN;
     }
     if (bc.slot >= 0) {
-      double* sl = slot + bc.slot * 12 * SW * 32 + lane;
-      T* cc[12] = {&cn.x, &cn.y, &cn.z, &cF.x, &cF.y, &cF.z, &cw.x, &cw.y, &cw.z, &cv.x, &cv.y, &cv.z};
-#pragma unroll
-      for (int i = 0; i < 12; ++i) {
-        if (SW == 2)
-          *cc[i] = *cc[i] + mk<T>(sl[(2 * i) * 32], sl[(2 * i + 1) * 32]);
-        else
-          *cc[i] = *cc[i] + mk<T>(sl[i * 32], 0.0);
-      }
+      const double* sl = slot + bc.slot * 12 * SW * 32 + lane;
+      slot_get(cn, sl, 0);
+      slot_get(cF, sl, 3);
+      slot_get(cw, sl, 6);
+      slot_get(cv, sl, 9);
     }
     if (l == 0) break;
     // ---- joint outputs
     emit.joint(l, dot(s.ax, cn), dot(s.ax, cw));
     // ---- contribution to the parent
     const int p = bc.parent;
-    const St<T> sp = load_state(sb, p, dir, T());
-    const V3<T> rho = s.o - sp.o;
+    V3<T> rho, wpar;
+    parent_link(sb, l, p, dir, rho, wpar);
     const double sd = zs[Z_SD + l - 1];
-    const V3<T> pn = cn + cross(rho, cF) + scale(sd, cross(s.ax, cw)) + cross(rho, cross(cv, sp.w));
+    const V3<T> pn = cn + cross(rho, cF) + scale(sd, cross(s.ax, cw)) + cross(rho, cross(cv, wpar));
     const V3<T> pw = cw + cross(rho, cv);
     if (p == l - 1) {
       cn = pn;
@@ -211,16 +267,10 @@ __device__ __forceinline__ void kin_backward(const KinoConst& C, const double* s
       Av = Av + cv;
     } else {
       double* sl = slot + C.body[p].slot * 12 * SW * 32 + lane;
-      const T vals[12] = {pn.x, pn.y, pn.z, cF.x, cF.y, cF.z, pw.x, pw.y, pw.z, cv.x, cv.y, cv.z};
-#pragma unroll
-      for (int i = 0; i < 12; ++i) {
-        if (SW == 2) {
-          sl[(2 * i) * 32] += prim(vals[i]);
-          sl[(2 * i + 1) * 32] += tang(vals[i]);
-        } else {
-          sl[i * 32] += prim(vals[i]);
-        }
-      }
+      slot_add(sl, 0, pn);
+      slot_add(sl, 3, cF);
+      slot_add(sl, 6, pw);
+      slot_add(sl, 9, cv);
     }
   }
   n0 = cn;
@@ -391,6 +441,7 @@ __global__ void __launch_bounds__(128) kino_kin_kernel(const KinoConst* __restri
       st3(bl + SB_AX, ax);
       st3(bl + SB_W, wp + scale(sd, ax));
       st3(bl + SB_V, vp + cross(wp, rho));
+      st3(bl + SB_RHO, rho);
     }
     __syncwarp();
   }
@@ -422,7 +473,9 @@ __global__ void __launch_bounds__(128) kino_kin_kernel(const KinoConst* __restri
     const D3 cd = v + cross(w, d);
     mc = scale(bc.mass, c);
     mcd = scale(bc.mass, cd);
-    hl = cross(mc, cd) + symmul(Iw, w);
+    const D3 Lw = symmul(Iw, w);
+    st3(bl + SB_L, Lw);
+    hl = cross(mc, cd) + Lw;
   }
   const double M = C.total_mass;
   const D3 Pm = v3<double>(warp_sum(mc.x), warp_sum(mc.y), warp_sum(mc.z));
@@ -545,7 +598,12 @@ __global__ void __launch_bounds__(128) kino_kin_kernel(const KinoConst* __restri
         cost += C.w_bq * eq[lane] * eq[lane];
         double gq = 0.0;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) gq += Aq[i][lane] * eq[i];
+        for (int a = 0; a < 4; ++a) {
+          double t = 0.0;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) t += Aq[i][a] * eq[i];
+          if (a == lane) gq = t;
+        }
         gbuf[7 + lane] += 2.0 * C.w_bq * gq;
       }
     }
@@ -571,10 +629,16 @@ __global__ void __launch_bounds__(128) kino_kin_kernel(const KinoConst* __restri
     Seeds<double> S;
     S.wc = S.hb = S.footF[0] = S.footF[1] = S.footN[0] = S.footN[1] = S.chestN = v3<double>(0.0, 0.0, 0.0);
     if (lane < 24) {
-      const int pt = lane / 3, a = lane % 3, f = pt >> 2;
+      const int pt = lane / 3, a = lane % 3;
       const D3 frc = v3<double>(a == 0 ? -1.0 : 0.0, a == 1 ? -1.0 : 0.0, a == 2 ? -1.0 : 0.0);
-      S.footF[f] = frc;
-      S.footN[f] = cross(ld3(sm + L.arms + 3 * pt), frc);
+      const D3 trq = cross(ld3(sm + L.arms + 3 * pt), frc);
+      if (pt < 4) {
+        S.footF[0] = frc;
+        S.footN[0] = trq;
+      } else {
+        S.footF[1] = frc;
+        S.footN[1] = trq;
+      }
     } else if (lane < 27) {
       const int a = lane - 24;
       S.wc = v3<double>(a == 0 ? -1.0 / M : 0.0, a == 1 ? -1.0 / M : 0.0, a == 2 ? -1.0 / M : 0.0);
@@ -658,14 +722,19 @@ __global__ void __launch_bounds__(128) kino_kin_kernel(const KinoConst* __restri
     Dir dir;
     dir.mask = 0u;
     dir.alpha = dir.pi = dir.wpi = dir.vpi = dir.u = v3<double>(0.0, 0.0, 0.0);
-    Dual qD[4] = {mkdual(q0, 0.0), mkdual(q1, 0.0), mkdual(q2, 0.0), mkdual(q3, 0.0)};
-    if (lane < 4) qD[lane].d = 1.0;
-    V3<Dual> gq[4], uq[4], wq[4];
-    quat_maps<Dual>(qD, qdv, gq, uq, wq);
     if (lane < 4) {
+      // only the primal maps are needed for the direction; the dual maps are rebuilt after the sweep
+      // so that they are not live (144 registers) across it
+      D3 gq0[4], uq0[4], wq0[4];
+      const double qraw[4] = {q0, q1, q2, q3};
+      quat_maps<double>(qraw, qdv, gq0, uq0, wq0);
       dir.mask = 0xffffffffu;
-      dir.alpha = v3<double>(gq[lane].x.v, gq[lane].y.v, gq[lane].z.v);
-      dir.u = v3<double>(uq[lane].x.v, uq[lane].y.v, uq[lane].z.v);
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+        if (a == lane) {
+          dir.alpha = gq0[a];
+          dir.u = uq0[a];
+        }
       dir.wpi = ld3(sb + SB_W);
       dir.vpi = ld3(sb + SB_V);
     } else if (lane < 27) {
@@ -697,11 +766,15 @@ __global__ void __launch_bounds__(128) kino_kin_kernel(const KinoConst* __restri
     {
       const int r0 = grow(C, HB_KF_COM_KIN, k, 0);
       const D3 lc = r0 >= 0 ? v3<double>(lb[r0], lb[r0 + 1], lb[r0 + 2]) : v3<double>(0.0, 0.0, 0.0);
-      S.wc = lift<Dual>(scale(-1.0 / M, lc), v3<double>(0.0, 0.0, 0.0));
+      S.wc = scale(-1.0 / M, lc);
       const int r1 = grow(C, HB_KF_MOM_KIN, k, 0);
       const D3 lh = r1 >= 0 ? v3<double>(lb[r1], lb[r1 + 1], lb[r1 + 2]) : v3<double>(0.0, 0.0, 0.0);
-      S.hb = lift<Dual>(scale(-1.0 / mass_p, lh), v3<double>(0.0, 0.0, 0.0));
+      S.hb = scale(-1.0 / mass_p, lh);
+      // stage I^w hbar (same for every lane of the dual sweep)
+      if (lane < nb) st3(sb + lane * SB_STRIDE + SB_IH, symmul(sb + lane * SB_STRIDE + SB_I, S.hb));
+      __syncwarp();
     }
+#pragma unroll
     for (int pt = 0; pt < 8; ++pt) {
       const int f = pt >> 2;
       const int r0 = grow(C, pt * HB_KF_PT_COUNT + HB_KF_PT_FK, k, 0);
@@ -764,17 +837,24 @@ __global__ void __launch_bounds__(128) kino_kin_kernel(const KinoConst* __restri
       em.put(2, v0.z.d);
       const int ru = grow(C, HB_KF_UNIT_QUAT, k, 0);
       const double lu = ru >= 0 ? lb[ru] : 0.0;
+      // dual quaternion maps, rebuilt from shared memory after the sweep (see above)
+      Dual qD[4];
+      double qdv2[4];
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        qD[a] = mkdual(zs[Z_Q + a], a == lane ? 1.0 : 0.0);
+        qdv2[a] = zs[Z_QD + a];
+      }
+      V3<Dual> gq[4], uq[4], wq[4];
+      quat_maps<Dual>(qD, qdv2, gq, uq, wq);
+      // Hessian of w_bq |qd^-1 (x) q - 1|^2 is 2 w_bq A^T A = 2 w_bq |qd|^2 I (left-multiplication matrix)
+      const double nqd = ref[R_BQ] * ref[R_BQ] + ref[R_BQ + 1] * ref[R_BQ + 1] + ref[R_BQ + 2] * ref[R_BQ + 2] +
+                         ref[R_BQ + 3] * ref[R_BQ + 3];
 #pragma unroll
       for (int a = 0; a < 4; ++a) {
         const Dual dq = dot(n0, gq[a]) + dot(w0, uq[a]);
         const Dual dqd = dot(w0, wq[a]);
-        double extra = 0.0;
-        if (lane < 4 && k1) {
-          double ata = 0.0;
-#pragma unroll
-          for (int i = 0; i < 4; ++i) ata += Aq[i][a] * Aq[i][lane];
-          extra = 2.0 * sg * C.w_bq * ata + (a == lane ? 2.0 * lu : 0.0);
-        }
+        const double extra = (a == lane && k1) ? 2.0 * sg * C.w_bq * nqd + 2.0 * lu : 0.0;
         em.put(3 + a, dqd.d);
         em.put(30 + a, dq.d + extra);
       }
