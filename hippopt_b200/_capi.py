@@ -12,7 +12,7 @@ import re
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 HEADER = os.path.join(os.path.dirname(_HERE), "include", "hippopt_b200.h")
-LIB_PATH = os.path.join(_HERE, "libhippopt_b200.so")
+LIB_PATH = os.environ.get("HIPPOPT_B200_LIB", os.path.join(_HERE, "libhippopt_b200.so"))  # override: kernel tuning
 
 
 def parse_header(path: str = HEADER) -> dict[str, int]:

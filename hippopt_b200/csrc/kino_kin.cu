@@ -357,8 +357,11 @@ struct HessEmit {
   }
 };
 
+// Measured on B200 (tools/time_kino.py): the dual sweep is fastest with the full 255 registers
+// (2 CTAs/SM; 168 registers spill 1 KB/thread and lose 12%), the fp64-only variant with 168
+// registers (3 CTAs/SM, -19%).
 template <bool WITH_HESS>
-__global__ void __launch_bounds__(128) kino_kin_kernel(const KinoConst* __restrict__ Cp, unsigned mask,
+__global__ void __launch_bounds__(128, WITH_HESS ? 2 : 3) kino_kin_kernel(const KinoConst* __restrict__ Cp, unsigned mask,
                                                        const double* __restrict__ x, const double* __restrict__ p,
                                                        long p_stride, const double* __restrict__ lam,
                                                        const double* __restrict__ sigma, double* __restrict__ fpart,

@@ -1,0 +1,33 @@
+"""Developer timing: kinodynamic evaluator at config-3 size, per-kernel CUDA-event times."""
+import sys
+import time
+
+import torch
+
+sys.path.insert(0, ".")
+from hippopt_b200.evaluator import ALL, KinoEvaluator  # noqa: E402
+from hippopt_b200.kino_layout import KinoSettings  # noqa: E402
+from hippopt_b200.robot_model import synthetic_ergocub  # noqa: E402
+from hippopt_b200.workloads import kino_batch  # noqa: E402
+
+model = synthetic_ergocub()
+ev = KinoEvaluator(model, KinoSettings(horizon=30))
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
+x, p, lam, sigma = kino_batch(ev.layout, model, B, seed=2)
+d = torch.device("cuda:0")
+X, P, L, S = (torch.tensor(a, device=d) for a in (x, p, lam, sigma))
+for mask, name in ((ALL, "f+g+grad+jac+hess"), (ALL & ~16, "f+g+grad+jac"), (1 | 4, "f+g")):
+    for _ in range(5):
+        ev.eval(mask, X, P, L, S)
+    torch.cuda.synchronize()
+    ev.profile(True)
+    t0 = time.perf_counter()
+    reps = 30
+    for _ in range(reps):
+        ev.eval(mask, X, P, L, S)
+    torch.cuda.synchronize()
+    dt = (time.perf_counter() - t0) / reps
+    ms, n = ev.profile_read()
+    ev.profile(False)
+    print(f"{name:20s} {dt * 1e3:7.3f} ms  {B * 30 / dt:.3e} knot-evals/s   " +
+          " ".join(f"{k}={v / n:.3f}" for k, v in ms.items()))
