@@ -106,9 +106,9 @@ extern "C" int hb_kino_create(const int32_t* icfg, const double* dcfg, const int
   C.foot_body[0] = icfg[HB_KI_FOOT_BODY_L];
   C.foot_body[1] = icfg[HB_KI_FOOT_BODY_R];
   C.chest_body = icfg[HB_KI_CHEST_BODY];
-  if (C.terrain != 0) {
+  if (C.terrain != 0 && C.terrain != 1) {
     delete h;
-    return fail(HB_ERR_UNSUPPORTED, "hb_kino_create: only the planar terrain is implemented on the device");
+    return fail(HB_ERR_UNSUPPORTED, "hb_kino_create: terrain must be 0 (planar) or 1 (two smooth steps)");
   }
   if (C.nb < 2 || C.nb > HB_MAX_BODIES || C.nb - 1 != HB_N_JOINTS) {
     delete h;
@@ -317,14 +317,20 @@ extern "C" int hb_eval(hb_handle h, uint32_t mask, const double* x, const double
     const size_t smem = (size_t)hb::contact_smem_layout(C.n_hc).total * sizeof(double) * warps_per_block;
     static bool attr_set = false;
     if (!attr_set) {
-      CUDA_TRY(cudaFuncSetAttribute(hb::kino_contact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      CUDA_TRY(cudaFuncSetAttribute(hb::kino_contact_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      CUDA_TRY(cudaFuncSetAttribute(hb::kino_contact_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
       CUDA_TRY(cudaFuncSetAttribute(hb::kino_kin_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
       CUDA_TRY(cudaFuncSetAttribute(hb::kino_kin_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
       attr_set = true;
     }
-    hb::kino_contact_kernel<<<grid, 32 * warps_per_block, smem, st>>>(h->dev, mask, x, p, (long)p_stride, lam_g, sigma,
-                                                                     d_fpart, grad_f, g, jac_vals, hess_vals,
-                                                                     (long)batch);
+    if (C.terrain == 0)
+      hb::kino_contact_kernel<0><<<grid, 32 * warps_per_block, smem, st>>>(h->dev, mask, x, p, (long)p_stride, lam_g,
+                                                                          sigma, d_fpart, grad_f, g, jac_vals, hess_vals,
+                                                                          (long)batch);
+    else
+      hb::kino_contact_kernel<1><<<grid, 32 * warps_per_block, smem, st>>>(h->dev, mask, x, p, (long)p_stride, lam_g,
+                                                                          sigma, d_fpart, grad_f, g, jac_vals, hess_vals,
+                                                                          (long)batch);
     CUDA_TRY(cudaGetLastError());
     h->launches++;
   }

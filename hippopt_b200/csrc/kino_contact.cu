@@ -22,6 +22,7 @@
 // through the (variable, variable) -> local entry table hc_index and accumulated per warp in shared
 // memory in a fixed order (deterministic), then scattered once.
 #include "kino_const.cuh"
+#include "kino_smooth.cuh"
 
 namespace hb {
 
@@ -93,6 +94,8 @@ __device__ __forceinline__ void linear_state(int j, int& so, int& ro, int& fam_d
   }
 }
 
+// TERRAIN: 0 = PlanarTerrain, 1 = sum of two smooth steps (kino_smooth.cuh)
+template <int TERRAIN>
 __global__ void __launch_bounds__(128) kino_contact_kernel(const KinoConst* __restrict__ Cp, unsigned mask,
                                                            const double* __restrict__ x, const double* __restrict__ p,
                                                            long p_stride, const double* __restrict__ lam,
@@ -226,23 +229,179 @@ __global__ void __launch_bounds__(128) kino_contact_kernel(const KinoConst* __re
       zs[Z_F + 2] + zs[17 + Z_F] + zs[32 + Z_F] + zs[47 + Z_F] + zs[62 + Z_F] + zs[77 + Z_F] + zs[92 + Z_F] + zs[107 + Z_F]);
   const D3 comv = ld3(zs + Z_COM);
 
+  if constexpr (TERRAIN == 1) {
+    // ---------------------------------------------------------------- smooth-step terrain (config 5)
+    const double* tp = pp + C.po_terrain;
+    if (lane < 8) {
+      const int fb_ = lane * HB_KF_PT_COUNT;
+      const int o = 15 * lane;
+      TFrame F;
+      smooth_terrain_frame(tp, ppos.x, ppos.y, ppos.z, F);
+      const double t0 = tanh(kt * F.h.c[0]);
+      const double t1 = kt * (1.0 - t0 * t0);
+      const TJ tauj = tj_compose(F.h, t0, t1, -kt * t0 * t1);
+      const TJ Nn = tj_dot(F.n, pf), Nd = tj_dot(F.n, pfd), X = tj_dot(F.xh, pf), Y = tj_dot(F.yh, pf);
+      const TJ Xv = tj_dot(F.xh, pv), Yv = tj_dot(F.yh, pv);
+      const TJ hv = pv.x * F.gx + pv.y * F.gy + pv.z;  // grad h . v
+      TJ Dnv[3], planar[3];
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        Dnv[a] = pv.x * F.Dn[a][0] + pv.y * F.Dn[a][1];
+        planar[a] = -(pu.x * (tauj * F.xh[a]) + pu.y * (tauj * F.yh[a]) + pu.z * F.n[a]) + comp(pv, a);
+      }
+      const TJ fDnv = tj_dot(Dnv, pf);
+      const TJ margin = -(kbs * (F.h * Nn)) - (hv * Nn + F.h * fDnv + F.h * Nd) + eps;
+      const TJ fric = (mu * mu) * (Nn * Nn) - X * X - Y * Y;
+      const double hd = ref[R_SWING];
+      const TJ dh = F.h + (-hd);
+      const TJ swing = 0.5 * (dh * dh + Xv * Xv + Yv * Yv);
+      const TJ DnTf0 = pf.x * F.Dn[0][0] + pf.y * F.Dn[1][0] + pf.z * F.Dn[2][0];
+      const TJ DnTf1 = pf.x * F.Dn[0][1] + pf.y * F.Dn[1][1] + pf.z * F.Dn[2][1];
+      if (want_g) {
+        int r = grow(C, fb_ + HB_KF_PT_PLANAR, k, 0);
+        if (r >= 0) {
+          gb[r] = planar[0].c[0];
+          gb[r + 1] = planar[1].c[0];
+          gb[r + 2] = planar[2].c[0];
+        }
+        r = grow(C, fb_ + HB_KF_PT_DCC, k, 0);
+        if (r >= 0) gb[r] = margin.c[0];
+        r = grow(C, fb_ + HB_KF_PT_HEIGHT, k, 0);
+        if (r >= 0) gb[r] = F.h.c[0];
+        r = grow(C, fb_ + HB_KF_PT_NORMAL, k, 0);
+        if (r >= 0) gb[r] = Nn.c[0];
+        r = grow(C, fb_ + HB_KF_PT_FRICTION, k, 0);
+        if (r >= 0) gb[r] = fric.c[0];
+      }
+      if (k1) {
+        cost += C.w_swing * swing.c[0];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+          gbuf[o + Z_P + a] += C.w_swing * swing.c[1 + a];
+          gbuf[o + Z_V + a] += C.w_swing * (Xv.c[0] * F.xh[a].c[0] + Yv.c[0] * F.yh[a].c[0]);
+        }
+      }
+      if (want_jac) {
+        const int pb0 = 846 + 58 * lane;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          jput(pb0 + c, 1.0);
+          jput(pb0 + 3 + 3 * c + 0, -t0 * F.xh[c].c[0]);
+          jput(pb0 + 3 + 3 * c + 1, -t0 * F.yh[c].c[0]);
+          jput(pb0 + 3 + 3 * c + 2, -F.n[c].c[0]);
+#pragma unroll
+          for (int d = 0; d < 3; ++d) jput(pb0 + 12 + 3 * c + d, planar[c].c[1 + d]);
+        }
+        const double h0 = F.h.c[0], N0 = Nn.c[0];
+        jput(pb0 + 21, -(F.gx.c[0] * N0 + h0 * DnTf0.c[0]));
+        jput(pb0 + 22, -(F.gy.c[0] * N0 + h0 * DnTf1.c[0]));
+        jput(pb0 + 23, -N0);
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+          jput(pb0 + 24 + d, -h0 * F.n[d].c[0]);
+          jput(pb0 + 27 + d, margin.c[1 + d]);
+          jput(pb0 + 30 + d, -kbs * h0 * F.n[d].c[0] - hv.c[0] * F.n[d].c[0] - h0 * Dnv[d].c[0]);
+          jput(pb0 + 33 + d, F.h.c[1 + d]);
+          jput(pb0 + 38 + d, F.n[d].c[0]);
+          jput(pb0 + 43 + d, 2.0 * mu * mu * N0 * F.n[d].c[0] - 2.0 * X.c[0] * F.xh[d].c[0] - 2.0 * Y.c[0] * F.yh[d].c[0]);
+          jput(pb0 + 46 + d, 1.0);
+          jput(pb0 + 49 + d, mass);
+          jput(pb0 + 52 + d, 1.0);
+          jput(pb0 + 55 + d, -1.0);
+        }
+        jput(pb0 + 36, Nn.c[1]);
+        jput(pb0 + 37, Nn.c[2]);
+        jput(pb0 + 41, fric.c[1]);
+        jput(pb0 + 42, fric.c[2]);
+      }
+      if (want_hess) {
+        const double lpl[3] = {lamrow(fb_ + HB_KF_PT_PLANAR, k, 0), lamrow(fb_ + HB_KF_PT_PLANAR, k, 1),
+                               lamrow(fb_ + HB_KF_PT_PLANAR, k, 2)};
+        const D3 lplv = v3<double>(lpl[0], lpl[1], lpl[2]);
+        const double ld = lamrow(fb_ + HB_KF_PT_DCC, k, 0), lh = lamrow(fb_ + HB_KF_PT_HEIGHT, k, 0);
+        const double ln = lamrow(fb_ + HB_KF_PT_NORMAL, k, 0), lfr = lamrow(fb_ + HB_KF_PT_FRICTION, k, 0);
+        const double sws = k1 ? sg * C.w_swing : 0.0;
+        const TJ Lp = lpl[0] * planar[0] + lpl[1] * planar[1] + lpl[2] * planar[2] + ld * margin + lh * F.h + ln * Nn +
+                      lfr * fric + sws * swing;
+        {
+          int e = 0;
+#pragma unroll
+          for (int a = 0; a < 3; ++a)
+#pragma unroll
+            for (int bb = a; bb < 3; ++bb) hadd(o + Z_P + a, o + Z_P + bb, tj_hess(Lp, e++));
+        }
+        const TJ Gu[3] = {-(tauj * tj_dot(F.xh, lplv)), -(tauj * tj_dot(F.yh, lplv)), -tj_dot(F.n, lplv)};
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+          const TJ gd = d == 0 ? F.gx * Nn + F.h * DnTf0 : (d == 1 ? F.gy * Nn + F.h * DnTf1 : Nn);
+          const TJ Gv = (-ld) * gd + sws * (Xv * F.xh[d] + Yv * F.yh[d]);
+          const TJ Gfd = (-ld) * (F.h * F.n[d]);
+          const TJ Gf = (-ld) * (kbs * (F.h * F.n[d]) + hv * F.n[d] + F.h * Dnv[d]) + ln * F.n[d] +
+                        lfr * ((2.0 * mu * mu) * (Nn * F.n[d]) - 2.0 * (X * F.xh[d]) - 2.0 * (Y * F.yh[d]));
+#pragma unroll
+          for (int a = 0; a < 3; ++a) {
+            hadd(o + Z_P + a, o + Z_U + d, Gu[d].c[1 + a]);
+            hadd(o + Z_P + a, o + Z_V + d, Gv.c[1 + a]);
+            hadd(o + Z_P + a, o + Z_FD + d, Gfd.c[1 + a]);
+            hadd(o + Z_P + a, o + Z_F + d, Gf.c[1 + a]);
+          }
+        }
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+#pragma unroll
+          for (int bb = 0; bb < 3; ++bb) {
+            const double ga = a == 0 ? F.gx.c[0] : (a == 1 ? F.gy.c[0] : 1.0);
+            const double dnba = a < 2 ? F.Dn[bb][a].c[0] : 0.0;
+            hadd(o + Z_V + a, o + Z_F + bb, -ld * (ga * F.n[bb].c[0] + F.h.c[0] * dnba));
+            if (bb >= a) {
+              hadd(o + Z_F + a, o + Z_F + bb,
+                   lfr * (2.0 * mu * mu * F.n[a].c[0] * F.n[bb].c[0] - 2.0 * F.xh[a].c[0] * F.xh[bb].c[0] -
+                          2.0 * F.yh[a].c[0] * F.yh[bb].c[0]));
+              hadd(o + Z_V + a, o + Z_V + bb, sws * (F.xh[a].c[0] * F.xh[bb].c[0] + F.yh[a].c[0] * F.yh[bb].c[0]));
+            }
+          }
+      }
+    }
+    if (lane == 8) {
+      // minimum CoM height: h(com) = com_z - T(com_x, com_y)
+      const BJ<2> T2 = bj_trunc<4, 2>(smooth_steps_surface(tp, comv.x, comv.y));
+      if (want_g) {
+        const int r = grow(C, HB_KF_COM_HEIGHT, k, 0);
+        if (r >= 0) gb[r] = comv.z - T2.c[0];
+      }
+      if (want_jac) {
+        jput(1310 + 12, -T2.c[bidx(1, 0)]);
+        jput(1310 + 13, -T2.c[bidx(0, 1)]);
+        jput(1310 + 14, 1.0);
+      }
+      if (want_hess) {
+        const double lc = lamrow(HB_KF_COM_HEIGHT, k, 0);
+        hadd(CV_COM, CV_COM, -2.0 * lc * T2.c[bidx(2, 0)]);
+        hadd(CV_COM, CV_COM + 1, -lc * T2.c[bidx(1, 1)]);
+        hadd(CV_COM + 1, CV_COM + 1, -2.0 * lc * T2.c[bidx(0, 2)]);
+      }
+    }
+  }
   if (lane < 8) {
     const int fb_ = lane * HB_KF_PT_COUNT;
     if (want_g) {
-      int r = grow(C, fb_ + HB_KF_PT_PLANAR, k, 0);
-      if (r >= 0) {
-        gb[r] = pv.x - tau * pu.x;
-        gb[r + 1] = pv.y - tau * pu.y;
-        gb[r + 2] = pv.z - pu.z;
+      int r;
+      if constexpr (TERRAIN == 0) {
+        r = grow(C, fb_ + HB_KF_PT_PLANAR, k, 0);
+        if (r >= 0) {
+          gb[r] = pv.x - tau * pu.x;
+          gb[r + 1] = pv.y - tau * pu.y;
+          gb[r + 2] = pv.z - pu.z;
+        }
+        r = grow(C, fb_ + HB_KF_PT_DCC, k, 0);
+        if (r >= 0) gb[r] = eps - kbs * (ppos.z * pf.z) - (pv.z * pf.z + ppos.z * pfd.z);
+        r = grow(C, fb_ + HB_KF_PT_HEIGHT, k, 0);
+        if (r >= 0) gb[r] = ppos.z;
+        r = grow(C, fb_ + HB_KF_PT_NORMAL, k, 0);
+        if (r >= 0) gb[r] = pf.z;
+        r = grow(C, fb_ + HB_KF_PT_FRICTION, k, 0);
+        if (r >= 0) gb[r] = -(pf.x * pf.x) - pf.y * pf.y + mu * mu * (pf.z * pf.z);
       }
-      r = grow(C, fb_ + HB_KF_PT_DCC, k, 0);
-      if (r >= 0) gb[r] = eps - kbs * (ppos.z * pf.z) - (pv.z * pf.z + ppos.z * pfd.z);
-      r = grow(C, fb_ + HB_KF_PT_HEIGHT, k, 0);
-      if (r >= 0) gb[r] = ppos.z;
-      r = grow(C, fb_ + HB_KF_PT_NORMAL, k, 0);
-      if (r >= 0) gb[r] = pf.z;
-      r = grow(C, fb_ + HB_KF_PT_FRICTION, k, 0);
-      if (r >= 0) gb[r] = -(pf.x * pf.x) - pf.y * pf.y + mu * mu * (pf.z * pf.z);
       r = grow(C, fb_ + HB_KF_PT_U_BOUNDS, k, 0);
       if (r >= 0) {
         gb[r] = pu.x;
@@ -258,15 +417,17 @@ __global__ void __launch_bounds__(128) kino_contact_kernel(const KinoConst* __re
     }
     // per-point costs (k >= 1): swing heuristic, control regularisations
     if (k1) {
-      const double hd = ref[R_SWING];
-      const double dh = ppos.z - hd;
-      cost += C.w_swing * 0.5 * (dh * dh + (pv.x * pv.x + pv.y * pv.y));
+      double* gp = gbuf + 15 * lane;
+      if constexpr (TERRAIN == 0) {
+        const double hd = ref[R_SWING];
+        const double dh = ppos.z - hd;
+        cost += C.w_swing * 0.5 * (dh * dh + (pv.x * pv.x + pv.y * pv.y));
+        gp[Z_P + 2] += C.w_swing * dh;
+        gp[Z_V] += C.w_swing * pv.x;
+        gp[Z_V + 1] += C.w_swing * pv.y;
+      }
       cost += C.w_u * (pu.x * pu.x + pu.y * pu.y + pu.z * pu.z);
       cost += C.w_fd * (pfd.x * pfd.x + pfd.y * pfd.y + pfd.z * pfd.z);
-      double* gp = gbuf + 15 * lane;
-      gp[Z_P + 2] += C.w_swing * dh;
-      gp[Z_V] += C.w_swing * pv.x;
-      gp[Z_V + 1] += C.w_swing * pv.y;
       gp[Z_U] += 2.0 * C.w_u * pu.x;
       gp[Z_U + 1] += 2.0 * C.w_u * pu.y;
       gp[Z_U + 2] += 2.0 * C.w_u * pu.z;
@@ -288,8 +449,11 @@ __global__ void __launch_bounds__(128) kino_contact_kernel(const KinoConst* __re
       if (r >= 0) gb[r] = zs[Z_H + 3 + lane] * mass;
     }
     if (lane == 3) {
-      int r = grow(C, HB_KF_COM_HEIGHT, k, 0);
-      if (r >= 0) gb[r] = comv.z;
+      int r = -1;
+      if constexpr (TERRAIN == 0) {
+        r = grow(C, HB_KF_COM_HEIGHT, k, 0);
+        if (r >= 0) gb[r] = comv.z;
+      }
       r = grow(C, HB_KF_FEET_RELH, k, 0);
       if (r >= 0) {
         const double lc = (((zs[Z_P + 2] + zs[15 + Z_P + 2]) + zs[30 + Z_P + 2]) + zs[45 + Z_P + 2]) / 4.0;
@@ -470,7 +634,7 @@ __global__ void __launch_bounds__(128) kino_contact_kernel(const KinoConst* __re
       }
     }
     base += 264;
-    if (lane < 8) {
+    if (TERRAIN == 0 && lane < 8) {
       const int pb0 = base + 29 * lane;
       jput(pb0 + 0, 1.0);
       jput(pb0 + 1, 1.0);
@@ -502,15 +666,21 @@ __global__ void __launch_bounds__(128) kino_contact_kernel(const KinoConst* __re
       jput(pb0 + 27, -1.0);
       jput(pb0 + 28, -1.0);
     }
-    base += 232;
-    for (int e = lane; e < 67; e += 32) {
+    // C6: robot rows with constant entries; the CoM-height row has 1 (planar) or 3 (smooth) entries,
+    // the smooth ones are written by the terrain block above
+    constexpr int NCH = TERRAIN == 0 ? 1 : 3;
+    base += TERRAIN == 0 ? 232 : 464;
+    for (int e = lane; e < 66 + NCH; e += 32) {
       double v;
       if (e < 3) v = 1.0;
       else if (e < 6) v = -1.0;
       else if (e < 9) v = 1.0;
       else if (e < 12) v = mass;
-      else if (e < 59) v = 1.0;
-      else v = (e - 59) < 4 ? 0.25 : -0.25;
+      else if (e < 12 + NCH) {
+        if (TERRAIN != 0) continue;
+        v = 1.0;
+      } else if (e < 58 + NCH) v = 1.0;
+      else v = (e - 58 - NCH) < 4 ? 0.25 : -0.25;
       jput(base + e, v);
     }
   }
@@ -522,18 +692,22 @@ __global__ void __launch_bounds__(128) kino_contact_kernel(const KinoConst* __re
       const int o = 15 * lane;
       const double l0 = lamrow(fb_ + HB_KF_PT_PLANAR, k, 0), l1 = lamrow(fb_ + HB_KF_PT_PLANAR, k, 1);
       const double ld = lamrow(fb_ + HB_KF_PT_DCC, k, 0), lf = lamrow(fb_ + HB_KF_PT_FRICTION, k, 0);
-      hadd(o + Z_P + 2, o + Z_P + 2, -(l0 * pu.x + l1 * pu.y) * ddtau + (k1 ? sg * C.w_swing : 0.0));
-      hadd(o + Z_P + 2, o + Z_U, -l0 * dtau);
-      hadd(o + Z_P + 2, o + Z_U + 1, -l1 * dtau);
-      hadd(o + Z_P + 2, o + Z_F + 2, -ld * kbs);
-      hadd(o + Z_V + 2, o + Z_F + 2, -ld);
-      hadd(o + Z_FD + 2, o + Z_P + 2, -ld);
+      if constexpr (TERRAIN == 0) {
+        hadd(o + Z_P + 2, o + Z_P + 2, -(l0 * pu.x + l1 * pu.y) * ddtau + (k1 ? sg * C.w_swing : 0.0));
+        hadd(o + Z_P + 2, o + Z_U, -l0 * dtau);
+        hadd(o + Z_P + 2, o + Z_U + 1, -l1 * dtau);
+        hadd(o + Z_P + 2, o + Z_F + 2, -ld * kbs);
+        hadd(o + Z_V + 2, o + Z_F + 2, -ld);
+        hadd(o + Z_FD + 2, o + Z_P + 2, -ld);
+        if (k1) {
+          hadd(o + Z_V, o + Z_V, sg * C.w_swing);
+          hadd(o + Z_V + 1, o + Z_V + 1, sg * C.w_swing);
+          hadd(o + Z_F, o + Z_F, -2.0 * lf);
+          hadd(o + Z_F + 1, o + Z_F + 1, -2.0 * lf);
+          hadd(o + Z_F + 2, o + Z_F + 2, 2.0 * mu * mu * lf);
+        }
+      }
       if (k1) {
-        hadd(o + Z_V, o + Z_V, sg * C.w_swing);
-        hadd(o + Z_V + 1, o + Z_V + 1, sg * C.w_swing);
-        hadd(o + Z_F, o + Z_F, -2.0 * lf);
-        hadd(o + Z_F + 1, o + Z_F + 1, -2.0 * lf);
-        hadd(o + Z_F + 2, o + Z_F + 2, 2.0 * mu * mu * lf);
         for (int c = 0; c < 3; ++c) {
           hadd(o + Z_U + c, o + Z_U + c, 2.0 * sg * C.w_u);
           hadd(o + Z_FD + c, o + Z_FD + c, 2.0 * sg * C.w_fd);

@@ -379,12 +379,12 @@ class KinoLayout:
                         put(self.row(f"pt{i}.dcc", k), o + blk + d)
                 for d in range(3):
                     put(self.row(f"pt{i}.height", k), o + P + d)
-                for blk in (P, F):
+                # n and R_t depend on (x, y) only: grad h = (-T_x, -T_y, 1)
+                for name in ("normal", "friction"):
+                    for d in range(2):
+                        put(self.row(f"pt{i}.{name}", k), o + P + d)
                     for d in range(3):
-                        put(self.row(f"pt{i}.normal", k), o + blk + d)
-                for blk in (P, F):
-                    for d in range(3):
-                        put(self.row(f"pt{i}.friction", k), o + blk + d)
+                        put(self.row(f"pt{i}.{name}", k), o + F + d)
             for c in range(3):
                 put(self.row(f"pt{i}.u_bounds", k, c), o + U + c)
             for c in range(3):
@@ -492,16 +492,20 @@ class KinoLayout:
                     add(o + V + 0, o + V + 0)  # swing heuristic
                     add(o + V + 1, o + V + 1)
             else:
+                # smooth terrain: h = z - T(x, y); n, R_t depend on (x, y) only, so the coefficient of
+                # u_z (= n) and d L / d v_z carry no z dependence
                 for a in range(3):
                     for b in range(3):
                         add(o + P + a, o + P + b)
-                        add(o + P + a, o + U + b)
                         add(o + P + a, o + F + b)
-                        add(o + P + a, o + V + b)
                         add(o + P + a, o + FD + b)
                         add(o + V + a, o + F + b)
-                        add(o + V + a, o + V + b)
-                        add(o + F + a, o + F + b)
+                        if not (a == 2 and b == 2):
+                            add(o + P + a, o + U + b)
+                            add(o + P + a, o + V + b)
+                        if not first:  # friction cone, swing heuristic
+                            add(o + V + a, o + V + b)
+                            add(o + F + a, o + F + b)
             for c in range(3):
                 if not first:
                     add(o + U + c, o + U + c)
@@ -529,6 +533,10 @@ class KinoLayout:
                     add(15 * i + P + c, 15 * j + P + c)
         for c in range(3):
             add(123 + c, 123 + c)  # com velocity cost on h[0:3]
+        if self.smooth and not first:  # minimum com height: h(com) = com_z - T(com_x, com_y)
+            add(120, 120)
+            add(120, 121)
+            add(121, 121)
         return sorted(pairs)
 
     # ------------------------------------------------------------------ patterns + maps

@@ -26,8 +26,10 @@ def kino_parameters(lay: KinoLayout, model: RobotModel, B: int, rng: np.random.G
     M = model.total_mass()
     p[:, po.mass] = M
     # initial / final state: feet flat at y = +-0.1, base above, forces = weight / 8 (mass-normalised)
+    # on the stairs the robot starts in front of the first step edge (x = 0.225) and ends on it
+    x_start = 0.15 if lay.st.n_terrain_params == 10 else 0.0
     for base, dx in ((po.init, 0.0), (po.final, 0.3)):
-        step = dx * rng.uniform(0.8, 1.2, B) * spread
+        step = x_start + dx * rng.uniform(0.8, 1.2, B) * spread
         for i in range(NPT):
             y0 = 0.1 if i < 4 else -0.1
             o = base + po.st_pt(i, "p")
@@ -70,6 +72,15 @@ def kino_parameters(lay: KinoLayout, model: RobotModel, B: int, rng: np.random.G
             p[:, r + o:r + o + 4] = qq / np.linalg.norm(qq, axis=1, keepdims=True)
         p[:, r + po.R_BQV:r + po.R_BQV + 4] = 0.01 * spread * rng.normal(size=(B, 4))
         p[:, r + po.R_JR:r + po.R_JR + NJ] = 0.05 * spread * rng.normal(size=(B, NJ))
+    if lay.st.n_terrain_params == 10:
+        # two smooth steps of `main_walking_on_stairs.py:18-28,397-403` (step_length 0.9, width 0.8), with
+        # the step height randomised per instance in U(0.05, 0.15) (BASELINE config 5)
+        L = 0.45
+        height = rng.uniform(0.05, 0.15, B)
+        tp = np.array([2 * L, 0.8, 0.0, 1.5 * L, 0.0, 0.9 * L, 0.8, 0.0, 2 * L, 0.0])
+        p[:, po.terrain:po.terrain + 10] = tp
+        p[:, po.terrain + 2] = height
+        p[:, po.terrain + 7] = height
     return p
 
 

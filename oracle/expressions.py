@@ -121,6 +121,37 @@ class TerrainSum(Terrain):
         return self.lhs.height(p) + self.rhs.height(p) - p[2]
 
 
+class TwoSmoothSteps(Terrain):
+    """The stairs of `main_walking_on_stairs.py:18-28`: ``SmoothTerrain.step(...) +
+    SmoothTerrain.step(...)`` (a TerrainSum).  The reference bakes length / width / height / origin
+    into the graph as Python floats (`smooth_terrain.py:271,306-308`); here they are the ten runtime
+    parameters (l, w, h, ox, oy) x 2 so that a batch can randomise the step heights."""
+
+    N_PARAMS = 10
+
+    def __init__(self, params=None):
+        self.params = params
+
+    def with_params(self, tp):
+        assert len(tp) == self.N_PARAMS
+        return TwoSmoothSteps(tp)
+
+    def _sum(self):
+        tp = self.params
+        a = SmoothStep(tp[0], tp[1], tp[2], origin=(tp[3], tp[4], 0.0))
+        b = SmoothStep(tp[5], tp[6], tp[7], origin=(tp[8], tp[9], 0.0))
+        return TerrainSum(a, b)
+
+    def height(self, p):
+        return self._sum().height(p)
+
+    @staticmethod
+    def stairs_parameters(step_length=0.9, width=0.8, height=0.1):
+        """Numeric values of `main_walking_on_stairs.py:18-28,397-403` (length = step_length / 2)."""
+        L = step_length / 2.0
+        return np.array([2 * L, width, height, 1.5 * L, 0.0, 0.9 * L, width, height, 2 * L, 0.0])
+
+
 def jtimes(expr, wrt, direction):
     """``cs.jtimes(expr, wrt, v)`` for a scalar or vector expr: J(expr, wrt) @ v."""
     exprs = [expr] if isinstance(expr, SX) else list(expr)

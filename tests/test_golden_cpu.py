@@ -16,11 +16,17 @@ GOLD = os.path.join(os.path.dirname(__file__), "golden")
 @pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLD, "kino_*.npz"))))
 def test_kino_fixture(model, path):
     d = np.load(path)
+    from oracle import expressions as ex
+
     N, fin, per = int(d["horizon"]), bool(d["final"]), bool(d["periodicity"])
-    nlp, _ = kd.build(model, kd.Settings(horizon=N, final_state_constraint=fin, periodicity_constraint=per))
+    smooth = bool(d["smooth"]) if "smooth" in d else False
+    extra = dict(terrain=ex.TwoSmoothSteps(), terrain_params=10) if smooth else {}
+    nlp, _ = kd.build(model, kd.Settings(horizon=N, final_state_constraint=fin, periodicity_constraint=per, **extra))
     assert nlp.eval_g(d["x"], d["p"]) == pytest.approx(d["g"], rel=1e-13, abs=1e-13)
     assert nlp.eval_f(d["x"], d["p"]) == pytest.approx(d["f"], rel=1e-13)
-    lay = KinoLayout(model, KinoSettings(horizon=N, final_state_constraint=fin, periodicity_constraint=per))
+    lay = KinoLayout(model, KinoSettings(horizon=N, final_state_constraint=fin, periodicity_constraint=per,
+                                         terrain="smooth_steps" if smooth else "planar",
+                                         n_terrain_params=10 if smooth else 0))
     assert np.array_equal(lay.jac_colind, d["jac_colind"]) and np.array_equal(lay.jac_row, d["jac_row"])
     assert np.array_equal(lay.hess_colind, d["hess_colind"]) and np.array_equal(lay.hess_row, d["hess_row"])
     lb, ub = lay.bounds(d["p"])

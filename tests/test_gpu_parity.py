@@ -41,8 +41,11 @@ def test_kino_golden(model, built_library, path):
     from hippopt_b200.kino_layout import KinoSettings
 
     d = np.load(path)
+    smooth = bool(d["smooth"]) if "smooth" in d else False
     ev = KinoEvaluator(model, KinoSettings(horizon=int(d["horizon"]), final_state_constraint=bool(d["final"]),
-                                           periodicity_constraint=bool(d["periodicity"])))
+                                           periodicity_constraint=bool(d["periodicity"]),
+                                           terrain="smooth_steps" if smooth else "planar",
+                                           n_terrain_params=10 if smooth else 0))
     assert np.array_equal(ev.jac_sparsity()[1], d["jac_row"]) and np.array_equal(ev.hess_sparsity()[1], d["hess_row"])
     out = run(ev, d["x"], d["p"], d["lam"], d["sigma"])
     for k in ("f", "grad_f", "g", "jac", "hess"):
@@ -100,6 +103,37 @@ def test_kino_against_oracle(model, built_library, N, fin, per, noise):
     close(out["grad_f"], nlp.eval_grad_f(x, p))
     close(out["jac"], nlp.eval_jac(x, p))
     close(out["hess"], nlp.eval_hess(x, p, lam, sigma))
+
+
+@pytest.mark.parametrize("N,fin,noise", [(3, True, 0.05), (4, False, 0.15)])
+def test_kino_smooth_terrain_against_oracle(model, built_library, N, fin, noise):
+    """BASELINE config 5: two smooth steps (SmoothTerrain.step + SmoothTerrain.step) with the terrain
+    parameters as runtime data.  Far from a step the reference's formula evaluates 0 * inf = NaN in the
+    high derivatives (exp(-g^20) underflows while g^k overflows); the kernel returns the limit 0 there,
+    so entries where the oracle is not finite are only required to be finite."""
+    from hippopt_b200.evaluator import KinoEvaluator
+    from hippopt_b200.kino_layout import KinoSettings
+    from hippopt_b200.workloads import kino_batch
+    from oracle import expressions as ex
+    from oracle import kinodynamic as kd
+
+    ev = KinoEvaluator(model, KinoSettings(horizon=N, terrain="smooth_steps", n_terrain_params=10,
+                                           final_state_constraint=fin))
+    x, p, lam, sigma = kino_batch(ev.layout, model, 3, seed=40 + N, noise=noise)
+    sigma = np.array([1.0, 0.3, 2.0])
+    nlp, _ = kd.build(model, kd.Settings(horizon=N, terrain=ex.TwoSmoothSteps(), terrain_params=10,
+                                         final_state_constraint=fin))
+    assert np.array_equal(ev.jac_sparsity()[1], nlp.jac_structure()[1])
+    assert np.array_equal(ev.hess_sparsity()[1], nlp.hess_structure()[1])
+    out = run(ev, x, p, lam, sigma)
+    with np.errstate(all="ignore"):
+        ref = {"f": nlp.eval_f(x, p), "g": nlp.eval_g(x, p), "grad_f": nlp.eval_grad_f(x, p),
+               "jac": nlp.eval_jac(x, p), "hess": nlp.eval_hess(x, p, lam, sigma)}
+    for k, r in ref.items():
+        assert np.isfinite(out[k]).all(), k
+        ok = np.isfinite(r)
+        assert ok.mean() > 0.9, f"oracle mostly non-finite for {k}"
+        close(np.where(ok, out[k], 0.0), np.where(ok, r, 0.0))
 
 
 def test_kino_edge_cases(model, built_library):
