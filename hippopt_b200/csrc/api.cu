@@ -106,6 +106,24 @@ extern "C" int hb_kino_create(const int32_t* icfg, const double* dcfg, const int
   C.foot_body[0] = icfg[HB_KI_FOOT_BODY_L];
   C.foot_body[1] = icfg[HB_KI_FOOT_BODY_R];
   C.chest_body = icfg[HB_KI_CHEST_BODY];
+  C.kind = icfg[HB_KI_KIND];
+  C.x_stride = icfg[HB_KI_X_STRIDE];
+  C.cost_k0 = icfg[HB_KI_COST_K0];
+  C.joint_cost_kind = icfg[HB_KI_JOINT_COST_KIND];
+  C.po_fq = icfg[HB_KI_PO_FQ];
+  C.po_bq = icfg[HB_KI_PO_BQ];
+  C.po_bqv = icfg[HB_KI_PO_BQV];
+  C.po_jr = icfg[HB_KI_PO_JR];
+  C.ref_stride = icfg[HB_KI_REF_STRIDE];
+  for (int i = 0; i < 192; ++i) C.zmap[i] = i < 189 ? (short)icfg[HB_KI_ZMAP0 + i] : (short)-1;
+  if (C.kind != 0 && C.kind != 1) {
+    delete h;
+    return fail(HB_ERR_INVALID, "hb_kino_create: kind must be 0 (kinodynamic) or 1 (pose finder)");
+  }
+  if (C.kind == 1 && (C.N != 1 || C.terrain != 0)) {
+    delete h;
+    return fail(HB_ERR_UNSUPPORTED, "hb_kino_create: the pose finder is a single-knot problem on the planar terrain");
+  }
   if (C.terrain != 0 && C.terrain != 1) {
     delete h;
     return fail(HB_ERR_UNSUPPORTED, "hb_kino_create: terrain must be 0 (planar) or 1 (two smooth steps)");
@@ -323,7 +341,16 @@ extern "C" int hb_eval(hb_handle h, uint32_t mask, const double* x, const double
       CUDA_TRY(cudaFuncSetAttribute(hb::kino_kin_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
       attr_set = true;
     }
-    if (C.terrain == 0)
+    if (C.kind == 1) {
+      static bool pose_attr = false;
+      if (!pose_attr) {
+        CUDA_TRY(cudaFuncSetAttribute(hb::pose_contact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        pose_attr = true;
+      }
+      hb::pose_contact_kernel<<<grid, 32 * warps_per_block, smem, st>>>(h->dev, mask, x, p, (long)p_stride, lam_g, sigma,
+                                                                       d_fpart, grad_f, g, jac_vals, hess_vals,
+                                                                       (long)batch);
+    } else if (C.terrain == 0)
       hb::kino_contact_kernel<0><<<grid, 32 * warps_per_block, smem, st>>>(h->dev, mask, x, p, (long)p_stride, lam_g,
                                                                           sigma, d_fpart, grad_f, g, jac_vals, hess_vals,
                                                                           (long)batch);

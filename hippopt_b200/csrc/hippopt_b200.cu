@@ -1,5 +1,6 @@
 // hippopt_b200.cu -- single translation unit of libhippopt_b200.so (kernels + C ABI).
 #include "kino_kin.cu"
 #include "kino_contact.cu"
+#include "pose_contact.cu"
 #include "toy.cu"
 #include "api.cu"

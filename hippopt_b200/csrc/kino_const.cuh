@@ -26,6 +26,12 @@ struct KinoConst {
       po_max_L, po_min_com_h, po_min_feet_d, po_max_feet_h, po_max_s, po_min_s, po_max_sd, po_min_sd, po_refs0,
       po_terrain;
   int yaw[3];
+  // problem kind: 0 = kinodynamic OCP, 1 = static pose finder (single knot, no velocities).  The
+  // kinematics kernel always works on a "virtual knot" in the kinodynamic 189-variable layout;
+  // zmap[i] is the offset of virtual variable i inside the knot block of x, or -1 (absent: value 0).
+  int kind, x_stride, cost_k0, joint_cost_kind;
+  int po_fq, po_bq, po_bqv, po_jr, ref_stride;  // reference parameters of the kinematics costs
+  short zmap[192];
   int nb, foot_body[2], chest_body, max_depth, n_slots;
   int fam[HB_KF_COUNT][4];
   unsigned sub_mask[HB_MAX_BODIES];  // bit l: body l is in the subtree rooted at this body

@@ -382,12 +382,15 @@ __global__ void __launch_bounds__(128, WITH_HESS ? 2 : 3) kino_kin_kernel(const 
   double* sb = sm + L.bodies;
   double* zs = sm + L.z;
   double* gbuf = sm + L.gbuf;
-  const double* xb = x + b * C.n_x + (long)k * NZ;
+  const double* xb = x + b * C.n_x + (long)k * C.x_stride;
   const double* pb_ = p + b * p_stride;
   const int nb = C.nb;
-  const bool k1 = k >= 1;
+  const bool k1 = k >= C.cost_k0;  // knots on which the "apply_to_first_elements=False" expressions exist
 
-  for (int i = lane; i < NZ; i += 32) zs[i] = xb[i];
+  for (int i = lane; i < NZ; i += 32) {
+    const int zi = C.zmap[i];
+    zs[i] = zi >= 0 ? xb[zi] : 0.0;
+  }
   for (int i = lane; i < 58; i += 32) gbuf[i] = 0.0;
   __syncwarp();
 
@@ -496,10 +499,13 @@ __global__ void __launch_bounds__(128, WITH_HESS ? 2 : 3) kino_kin_kernel(const 
     const D3 a = matvec(sb + C.foot_body[f] * SB_STRIDE + SB_R, bf);
     st3(sm + L.arms + 3 * lane, a);
   }
-  const double* ref = pb_ + C.po_refs0 + R_COUNT * k;
+  const double* rfq = pb_ + C.po_fq + C.ref_stride * k;
+  const double* rbq = pb_ + C.po_bq + C.ref_stride * k;
+  const double* rbqv = pb_ + C.po_bqv + C.ref_stride * k;
+  const double* rjr = pb_ + C.po_jr + C.ref_stride * k;
   if (lane == 8) {
     // G = R_chest_body * (R_c * R(qd)^T), qd = desired frame quaternion (not normalised, kinematics.py:447)
-    const double vx = ref[R_FQ], vy = ref[R_FQ + 1], vz = ref[R_FQ + 2], w = ref[R_FQ + 3];
+    const double vx = rfq[0], vy = rfq[1], vz = rfq[2], w = rfq[3];
     double Rd[9];
     Rd[0] = 1.0 - 2.0 * (vy * vy + vz * vz);
     Rd[1] = 2.0 * (vx * vy - w * vz);
@@ -578,7 +584,7 @@ __global__ void __launch_bounds__(128, WITH_HESS ? 2 : 3) kino_kin_kernel(const 
   // base-quaternion error e = qd^-1 (x) q - (0,0,0,1) = A q - e4 (quaternion.py:64-70); columns of A
   double Aq[4][4];
   {
-    const double dx = -ref[R_BQ], dy = -ref[R_BQ + 1], dz = -ref[R_BQ + 2], dw = ref[R_BQ + 3];
+    const double dx = -rbq[0], dy = -rbq[1], dz = -rbq[2], dw = rbq[3];
     // (dw, dv) (x) (bw, bv): v = dw bv + bw dv + dv x bv ; w = dw bw - dv.bv ; column a: b = e_a
     // b = e_x
     Aq[0][0] = dw; Aq[1][0] = dz; Aq[2][0] = -dy; Aq[3][0] = -dx;
@@ -594,7 +600,7 @@ __global__ void __launch_bounds__(128, WITH_HESS ? 2 : 3) kino_kin_kernel(const 
     double cost = 0.0;
     // quaternion-velocity cost (all knots) and, for k >= 1, base quaternion / joint / frame costs
     if (lane < 4) {
-      const double e = qdv[lane] - ref[R_BQV + lane];
+      const double e = qdv[lane] - rbqv[lane];
       cost += C.w_bqv * e * e;
       gbuf[3 + lane] += 2.0 * C.w_bqv * e;
       if (k1) {
@@ -611,11 +617,18 @@ __global__ void __launch_bounds__(128, WITH_HESS ? 2 : 3) kino_kin_kernel(const 
       }
     }
     if (lane < HB_N_JOINTS && k1) {
-      const double sd = zs[Z_SD + lane], e = zs[Z_S + lane] - ref[R_JR + lane];
-      const double t = sd + C.wj[lane] * e;
-      cost += C.w_joint * ((HB_N_JOINTS - 1) * sd * sd + t * t);
-      gbuf[11 + lane] += C.w_joint * (2.0 * (HB_N_JOINTS - 1) * sd + 2.0 * t);
-      gbuf[34 + lane] += C.w_joint * 2.0 * C.wj[lane] * t;
+      const double sd = zs[Z_SD + lane], e = zs[Z_S + lane] - rjr[lane];
+      if (C.joint_cost_kind == 0) {
+        // kinodynamic planner.py:506-520: sumsqr of the broadcast n x n matrix
+        const double t = sd + C.wj[lane] * e;
+        cost += C.w_joint * ((HB_N_JOINTS - 1) * sd * sd + t * t);
+        gbuf[11 + lane] += C.w_joint * (2.0 * (HB_N_JOINTS - 1) * sd + 2.0 * t);
+        gbuf[34 + lane] += C.w_joint * 2.0 * C.wj[lane] * t;
+      } else {
+        // pose finder planner.py:584-588: e^T diag(w) e
+        cost += C.w_joint * (e * C.wj[lane]) * e;
+        gbuf[34 + lane] += C.w_joint * 2.0 * C.wj[lane] * e;
+      }
     }
     if (lane == 31 && k1) cost += C.w_frame * frame_cost;
     cost = warp_sum(cost);
@@ -702,7 +715,7 @@ __global__ void __launch_bounds__(128, WITH_HESS ? 2 : 3) kino_kin_kernel(const 
     __syncwarp();
     if (want_grad) {
       // gbuf order vb3 qd4 q4 sd23 s23 -> x offsets
-      double* gf = grad_f + b * C.n_x + (long)k * NZ;
+      double* gf = grad_f + b * C.n_x + (long)k * C.x_stride;
       for (int i = lane; i < 57; i += 32) {
         int off;
         if (i < 3) off = Z_VB + i;
@@ -710,9 +723,9 @@ __global__ void __launch_bounds__(128, WITH_HESS ? 2 : 3) kino_kin_kernel(const 
         else if (i < 11) off = Z_Q + i - 7;
         else if (i < 34) off = Z_SD + i - 11;
         else off = Z_S + i - 34;
-        gf[off] = gbuf[i];
+        if (C.zmap[off] >= 0) gf[C.zmap[off]] = gbuf[i];
       }
-      if (lane < 3) gf[Z_PB + lane] = 0.0;
+      if (lane < 3 && C.zmap[Z_PB + lane] >= 0) gf[C.zmap[Z_PB + lane]] = 0.0;
     }
   }
   if (!WITH_HESS) return;
@@ -829,8 +842,8 @@ __global__ void __launch_bounds__(128, WITH_HESS ? 2 : 3) kino_kin_kernel(const 
     em.add_sd = em.add_s = 0.0;
     if (lane >= 4 && lane < 27 && k1) {
       const double wjl = C.wj[lane - 4];
-      em.add_sd = sg * C.w_joint * 2.0 * wjl;
-      em.add_s = sg * C.w_joint * 2.0 * wjl * wjl;
+      em.add_sd = C.joint_cost_kind == 0 ? sg * C.w_joint * 2.0 * wjl : 0.0;
+      em.add_s = C.joint_cost_kind == 0 ? sg * C.w_joint * 2.0 * wjl * wjl : sg * C.w_joint * 2.0 * wjl;
     }
     V3<Dual> n0, w0, v0;
     kin_backward<Dual>(C, sb, zs, dir, S, xcD, xdD, slot, em, n0, w0, v0);
@@ -851,8 +864,8 @@ __global__ void __launch_bounds__(128, WITH_HESS ? 2 : 3) kino_kin_kernel(const 
       V3<Dual> gq[4], uq[4], wq[4];
       quat_maps<Dual>(qD, qdv2, gq, uq, wq);
       // Hessian of w_bq |qd^-1 (x) q - 1|^2 is 2 w_bq A^T A = 2 w_bq |qd|^2 I (left-multiplication matrix)
-      const double nqd = ref[R_BQ] * ref[R_BQ] + ref[R_BQ + 1] * ref[R_BQ + 1] + ref[R_BQ + 2] * ref[R_BQ + 2] +
-                         ref[R_BQ + 3] * ref[R_BQ + 3];
+      const double nqd = rbq[0] * rbq[0] + rbq[1] * rbq[1] + rbq[2] * rbq[2] +
+                         rbq[3] * rbq[3];
 #pragma unroll
       for (int a = 0; a < 4; ++a) {
         const Dual dq = dot(n0, gq[a]) + dot(w0, uq[a]);

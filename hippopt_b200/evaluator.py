@@ -215,9 +215,12 @@ class KinoEvaluator(_Evaluator):
             "FOOT_BODY_L": model.frames[settings.foot_frames[0]][0],
             "FOOT_BODY_R": model.frames[settings.foot_frames[1]][0],
             "CHEST_BODY": model.frames[settings.frame_quaternion_cost_frame][0],
+            "KIND": 0, "X_STRIDE": 189, "COST_K0": 1, "JOINT_COST_KIND": 0, "PO_FQ": po.refs0 + po.R_FQ,
+            "PO_BQ": po.refs0 + po.R_BQ, "PO_BQV": po.refs0 + po.R_BQV, "PO_JR": po.refs0 + po.R_JR, "REF_STRIDE": 55,
         }
         for k, v in ints.items():
             icfg[H["HB_KI_" + k]] = v
+        icfg[H["HB_KI_ZMAP0"]:H["HB_KI_ZMAP0"] + 189] = np.arange(189)
         icfg[H["HB_KI_PARENT0"]:H["HB_KI_PARENT0"] + model.n_bodies] = model.parent
         pt_names = ["f_ic", "f_dyn", "p_ic", "p_dyn", "planar", "dcc", "height", "normal", "friction", "u_bounds",
                     "fd_bounds", "fk"]
@@ -253,21 +256,10 @@ class KinoEvaluator(_Evaluator):
         dcfg[H["HB_KD_W_RATIO"]] = s.force_regularization_cost_multiplier
         dcfg[H["HB_KD_W_YAW"]] = s.foot_yaw_regularization_cost_multiplier
         dcfg[H["HB_KD_WJ0"]:H["HB_KD_WJ0"] + NJ] = s.joint_regularization_cost_weights
-        dcfg[H["HB_KD_TOTAL_MASS"]] = model.total_mass()
-        for f, fr in enumerate(s.foot_frames):
-            _, R, t = model.frames[fr]
-            dcfg[H["HB_KD_FOOT_R0"] + 9 * f:H["HB_KD_FOOT_R0"] + 9 * f + 9] = R.ravel()
-            dcfg[H["HB_KD_FOOT_T0"] + 3 * f:H["HB_KD_FOOT_T0"] + 3 * f + 3] = t
-        dcfg[H["HB_KD_CHEST_R0"]:H["HB_KD_CHEST_R0"] + 9] = model.frames[s.frame_quaternion_cost_frame][1].ravel()
-        st = H["HB_KD_BODY_STRIDE"]
-        for b in range(model.n_bodies):
-            o = H["HB_KD_BODY0"] + st * b
-            dcfg[o:o + 9] = model.joint_rot[b].ravel()
-            dcfg[o + 9:o + 12] = model.joint_xyz[b]
-            dcfg[o + 12:o + 15] = model.joint_axis[b]
-            dcfg[o + 15] = model.mass[b]
-            dcfg[o + 16:o + 19] = model.com[b]
-            dcfg[o + 19:o + 28] = model.inertia[b].ravel()
+        _fill_model_tables(dcfg, model, s.foot_frames, s.frame_quaternion_cost_frame)
+        self._create_handle(icfg, dcfg, lay)
+
+    def _create_handle(self, icfg, dcfg, lay):
         self._keep = (icfg, dcfg, _i32(lay.jc_map), _i32(lay.jk_map), np.ascontiguousarray(lay.hc_index, dtype=np.int16),
                       _i32(lay.hc_map), _i32(lay.hk_map), _i32(lay.hk2_map))
         i32p, i16p, f64p = (ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int16),
@@ -290,6 +282,84 @@ class KinoEvaluator(_Evaluator):
 
     def bounds(self, p):
         return self.layout.bounds(np.asarray(p))
+
+
+def _fill_model_tables(dcfg, model, foot_frames, chest_frame):
+    dcfg[H["HB_KD_TOTAL_MASS"]] = model.total_mass()
+    for f, fr in enumerate(foot_frames):
+        _, R, t = model.frames[fr]
+        dcfg[H["HB_KD_FOOT_R0"] + 9 * f:H["HB_KD_FOOT_R0"] + 9 * f + 9] = R.ravel()
+        dcfg[H["HB_KD_FOOT_T0"] + 3 * f:H["HB_KD_FOOT_T0"] + 3 * f + 3] = t
+    dcfg[H["HB_KD_CHEST_R0"]:H["HB_KD_CHEST_R0"] + 9] = model.frames[chest_frame][1].ravel()
+    st = H["HB_KD_BODY_STRIDE"]
+    for b in range(model.n_bodies):
+        o = H["HB_KD_BODY0"] + st * b
+        dcfg[o:o + 9] = model.joint_rot[b].ravel()
+        dcfg[o + 9:o + 12] = model.joint_xyz[b]
+        dcfg[o + 12:o + 15] = model.joint_axis[b]
+        dcfg[o + 15] = model.mass[b]
+        dcfg[o + 16:o + 19] = model.com[b]
+        dcfg[o + 19:o + 28] = model.inertia[b].ravel()
+
+
+class PoseEvaluator(KinoEvaluator):
+    """Evaluator of the static pose finder
+    (`/root/reference/src/hippopt/turnkey_planners/humanoid_pose_finder/planner.py:303-413`), the one
+    reference configuration IPOPT solves with the exact Hessian."""
+
+    def __init__(self, model: RobotModel, settings=None):
+        from .pose_layout import PoseLayout, PoseSettings
+
+        _Evaluator.__init__(self)
+        self.model = model
+        self.settings = s = settings or PoseSettings()
+        self.layout = lay = PoseLayout(model, s)
+        po = lay.po
+        icfg = np.zeros(H["HB_KI_COUNT"], dtype=np.int32)
+        ints = {
+            "HORIZON": 1, "N_X": lay.n_x, "N_P": lay.n_p, "M": lay.m, "NNZ_J": lay.nnz_j, "NNZ_H": lay.nnz_h,
+            "N_JC": lay.n_jc, "N_JK": lay.n_jk, "N_HC": lay.n_hc, "TERRAIN": 0, "HAS_FINAL": 0, "HAS_PERIODICITY": 0,
+            "H_INIT": 0, "PO_DESC0": po.desc0, "PO_MASS": po.mass, "PO_INIT": po.ref, "PO_GRAVITY": po.gravity,
+            "PO_EPS": po.eps, "PO_MU": po.mu, "PO_MAX_S": po.max_s, "PO_MIN_S": po.min_s,
+            "N_BODIES": model.n_bodies, "FOOT_BODY_L": model.frames[s.foot_frames[0]][0],
+            "FOOT_BODY_R": model.frames[s.foot_frames[1]][0],
+            "CHEST_BODY": model.frames[s.frame_quaternion_cost_frame][0],
+            "KIND": 1, "X_STRIDE": 0, "COST_K0": 0, "JOINT_COST_KIND": 1, "PO_FQ": po.ref_fq,
+            "PO_BQ": po.ref + po.ST_Q, "PO_BQV": po.ref + po.ST_Q, "PO_JR": po.ref + po.ST_S, "REF_STRIDE": 0,
+        }
+        for k, v in ints.items():
+            icfg[H["HB_KI_" + k]] = v
+        icfg[H["HB_KI_ZMAP0"]:H["HB_KI_ZMAP0"] + 189] = lay.zmap
+        icfg[H["HB_KI_PARENT0"]:H["HB_KI_PARENT0"] + model.n_bodies] = model.parent
+        for fid in range(H["HB_KF_COUNT"]):
+            icfg[H["HB_KI_FAM0"] + 4 * fid:H["HB_KI_FAM0"] + 4 * fid + 4] = (-1, 0, 1, 0)
+
+        def put_fam(fid, name):
+            icfg[H["HB_KI_FAM0"] + 4 * fid:H["HB_KI_FAM0"] + 4 * fid + 4] = lay.fam[name]
+
+        for i in range(8):
+            base = i * H["HB_KF_PT_COUNT"]
+            put_fam(base + H["HB_KF_PT_DCC"], f"pt{i}.complementarity")
+            put_fam(base + H["HB_KF_PT_HEIGHT"], f"pt{i}.height")
+            put_fam(base + H["HB_KF_PT_NORMAL"], f"pt{i}.normal")
+            put_fam(base + H["HB_KF_PT_FRICTION"], f"pt{i}.friction")
+            put_fam(base + H["HB_KF_PT_FK"], f"pt{i}.fk")
+        put_fam(H["HB_KF_UNIT_QUAT"], "unit_quat")
+        put_fam(H["HB_KF_COM_KIN"], "com_kin")
+        put_fam(H["HB_KF_H_DYN"], "balance")
+        put_fam(H["HB_KF_S_BOUNDS"], "s_bounds")
+        dcfg = np.zeros(H["HB_KD_COUNT"], dtype=np.float64)
+        # cost-weight slots shared with the kinodynamic table (csrc/pose_contact.cu header)
+        dcfg[H["HB_KD_W_CENTROID"]] = s.com_regularization_cost_multiplier
+        dcfg[H["HB_KD_W_RATIO"]] = s.average_force_regularization_cost_multiplier
+        dcfg[H["HB_KD_W_SWING"]] = s.point_position_regularization_cost_multiplier
+        dcfg[H["HB_KD_W_FD"]] = s.force_regularization_cost_multiplier
+        dcfg[H["HB_KD_W_FRAME"]] = s.desired_frame_quaternion_cost_multiplier
+        dcfg[H["HB_KD_W_BQ"]] = s.base_quaternion_cost_multiplier
+        dcfg[H["HB_KD_W_JOINT"]] = s.joint_regularization_cost_multiplier
+        dcfg[H["HB_KD_WJ0"]:H["HB_KD_WJ0"] + NJ] = s.joint_regularization_cost_weights
+        _fill_model_tables(dcfg, model, s.foot_frames, s.frame_quaternion_cost_frame)
+        self._create_handle(icfg, dcfg, lay)
 
 
 class ToyEvaluator(_Evaluator):

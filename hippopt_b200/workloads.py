@@ -110,6 +110,47 @@ def kino_points(lay: KinoLayout, p: np.ndarray, rng: np.random.Generator, noise:
     return x
 
 
+def pose_batch(lay, model: RobotModel, B: int, seed: int = 1, noise: float = 0.05):
+    """Pose-finder instances (BASELINE config 2, `humanoid_pose_finder/main.py:100-130`): references
+    com = (0, 0, 0.7) + U(-0.05, 0.05) in xy, feet at (U(-0.15, 0.15), +-0.1, 0), identity quaternions, the
+    reference joint configuration; evaluation points = references + N(0, noise)."""
+    rng = np.random.default_rng(seed)
+    po = lay.po
+    p = np.zeros((B, lay.n_p))
+    for i in range(NPT):
+        p[:, po.desc0 + 3 * i:po.desc0 + 3 * i + 3] = FOOT_CORNERS[i % 4]
+    p[:, po.mass] = model.total_mass()
+    p[:, po.gravity:po.gravity + 6] = GRAVITY
+    foot_x = rng.uniform(-0.15, 0.15, (B, 2))
+    for i in range(NPT):
+        o = po.ref + 9 * i
+        p[:, o] = FOOT_CORNERS[i % 4, 0] + foot_x[:, i // 4]
+        p[:, o + 1] = FOOT_CORNERS[i % 4, 1] + (0.1 if i < 4 else -0.1)
+        p[:, o + 5] = 9.80665 / 8.0
+        p[:, o + 6:o + 9] = FOOT_CORNERS[i % 4]
+    p[:, po.ref + po.ST_PB:po.ref + po.ST_PB + 3] = [0.0, 0.0, 0.75]
+    p[:, po.ref + po.ST_Q + 3] = 1.0
+    s_ref = np.deg2rad([7, 0.12, -0.01, 12, 7, -12, 40.769, 12, 7, -12, 40.769, 5.76, 1.61, -0.31, -31.64, -20.52,
+                        -1.52, 5.76, 1.61, -0.31, -31.64, -20.52, -1.52])
+    p[:, po.ref + po.ST_S:po.ref + po.ST_S + NJ] = s_ref
+    p[:, po.ref + po.ST_COM:po.ref + po.ST_COM + 3] = np.concatenate(
+        [rng.uniform(-0.05, 0.05, (B, 2)), 0.7 * np.ones((B, 1))], axis=1)
+    p[:, po.ref_fq + 3] = 1.0
+    p[:, po.eps], p[:, po.mu] = 1e-4, 0.3
+    p[:, po.max_s:po.max_s + NJ] = 1.5
+    p[:, po.min_s:po.min_s + NJ] = -1.5
+    x = np.zeros((B, lay.n_x))
+    for i in range(NPT):
+        x[:, 6 * i:6 * i + 6] = p[:, po.ref + 9 * i:po.ref + 9 * i + 6]
+    x[:, 48:51] = p[:, po.ref + po.ST_PB:po.ref + po.ST_PB + 3]
+    x[:, 51:55] = p[:, po.ref + po.ST_Q:po.ref + po.ST_Q + 4]
+    x[:, 55:78] = p[:, po.ref + po.ST_S:po.ref + po.ST_S + NJ]
+    x[:, 78:81] = p[:, po.ref + po.ST_COM:po.ref + po.ST_COM + 3]
+    x += noise * rng.normal(size=x.shape)
+    lam = rng.normal(size=(B, lay.m))
+    return x, p, lam, np.ones(B)
+
+
 def kino_batch(lay: KinoLayout, model: RobotModel, B: int, seed: int = 2, noise: float = 1e-2, spread: float = 1.0):
     """x, p, lam_g ~ N(0,1), sigma = 1 for B instances (seeded)."""
     rng = np.random.default_rng(seed)

@@ -92,7 +92,18 @@ enum {
   HB_KI_FOOT_BODY_L,
   HB_KI_FOOT_BODY_R,
   HB_KI_CHEST_BODY,
-  HB_KI_PARENT0,                                   /* HB_MAX_BODIES entries */
+  /* problem kind and the "virtual knot" mapping used by the kinematics kernel */
+  HB_KI_KIND,             /* 0 kinodynamic OCP (planner.py:27-176), 1 pose finder (humanoid_pose_finder/planner.py:303-413) */
+  HB_KI_X_STRIDE,         /* doubles between consecutive knots in x (189, or 0 for a single knot) */
+  HB_KI_COST_K0,          /* first knot on which apply_to_first_elements=False expressions exist (1, or 0) */
+  HB_KI_JOINT_COST_KIND,  /* 0: planner.py:506-520 (kinodynamic), 1: e^T diag(w) e (pose finder :584-588) */
+  HB_KI_PO_FQ,            /* parameter offsets of the cost references at knot 0 ... */
+  HB_KI_PO_BQ,
+  HB_KI_PO_BQV,
+  HB_KI_PO_JR,
+  HB_KI_REF_STRIDE,       /* ... and their stride per knot */
+  HB_KI_ZMAP0,            /* 189 entries: virtual knot variable -> offset inside the knot block of x, or -1 */
+  HB_KI_PARENT0 = HB_KI_ZMAP0 + 189,               /* HB_MAX_BODIES entries */
   HB_KI_FAM0 = HB_KI_PARENT0 + HB_MAX_BODIES,      /* HB_KF_COUNT x 4 entries: base, rows, k0, k1 */
   HB_KI_COUNT_BASE = HB_KI_FAM0
 };

@@ -136,6 +136,47 @@ def test_kino_smooth_terrain_against_oracle(model, built_library, N, fin, noise)
         close(np.where(ok, out[k], 0.0), np.where(ok, r, 0.0))
 
 
+@pytest.mark.parametrize("noise", [0.05, 0.4])
+def test_pose_finder_against_oracle(model, built_library, noise):
+    """BASELINE config 2: humanoid_pose_finder static pose, single knot, exact Hessian."""
+    from hippopt_b200.evaluator import PoseEvaluator
+    from hippopt_b200.workloads import pose_batch
+    from oracle import pose_finder as pf
+
+    ev = PoseEvaluator(model)
+    assert (ev.n_x, ev.n_p, ev.m) == (81, 202, 89)  # SURVEY.md Appendix B.4
+    nlp, _ = pf.build(model)
+    assert np.array_equal(ev.jac_sparsity()[0], nlp.jac_structure()[0])
+    assert np.array_equal(ev.jac_sparsity()[1], nlp.jac_structure()[1])
+    assert np.array_equal(ev.hess_sparsity()[1], nlp.hess_structure()[1])
+    x, p, lam, sigma = pose_batch(ev.layout, model, 6, seed=9, noise=noise)
+    sigma = np.linspace(0.2, 2.0, 6)
+    lb, ub = ev.bounds(p)
+    olb, oub = nlp.eval_bounds(p)
+    assert np.array_equal(lb, olb) and np.array_equal(ub, oub)
+    out = run(ev, x, p, lam, sigma)
+    close(out["f"], nlp.eval_f(x, p))
+    close(out["g"], nlp.eval_g(x, p))
+    close(out["grad_f"], nlp.eval_grad_f(x, p))
+    close(out["jac"], nlp.eval_jac(x, p))
+    close(out["hess"], nlp.eval_hess(x, p, lam, sigma))
+
+
+def test_pose_finder_config2_batch(model, built_library):
+    """Config 2 at its stated batch (4096): deterministic, batch-order independent, finite."""
+    from hippopt_b200.evaluator import PoseEvaluator
+    from hippopt_b200.workloads import pose_batch
+
+    ev = PoseEvaluator(model)
+    x, p, lam, sigma = pose_batch(ev.layout, model, 4096, seed=1)
+    out = run(ev, x, p, lam, sigma)
+    perm = np.random.default_rng(3).permutation(4096)
+    again = run(ev, x[perm], p[perm], lam[perm], sigma[perm])
+    for k in out:
+        assert np.isfinite(out[k]).all()
+        assert np.array_equal(again[k], out[k][perm]), k
+
+
 def test_kino_edge_cases(model, built_library):
     """Single instance, shared parameter vector, zero multipliers, partial masks, argument errors."""
     from hippopt_b200 import _capi
