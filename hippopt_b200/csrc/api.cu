@@ -189,6 +189,16 @@ extern "C" int hb_kino_create(const int32_t* icfg, const double* dcfg, const int
     B.slot = -1;
     B.carry = 0;
   }
+  C.max_sib = 1;
+  {
+    int n_children[HB_MAX_BODIES] = {0};
+    C.body[0].sib_rank = 0;
+    for (int l = 1; l < C.nb; ++l) {
+      const int p = C.body[l].parent;
+      C.body[l].sib_rank = n_children[p]++;
+      if (n_children[p] > C.max_sib) C.max_sib = n_children[p];
+    }
+  }
   for (int l = 1; l < C.nb; ++l) {
     const int p = C.body[l].parent;
     if (p == l - 1) C.body[p].carry = 1;

@@ -18,6 +18,7 @@ struct BodyC {
   int depth;
   int slot;   // >= 0: this body owns a shared-memory branch accumulator
   int carry;  // 1: the contribution of body index+1 continues into this body (parent[index+1] == index)
+  int sib_rank;  // index of this body among the children of its parent (level-wise primal adjoint pass)
 };
 
 struct KinoConst {
@@ -32,7 +33,7 @@ struct KinoConst {
   int kind, x_stride, cost_k0, joint_cost_kind;
   int po_fq, po_bq, po_bqv, po_jr, ref_stride;  // reference parameters of the kinematics costs
   short zmap[192];
-  int nb, foot_body[2], chest_body, max_depth, n_slots;
+  int nb, foot_body[2], chest_body, max_depth, n_slots, max_sib;
   int fam[HB_KF_COUNT][4];
   unsigned sub_mask[HB_MAX_BODIES];  // bit l: body l is in the subtree rooted at this body
   double w_swing, w_u, w_fd, w_centroid, w_comvel[3], w_frame, w_bq, w_bqv, w_joint, w_ratio, w_yaw;

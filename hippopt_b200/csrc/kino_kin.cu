@@ -24,7 +24,13 @@
 
 namespace hb {
 
-enum { SB_O = 0, SB_D = 3, SB_W = 6, SB_V = 9, SB_AX = 12, SB_I = 15, SB_R = 21, SB_L = 30, SB_IH = 33, SB_RHO = 36, SB_STRIDE = 39 };
+// per-body staging in shared memory (doubles): origin, CoM arm, twist, world axis, world inertia, rotation,
+// I.w, I.hbar, rho = o - o_parent, and (Hessian pass) the primal adjoint totals (n, F, wbar, vbar) plus the
+// local primal adjoints cbar, cdbar
+enum {
+  SB_O = 0, SB_D = 3, SB_W = 6, SB_V = 9, SB_AX = 12, SB_I = 15, SB_R = 21, SB_L = 30, SB_IH = 33, SB_RHO = 36,
+  SB_ACC = 39, SB_CB = 51, SB_CDB = 54, SB_STRIDE = 57
+};
 
 struct KinSmem {
   int bodies, arms, fdu, fdal, fdar, G, z, gbuf, slot, total;
@@ -49,7 +55,8 @@ __host__ __device__ inline KinSmem kin_smem_layout(int nb, int n_slots, bool wit
   s.gbuf = o;
   o += 58;
   s.slot = o;
-  o += n_slots * 32 * (with_hess ? 24 : 12);
+  (void)with_hess;
+  o += n_slots * 32 * 12;  // fp64 sweep: adjoints; Hessian sweep: their tangents (primal totals are per body)
   s.total = o;
   return s;
 }
@@ -278,6 +285,171 @@ __device__ __forceinline__ void kin_backward(const KinoConst& C, const double* s
   v0 = cv;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Hessian pass, split in two so that no lane recomputes what is identical for all of them:
+//   (1) primal_adjoint_pass: the adjoints of the Lagrangian (true multipliers as seeds) are the same
+//       for every direction; they are computed ONCE per warp, lane = body, accumulated leaf-to-root by
+//       depth level, and left in shared memory (SB_ACC totals, SB_CB / SB_CDB local terms);
+//   (2) kin_tangent_sweep: each lane propagates only the TANGENT of those adjoints along its
+//       direction (product rule with the staged primal values) -- 2/3 of the dual-number arithmetic
+//       and half of its registers.
+struct SeedsP {
+  D3 wc, hb, footF[2], footN[2], chestN;
+};
+struct SeedsT {
+  D3 footF[2], footN[2], chestN;  // wc and hb are constants: zero tangent
+};
+
+__device__ __forceinline__ void primal_adjoint_pass(const KinoConst& C, double* sb, const double* zs, const SeedsP& S,
+                                                    D3 xc, D3 xd) {
+  const int lane = threadIdx.x & 31;
+  const int nb = C.nb;
+  if (lane < nb) {
+    const BodyC& bc = C.body[lane];
+    double* bl = sb + lane * SB_STRIDE;
+    const D3 o = ld3(bl + SB_O), d = ld3(bl + SB_D), w = ld3(bl + SB_W), v = ld3(bl + SB_V);
+    const double m = bc.mass;
+    const D3 c = o + d;
+    const D3 cd = v + cross(w, d);
+    const D3 cbar = scale(m, cross(cd - xd, S.hb) + S.wc);
+    const D3 cdbar = scale(m, cross(S.hb, c - xc));
+    const D3 Iw = ld3(bl + SB_L), Ih = ld3(bl + SB_IH);
+    D3 F = cbar;
+    D3 n = cross(d, cbar) + cross(d, cross(cdbar, w)) + cross(Iw, S.hb) + cross(Ih, w);
+    const D3 wb = cross(d, cdbar) + Ih;
+    if (lane == C.foot_body[0]) {
+      F = F + S.footF[0];
+      n = n + S.footN[0];
+    }
+    if (lane == C.foot_body[1]) {
+      F = F + S.footF[1];
+      n = n + S.footN[1];
+    }
+    if (lane == C.chest_body) n = n + S.chestN;
+    st3(bl + SB_ACC, n);
+    st3(bl + SB_ACC + 3, F);
+    st3(bl + SB_ACC + 6, wb);
+    st3(bl + SB_ACC + 9, cdbar);
+    st3(bl + SB_CB, cbar);
+    st3(bl + SB_CDB, cdbar);
+  }
+  __syncwarp();
+  for (int dep = C.max_depth; dep >= 1; --dep)
+    for (int r = 0; r < C.max_sib; ++r) {
+      if (lane > 0 && lane < nb && C.body[lane].depth == dep && C.body[lane].sib_rank == r) {
+        const BodyC& bc = C.body[lane];
+        const double* bl = sb + lane * SB_STRIDE;
+        double* bp = sb + bc.parent * SB_STRIDE;
+        const D3 n = ld3(bl + SB_ACC), F = ld3(bl + SB_ACC + 3), wb = ld3(bl + SB_ACC + 6), vb = ld3(bl + SB_ACC + 9);
+        const D3 ax = ld3(bl + SB_AX), rho = ld3(bl + SB_RHO), wpar = ld3(bp + SB_W);
+        const double sd = zs[Z_SD + lane - 1];
+        const D3 pn = n + cross(rho, F) + scale(sd, cross(ax, wb)) + cross(rho, cross(vb, wpar));
+        const D3 pw = wb + cross(rho, vb);
+        st3(bp + SB_ACC, ld3(bp + SB_ACC) + pn);
+        st3(bp + SB_ACC + 3, ld3(bp + SB_ACC + 3) + F);
+        st3(bp + SB_ACC + 6, ld3(bp + SB_ACC + 6) + pw);
+        st3(bp + SB_ACC + 9, ld3(bp + SB_ACC + 9) + vb);
+      }
+      __syncwarp();
+    }
+}
+
+__device__ __forceinline__ D3 tangent_of(const V3<Dual>& a) { return v3<double>(a.x.d, a.y.d, a.z.d); }
+__device__ __forceinline__ D3 primal_of(const V3<Dual>& a) { return v3<double>(a.x.v, a.y.v, a.z.v); }
+
+template <class Emit>
+__device__ __forceinline__ void kin_tangent_sweep(const KinoConst& C, const double* sb, const double* zs,
+                                                  const Dir& dir, D3 hb, const SeedsT& S, D3 txc, D3 txd, double* slot,
+                                                  Emit& emit, D3& n0, D3& w0, D3& v0) {
+  const int nb = C.nb;
+  const int lane = threadIdx.x & 31;
+  const D3 zero = v3<double>(0.0, 0.0, 0.0);
+  for (int i = 0; i < C.n_slots * 12; ++i) slot[i * 32 + lane] = 0.0;
+  D3 cn = zero, cF = zero, cw = zero, cv = zero;
+  D3 An = zero, AF = zero, Aw = zero, Av = zero;
+  for (int l = nb - 1; l >= 0; --l) {
+    const BodyC& bc = C.body[l];
+    if (!bc.carry) cn = cF = cw = cv = zero;
+    if (l == 0) {
+      cn = cn + An;
+      cF = cF + AF;
+      cw = cw + Aw;
+      cv = cv + Av;
+    }
+    const double* bl = sb + l * SB_STRIDE;
+    const St<Dual> s = load_state(sb, l, dir, Dual());
+    const D3 d = primal_of(s.d), w = primal_of(s.w), ax = primal_of(s.ax);
+    const D3 to = tangent_of(s.o), td = tangent_of(s.d), tw = tangent_of(s.w), tv = tangent_of(s.v),
+             tax = tangent_of(s.ax);
+    const double in = ((dir.mask >> l) & 1u) ? 1.0 : 0.0;
+    const D3 a = scale(in, dir.alpha);
+    {
+      const double m = bc.mass;
+      const double* I = bl + SB_I;
+      const D3 cbar = ld3(bl + SB_CB), cdbar = ld3(bl + SB_CDB), Ih = ld3(bl + SB_IH), Iw = ld3(bl + SB_L);
+      const D3 tc = to + td;
+      const D3 tcd = tv + cross(tw, d) + cross(w, td);
+      const D3 tcbar = scale(m, cross(tcd - txd, hb));
+      const D3 tcdbar = scale(m, cross(hb, tc - txc));
+      const D3 tIw = symmul(I, tw - cross(a, w)) + cross(a, Iw);
+      const D3 tIh = cross(a, Ih) - symmul(I, cross(a, hb));
+      cF = cF + tcbar;
+      cn = cn + cross(td, cbar) + cross(d, tcbar) + cross(td, cross(cdbar, w)) +
+           cross(d, cross(tcdbar, w) + cross(cdbar, tw)) + cross(tIw, hb) + cross(tIh, w) + cross(Ih, tw);
+      cv = cv + tcdbar;
+      cw = cw + cross(td, cdbar) + cross(d, tcdbar) + tIh;
+      if (l == C.foot_body[0]) {
+        cF = cF + S.footF[0];
+        cn = cn + S.footN[0];
+      }
+      if (l == C.foot_body[1]) {
+        cF = cF + S.footF[1];
+        cn = cn + S.footN[1];
+      }
+      if (l == C.chest_body) cn = cn + S.chestN;
+    }
+    if (bc.slot >= 0) {
+      const double* sl = slot + bc.slot * 12 * 32 + lane;
+      slot_get(cn, sl, 0);
+      slot_get(cF, sl, 3);
+      slot_get(cw, sl, 6);
+      slot_get(cv, sl, 9);
+    }
+    if (l == 0) break;
+    // primal totals of body l (all children included)
+    const D3 np = ld3(bl + SB_ACC), Fp = ld3(bl + SB_ACC + 3), wp = ld3(bl + SB_ACC + 6), vp = ld3(bl + SB_ACC + 9);
+    emit.joint_t(l, dot(tax, np) + dot(ax, cn), dot(tax, wp) + dot(ax, cw));
+    const int p = bc.parent;
+    const D3 rho = ld3(bl + SB_RHO), wpar = ld3(sb + p * SB_STRIDE + SB_W);
+    const double inp = ((dir.mask >> p) & 1u) ? 1.0 : 0.0;
+    const D3 ap = scale(inp, dir.alpha);
+    const D3 trho = cross(ap, rho);
+    const D3 twpar = cross(ap, wpar - dir.wpi) + scale(inp, dir.u);
+    const double sd = zs[Z_SD + l - 1];
+    const D3 pn = cn + cross(trho, Fp) + cross(rho, cF) + scale(sd, cross(tax, wp) + cross(ax, cw)) +
+                  cross(trho, cross(vp, wpar)) + cross(rho, cross(cv, wpar) + cross(vp, twpar));
+    const D3 pw = cw + cross(trho, vp) + cross(rho, cv);
+    if (p == l - 1) {
+      cn = pn;
+      cw = pw;
+    } else if (p == 0) {
+      An = An + pn;
+      AF = AF + cF;
+      Aw = Aw + pw;
+      Av = Av + cv;
+    } else {
+      double* sl = slot + C.body[p].slot * 12 * 32 + lane;
+      slot_add(sl, 0, pn);
+      slot_add(sl, 3, cF);
+      slot_add(sl, 6, pw);
+      slot_add(sl, 9, cv);
+    }
+  }
+  n0 = cn;
+  w0 = cw;
+  v0 = cv;
+}
+
 // quaternion maps: g_a (rotation tangent of R(q/|q|) along q_a), u_a = d omega_0 / d q_a,
 // w_a = d omega_0 / d q_dot_a.
 template <class T>
@@ -348,20 +520,24 @@ struct HessEmit {
     const int slot = map[dirj * 57 + row];
     if (slot >= 0) hess[slot] = v;
   }
-  __device__ __forceinline__ void joint(int l, Dual sbar, Dual sdbar) const {
+  __device__ __forceinline__ void joint_t(int l, double tsbar, double tsdbar) const {
     if (dirj < 0) return;
     const int j = l - 1;
     const bool own = (dirj - 4 == j);
-    put(7 + j, sdbar.d + (own ? add_sd : 0.0));   // rows: vb3 qd4 sd23 q4 s23
-    put(34 + j, sbar.d + (own ? add_s : 0.0));
+    put(7 + j, tsdbar + (own ? add_sd : 0.0));   // rows: vb3 qd4 sd23 q4 s23
+    put(34 + j, tsbar + (own ? add_s : 0.0));
   }
+  __device__ __forceinline__ void joint(int l, Dual sbar, Dual sdbar) const { joint_t(l, sbar.d, sdbar.d); }
 };
 
 // Measured on B200 (tools/time_kino.py): the dual sweep is fastest with the full 255 registers
 // (2 CTAs/SM; 168 registers spill 1 KB/thread and lose 12%), the fp64-only variant with 168
 // registers (3 CTAs/SM, -19%).
 template <bool WITH_HESS>
-__global__ void __launch_bounds__(128, WITH_HESS ? 2 : 3) kino_kin_kernel(const KinoConst* __restrict__ Cp, unsigned mask,
+#ifndef KIN_H_MIN_BLOCKS
+#define KIN_H_MIN_BLOCKS 2
+#endif
+__global__ void __launch_bounds__(128, WITH_HESS ? KIN_H_MIN_BLOCKS : 3) kino_kin_kernel(const KinoConst* __restrict__ Cp, unsigned mask,
                                                        const double* __restrict__ x, const double* __restrict__ p,
                                                        long p_stride, const double* __restrict__ lam,
                                                        const double* __restrict__ sigma, double* __restrict__ fpart,
@@ -846,7 +1022,33 @@ __global__ void __launch_bounds__(128, WITH_HESS ? 2 : 3) kino_kin_kernel(const 
       em.add_s = C.joint_cost_kind == 0 ? sg * C.w_joint * 2.0 * wjl * wjl : sg * C.w_joint * 2.0 * wjl;
     }
     V3<Dual> n0, w0, v0;
+#ifdef HB_DUAL_SWEEP
+    // reference implementation: the whole adjoint sweep in dual arithmetic on every lane
     kin_backward<Dual>(C, sb, zs, dir, S, xcD, xdD, slot, em, n0, w0, v0);
+#else
+    {
+      SeedsP SP;
+      SeedsT ST;
+      SP.wc = S.wc;
+      SP.hb = S.hb;
+#pragma unroll
+      for (int f = 0; f < 2; ++f) {
+        SP.footF[f] = primal_of(S.footF[f]);
+        SP.footN[f] = primal_of(S.footN[f]);
+        ST.footF[f] = tangent_of(S.footF[f]);
+        ST.footN[f] = tangent_of(S.footN[f]);
+      }
+      SP.chestN = primal_of(S.chestN);
+      ST.chestN = tangent_of(S.chestN);
+      __syncwarp();
+      primal_adjoint_pass(C, sb, zs, SP, xc, xcd);
+      D3 tn0, tw0, tv0;
+      kin_tangent_sweep(C, sb, zs, dir, S.hb, ST, tangent_of(xcD), tangent_of(xdD), slot, em, tn0, tw0, tv0);
+      n0 = lift<Dual>(ld3(sb + SB_ACC), tn0);
+      w0 = lift<Dual>(ld3(sb + SB_ACC + 6), tw0);
+      v0 = lift<Dual>(ld3(sb + SB_ACC + 9), tv0);
+    }
+#endif
     if (dirj >= 0) {
       em.put(0, v0.x.d);
       em.put(1, v0.y.d);
