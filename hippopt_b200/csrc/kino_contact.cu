@@ -591,19 +591,24 @@ __global__ void __launch_bounds__(128) kino_contact_kernel(const KinoConst* __re
   // ------------------------------------------------------------------ Jacobian values
   if (want_jac) {
     int base = 0;
+#pragma unroll
     for (int e = lane; e < 324; e += 32) {
       const int t = e & 3;
       jput(e, t == 0 ? 1.0 : (t == 2 ? -1.0 : -hdt));
     }
     base = 324;
+#pragma unroll
     for (int e = lane; e < 93; e += 32) jput(base + e, e < 87 ? 1.0 : -1.0);
     base += 93;
+#pragma unroll
     for (int e = lane; e < 81; e += 32) jput(base + e, 1.0);
     base += 81;
+#pragma unroll
     for (int e = lane; e < 84; e += 32) jput(base + e, k == 0 ? 1.0 : -1.0);
     base += 84;
     for (int side = 0; side < 2; ++side) {
       const int sbase = base + side * 132;
+#pragma unroll
       for (int e = lane; e < 132; e += 32) {
         double v;
         if (e < 6) v = side == 0 ? 1.0 : -1.0;
@@ -670,6 +675,7 @@ __global__ void __launch_bounds__(128) kino_contact_kernel(const KinoConst* __re
     // the smooth ones are written by the terrain block above
     constexpr int NCH = TERRAIN == 0 ? 1 : 3;
     base += TERRAIN == 0 ? 232 : 464;
+#pragma unroll
     for (int e = lane; e < 66 + NCH; e += 32) {
       double v;
       if (e < 3) v = 1.0;
@@ -728,6 +734,7 @@ __global__ void __launch_bounds__(128) kino_contact_kernel(const KinoConst* __re
     __syncwarp();
     const int* hmap = C.hc_map + (size_t)k * C.n_hc;
     double* hb_ = hess + b * C.nnz_h;
+#pragma unroll 4
     for (int e = lane; e < C.n_hc; e += 32) {
       const int slot = hmap[e];
       if (slot >= 0) hb_[slot] = hbuf[e];
