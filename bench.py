@@ -38,7 +38,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--cpu-sample", type=int, default=64, help="instances in the CPU baseline sample")
+    ap.add_argument("--cpu-sample", type=int, default=256, help="instances in the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -127,7 +127,8 @@ def run_reference(args):
         t += dt
     pool.close()
     value = steps * n * HORIZON / t
-    sample = f"{n} of the {INSTANCES_PER_GPU} instances x {HORIZON} knots per step ({steps} timed steps, {warm} warm-up)"
+    sample = (f"{n} of the {INSTANCES_PER_GPU} instances x {HORIZON} knots per step ({steps} timed steps, {warm} warm-up); "
+              f"{pool.description}")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
         "warmup": warm, "ms_per_step": 1e3 * t / steps, "higher_is_better": True, "scaling": "weak",
@@ -135,8 +136,9 @@ def run_reference(args):
         "config": {"workload": WORKLOAD, "horizon": HORIZON, "sample": sample},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": pool.cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "note": "CasADi/IPOPT are not installable offline; this is the repo's CPU oracle (numpy SX virtual "
-                "machine restating CasADi's evaluation), a stand-in CPU baseline, not CasADi",
+        "note": "CasADi/IPOPT are not installable offline; this is the repo's CPU oracle (an SX virtual machine "
+                "restating CasADi's evaluation scheme, forward-mode sweeps for the derivatives), a stand-in CPU "
+                "baseline, not CasADi",
     }
     print(json.dumps(line))
 
@@ -251,10 +253,10 @@ def main():
     knot_evals_per_launch = B * HORIZON
     kin_ms = kernel_ms["kinematics"] / max(n_evals, 1)
     hbm_peak, hbm_src = measured_peaks()
-    bytes_per_knot = lay.algorithmic_bytes_per_knot(True)
+    bytes_per_knot = lay.kernel_bytes_per_knot()["kinematics"]
     achieved_gbs = bytes_per_knot * knot_evals_per_launch / (kin_ms * 1e-3) / 1e9
     counts_path = os.path.join(ROOT, "profiles", "algorithmic_counts.json")
-    flops_per_knot = json.load(open(counts_path))["total"] if os.path.exists(counts_path) else None
+    flops_per_knot = json.load(open(counts_path))["kinematics_kernel_flops"] if os.path.exists(counts_path) else None
     fp64_peak = probe_fp64_tflops()
     roofline_fp64 = None
     if flops_per_knot:
@@ -281,7 +283,7 @@ def main():
         pool.close()
         cpu_baseline = {"value": ke / dt, "unit": UNIT, "cores": pool.cores, "kind": "port",
                         "sample": f"{n} of the {B} instances x {HORIZON} knots, one pass ({dt:.1f} s), "
-                                  "numpy SX-VM oracle, one process per core"}
+                                  f"{pool.description}"}
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,

@@ -646,6 +646,21 @@ class KinoLayout:
                 if hk2_present(k, e):
                     self.hk2_map[k, e] = np.searchsorted(hkeys, (xk + c) * self.n_x + xk + r)
 
+    def kernel_bytes_per_knot(self) -> dict:
+        """Algorithmic bytes per knot-eval of each kernel (f+J+H): its inputs (the knot of x, the knot's
+        parameters, the multipliers of the rows it owns, sigma) plus every output value it writes."""
+        N = self.N
+        jk = float((self.jk_map >= 0).sum()) / N
+        jc = float((self.jc_map >= 0).sum()) / N
+        hk = float((self.hk_map >= 0).sum() + (self.hk2_map >= 0).sum()) / N
+        hc = float((self.hc_map >= 0).sum()) / N
+        kin_rows = sum(self.fam[n][1] * (self.fam[n][3] - self.fam[n][2] + 1) for n in self.fam
+                       if n.endswith(".fk") or n in ("unit_quat", "com_kin", "mom_kin", "feet_dist")) / N
+        con_rows = self.m / N - kin_rows
+        kin = 8.0 * ((NZ + 79 + kin_rows + 1) + (1 + 57 + kin_rows + jk + hk))
+        con = 8.0 * ((2 * NZ + 79 + con_rows + 1) + (1 + 132 + con_rows + jc + hc))
+        return {"kinematics": kin, "contact": con}
+
     # per-knot counts, for the roofline arithmetic (DESIGN.md)
     def algorithmic_bytes_per_knot(self, with_hessian: bool = True) -> float:
         """8 (n_xk + n_pk + m_k + 1) + 8 (1 + n_xk + m_k + nnzJ_k [+ nnzH_k])."""

@@ -79,6 +79,7 @@ class NLP:
         self.row_names: list[str] = []
         self._jac = None
         self._hess = None
+        self._plans: dict = {}
 
     # -- recording ------------------------------------------------------------------
     def subject_to(self, template: Template, binding, name: str = "") -> int:
@@ -230,14 +231,23 @@ class NLP:
                 continue
             _, tang = t.tape.eval_fwd(U, xin)
             tang = tang.reshape(B, len(apps), len(t.rows), len(xin))
-            pos = {i: d for d, i in enumerate(xin)}
-            for a, (_, binding, off) in enumerate(apps):
-                for r, deps in enumerate(t.pattern):
-                    for i in deps:
-                        c = int(binding[i])
-                        if c < self.n_x:
-                            slot = np.searchsorted(keys, c * self.m + off + r)
-                            vals[:, slot] = tang[:, a, r, pos[i]]
+            plan = self._plans.get(("jac", id(t)))
+            if plan is None:  # scatter plan (application, row, direction) -> CCS slot, built once
+                pos = {i: d for d, i in enumerate(xin)}
+                A, R, D, S = [], [], [], []
+                for a, (_, binding, off) in enumerate(apps):
+                    for r, deps in enumerate(t.pattern):
+                        for i in deps:
+                            c = int(binding[i])
+                            if c < self.n_x:
+                                A.append(a)
+                                R.append(r)
+                                D.append(pos[i])
+                                S.append(c * self.m + off + r)
+                plan = (np.array(A), np.array(R), np.array(D), np.searchsorted(keys, np.array(S, dtype=np.int64)))
+                self._plans[("jac", id(t))] = plan
+            A, R, D, S = plan
+            vals[:, S] = tang[:, A, R, D]
         return vals
 
     # -- Hessian of the Lagrangian ---------------------------------------------------------
@@ -284,21 +294,31 @@ class NLP:
             L = np.stack([lam_of_app(app) for app in apps], axis=1).reshape(B * len(apps), -1)
             _, tang = tape.eval_fwd(np.concatenate([U, L], axis=1), xin)
             tang = tang.reshape(B, len(apps), len(t.inputs), len(xin))
-            pos = {j: d for d, j in enumerate(xin)}
-            for a, app in enumerate(apps):
-                binding = app[1]
-                for i, deps in enumerate(pat):
-                    ci = int(binding[i])
-                    if ci >= self.n_x:
-                        continue
-                    for j in deps:
-                        cj = int(binding[j])
-                        if cj >= self.n_x or ci > cj:
-                            continue  # lower triangle is the mirror image
-                        if ci == cj and i != j:
-                            raise AssertionError("two template inputs bound to one variable")
-                        slot = np.searchsorted(keys, cj * self.n_x + ci)
-                        vals[:, slot] += tang[:, a, i, pos[j]]
+            plan = self._plans.get(("hess", id(t)))
+            if plan is None:
+                pos = {j: d for d, j in enumerate(xin)}
+                A, I, D, S = [], [], [], []
+                for a, app in enumerate(apps):
+                    binding = app[1]
+                    for i, deps in enumerate(pat):
+                        ci = int(binding[i])
+                        if ci >= self.n_x:
+                            continue
+                        for j in deps:
+                            cj = int(binding[j])
+                            if cj >= self.n_x or ci > cj:
+                                continue  # lower triangle is the mirror image
+                            if ci == cj and i != j:
+                                raise AssertionError("two template inputs bound to one variable")
+                            A.append(a)
+                            I.append(i)
+                            D.append(pos[j])
+                            S.append(cj * self.n_x + ci)
+                plan = (np.array(A), np.array(I), np.array(D), np.searchsorted(keys, np.array(S, dtype=np.int64)))
+                self._plans[("hess", id(t))] = plan
+            A, I, D, S = plan
+            if len(S):
+                np.add.at(vals, (slice(None), S), tang[:, A, I, D])
 
         for apps in self._group(self.row_apps):
             n = len(apps[0][0].rows)

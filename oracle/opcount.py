@@ -64,6 +64,7 @@ def per_knot_counts(nlp, knot_of_app, n_x, interior_knot: int) -> dict:
     vals = jac = hess = 0
     apps = [(t, b, False) for (t, b, _) in nlp.row_apps] + [(t, b, True) for (t, b, _) in nlp.cost_apps]
     seen = {}
+    by_template: dict[str, int] = {}
     for (t, binding, is_cost) in apps:
         if knot_of_app(binding) != interior_knot:
             continue
@@ -71,7 +72,7 @@ def per_knot_counts(nlp, knot_of_app, n_x, interior_knot: int) -> dict:
         if key not in seen:
             xin = [i for i in range(len(t.inputs)) if binding[i] < n_x]
             v = t.tape.n_ops
-            j = forward_mode_ops(t.rows, t.inputs, xin)
+            j = 0 if is_cost else forward_mode_ops(t.rows, t.inputs, xin)
             lam, g, gtape, pat = t.lagrangian_gradient()
             h = gtape.n_ops + forward_mode_ops(g, t.inputs + lam, xin)
             seen[key] = (v, j, h)
@@ -79,7 +80,20 @@ def per_knot_counts(nlp, knot_of_app, n_x, interior_knot: int) -> dict:
         vals += v
         jac += j
         hess += h
-    return {"values": vals, "jacobian": jac, "hessian": hess, "total": vals + jac + hess}
+        by_template[t.name] = by_template.get(t.name, 0) + v + j + h
+    return {"values": vals, "jacobian": jac, "hessian": hess, "total": vals + jac + hess, "by_template": by_template}
+
+
+KINEMATICS_TEMPLATES = (
+    "fk_", "com_kinematics_consistency", "centroidal_momentum_kinematics_consistency", "minimum_feet_distance",
+    "unitary_quaternion", "frame_quaternion_error", "base_quaternion_error", "base_quaternion_velocity_error",
+    "joint_positions_error",
+)
+
+
+def kinematics_share(counts: dict) -> int:
+    """Flops of the templates evaluated by kino_kin_kernel (the rest belongs to kino_contact_kernel)."""
+    return sum(v for k, v in counts["by_template"].items() if k.startswith(KINEMATICS_TEMPLATES))
 
 
 def kinodynamic_counts(model, horizon: int = 30, **settings) -> dict:
