@@ -1,0 +1,291 @@
+"""Batched primal-dual interior-point driver.
+
+What sits directly above the evaluation path in the reference is IPOPT (`opti.solve()`,
+`/root/reference/src/hippopt/base/opti_solver.py:479`), one serial solve at a time.  Here B independent
+instances advance in lock-step on the GPU: every iteration makes ONE batched `hb_eval` call (f, grad_f,
+g, jac_g, hess_l for all instances) and one batched dense KKT solve.  The algorithm is the textbook
+line-search barrier method IPOPT implements (Waechter & Biegler 2006) reduced to what a dense batched
+solver needs: slacks on the inequality rows, monotone (Fiacco-McCormick) barrier update,
+fraction-to-boundary rule, l1 merit function with Armijo backtracking, and a Levenberg-type Hessian shift
+when the reduced Hessian is not positive along the step.  The dense KKT factorisation is a library
+call (torch.linalg); the evaluation kernels are the product.
+
+Conventions follow IPOPT / CasADi: L = sigma f + lam^T g, lam > 0 on an active upper bound.
+Sized for the small NLPs (toy OCP, pose finder); the KKT systems of the 30-knot kinodynamic OCP need the
+stage-wise factorisation of row f2.
+"""
+from __future__ import annotations
+
+import dataclasses
+
+import numpy as np
+import torch
+
+from .evaluator import ALL, F, G
+
+
+class OptiFailure(Exception):
+    """Mirror of `hippopt.OptiFailure` (`base/opti_solver.py:28-37`): raised when no instance converged."""
+
+    def __init__(self, message: str):
+        super().__init__("Opti failed to solve the problem. Message: " + message)
+
+
+@dataclasses.dataclass
+class BatchedOutput:
+    """Per-instance counterpart of `hippopt.Output` (`base/problem.py:28-79`)."""
+
+    values: torch.Tensor                  # (B, n_x) primal solution
+    cost_value: torch.Tensor              # (B,)
+    constraint_multipliers: torch.Tensor  # (B, m)   lam_g
+    success: torch.Tensor                 # (B,) bool
+    iterations: torch.Tensor              # (B,) int
+    kkt_error: torch.Tensor               # (B,) scaled optimality error at exit
+    evaluations: int = 0                  # batched hb_eval calls made
+
+
+class BatchedInteriorPoint:
+    def __init__(self, ev, tol: float = 1e-8, max_iter: int = 300, mu_init: float = 0.1, kappa_eps: float = 10.0,
+                 kappa_mu: float = 0.2, theta_mu: float = 1.5, tau_min: float = 0.99, eta: float = 1e-4,
+                 max_backtrack: int = 16, delta_min: float = 1e-8, delta_max: float = 1e8, exact_inertia: bool = False,
+                 verbose: bool = False):
+        self.ev = ev
+        self.exact_inertia = exact_inertia
+        self.tol, self.max_iter, self.mu_init = tol, max_iter, mu_init
+        self.kappa_eps, self.kappa_mu, self.theta_mu = kappa_eps, kappa_mu, theta_mu
+        self.tau_min, self.eta, self.max_backtrack = tau_min, eta, max_backtrack
+        self.delta_min, self.delta_max = delta_min, delta_max
+        self.verbose = verbose
+        colind, row = ev.jac_sparsity()
+        self._jr = torch.as_tensor(np.asarray(row), dtype=torch.long)
+        self._jc = torch.as_tensor(np.repeat(np.arange(ev.n_x), np.diff(colind)), dtype=torch.long)
+        hcolind, hrow = ev.hess_sparsity()
+        self._hr = torch.as_tensor(np.asarray(hrow), dtype=torch.long)
+        self._hc = torch.as_tensor(np.repeat(np.arange(ev.n_x), np.diff(hcolind)), dtype=torch.long)
+
+    # ------------------------------------------------------------------ dense assembly
+    def _dense_jac(self, vals):
+        B = vals.shape[0]
+        J = torch.zeros((B, self.ev.m, self.ev.n_x), dtype=vals.dtype, device=vals.device)
+        J[:, self._jr.to(vals.device), self._jc.to(vals.device)] = vals
+        return J
+
+    def _dense_hess(self, vals):
+        B = vals.shape[0]
+        H = torch.zeros((B, self.ev.n_x, self.ev.n_x), dtype=vals.dtype, device=vals.device)
+        r, c = self._hr.to(vals.device), self._hc.to(vals.device)
+        H[:, r, c] = vals
+        H[:, c, r] = vals
+        return H
+
+    # ------------------------------------------------------------------ solve
+    def solve(self, x0: torch.Tensor, p: torch.Tensor, lbg, ubg) -> BatchedOutput:
+        ev, dev = self.ev, x0.device
+        B, n, m = x0.shape[0], ev.n_x, ev.m
+        lbg = torch.as_tensor(np.broadcast_to(np.asarray(lbg, dtype=np.float64), (B, m)).copy(), device=dev)
+        ubg = torch.as_tensor(np.broadcast_to(np.asarray(ubg, dtype=np.float64), (B, m)).copy(), device=dev)
+        eq = (lbg[0] == ubg[0])
+        free = torch.isinf(lbg[0]) & torch.isinf(ubg[0])
+        ine = ~eq & ~free
+        if not (torch.equal((lbg == ubg), eq.expand(B, m)) and torch.equal(torch.isinf(lbg) & torch.isinf(ubg), free.expand(B, m))):
+            raise ValueError("all instances must share the equality / inequality structure of their bounds")
+        iE, iI = torch.nonzero(eq).ravel(), torch.nonzero(ine).ravel()
+        mE, mI = len(iE), len(iI)
+        lb, ub = lbg[:, iI], ubg[:, iI]
+        hasL, hasU = torch.isfinite(lb), torch.isfinite(ub)
+        lbE = lbg[:, iE]
+        x = x0.clone().contiguous()
+        ones = torch.ones(B, dtype=torch.float64, device=dev)
+        zeros_m = torch.zeros((B, m), dtype=torch.float64, device=dev)
+
+        def evaluate(xx, lam=None, full=True):
+            out = ev.eval(ALL if full else (F | G), xx, p, lam if lam is not None else zeros_m, ones)
+            return {k: v.clone() for k, v in out.items()}
+
+        big = 1e300
+        lbs = torch.where(hasL, lb, torch.full_like(lb, -big))
+        ubs = torch.where(hasU, ub, torch.full_like(ub, big))
+
+        out = evaluate(x, full=False)
+        n_eval = 1
+        gI = out["g"][:, iI]
+        # push the slacks strictly inside their bounds (IPOPT bound_push / bound_frac)
+        push = 1e-2
+        pl = torch.minimum(push * torch.clamp(lbs.abs(), min=1.0), 1e-2 * (ubs - lbs))
+        s = torch.minimum(torch.maximum(gI, lbs + pl), ubs - pl)
+        mu = torch.full((B,), self.mu_init, dtype=torch.float64, device=dev)
+        zL = torch.where(hasL, mu[:, None] / (s - lbs), torch.zeros_like(s))
+        zU = torch.where(hasU, mu[:, None] / (ubs - s), torch.zeros_like(s))
+        lamE = torch.zeros((B, mE), dtype=torch.float64, device=dev)
+        delta = torch.zeros(B, dtype=torch.float64, device=dev)
+        nu = torch.ones(B, dtype=torch.float64, device=dev)
+        done = torch.zeros(B, dtype=torch.bool, device=dev)
+        iters = torch.zeros(B, dtype=torch.long, device=dev)
+        err0 = torch.full((B,), float("inf"), dtype=torch.float64, device=dev)
+        eye = torch.eye(n, dtype=torch.float64, device=dev)
+
+        def barrier(fv, ss, muv):
+            t = torch.where(hasL, torch.log(ss - lbs), torch.zeros_like(ss)) + torch.where(hasU, torch.log(ubs - ss), torch.zeros_like(ss))
+            return fv - muv * t.sum(dim=1)
+
+        for it in range(self.max_iter):
+            lam = zeros_m.clone()
+            lam[:, iE] = lamE
+            lam[:, iI] = zU - zL
+            out = evaluate(x, lam)
+            n_eval += 1
+            fv, grad, g = out["f"], out["grad_f"], out["g"]
+            J = self._dense_jac(out["jac"])
+            W = self._dense_hess(out["hess"])
+            JE, JI = J[:, iE, :], J[:, iI, :]
+            cE = g[:, iE] - lbE
+            cI = g[:, iI] - s
+            rd = grad + torch.einsum("bmn,bm->bn", J, lam)
+            dL, dU = s - lbs, ubs - s
+            compL = torch.where(hasL, dL * zL, torch.zeros_like(s))
+            compU = torch.where(hasU, dU * zU, torch.zeros_like(s))
+
+            def linf(t):
+                return t.abs().amax(dim=1) if t.shape[1] else torch.zeros(B, dtype=torch.float64, device=dev)
+
+            # IPOPT's scaled optimality error E_mu
+            sd = torch.clamp((lam.abs().sum(1) + zL.sum(1) + zU.sum(1)) / max(1, m + 2 * mI) / 100.0, min=1.0)
+            prim = torch.maximum(linf(cE), linf(cI))
+
+            def emu(muv):
+                cL = torch.where(hasL, compL - muv[:, None], torch.zeros_like(s))
+                cU = torch.where(hasU, compU - muv[:, None], torch.zeros_like(s))
+                return torch.maximum(torch.maximum(linf(rd) / sd, prim), torch.maximum(linf(cL), linf(cU)) / sd)
+
+            err0 = torch.where(done, err0, emu(torch.zeros_like(mu)))
+            newly = (~done) & (err0 <= self.tol)
+            done |= newly
+            if self.verbose and it % 10 == 0:
+                print(f"it {it:3d} done {int(done.sum())}/{B} err0 med {err0.median().item():.2e} max {err0.max().item():.2e} "
+                      f"mu med {mu.median().item():.1e} delta med {delta.median().item():.1e} max {delta.max().item():.1e} "
+                      f"| dual med {(linf(rd) / sd).median().item():.2e} prim med {prim.median().item():.2e}")
+            if bool(done.all()):
+                break
+            iters += (~done).long()
+            # barrier parameter update (possibly several reductions in one go)
+            for _ in range(4):
+                dec = (~done) & (emu(mu) <= self.kappa_eps * mu) & (mu > self.tol / 10.0)
+                if not bool(dec.any()):
+                    break
+                mu = torch.where(dec, torch.clamp(torch.minimum(self.kappa_mu * mu, mu ** self.theta_mu), min=self.tol / 10.0), mu)
+            tau = torch.clamp(1.0 - mu, min=self.tau_min)
+            SigL = torch.where(hasL, zL / dL, torch.zeros_like(s))
+            SigU = torch.where(hasU, zU / dU, torch.zeros_like(s))
+            Sig = SigL + SigU
+            lamhat = torch.where(hasU, mu[:, None] / dU, torch.zeros_like(s)) - torch.where(hasL, mu[:, None] / dL, torch.zeros_like(s))
+            Hr = W + torch.einsum("bin,bi,bik->bnk", JI, Sig, JI)
+            rhs_x = -(grad + torch.einsum("bin,bi->bn", JI, lamhat + Sig * cI))
+            # solve with a per-instance Levenberg shift until the step has positive curvature
+            dx = torch.zeros_like(x)
+            lamE_new = lamE.clone()
+            need = ~done
+            for attempt in range(12):
+                K = torch.zeros((B, n + mE, n + mE), dtype=torch.float64, device=dev)
+                K[:, :n, :n] = Hr + delta[:, None, None] * eye
+                K[:, :n, n:] = JE.transpose(1, 2)
+                K[:, n:, :n] = JE
+                if mE and attempt > 0:  # delta_c only once a plain solve has failed (rank-deficient J_E)
+                    K[:, n:, n:] = -1e-11 * torch.eye(mE, dtype=torch.float64, device=dev)
+                rhs = torch.cat([rhs_x, -cE], dim=1)
+                try:
+                    sol = torch.linalg.solve(K, rhs)
+                except RuntimeError:
+                    sol = torch.full_like(rhs, float("nan"))
+                dxt, lamt = sol[:, :n], sol[:, n:]
+                dst = torch.einsum("bin,bn->bi", JI, dxt) + cI
+                # inertia test (IPOPT's criterion): the KKT matrix must have exactly n positive and mE negative
+                # eigenvalues, i.e. the reduced Hessian is positive definite on the null space of J_E
+                if self.exact_inertia and attempt < 11:
+                    inertia_ok = (torch.linalg.eigvalsh(K) < 0).sum(dim=1) == mE
+                else:  # cheap proxy: positive curvature of the barrier Lagrangian along the step
+                    curv = (torch.einsum("bn,bnk,bk->b", dxt, W, dxt) + delta * (dxt * dxt).sum(1)
+                            + (Sig * dst * dst).sum(1))
+                    inertia_ok = curv > 1e-12 * (dxt * dxt).sum(1)
+                ok = torch.isfinite(sol).all(dim=1) & inertia_ok
+                take = need & ok
+                dx = torch.where(take[:, None], dxt, dx)
+                lamE_new = torch.where(take[:, None], lamt, lamE_new)
+                need = need & ~ok
+                if not bool(need.any()):
+                    break
+                delta = torch.where(need, torch.clamp(torch.maximum(delta * 8.0, torch.full_like(delta, 1e-4)), max=self.delta_max), delta)
+            ds = torch.einsum("bin,bn->bi", JI, dx) + cI
+            lamI_new = lamhat + Sig * ds
+            zL_new = torch.where(hasL, mu[:, None] / dL - SigL * ds, torch.zeros_like(s))
+            zU_new = torch.where(hasU, mu[:, None] / dU + SigU * ds, torch.zeros_like(s))
+
+            # fraction to the boundary
+            def max_step(val, dval, t):
+                r = torch.where(dval < 0, -t[:, None] * val / dval, torch.full_like(val, float("inf")))
+                return torch.clamp(r.amin(dim=1), max=1.0) if val.shape[1] else torch.ones(B, dtype=torch.float64, device=dev)
+
+            a_p = torch.minimum(max_step(torch.where(hasL, dL, torch.full_like(s, big)), ds, tau),
+                                max_step(torch.where(hasU, dU, torch.full_like(s, big)), -ds, tau))
+            a_d = torch.minimum(max_step(torch.where(hasL, zL, torch.full_like(s, big)), zL_new - zL, tau),
+                                max_step(torch.where(hasU, zU, torch.full_like(s, big)), zU_new - zU, tau))
+            # l1 merit function and Armijo backtracking (batched: every trial evaluates all instances)
+            cnorm = cE.abs().sum(1) + cI.abs().sum(1)
+            lam_all = torch.cat([lamE_new, lamI_new], dim=1)
+            nu = torch.maximum(nu, lam_all.abs().amax(dim=1) + 1.0) if lam_all.shape[1] else nu
+            dbar = (grad * dx).sum(1) - mu * (torch.where(hasL, ds / dL, torch.zeros_like(s)) - torch.where(hasU, ds / dU, torch.zeros_like(s))).sum(1)
+            dphi = dbar - nu * cnorm
+            bar0 = barrier(fv, s, mu)
+            phi0 = bar0 + nu * cnorm
+            if it == 0:
+                cnorm0 = cnorm.clone()
+            alpha = a_p.clone()
+            accepted = done.clone()
+            x_new, s_new = x.clone(), s.clone()
+            for bt in range(self.max_backtrack):
+                xt = x + alpha[:, None] * dx
+                st = s + alpha[:, None] * ds
+                ot = evaluate(xt, full=False)
+                n_eval += 1
+                ct = (ot["g"][:, iE] - lbE).abs().sum(1) + (ot["g"][:, iI] - st).abs().sum(1)
+                phit = barrier(ot["f"], st, mu) + nu * ct
+                armijo = phit <= phi0 + self.eta * alpha * torch.minimum(dphi, torch.zeros_like(dphi)) + 1e-13 * phi0.abs()
+                # filter-type acceptance against the current iterate (Waechter & Biegler, eq. 18): enough
+                # progress in the constraint violation OR in the barrier objective
+                bart = barrier(ot["f"], st, mu)
+                filt = (ct <= (1.0 - 1e-5) * cnorm) | (bart <= bar0 - 1e-5 * cnorm)
+                good = torch.isfinite(phit) & (armijo | (filt & (cnorm > 1e-4 * torch.clamp(cnorm0, min=1.0))))
+                take = good & ~accepted
+                x_new = torch.where(take[:, None], xt, x_new)
+                s_new = torch.where(take[:, None], st, s_new)
+                accepted |= take
+                if bool(accepted.all()):
+                    break
+                alpha = torch.where(accepted, alpha, alpha * 0.5)
+            moved = accepted & ~done
+            # instances whose line search failed get a larger Hessian shift and try again
+            failed = ~accepted
+            delta = torch.where(failed, torch.clamp(torch.maximum(delta * 8.0, torch.full_like(delta, 1e-4)), max=self.delta_max),
+                                torch.where(moved, delta / 3.0, delta))
+            delta = torch.where(delta < self.delta_min, torch.zeros_like(delta), delta)
+            am = torch.where(moved, alpha, torch.zeros_like(alpha))[:, None]
+            ad = torch.where(moved, a_d, torch.zeros_like(a_d))[:, None]
+            x, s = x_new.contiguous(), s_new
+            lamE = lamE + am * (lamE_new - lamE)
+            zL = zL + ad * (zL_new - zL)
+            zU = zU + ad * (zU_new - zU)
+            # keep the bound multipliers in the IPOPT safeguard band around mu / slack
+            dLn, dUn = s - lbs, ubs - s
+            ks = 1e10
+            zL = torch.where(hasL, torch.minimum(torch.maximum(zL, mu[:, None] / (ks * dLn)), ks * mu[:, None] / dLn), zL)
+            zU = torch.where(hasU, torch.minimum(torch.maximum(zU, mu[:, None] / (ks * dUn)), ks * mu[:, None] / dUn), zU)
+
+        lam = zeros_m.clone()
+        lam[:, iE] = lamE
+        lam[:, iI] = zU - zL
+        final = evaluate(x, full=False)
+        n_eval += 1
+        if not bool(done.any()):
+            raise OptiFailure(f"no instance reached tol={self.tol} in {self.max_iter} iterations "
+                              f"(best error {err0.min().item():.3e})")
+        return BatchedOutput(values=x, cost_value=final["f"], constraint_multipliers=lam, success=done, iterations=iters,
+                             kkt_error=err0, evaluations=n_eval)
