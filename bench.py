@@ -271,6 +271,39 @@ def main():
     if os.path.exists(tpath):
         traffic = json.load(open(tpath)).get("kinematics_dram_bytes_per_launch")
 
+    # ---- the other BASELINE configs (device-resident, 10 timed steps each; parity cases, not the headline)
+    other = None
+    if world == 1 and not args.no_cpu_baseline:
+        from hippopt_b200.evaluator import PoseEvaluator
+        from hippopt_b200.workloads import pose_batch
+
+        def quick(evx, data, knots, name):
+            t = [torch.tensor(a, device=dev) for a in data]
+            for _ in range(3):
+                evx.eval(ALL, *t)
+            torch.cuda.synchronize(dev)
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record()
+            for _ in range(10):
+                evx.eval(ALL, *t)
+            a1.record()
+            torch.cuda.synchronize(dev)
+            ms = a0.elapsed_time(a1) / 10
+            return {"workload": name, "ms_per_step": ms, "knot_evals_per_s": knots / (ms * 1e-3)}
+
+        other = []
+        pev = PoseEvaluator(model)
+        other.append(quick(pev, pose_batch(pev.layout, model, 4096, seed=1), 4096,
+                           "config 2: humanoid_pose_finder static pose, 4096 instances (1 knot each)"))
+        ev4 = KinoEvaluator(model, KinoSettings(horizon=30, final_state_constraint=True, periodicity_constraint=True))
+        other.append(quick(ev4, kino_batch(ev4.layout, model, 512, seed=3), 512 * 30,
+                           "config 4: periodic walking step, 512-instance shard of 4096, horizon 30"))
+        ev5 = KinoEvaluator(model, KinoSettings(horizon=50, terrain="smooth_steps", n_terrain_params=10,
+                                                final_state_constraint=True))
+        other.append(quick(ev5, kino_batch(ev5.layout, model, 512, seed=4), 512 * 50,
+                           "config 5: walking on stairs (two smooth steps, randomised heights), 512-instance shard, horizon 50"))
+        del pev, ev4, ev5
+
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
         from oracle.cpu_baseline import OraclePool
@@ -305,6 +338,7 @@ def main():
                      "note": "the kernel is fp64-FMA bound, not HBM bound: see roofline_fp64"},
         "roofline_fp64": roofline_fp64,
         "cpu_baseline": cpu_baseline,
+        "other_configs": other,
     }
     print(json.dumps(line))
     if world > 1:

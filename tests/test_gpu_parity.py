@@ -270,6 +270,60 @@ def test_config3_full_size_properties(config3):
     assert np.abs(fdh - Hd).max() <= 2e-5 * max(1.0, np.abs(Hd).max())
 
 
+def test_config4_periodic_step_full_size(model, built_library):
+    """BASELINE config 4: periodic walking step (final-state and periodicity constraints), 4096 instances;
+    the 512-instance shard one of 8 GPUs owns is evaluated, plus two instances against the oracle."""
+    from hippopt_b200.evaluator import KinoEvaluator
+    from hippopt_b200.kino_layout import KinoSettings
+    from hippopt_b200.sharding import shard_range
+    from hippopt_b200.workloads import kino_batch
+    from oracle import kinodynamic as kd
+
+    ev = KinoEvaluator(model, KinoSettings(horizon=30, final_state_constraint=True, periodicity_constraint=True))
+    assert ev.m == 8142 + 105 + 84 - 6
+    lo, hi = shard_range(4096, 3, 8)
+    x, p, lam, sigma = kino_batch(ev.layout, model, hi - lo, seed=3)
+    out = run(ev, x, p, lam, sigma)
+    again = run(ev, x[::-1].copy(), p[::-1].copy(), lam[::-1].copy(), sigma[::-1].copy())
+    for k in out:
+        assert np.isfinite(out[k]).all()
+        assert np.array_equal(again[k][::-1], out[k]), k
+    idx = np.array([5, 400])
+    nlp, _ = kd.build(model, kd.Settings(horizon=30, final_state_constraint=True, periodicity_constraint=True))
+    close(out["g"][idx], nlp.eval_g(x[idx], p[idx]))
+    close(out["jac"][idx], nlp.eval_jac(x[idx], p[idx]))
+    close(out["hess"][idx], nlp.eval_hess(x[idx], p[idx], lam[idx], sigma[idx]))
+    close(out["grad_f"][idx], nlp.eval_grad_f(x[idx], p[idx]))
+    close(out["f"][idx], nlp.eval_f(x[idx], p[idx]))
+
+
+def test_config5_stairs_full_size(model, built_library):
+    """BASELINE config 5: walking on stairs, horizon 50, randomised step heights as runtime terrain
+    parameters; one 512-instance shard: finite, deterministic, first-order consistent (J d vs central
+    differences of g)."""
+    from hippopt_b200.evaluator import G, JAC_G, KinoEvaluator
+    from hippopt_b200.kino_layout import KinoSettings
+    from hippopt_b200.workloads import kino_batch
+
+    ev = KinoEvaluator(model, KinoSettings(horizon=50, terrain="smooth_steps", n_terrain_params=10,
+                                           final_state_constraint=True))
+    assert ev.n_x == 189 * 50 + 6
+    x, p, lam, sigma = kino_batch(ev.layout, model, 512, seed=4)
+    assert len(np.unique(p[:, ev.layout.po.terrain + 2])) == 512  # a different step height per instance
+    out = run(ev, x, p, lam, sigma)
+    again = run(ev, x, p, lam, sigma)
+    for k in out:
+        assert np.isfinite(out[k]).all(), k
+        assert np.array_equal(out[k], again[k]), k
+    lay = ev.layout
+    d = np.random.default_rng(2).normal(size=x.shape)
+    eps = 1e-6
+    gp = run(ev, x + eps * d, p, lam, sigma, G)["g"]
+    gm = run(ev, x - eps * d, p, lam, sigma, G)["g"]
+    Jd = _spmv_ccs(lay.jac_colind, lay.jac_row, run(ev, x, p, lam, sigma, JAC_G)["jac"], d, lay.m)
+    assert np.abs((gp - gm) / (2 * eps) - Jd).max() <= 1e-4 * max(1.0, np.abs(Jd).max())
+
+
 def test_config3_samples_against_oracle(model, config3):
     """Two instances of the full-size batch against the CPU oracle (finishes in seconds)."""
     from oracle import kinodynamic as kd
