@@ -337,3 +337,53 @@ def test_config3_samples_against_oracle(model, config3):
     close(out["grad_f"], nlp.eval_grad_f(x[idx], p[idx]))
     close(out["jac"], nlp.eval_jac(x[idx], p[idx]))
     close(out["hess"], nlp.eval_hess(x[idx], p[idx], lam[idx], sigma[idx]))
+
+
+@pytest.mark.parametrize("B", [1, 3, 5, 130])
+def test_kino_batch_sizes_not_multiple_of_the_cta(model, built_library, B):
+    """Ragged batches: B * N is not a multiple of the 4 warps per CTA; every instance must still be
+    written, identically to evaluating it alone."""
+    from hippopt_b200.evaluator import KinoEvaluator
+    from hippopt_b200.kino_layout import KinoSettings
+    from hippopt_b200.workloads import kino_batch
+
+    ev = KinoEvaluator(model, KinoSettings(horizon=3))
+    x, p, lam, sigma = kino_batch(ev.layout, model, B, seed=60 + B, noise=0.1)
+    out = run(ev, x, p, lam, sigma)
+    last = run(ev, x[-1:], p[-1:], lam[-1:], sigma[-1:])
+    for k in out:
+        assert np.isfinite(out[k]).all()
+        assert np.array_equal(out[k][-1], last[k][0]), k
+
+
+def test_non_finite_inputs_are_passed_through(model, built_library):
+    """NaN / Inf are not trapped (include/hippopt_b200.h): a NaN in one instance poisons only that
+    instance's outputs -- IPOPT handles it by rejecting the step [ext]."""
+    from hippopt_b200.evaluator import KinoEvaluator
+    from hippopt_b200.kino_layout import KinoSettings
+    from hippopt_b200.workloads import kino_batch
+
+    ev = KinoEvaluator(model, KinoSettings(horizon=3))
+    x, p, lam, sigma = kino_batch(ev.layout, model, 3, seed=77, noise=0.1)
+    clean = run(ev, x, p, lam, sigma)
+    x[1, 189 + 157] = np.nan  # a joint position of knot 1 of instance 1
+    out = run(ev, x, p, lam, sigma)
+    assert np.isnan(out["g"][1]).any() and np.isnan(out["hess"][1]).any()
+    for k in out:
+        assert np.array_equal(out[k][0], clean[k][0]) and np.array_equal(out[k][2], clean[k][2]), k
+
+
+def test_minimal_horizon(model, built_library):
+    """Horizon 2 (one interval): first and last knot only, with final state and periodicity rows."""
+    from hippopt_b200.evaluator import KinoEvaluator
+    from hippopt_b200.kino_layout import KinoSettings
+    from hippopt_b200.workloads import kino_batch
+    from oracle import kinodynamic as kd
+
+    ev = KinoEvaluator(model, KinoSettings(horizon=2, final_state_constraint=True, periodicity_constraint=True))
+    x, p, lam, sigma = kino_batch(ev.layout, model, 2, seed=5, noise=0.2)
+    nlp, _ = kd.build(model, kd.Settings(horizon=2, final_state_constraint=True, periodicity_constraint=True))
+    out = run(ev, x, p, lam, sigma)
+    close(out["g"], nlp.eval_g(x, p))
+    close(out["jac"], nlp.eval_jac(x, p))
+    close(out["hess"], nlp.eval_hess(x, p, lam, sigma))
