@@ -39,6 +39,12 @@ enum { HSTAGE = 27 * 57 };  // per-warp staging of the Hessian columns (and, bef
 #ifndef HB_KIN_STAGE_F
 #define HB_KIN_STAGE_F 0  // Jacobian-only kernel: staging costs a CTA per SM
 #endif
+#ifndef HB_FWD_JAC
+#define HB_FWD_JAC 1      // Hessian kernel: Jacobian columns from forward tangents instead of a second sweep
+#endif
+#if HB_FWD_JAC && !HB_KIN_STAGE
+#error "HB_FWD_JAC stages the Jacobian columns: it needs HB_KIN_STAGE"
+#endif
 
 struct KinSmem {
   int bodies, arms, fdu, fdal, fdar, G, z, gbuf, slot, stage, total;
@@ -858,7 +864,9 @@ __global__ void __launch_bounds__(128, WITH_HESS ? KIN_H_MIN_BLOCKS : 3) kino_ki
   Dir nodir;
   nodir.mask = 0u;
   // ------------------------------------------------------------------ adjoint sweep, fp64: Jacobian rows
-  if (want_jac || want_grad) {
+  // (Jacobian-only kernel.  The Hessian kernel gets the same values from forward tangents that its
+  // direction lanes need anyway -- see "forward-mode Jacobian" below.)
+  if ((want_jac || want_grad) && !(WITH_HESS && HB_FWD_JAC)) {
     Seeds<double> S;
     S.wc = S.hb = S.footF[0] = S.footF[1] = S.footN[0] = S.footN[1] = S.chestN = v3<double>(0.0, 0.0, 0.0);
     if (lane < 24) {
@@ -971,19 +979,24 @@ __global__ void __launch_bounds__(128, WITH_HESS ? KIN_H_MIN_BLOCKS : 3) kino_ki
     Dir dir;
     dir.mask = 0u;
     dir.alpha = dir.pi = dir.wpi = dir.vpi = dir.u = v3<double>(0.0, 0.0, 0.0);
-    if (lane < 4) {
-      // only the primal maps are needed for the direction; the dual maps are rebuilt after the sweep
-      // so that they are not live (144 registers) across it
+    // only the primal maps are needed for the directions; the dual maps are rebuilt after the sweep
+    // so that they are not live (144 registers) across it
+    D3 wq_lane = v3<double>(0.0, 0.0, 0.0);  // d omega_0 / d qd_a for the velocity-direction lanes 3..6
+    {
       D3 gq0[4], uq0[4], wq0[4];
       const double qraw[4] = {q0, q1, q2, q3};
       quat_maps<double>(qraw, qdv, gq0, uq0, wq0);
-      dir.mask = 0xffffffffu;
 #pragma unroll
-      for (int a = 0; a < 4; ++a)
+      for (int a = 0; a < 4; ++a) {
         if (a == lane) {
           dir.alpha = gq0[a];
           dir.u = uq0[a];
         }
+        if (a + 3 == lane) wq_lane = wq0[a];
+      }
+    }
+    if (lane < 4) {
+      dir.mask = 0xffffffffu;
       dir.wpi = ld3(sb + SB_W);
       dir.vpi = ld3(sb + SB_V);
     } else if (lane < 27) {
@@ -996,7 +1009,8 @@ __global__ void __launch_bounds__(128, WITH_HESS ? KIN_H_MIN_BLOCKS : 3) kino_ki
       dir.vpi = ld3(bl + SB_V);
     }
     // tangents of the CoM position / velocity along this direction
-    D3 tP = v3<double>(0.0, 0.0, 0.0), tPd = tP;
+    D3 tP = v3<double>(0.0, 0.0, 0.0), tPd = tP, th = tP;
+    const bool fwd_jac = HB_FWD_JAC && want_jac;
     for (int l = 0; l < nb; ++l) {
       const St<Dual> s = load_state(sb, l, dir, Dual());
       const V3<Dual> c = s.o + s.d;
@@ -1004,12 +1018,14 @@ __global__ void __launch_bounds__(128, WITH_HESS ? KIN_H_MIN_BLOCKS : 3) kino_ki
       const double m = C.body[l].mass;
       tP = tP + scale(m, v3<double>(c.x.d, c.y.d, c.z.d));
       tPd = tPd + scale(m, v3<double>(cd.x.d, cd.y.d, cd.z.d));
+      if (fwd_jac) th = th + tangent_of(cross(scale(m, c), cd) + iw_omega(sb, l, dir, s));
     }
     const V3<Dual> xcD = lift<Dual>(xc, scale(1.0 / M, tP));
     const V3<Dual> xdD = lift<Dual>(xcd, scale(1.0 / M, tPd));
     const double inL = ((dir.mask >> C.foot_body[0]) & 1u) ? 1.0 : 0.0;
     const double inR = ((dir.mask >> C.foot_body[1]) & 1u) ? 1.0 : 0.0;
     const double inC = ((dir.mask >> C.chest_body) & 1u) ? 1.0 : 0.0;
+    double ty_lane = 0.0, tphi_lane = 0.0;  // tangents of the feet distance and of trace(G) along this direction
     Seeds<Dual> S;
     S.footF[0] = S.footF[1] = S.footN[0] = S.footN[1] = vzero<Dual>();
     {
@@ -1044,6 +1060,7 @@ __global__ void __launch_bounds__(128, WITH_HESS ? KIN_H_MIN_BLOCKS : 3) kino_ki
       const V3<Dual> alD = lift<Dual>(fdal, scale(inL, cross(dir.alpha, fdal)));
       const V3<Dual> arD = lift<Dual>(fdar, scale(inR, cross(dir.alpha, fdar)));
       const V3<Dual> dD = (sL.o + alD) - (sR.o + arD);
+      ty_lane = dot(uD, dD).d;
       const V3<Dual> ku = scale(kd, uD);
       S.footF[0] = S.footF[0] + ku;
       S.footN[0] = S.footN[0] + cross(alD, ku);
@@ -1063,11 +1080,108 @@ __global__ void __launch_bounds__(128, WITH_HESS ? KIN_H_MIN_BLOCKS : 3) kino_ki
         tG[6 + j] = t.z;
       }
       const double tphi = tG[0] + tG[4] + tG[8];
+      tphi_lane = tphi;
       const double cw = k1 ? 2.0 * sg * C.w_frame : 0.0;
       const Dual kappa = mkdual(cw * (phi - 3.0), cw * tphi);
       const V3<Dual> mGD = lift<Dual>(mG, v3<double>(tG[5] - tG[7], tG[6] - tG[2], tG[1] - tG[3]));
       S.chestN = scale(kappa, mGD);
     }
+#if HB_FWD_JAC
+    // ---------------------------------------------------------------- forward-mode Jacobian
+    // The direction lanes already hold the tangent of every link state along q_a / s_j, so column j of
+    // the kinematic rows is a few products here; the velocity columns of the momentum rows (the map is
+    // linear in the velocities) take one more pass over the bodies.  This replaces the row-per-lane
+    // fp64 adjoint sweep of the Jacobian-only kernel (2.87 -> see DESIGN.md).
+    if (want_jac || want_grad) {
+      double* stg = sm + L.stage;
+      const int bm = 4 + 648 + 81;  // momentum rows inside JK (kino_layout.py::_enumerate_jk)
+      if (want_jac) {
+        if (lane < 27) {
+#pragma unroll
+          for (int pt = 0; pt < 8; ++pt) {
+            const int f = pt >> 2;
+            const double in = f == 0 ? inL : inR;
+            const D3 r = (ld3(sb + C.foot_body[f] * SB_STRIDE + SB_O) - dir.pi) + ld3(sm + L.arms + 3 * pt);
+            const D3 t = scale(-in, cross(dir.alpha, r));
+            stg[4 + (3 * pt) * 27 + lane] = t.x;
+            stg[4 + (3 * pt + 1) * 27 + lane] = t.y;
+            stg[4 + (3 * pt + 2) * 27 + lane] = t.z;
+          }
+          const D3 tc = scale(-1.0 / M, tP);
+          stg[4 + 648 + lane] = tc.x;
+          stg[4 + 648 + 27 + lane] = tc.y;
+          stg[4 + 648 + 54 + lane] = tc.z;
+          const D3 dh = scale(-1.0 / mass_p, th - scale(1.0 / M, cross(tP, Pd) + cross(Pm, tPd)));
+          const int cq = lane < 4 ? 7 + lane : 34 + lane - 4;
+          stg[bm + cq] = dh.x;
+          stg[bm + 57 + cq] = dh.y;
+          stg[bm + 114 + cq] = dh.z;
+          if (lane < 4) stg[lane] = 2.0 * zs[Z_Q + lane];  // unit quaternion row
+          else stg[bm + 171 + lane - 4] = ty_lane;          // feet distance row
+        }
+        if (lane < 30) {
+          // velocity direction of this lane: w_l += in_l A, v_l += in_l A x (o_l - pivot) + B
+          D3 A = v3<double>(0.0, 0.0, 0.0), B = A, piv = A;
+          unsigned vm = 0xffffffffu;
+          if (lane < 3) B = v3<double>(lane == 0 ? 1.0 : 0.0, lane == 1 ? 1.0 : 0.0, lane == 2 ? 1.0 : 0.0);
+          else if (lane < 7) A = wq_lane;
+          else {
+            const int l = lane - 7 + 1;
+            A = ld3(sb + l * SB_STRIDE + SB_AX);
+            piv = ld3(sb + l * SB_STRIDE + SB_O);
+            vm = C.sub_mask[l];
+          }
+          D3 hv = v3<double>(0.0, 0.0, 0.0), pv = hv;
+          for (int l = 0; l < nb; ++l) {
+            const double* bl = sb + l * SB_STRIDE;
+            const D3 o = ld3(bl + SB_O), d = ld3(bl + SB_D);
+            const D3 Al = scale(((vm >> l) & 1u) ? 1.0 : 0.0, A);
+            const D3 tcd = cross(Al, (o - piv) + d) + B;
+            const double m = C.body[l].mass;
+            pv = pv + scale(m, tcd);
+            hv = hv + cross(scale(m, o + d), tcd) + symmul(bl + SB_I, Al);
+          }
+          const D3 dh = scale(-1.0 / mass_p, hv - scale(1.0 / M, cross(Pm, pv)));
+          const int cv = lane < 7 ? lane : lane + 4;  // vb 0..2, qd 3..6, sd 11..33
+          stg[bm + cv] = dh.x;
+          stg[bm + 57 + cv] = dh.y;
+          stg[bm + 114 + cv] = dh.z;
+        }
+      }
+      // frame-orientation cost: d/dz w (phi - 3)^2 = 2 w (phi - 3) dphi/dz
+      if (want_grad && lane < 27 && k1)
+        gbuf[lane < 4 ? 7 + lane : 34 + lane - 4] += 2.0 * C.w_frame * (phi - 3.0) * tphi_lane;
+      __syncwarp();
+      if (want_jac) {
+        const int* jmap = C.jk_map + (size_t)k * C.n_jk;
+        double* jb = jac + b * C.nnz_j;
+        const int n = C.n_jk;
+        for (int eb = lane; eb < n; eb += 256) {  // 8 map loads in flight before the dependent stores
+          int sl[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) sl[u] = (eb + 32 * u) < n ? jmap[eb + 32 * u] : -1;
+#pragma unroll
+          for (int u = 0; u < 8; ++u)
+            if (sl[u] >= 0) jb[sl[u]] = stg[eb + 32 * u];
+        }
+      }
+      if (want_grad) {
+        // gbuf order vb3 qd4 q4 sd23 s23 -> x offsets
+        double* gf = grad_f + b * C.n_x + (long)k * C.x_stride;
+        for (int i = lane; i < 57; i += 32) {
+          int off;
+          if (i < 3) off = Z_VB + i;
+          else if (i < 7) off = Z_QD + i - 3;
+          else if (i < 11) off = Z_Q + i - 7;
+          else if (i < 34) off = Z_SD + i - 11;
+          else off = Z_S + i - 34;
+          if (C.zmap[off] >= 0) gf[C.zmap[off]] = gbuf[i];
+        }
+        if (lane < 3 && C.zmap[Z_PB + lane] >= 0) gf[C.zmap[Z_PB + lane]] = 0.0;
+      }
+      __syncwarp();  // the Hessian columns reuse the stage
+    }
+#endif
     HessEmit em;
     em.map = C.hk_map + (size_t)k * (27 * 57);
     em.hess = hess + b * C.nnz_h;
