@@ -227,7 +227,7 @@ def main():
     value = total_instances * HORIZON / (ms_per_step * 1e-3)
 
     # ---- end-to-end through the host-buffer API (what a CPU-side IPOPT would call)
-    pipe = HostPipeline(ev, B, ALL, chunk=128, n_streams=3, device=dev)
+    pipe = HostPipeline(ev, B, ALL)
     xh, ph, lh, sh = (a.cpu().pin_memory() for a in host)
     pipe.set_parameters(ph)
     for _ in range(2):
@@ -328,7 +328,8 @@ def main():
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": pipe.h2d_bytes,
                 "d2h_bytes_per_step": pipe.d2h_bytes, "steps": e2e_steps,
-                "path": "HostPipeline: pinned host x/lam/sigma -> device, hb_eval, all five outputs -> pinned host",
+                "path": "hb_eval_host (C ABI, host pointers): pinned host x/lam/sigma -> device, kernels, all five "
+                        "outputs -> pinned host; 128-instance chunks over 3 internal streams",
                 "checksum_f": checksum},
         "gpu_launches": ev.last_launch_count() * args.steps,
         "kernel_ms_per_step": {k: v / max(n_evals, 1) for k, v in kernel_ms.items()},

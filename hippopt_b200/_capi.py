@@ -83,6 +83,16 @@ def lib() -> ctypes.CDLL:
     L.hb_pattern_hess.argtypes = [vp, i64p, i64p]
     L.hb_eval.restype = ctypes.c_int
     L.hb_eval.argtypes = [vp, ctypes.c_uint32, vp, vp, ctypes.c_int64, vp, vp, vp, vp, vp, vp, vp, ctypes.c_int64, vp]
+    L.hb_host_set_parameters.restype = ctypes.c_int
+    L.hb_host_set_parameters.argtypes = [vp, vp, ctypes.c_int64, ctypes.c_int64]
+    L.hb_eval_host.restype = ctypes.c_int
+    L.hb_eval_host.argtypes = [vp, ctypes.c_uint32, vp, vp, vp, vp, vp, vp, vp, vp, ctypes.c_int64]
+    L.hb_host_last_traffic.restype = ctypes.c_int
+    L.hb_host_last_traffic.argtypes = [vp, i64p, i64p]
+    L.hb_host_alloc.restype = ctypes.c_int
+    L.hb_host_alloc.argtypes = [ctypes.POINTER(vp), ctypes.c_int64]
+    L.hb_host_free.restype = ctypes.c_int
+    L.hb_host_free.argtypes = [vp]
     L.hb_last_launch_count.restype = ctypes.c_int
     L.hb_last_launch_count.argtypes = [vp]
     L.hb_last_error.restype = ctypes.c_char_p
@@ -100,6 +110,7 @@ def lib() -> ctypes.CDLL:
 EXPORTED_SYMBOLS = [
     "hb_kino_create", "hb_toy_create", "hb_destroy", "hb_dims", "hb_pattern_jac", "hb_pattern_hess", "hb_eval",
     "hb_last_launch_count", "hb_last_error", "hb_probe_fp64_tflops", "hb_profile_enable", "hb_profile_read",
+    "hb_host_set_parameters", "hb_eval_host", "hb_host_last_traffic", "hb_host_alloc", "hb_host_free",
 ]
 
 

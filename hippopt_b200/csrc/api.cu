@@ -38,6 +38,14 @@ struct hb_problem_s {
   std::vector<cudaEvent_t> prof_ev;  // 4 events per hb_eval: start, after contact, after kin, after reduce
   // toy
   hb::ToyProblem* toy = nullptr;
+  // host-buffer pipeline (hb_eval_host): device staging slabs, one per internal stream
+  enum { HOST_STREAMS = 3, HOST_CHUNK = 128 };
+  cudaStream_t hst[HOST_STREAMS] = {nullptr, nullptr, nullptr};
+  double* hslab[HOST_STREAMS] = {nullptr, nullptr, nullptr};
+  int64_t hslab_chunk = 0;  // instances one slab holds
+  double* d_p = nullptr;    // parameters of the current solve
+  int64_t p_cap = 0, p_stride = -1, p_batch = 0;
+  int64_t h2d_bytes = 0, d2h_bytes = 0;
 };
 
 __global__ void reduce_f_kernel(const double* __restrict__ fpart, double* __restrict__ f, int n_terms, long batch) {
@@ -259,6 +267,11 @@ extern "C" int hb_destroy(hb_handle h) {
   cudaFree(h->dev);
   for (auto& kv : h->fpart) cudaFree(kv.second.first);
   for (cudaEvent_t e : h->prof_ev) cudaEventDestroy(e);
+  for (int i = 0; i < hb_problem_s::HOST_STREAMS; ++i) {
+    cudaFree(h->hslab[i]);
+    if (h->hst[i]) cudaStreamDestroy(h->hst[i]);
+  }
+  cudaFree(h->d_p);
   if (h->toy) hb::toy_destroy(h->toy);
   delete h;
   return HB_OK;
@@ -392,6 +405,128 @@ extern "C" int hb_eval(hb_handle h, uint32_t mask, const double* x, const double
     h->launches++;
   }
   if (mark() != HB_OK) return HB_ERR_CUDA;
+  return HB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// host-buffer pipeline
+extern "C" int hb_host_set_parameters(hb_handle h, const double* p, int64_t p_stride, int64_t batch) {
+  if (!h || !p) return fail(HB_ERR_INVALID, "hb_host_set_parameters: null argument");
+  int64_t n_p = 0;
+  hb_dims(h, nullptr, &n_p, nullptr, nullptr, nullptr);
+  if (p_stride != 0 && p_stride != n_p) return fail(HB_ERR_INVALID, "hb_host_set_parameters: p_stride must be 0 or n_p");
+  if (p_stride != 0 && batch <= 0) return fail(HB_ERR_INVALID, "hb_host_set_parameters: batch must be positive");
+  const int64_t need = p_stride == 0 ? n_p : n_p * batch;
+  if (need > h->p_cap) {
+    cudaFree(h->d_p);
+    h->d_p = nullptr;
+    h->p_cap = 0;
+    CUDA_TRY(cudaMalloc(&h->d_p, (size_t)need * sizeof(double)));
+    h->p_cap = need;
+  }
+  CUDA_TRY(cudaMemcpy(h->d_p, p, (size_t)need * sizeof(double), cudaMemcpyHostToDevice));
+  h->p_stride = p_stride;
+  h->p_batch = p_stride == 0 ? 0 : batch;
+  return HB_OK;
+}
+
+extern "C" int hb_eval_host(hb_handle h, uint32_t mask, const double* x, const double* lam_g, const double* sigma,
+                            double* f, double* grad_f, double* g, double* jac_vals, double* hess_vals,
+                            int64_t batch) {
+  if (!h) return fail(HB_ERR_INVALID, "hb_eval_host: null handle");
+  if (batch <= 0) return fail(HB_ERR_INVALID, "hb_eval_host: batch must be positive");
+  if (!x) return fail(HB_ERR_INVALID, "hb_eval_host: x is required");
+  if (h->p_stride < 0) return fail(HB_ERR_INVALID, "hb_eval_host: call hb_host_set_parameters first");
+  if (h->p_stride != 0 && batch > h->p_batch)
+    return fail(HB_ERR_INVALID, "hb_eval_host: batch exceeds the batch the parameters were set for");
+  if ((mask & HB_EVAL_F) && !f) return fail(HB_ERR_INVALID, "hb_eval_host: f requested but NULL");
+  if ((mask & HB_EVAL_GRAD_F) && !grad_f) return fail(HB_ERR_INVALID, "hb_eval_host: grad_f requested but NULL");
+  if ((mask & HB_EVAL_G) && !g) return fail(HB_ERR_INVALID, "hb_eval_host: g requested but NULL");
+  if ((mask & HB_EVAL_JAC_G) && !jac_vals) return fail(HB_ERR_INVALID, "hb_eval_host: jac_vals requested but NULL");
+  const bool need_l = (mask & HB_EVAL_HESS_L) != 0;
+  if (need_l && (!hess_vals || !lam_g || !sigma))
+    return fail(HB_ERR_INVALID, "hb_eval_host: hess_vals, lam_g and sigma are required for HB_EVAL_HESS_L");
+  if (!(mask & 31u)) return fail(HB_ERR_INVALID, "hb_eval_host: empty mask");
+  int64_t n_x = 0, n_p = 0, m = 0, nnz_j = 0, nnz_h = 0;
+  hb_dims(h, &n_x, &n_p, &m, &nnz_j, &nnz_h);
+  const int S = hb_problem_s::HOST_STREAMS;
+  const int64_t chunk = batch < hb_problem_s::HOST_CHUNK ? batch : (int64_t)hb_problem_s::HOST_CHUNK;
+  // slab of one stream: x | lam | sigma | f | grad_f | g | jac | hess, each for `chunk` instances
+  const int64_t per_inst = n_x + m + 1 + 1 + n_x + m + nnz_j + nnz_h;
+  if (chunk > h->hslab_chunk) {
+    for (int i = 0; i < S; ++i) {
+      cudaFree(h->hslab[i]);
+      h->hslab[i] = nullptr;
+    }
+    h->hslab_chunk = 0;
+    for (int i = 0; i < S; ++i) {
+      if (!h->hst[i]) CUDA_TRY(cudaStreamCreateWithFlags(&h->hst[i], cudaStreamNonBlocking));
+      CUDA_TRY(cudaMalloc(&h->hslab[i], (size_t)(per_inst * chunk) * sizeof(double)));
+    }
+    h->hslab_chunk = chunk;
+  }
+  const int64_t cap = h->hslab_chunk;
+  int launches = 0;
+  int64_t h2d = 0, d2h = 0;
+  const int64_t n_chunks = (batch + chunk - 1) / chunk;
+  for (int64_t ci = 0; ci < n_chunks; ++ci) {
+    const int64_t lo = ci * chunk, n = (lo + chunk <= batch ? chunk : batch - lo);
+    const int si = (int)(ci % S);
+    cudaStream_t st = h->hst[si];
+    double* d_x = h->hslab[si];
+    double* d_lam = d_x + cap * n_x;
+    double* d_sig = d_lam + cap * m;
+    double* d_f = d_sig + cap;
+    double* d_gf = d_f + cap;
+    double* d_g = d_gf + cap * n_x;
+    double* d_j = d_g + cap * m;
+    double* d_h = d_j + cap * nnz_j;
+    auto up = [&](double* dst, const double* src, int64_t count) {
+      h2d += count * 8;
+      return cudaMemcpyAsync(dst, src, (size_t)count * 8, cudaMemcpyHostToDevice, st);
+    };
+    auto down = [&](double* dst, const double* src, int64_t count) {
+      d2h += count * 8;
+      return cudaMemcpyAsync(dst, src, (size_t)count * 8, cudaMemcpyDeviceToHost, st);
+    };
+    CUDA_TRY(up(d_x, x + lo * n_x, n * n_x));
+    if (need_l) {
+      CUDA_TRY(up(d_lam, lam_g + lo * m, n * m));
+      CUDA_TRY(up(d_sig, sigma + lo, n));
+    }
+    const double* pc = h->p_stride == 0 ? h->d_p : h->d_p + lo * n_p;
+    const int rc = hb_eval(h, mask, d_x, pc, h->p_stride, need_l ? d_lam : nullptr, need_l ? d_sig : nullptr, d_f, d_gf,
+                           d_g, d_j, d_h, n, st);
+    if (rc != HB_OK) return rc;
+    launches += h->launches;
+    if (mask & HB_EVAL_F) CUDA_TRY(down(f + lo, d_f, n));
+    if (mask & HB_EVAL_GRAD_F) CUDA_TRY(down(grad_f + lo * n_x, d_gf, n * n_x));
+    if (mask & HB_EVAL_G) CUDA_TRY(down(g + lo * m, d_g, n * m));
+    if (mask & HB_EVAL_JAC_G) CUDA_TRY(down(jac_vals + lo * nnz_j, d_j, n * nnz_j));
+    if (need_l) CUDA_TRY(down(hess_vals + lo * nnz_h, d_h, n * nnz_h));
+  }
+  for (int i = 0; i < S; ++i) CUDA_TRY(cudaStreamSynchronize(h->hst[i]));
+  h->launches = launches;
+  h->h2d_bytes = h2d;
+  h->d2h_bytes = d2h;
+  return HB_OK;
+}
+
+extern "C" int hb_host_last_traffic(hb_handle h, int64_t* h2d_bytes, int64_t* d2h_bytes) {
+  if (!h) return fail(HB_ERR_INVALID, "hb_host_last_traffic: null handle");
+  if (h2d_bytes) *h2d_bytes = h->h2d_bytes;
+  if (d2h_bytes) *d2h_bytes = h->d2h_bytes;
+  return HB_OK;
+}
+
+extern "C" int hb_host_alloc(void** ptr, int64_t bytes) {
+  if (!ptr || bytes <= 0) return fail(HB_ERR_INVALID, "hb_host_alloc: bad argument");
+  CUDA_TRY(cudaHostAlloc(ptr, (size_t)bytes, cudaHostAllocDefault));
+  return HB_OK;
+}
+
+extern "C" int hb_host_free(void* ptr) {
+  if (ptr) CUDA_TRY(cudaFreeHost(ptr));
   return HB_OK;
 }
 

@@ -124,65 +124,59 @@ class HostPipeline:
     """The call a CPU-side solver makes: host buffers in, host buffers out.
 
     IPOPT lives on the host, so every evaluation needs x (and lam_g, sigma) copied
-    to the device and the values copied back.  The batch is cut into chunks that are pipelined over a
-    few CUDA streams so that H2D copies, the kernels and D2H copies of different chunks overlap; all
-    host buffers are pinned.  Parameters are uploaded once per solve (``set_parameters``), as they do
-    not change between IPOPT iterations."""
+    to the device and the values copied back.  This is a thin owner of pinned host output buffers
+    around ``hb_eval_host`` (include/hippopt_b200.h): the library cuts the batch into chunks pipelined
+    over its own CUDA streams so that H2D copies, the kernels and D2H copies of different chunks
+    overlap.  Parameters are uploaded once per solve (``set_parameters``), as they do not change
+    between IPOPT iterations."""
 
-    def __init__(self, ev: _Evaluator, batch: int, mask: int = ALL, chunk: int = 128, n_streams: int = 3,
-                 device: torch.device | None = None):
+    def __init__(self, ev: _Evaluator, batch: int, mask: int = ALL, pinned: bool = True):
         self.ev, self.B, self.mask = ev, batch, mask
-        self.dev = device if device is not None else torch.device("cuda", torch.cuda.current_device())
-        self.chunk = min(chunk, batch)
-        self.streams = [torch.cuda.Stream(self.dev) for _ in range(n_streams)]
-        c = self.chunk
-
-        def dbuf(*shape):
-            return torch.empty(shape, dtype=torch.float64, device=self.dev)
-
-        def hbuf(*shape):
-            return torch.empty(shape, dtype=torch.float64).pin_memory()
-
         shapes = {"f": (), "grad_f": (ev.n_x,), "g": (ev.m,), "jac": (ev.nnz_j,), "hess": (ev.nnz_h,)}
         bits = {"f": F, "grad_f": GRAD_F, "g": G, "jac": JAC_G, "hess": HESS_L}
         self.names = [n for n in shapes if mask & bits[n]]
-        self.slots = []
-        for _ in self.streams:
-            self.slots.append({
-                "x": dbuf(c, ev.n_x), "lam": dbuf(c, ev.m), "sigma": dbuf(c),
-                "out": {n: dbuf(c, *shapes[n]) for n in self.names},
-            })
-        self.p_dev = dbuf(batch, ev.n_p)
-        self.host_out = {n: hbuf(batch, *shapes[n]) for n in self.names}
-        self.h2d_bytes = 8 * batch * (ev.n_x + (ev.m + 1 if mask & HESS_L else 0))
-        self.d2h_bytes = 8 * sum(self.host_out[n].numel() for n in self.names)
+        self.host_out = {n: self.host_buffer((batch, *shapes[n]), pinned) for n in self.names}
+        self.h2d_bytes = self.d2h_bytes = 0
+
+    @staticmethod
+    def host_buffer(shape, pinned: bool = True) -> torch.Tensor:
+        t = torch.empty(shape, dtype=torch.float64)
+        return t.pin_memory() if pinned else t
 
     def set_parameters(self, p_host: torch.Tensor) -> None:
-        self.p_dev.copy_(p_host, non_blocking=True)
-        torch.cuda.current_stream(self.dev).synchronize()
+        """p_host: (B, n_p) or (n_p,) float64 host tensor; uploaded once per solve."""
+        if p_host.is_cuda or p_host.dtype != torch.float64 or not p_host.is_contiguous():
+            raise ValueError("p_host must be a contiguous float64 host tensor")
+        if p_host.dim() == 1 and p_host.shape[0] == self.ev.n_p:
+            stride, batch = 0, 0
+        elif p_host.dim() == 2 and p_host.shape[1] == self.ev.n_p:
+            stride, batch = self.ev.n_p, p_host.shape[0]
+        else:
+            raise ValueError(f"p_host must have shape (B, {self.ev.n_p}) or ({self.ev.n_p},)")
+        _capi.check(_capi.lib().hb_host_set_parameters(self.ev._h, _ptr(p_host), stride, batch), "hb_host_set_parameters")
 
     def run(self, x_host: torch.Tensor, lam_host: torch.Tensor | None = None,
             sigma_host: torch.Tensor | None = None) -> dict:
-        """x_host (B, n_x), lam_host (B, m), sigma_host (B,): pinned float64 host tensors."""
+        """x_host (B, n_x), lam_host (B, m), sigma_host (B,): float64 host tensors (pinned for full overlap).
+        One blocking ``hb_eval_host`` call; returns the host output tensors."""
+        ev, B = self.ev, self.B
         need_l = bool(self.mask & HESS_L)
-        n_chunks = -(-self.B // self.chunk)
-        for ci in range(n_chunks):
-            lo, hi = ci * self.chunk, min(self.B, (ci + 1) * self.chunk)
-            n = hi - lo
-            st = self.streams[ci % len(self.streams)]
-            sl = self.slots[ci % len(self.streams)]
-            with torch.cuda.stream(st):
-                sl["x"][:n].copy_(x_host[lo:hi], non_blocking=True)
-                if need_l:
-                    sl["lam"][:n].copy_(lam_host[lo:hi], non_blocking=True)
-                    sl["sigma"][:n].copy_(sigma_host[lo:hi], non_blocking=True)
-                self.ev.eval(self.mask, sl["x"][:n], self.p_dev[lo:hi], sl["lam"][:n] if need_l else None,
-                             sl["sigma"][:n] if need_l else None, stream=st,
-                             out={k: v[:n] for k, v in sl["out"].items()})
-                for k in self.names:
-                    self.host_out[k][lo:hi].copy_(sl["out"][k][:n], non_blocking=True)
-        for st in self.streams:
-            st.synchronize()
+        for name, t, shape in (("x_host", x_host, (B, ev.n_x)), ("lam_host", lam_host, (B, ev.m)),
+                               ("sigma_host", sigma_host, (B,))):
+            if t is None:
+                if name != "x_host" and not need_l:
+                    continue
+                raise ValueError(f"{name} is required")
+            if t.is_cuda or t.dtype != torch.float64 or not t.is_contiguous() or tuple(t.shape) != shape:
+                raise ValueError(f"{name} must be a contiguous float64 host tensor of shape {shape}")
+        o = self.host_out
+        rc = _capi.lib().hb_eval_host(ev._h, self.mask, _ptr(x_host), _ptr(lam_host if need_l else None),
+                                      _ptr(sigma_host if need_l else None), _ptr(o.get("f")), _ptr(o.get("grad_f")),
+                                      _ptr(o.get("g")), _ptr(o.get("jac")), _ptr(o.get("hess")), B)
+        _capi.check(rc, "hb_eval_host")
+        up, down = ctypes.c_int64(), ctypes.c_int64()
+        _capi.check(_capi.lib().hb_host_last_traffic(ev._h, ctypes.byref(up), ctypes.byref(down)), "hb_host_last_traffic")
+        self.h2d_bytes, self.d2h_bytes = int(up.value), int(down.value)
         return self.host_out
 
 

@@ -211,7 +211,27 @@ int hb_eval(hb_handle h, uint32_t mask, const double* x, const double* p, int64_
             const double* lam_g, const double* sigma, double* f, double* grad_f, double* g,
             double* jac_vals, double* hess_vals, int64_t batch, void* stream);
 
-/* number of kernel launches the last hb_eval enqueued (for bench.py's gpu_launches claim) */
+/* Host-buffer form of hb_eval: the call a CPU-side solver (IPOPT inside opti_solver.py:479) makes.
+ * Every pointer is a HOST pointer (pinned memory from hb_host_alloc gives full copy/compute overlap;
+ * pageable memory works, more slowly).  The batch is cut into chunks pipelined over internal CUDA
+ * streams: H2D of x / lam_g / sigma, the kernels, D2H of the requested outputs.  Blocking: all outputs
+ * are complete in host memory when the call returns.  Device staging buffers belong to the handle.
+ *
+ * Parameters do not change between the iterations of one solve (opti.set_value before opti.solve,
+ * opti_solver.py:296-344), so they are uploaded once with hb_host_set_parameters:
+ *   p host [batch*n_p] (p_stride = n_p) or [n_p] (p_stride = 0, shared by every instance).
+ * hb_eval_host fails with HB_ERR_INVALID if no parameters were set or `batch` exceeds the batch they
+ * were set for (p_stride = n_p). */
+int hb_host_set_parameters(hb_handle h, const double* p, int64_t p_stride, int64_t batch);
+int hb_eval_host(hb_handle h, uint32_t mask, const double* x, const double* lam_g, const double* sigma,
+                 double* f, double* grad_f, double* g, double* jac_vals, double* hess_vals, int64_t batch);
+/* bytes copied host->device and device->host by the last hb_eval_host */
+int hb_host_last_traffic(hb_handle h, int64_t* h2d_bytes, int64_t* d2h_bytes);
+/* page-locked host memory for callers that do not link the CUDA runtime themselves */
+int hb_host_alloc(void** ptr, int64_t bytes);
+int hb_host_free(void* ptr);
+
+/* number of kernel launches the last hb_eval / hb_eval_host enqueued (for bench.py's gpu_launches claim) */
 int hb_last_launch_count(hb_handle h);
 
 /* Per-kernel device timing of the kinodynamic evaluator.  While enabled, every hb_eval records CUDA

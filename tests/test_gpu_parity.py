@@ -180,7 +180,7 @@ def test_pose_finder_config2_batch(model, built_library):
 def test_kino_edge_cases(model, built_library):
     """Single instance, shared parameter vector, zero multipliers, partial masks, argument errors."""
     from hippopt_b200 import _capi
-    from hippopt_b200.evaluator import ALL, F, G, HESS_L, JAC_G, KinoEvaluator
+    from hippopt_b200.evaluator import ALL, F, G, GRAD_F, HESS_L, JAC_G, KinoEvaluator
     from hippopt_b200.kino_layout import KinoSettings
     from hippopt_b200.workloads import kino_batch
 
@@ -198,8 +198,16 @@ def test_kino_edge_cases(model, built_library):
         assert np.array_equal(one[k][0], full[k][2]), k  # batching does not change results
     part = run(ev, x, p, lam, sigma, F | G)
     assert set(part) == {"f", "g"} and np.array_equal(part["g"], full["g"]) and np.array_equal(part["f"], full["f"])
+    # Without the Hessian bit the kinematic rows come from the row-per-lane adjoint sweep, with it from
+    # the forward tangents of the direction lanes: two algorithms, equal to rounding, not bit-identical.
     jac_only = run(ev, x, p, lam, sigma, JAC_G)
-    assert np.array_equal(jac_only["jac"], full["jac"])
+    close(jac_only["jac"], full["jac"], rtol=1e-13)
+    jac_grad = run(ev, x, p, lam, sigma, JAC_G | GRAD_F)
+    assert np.array_equal(jac_grad["jac"], jac_only["jac"])
+    close(jac_grad["grad_f"], full["grad_f"], rtol=1e-12)
+    again = run(ev, x, p, lam, sigma)
+    for k in full:
+        assert np.array_equal(again[k], full[k]), k  # same mask: bit-reproducible
     zero = run(ev, x, p, np.zeros_like(lam), np.zeros_like(sigma), HESS_L)
     assert np.abs(zero["hess"]).max() == 0.0
     with pytest.raises(ValueError):
