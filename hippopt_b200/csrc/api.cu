@@ -28,6 +28,7 @@ struct hb_problem_s {
   // kinodynamic
   hb::KinoConst host{};
   hb::KinoConst* dev = nullptr;
+  hb::KinTopo topo{};  // warp-uniform tables, passed by value to the kinematics kernel
   int *d_jc = nullptr, *d_jk = nullptr, *d_hc = nullptr, *d_hk = nullptr, *d_hk2 = nullptr;
   short* d_hci = nullptr;
   // per-knot cost partial sums, one scratch buffer per stream so that evaluations enqueued on
@@ -220,6 +221,36 @@ extern "C" int hb_kino_create(const int32_t* icfg, const double* dcfg, const int
       bdy = C.body[bdy].parent;
     }
   }
+  {
+    hb::KinTopo& T = h->topo;
+    for (int l = 0; l < HB_MAX_BODIES; ++l) {
+      const bool in = l < C.nb;
+      T.mass[l] = in ? C.body[l].mass : 0.0;
+      T.sub_mask[l] = C.sub_mask[l];
+      T.parent[l] = (signed char)(in ? C.body[l].parent : -1);
+      T.slot[l] = (signed char)(in ? C.body[l].slot : -1);
+      T.carry[l] = (signed char)(in ? C.body[l].carry : 0);
+    }
+    T.n_steps = 0;
+    for (int dep = C.max_depth; dep >= 1; --dep)
+      for (int r = 0; r < C.max_sib; ++r) {
+        bool any = false;
+        for (int l = 1; l < C.nb; ++l) any = any || (C.body[l].depth == dep && C.body[l].sib_rank == r);
+        if (any) {
+          T.step_depth[T.n_steps] = (signed char)dep;
+          T.step_rank[T.n_steps] = (signed char)r;
+          T.n_steps++;
+        }
+      }
+    std::memcpy(T.fam, C.fam, sizeof(T.fam));
+    T.nb = C.nb;
+    T.foot_body[0] = C.foot_body[0];
+    T.foot_body[1] = C.foot_body[1];
+    T.chest_body = C.chest_body;
+    T.max_depth = C.max_depth;
+    T.n_slots = C.n_slots;
+    T.max_sib = C.max_sib;
+  }
   const size_t N = C.N;
   cudaError_t e = cudaSuccess;
   if (e == cudaSuccess) e = upload(&h->d_jc, jc_map, N * C.n_jc);
@@ -388,12 +419,12 @@ extern "C" int hb_eval(hb_handle h, uint32_t mask, const double* x, const double
   {
     const size_t smem = (size_t)hb::kin_smem_layout(C.nb, C.n_slots, with_hess).total * sizeof(double) * warps_per_block;
     if (with_hess)
-      hb::kino_kin_kernel<true><<<grid, 32 * warps_per_block, smem, st>>>(h->dev, mask, x, p, (long)p_stride, lam_g, sigma,
-                                                                         d_fpart, grad_f, g, jac_vals, hess_vals,
-                                                                         (long)batch);
+      hb::kino_kin_kernel<true><<<grid, 32 * warps_per_block, smem, st>>>(h->topo, h->dev, mask, x, p, (long)p_stride,
+                                                                         lam_g, sigma, d_fpart, grad_f, g, jac_vals,
+                                                                         hess_vals, (long)batch);
     else
-      hb::kino_kin_kernel<false><<<grid, 32 * warps_per_block, smem, st>>>(h->dev, mask, x, p, (long)p_stride, lam_g,
-                                                                          sigma, d_fpart, grad_f, g, jac_vals,
+      hb::kino_kin_kernel<false><<<grid, 32 * warps_per_block, smem, st>>>(h->topo, h->dev, mask, x, p, (long)p_stride,
+                                                                          lam_g, sigma, d_fpart, grad_f, g, jac_vals,
                                                                           hess_vals, (long)batch);
     CUDA_TRY(cudaGetLastError());
     h->launches++;

@@ -49,8 +49,26 @@ struct KinoConst {
   const int* hk2_map;
 };
 
+// Warp-uniform part of KinoConst.  It is passed BY VALUE as a __grid_constant__ kernel parameter:
+// reads whose index is the same for every lane (tree topology inside the sweeps, row families with a
+// compile-time id) become constant-bank operands instead of global loads -- in the ncu capture of the
+// previous version those loads were ~40 % of the long-scoreboard stalls of the kinematics kernel.
+// Lane-indexed data (joint frames, inertias, per-point families) stays in KinoConst / global memory,
+// where a divergent index costs one coalesced load rather than a serialised constant fetch.
+struct KinTopo {
+  double mass[HB_MAX_BODIES];
+  unsigned sub_mask[HB_MAX_BODIES];
+  signed char parent[HB_MAX_BODIES], slot[HB_MAX_BODIES], carry[HB_MAX_BODIES];
+  // (depth, sibling rank) pairs that hold at least one body, deepest first (level-wise adjoint pass)
+  signed char step_depth[2 * HB_MAX_BODIES], step_rank[2 * HB_MAX_BODIES];
+  int n_steps;
+  int fam[HB_KF_COUNT][4];
+  int nb, foot_body[2], chest_body, max_depth, n_slots, max_sib;
+};
+
 // global g index of local row r of family `fam` at knot k, or -1 when the row does not exist
-__device__ __forceinline__ int grow(const KinoConst& C, int fam, int k, int r) {
+template <class Tab>
+__device__ __forceinline__ int grow(const Tab& C, int fam, int k, int r) {
   const int base = C.fam[fam][0];
   if (base < 0 || k < C.fam[fam][2] || k > C.fam[fam][3]) return -1;
   return base + (k - C.fam[fam][2]) * C.fam[fam][1] + r;

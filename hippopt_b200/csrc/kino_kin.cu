@@ -219,7 +219,7 @@ __device__ __forceinline__ V3<typename Prom<A, B>::type> omega_map(const A* a, c
 // One adjoint sweep over the tree.  `emit.joint(l, sbar, sdbar)` receives d Phi / d s_{l-1} and
 // d Phi / d s_dot_{l-1}; the totals at the root are returned for the base chain rule.
 template <class T, class Emit>
-__device__ __forceinline__ void kin_backward(const KinoConst& C, const double* sb, const double* zs, const Dir& dir,
+__device__ __forceinline__ void kin_backward(const KinTopo& C, const double* sb, const double* zs, const Dir& dir,
                                              const Seeds<T>& S, const V3<T>& xc, const V3<T>& xd, double* slot,
                                              Emit& emit, V3<T>& n0, V3<T>& w0, V3<T>& v0) {
   const int nb = C.nb;
@@ -229,9 +229,8 @@ __device__ __forceinline__ void kin_backward(const KinoConst& C, const double* s
   V3<T> cn = vzero<T>(), cF = vzero<T>(), cw = vzero<T>(), cv = vzero<T>();
   V3<T> An = vzero<T>(), AF = vzero<T>(), Aw = vzero<T>(), Av = vzero<T>();
   for (int l = nb - 1; l >= 0; --l) {
-    const BodyC& bc = C.body[l];
     emit.prefetch(l);
-    if (!bc.carry) {
+    if (!C.carry[l]) {
       cn = vzero<T>();
       cF = vzero<T>();
       cw = vzero<T>();
@@ -246,7 +245,7 @@ __device__ __forceinline__ void kin_backward(const KinoConst& C, const double* s
     const St<T> s = load_state(sb, l, dir, T());
     // ---- local adjoints of body l
     {
-      const double m = bc.mass;
+      const double m = C.mass[l];
       const V3<T> c = s.o + s.d;
       const V3<T> cd = s.v + cross(s.w, s.d);
       const V3<T> cbar = scale(m, cross(cd - xd, S.hb) + S.wc);
@@ -267,8 +266,8 @@ __device__ __forceinline__ void kin_backward(const KinoConst& C, const double* s
       }
       if (l == C.chest_body) cn = cn + S.chestN;
     }
-    if (bc.slot >= 0) {
-      const double* sl = slot + bc.slot * 12 * SW * 32 + lane;
+    if (C.slot[l] >= 0) {
+      const double* sl = slot + C.slot[l] * 12 * SW * 32 + lane;
       slot_get(cn, sl, 0);
       slot_get(cF, sl, 3);
       slot_get(cw, sl, 6);
@@ -278,7 +277,7 @@ __device__ __forceinline__ void kin_backward(const KinoConst& C, const double* s
     // ---- joint outputs
     emit.joint(l, dot(s.ax, cn), dot(s.ax, cw));
     // ---- contribution to the parent
-    const int p = bc.parent;
+    const int p = C.parent[l];
     V3<T> rho, wpar;
     parent_link(sb, l, p, dir, rho, wpar);
     const double sd = zs[Z_SD + l - 1];
@@ -293,7 +292,7 @@ __device__ __forceinline__ void kin_backward(const KinoConst& C, const double* s
       Aw = Aw + pw;
       Av = Av + cv;
     } else {
-      double* sl = slot + C.body[p].slot * 12 * SW * 32 + lane;
+      double* sl = slot + C.slot[p] * 12 * SW * 32 + lane;
       slot_add(sl, 0, pn);
       slot_add(sl, 3, cF);
       slot_add(sl, 6, pw);
@@ -320,15 +319,14 @@ struct SeedsT {
   D3 footF[2], footN[2], chestN;  // wc and hb are constants: zero tangent
 };
 
-__device__ __forceinline__ void primal_adjoint_pass(const KinoConst& C, double* sb, const double* zs, const SeedsP& S,
-                                                    D3 xc, D3 xd) {
+__device__ __forceinline__ void primal_adjoint_pass(const KinoConst& C, const KinTopo& T, double* sb, const double* zs,
+                                                    const SeedsP& S, D3 xc, D3 xd) {
   const int lane = threadIdx.x & 31;
-  const int nb = C.nb;
+  const int nb = T.nb;
   if (lane < nb) {
-    const BodyC& bc = C.body[lane];
     double* bl = sb + lane * SB_STRIDE;
     const D3 o = ld3(bl + SB_O), d = ld3(bl + SB_D), w = ld3(bl + SB_W), v = ld3(bl + SB_V);
-    const double m = bc.mass;
+    const double m = C.body[lane].mass;
     const D3 c = o + d;
     const D3 cd = v + cross(w, d);
     const D3 cbar = scale(m, cross(cd - xd, S.hb) + S.wc);
@@ -337,15 +335,15 @@ __device__ __forceinline__ void primal_adjoint_pass(const KinoConst& C, double* 
     D3 F = cbar;
     D3 n = cross(d, cbar) + cross(d, cross(cdbar, w)) + cross(Iw, S.hb) + cross(Ih, w);
     const D3 wb = cross(d, cdbar) + Ih;
-    if (lane == C.foot_body[0]) {
+    if (lane == T.foot_body[0]) {
       F = F + S.footF[0];
       n = n + S.footN[0];
     }
-    if (lane == C.foot_body[1]) {
+    if (lane == T.foot_body[1]) {
       F = F + S.footF[1];
       n = n + S.footN[1];
     }
-    if (lane == C.chest_body) n = n + S.chestN;
+    if (lane == T.chest_body) n = n + S.chestN;
     st3(bl + SB_ACC, n);
     st3(bl + SB_ACC + 3, F);
     st3(bl + SB_ACC + 6, wb);
@@ -354,31 +352,35 @@ __device__ __forceinline__ void primal_adjoint_pass(const KinoConst& C, double* 
     st3(bl + SB_CDB, cdbar);
   }
   __syncwarp();
-  for (int dep = C.max_depth; dep >= 1; --dep)
-    for (int r = 0; r < C.max_sib; ++r) {
-      if (lane > 0 && lane < nb && C.body[lane].depth == dep && C.body[lane].sib_rank == r) {
-        const BodyC& bc = C.body[lane];
-        const double* bl = sb + lane * SB_STRIDE;
-        double* bp = sb + bc.parent * SB_STRIDE;
-        const D3 n = ld3(bl + SB_ACC), F = ld3(bl + SB_ACC + 3), wb = ld3(bl + SB_ACC + 6), vb = ld3(bl + SB_ACC + 9);
-        const D3 ax = ld3(bl + SB_AX), rho = ld3(bl + SB_RHO), wpar = ld3(bp + SB_W);
-        const double sd = zs[Z_SD + lane - 1];
-        const D3 pn = n + cross(rho, F) + scale(sd, cross(ax, wb)) + cross(rho, cross(vb, wpar));
-        const D3 pw = wb + cross(rho, vb);
-        st3(bp + SB_ACC, ld3(bp + SB_ACC) + pn);
-        st3(bp + SB_ACC + 3, ld3(bp + SB_ACC + 3) + F);
-        st3(bp + SB_ACC + 6, ld3(bp + SB_ACC + 6) + pw);
-        st3(bp + SB_ACC + 9, ld3(bp + SB_ACC + 9) + vb);
-      }
-      __syncwarp();
+  // lane-indexed topology, read once (not inside the level loops)
+  const bool mine = lane > 0 && lane < nb;
+  const int my_depth = mine ? C.body[lane].depth : -1, my_rank = mine ? C.body[lane].sib_rank : -1;
+  const int my_parent = mine ? C.body[lane].parent : 0;
+  // (depth, sibling rank) steps that have at least one body, deepest first: children of one parent are
+  // serialised by rank so that the read-modify-write of the parent's totals needs no atomics
+  for (int st = 0; st < T.n_steps; ++st) {
+    if (my_depth == T.step_depth[st] && my_rank == T.step_rank[st]) {
+      const double* bl = sb + lane * SB_STRIDE;
+      double* bp = sb + my_parent * SB_STRIDE;
+      const D3 n = ld3(bl + SB_ACC), F = ld3(bl + SB_ACC + 3), wb = ld3(bl + SB_ACC + 6), vb = ld3(bl + SB_ACC + 9);
+      const D3 ax = ld3(bl + SB_AX), rho = ld3(bl + SB_RHO), wpar = ld3(bp + SB_W);
+      const double sd = zs[Z_SD + lane - 1];
+      const D3 pn = n + cross(rho, F) + scale(sd, cross(ax, wb)) + cross(rho, cross(vb, wpar));
+      const D3 pw = wb + cross(rho, vb);
+      st3(bp + SB_ACC, ld3(bp + SB_ACC) + pn);
+      st3(bp + SB_ACC + 3, ld3(bp + SB_ACC + 3) + F);
+      st3(bp + SB_ACC + 6, ld3(bp + SB_ACC + 6) + pw);
+      st3(bp + SB_ACC + 9, ld3(bp + SB_ACC + 9) + vb);
     }
+    __syncwarp();
+  }
 }
 
 __device__ __forceinline__ D3 tangent_of(const V3<Dual>& a) { return v3<double>(a.x.d, a.y.d, a.z.d); }
 __device__ __forceinline__ D3 primal_of(const V3<Dual>& a) { return v3<double>(a.x.v, a.y.v, a.z.v); }
 
 template <class Emit>
-__device__ __forceinline__ void kin_tangent_sweep(const KinoConst& C, const double* sb, const double* zs,
+__device__ __forceinline__ void kin_tangent_sweep(const KinTopo& C, const double* sb, const double* zs,
                                                   const Dir& dir, D3 hb, const SeedsT& S, D3 txc, D3 txd, double* slot,
                                                   Emit& emit, D3& n0, D3& w0, D3& v0) {
   const int nb = C.nb;
@@ -388,8 +390,7 @@ __device__ __forceinline__ void kin_tangent_sweep(const KinoConst& C, const doub
   D3 cn = zero, cF = zero, cw = zero, cv = zero;
   D3 An = zero, AF = zero, Aw = zero, Av = zero;
   for (int l = nb - 1; l >= 0; --l) {
-    const BodyC& bc = C.body[l];
-    if (!bc.carry) cn = cF = cw = cv = zero;
+    if (!C.carry[l]) cn = cF = cw = cv = zero;
     if (l == 0) {
       cn = cn + An;
       cF = cF + AF;
@@ -404,7 +405,7 @@ __device__ __forceinline__ void kin_tangent_sweep(const KinoConst& C, const doub
     const double in = ((dir.mask >> l) & 1u) ? 1.0 : 0.0;
     const D3 a = scale(in, dir.alpha);
     {
-      const double m = bc.mass;
+      const double m = C.mass[l];
       const double* I = bl + SB_I;
       const D3 cbar = ld3(bl + SB_CB), cdbar = ld3(bl + SB_CDB), Ih = ld3(bl + SB_IH), Iw = ld3(bl + SB_L);
       const D3 tc = to + td;
@@ -428,8 +429,8 @@ __device__ __forceinline__ void kin_tangent_sweep(const KinoConst& C, const doub
       }
       if (l == C.chest_body) cn = cn + S.chestN;
     }
-    if (bc.slot >= 0) {
-      const double* sl = slot + bc.slot * 12 * 32 + lane;
+    if (C.slot[l] >= 0) {
+      const double* sl = slot + C.slot[l] * 12 * 32 + lane;
       slot_get(cn, sl, 0);
       slot_get(cF, sl, 3);
       slot_get(cw, sl, 6);
@@ -439,7 +440,7 @@ __device__ __forceinline__ void kin_tangent_sweep(const KinoConst& C, const doub
     // primal totals of body l (all children included)
     const D3 np = ld3(bl + SB_ACC), Fp = ld3(bl + SB_ACC + 3), wp = ld3(bl + SB_ACC + 6), vp = ld3(bl + SB_ACC + 9);
     emit.joint_t(l, dot(tax, np) + dot(ax, cn), dot(tax, wp) + dot(ax, cw));
-    const int p = bc.parent;
+    const int p = C.parent[l];
     const D3 rho = ld3(bl + SB_RHO), wpar = ld3(sb + p * SB_STRIDE + SB_W);
     const double inp = ((dir.mask >> p) & 1u) ? 1.0 : 0.0;
     const D3 ap = scale(inp, dir.alpha);
@@ -458,7 +459,7 @@ __device__ __forceinline__ void kin_tangent_sweep(const KinoConst& C, const doub
       Aw = Aw + pw;
       Av = Av + cv;
     } else {
-      double* sl = slot + C.body[p].slot * 12 * 32 + lane;
+      double* sl = slot + C.slot[p] * 12 * 32 + lane;
       slot_add(sl, 0, pn);
       slot_add(sl, 3, cF);
       slot_add(sl, 6, pw);
@@ -584,7 +585,8 @@ template <bool WITH_HESS>
 #ifndef KIN_H_MIN_BLOCKS
 #define KIN_H_MIN_BLOCKS 2
 #endif
-__global__ void __launch_bounds__(128, WITH_HESS ? KIN_H_MIN_BLOCKS : 3) kino_kin_kernel(const KinoConst* __restrict__ Cp, unsigned mask,
+__global__ void __launch_bounds__(128, WITH_HESS ? KIN_H_MIN_BLOCKS : 3) kino_kin_kernel(const __grid_constant__ KinTopo T,
+                                                       const KinoConst* __restrict__ Cp, unsigned mask,
                                                        const double* __restrict__ x, const double* __restrict__ p,
                                                        long p_stride, const double* __restrict__ lam,
                                                        const double* __restrict__ sigma, double* __restrict__ fpart,
@@ -600,14 +602,14 @@ __global__ void __launch_bounds__(128, WITH_HESS ? KIN_H_MIN_BLOCKS : 3) kino_ki
   if (wid >= batch * N) return;
   const long b = wid / N;
   const int k = (int)(wid % N);
-  const KinSmem L = kin_smem_layout(C.nb, C.n_slots, WITH_HESS);
+  const KinSmem L = kin_smem_layout(T.nb, T.n_slots, WITH_HESS);
   double* sm = smem + (size_t)warp * L.total;
   double* sb = sm + L.bodies;
   double* zs = sm + L.z;
   double* gbuf = sm + L.gbuf;
   const double* xb = x + b * C.n_x + (long)k * C.x_stride;
   const double* pb_ = p + b * p_stride;
-  const int nb = C.nb;
+  const int nb = T.nb;
   const bool k1 = k >= C.cost_k0;  // knots on which the "apply_to_first_elements=False" expressions exist
 
   for (int i = lane; i < NZ; i += 32) {
@@ -643,8 +645,9 @@ __global__ void __launch_bounds__(128, WITH_HESS ? KIN_H_MIN_BLOCKS : 3) kino_ki
   }
   __syncwarp();
   // ------------------------------------------------------------------ forward kinematics by depth
-  for (int d = 1; d <= C.max_depth; ++d) {
-    if (lane < nb && lane > 0 && C.body[lane].depth == d) {
+  const int my_depth = (lane < nb && lane > 0) ? C.body[lane].depth : -1;
+  for (int d = 1; d <= T.max_depth; ++d) {
+    if (my_depth == d) {
       const BodyC& bc = C.body[lane];
       const double* bp = sb + bc.parent * SB_STRIDE;
       double* bl = sb + lane * SB_STRIDE;
@@ -719,7 +722,7 @@ __global__ void __launch_bounds__(128, WITH_HESS ? KIN_H_MIN_BLOCKS : 3) kino_ki
     const double* Rf = C.foot_R[f];
     const D3 r = ld3(pb_ + po_desc + 3 * lane);
     const D3 bf = matvec(Rf, r) + ld3(C.foot_t[f]);
-    const D3 a = matvec(sb + C.foot_body[f] * SB_STRIDE + SB_R, bf);
+    const D3 a = matvec(sb + T.foot_body[f] * SB_STRIDE + SB_R, bf);
     st3(sm + L.arms + 3 * lane, a);
   }
   const double* rfq = pb_ + C.po_fq + C.ref_stride * k;
@@ -745,15 +748,15 @@ __global__ void __launch_bounds__(128, WITH_HESS ? KIN_H_MIN_BLOCKS : 3) kino_ki
 #pragma unroll
       for (int j = 0; j < 3; ++j)
         Kc[3 * i + j] = C.chest_R[3 * i] * Rd[3 * j] + C.chest_R[3 * i + 1] * Rd[3 * j + 1] + C.chest_R[3 * i + 2] * Rd[3 * j + 2];
-    const double* Rb = sb + C.chest_body * SB_STRIDE + SB_R;
+    const double* Rb = sb + T.chest_body * SB_STRIDE + SB_R;
 #pragma unroll
     for (int i = 0; i < 3; ++i)
 #pragma unroll
       for (int j = 0; j < 3; ++j) sm[L.G + 3 * i + j] = Rb[3 * i] * Kc[j] + Rb[3 * i + 1] * Kc[3 + j] + Rb[3 * i + 2] * Kc[6 + j];
   }
   if (lane == 9) {
-    const double* RR = sb + C.foot_body[1] * SB_STRIDE + SB_R;
-    const double* RL = sb + C.foot_body[0] * SB_STRIDE + SB_R;
+    const double* RR = sb + T.foot_body[1] * SB_STRIDE + SB_R;
+    const double* RL = sb + T.foot_body[0] * SB_STRIDE + SB_R;
     const double* Rf = C.foot_R[1];
     st3(sm + L.fdu, matvec(RR, v3<double>(Rf[1], Rf[4], Rf[7])));  // y axis of the reference sole frame
     st3(sm + L.fdal, matvec(RL, ld3(C.foot_t[0])));
@@ -764,7 +767,7 @@ __global__ void __launch_bounds__(128, WITH_HESS ? KIN_H_MIN_BLOCKS : 3) kino_ki
   const double phi = G[0] + G[4] + G[8];
   const D3 mG = v3<double>(G[5] - G[7], G[6] - G[2], G[1] - G[3]);
   const D3 fdu = ld3(sm + L.fdu), fdal = ld3(sm + L.fdal), fdar = ld3(sm + L.fdar);
-  const D3 oL = ld3(sb + C.foot_body[0] * SB_STRIDE + SB_O), oR = ld3(sb + C.foot_body[1] * SB_STRIDE + SB_O);
+  const D3 oL = ld3(sb + T.foot_body[0] * SB_STRIDE + SB_O), oR = ld3(sb + T.foot_body[1] * SB_STRIDE + SB_O);
   const D3 fdDelta = (oL + fdal) - (oR + fdar);
   const double feet_y = dot(fdu, fdDelta);
   const double mass_p = pb_[C.po_mass];
@@ -776,8 +779,8 @@ __global__ void __launch_bounds__(128, WITH_HESS ? KIN_H_MIN_BLOCKS : 3) kino_ki
     if (lane < 8 && k1) {
       const int f = lane >> 2;
       const D3 a = ld3(sm + L.arms + 3 * lane);
-      const D3 o = ld3(sb + C.foot_body[f] * SB_STRIDE + SB_O);
-      const int r0 = grow(C, lane * HB_KF_PT_COUNT + HB_KF_PT_FK, k, 0);
+      const D3 o = ld3(sb + T.foot_body[f] * SB_STRIDE + SB_O);
+      const int r0 = grow(C, lane * HB_KF_PT_COUNT + HB_KF_PT_FK, k, 0);  // lane-indexed family: global table
       const double* pp = zs + 15 * lane + Z_P;
       if (r0 >= 0) {
         gb[r0] = pp[0] - (zs[Z_PB] + o.x + a.x);
@@ -786,21 +789,21 @@ __global__ void __launch_bounds__(128, WITH_HESS ? KIN_H_MIN_BLOCKS : 3) kino_ki
       }
     }
     if (lane == 8) {
-      int r0 = grow(C, HB_KF_UNIT_QUAT, k, 0);
+      int r0 = grow(T, HB_KF_UNIT_QUAT, k, 0);
       if (r0 >= 0) gb[r0] = qq;
-      r0 = grow(C, HB_KF_COM_KIN, k, 0);
+      r0 = grow(T, HB_KF_COM_KIN, k, 0);
       if (r0 >= 0) {
         gb[r0] = zs[Z_COM] - (zs[Z_PB] + xc.x);
         gb[r0 + 1] = zs[Z_COM + 1] - (zs[Z_PB + 1] + xc.y);
         gb[r0 + 2] = zs[Z_COM + 2] - (zs[Z_PB + 2] + xc.z);
       }
-      r0 = grow(C, HB_KF_MOM_KIN, k, 0);
+      r0 = grow(T, HB_KF_MOM_KIN, k, 0);
       if (r0 >= 0) {
         gb[r0] = zs[Z_H + 3] - hang.x / mass_p;
         gb[r0 + 1] = zs[Z_H + 4] - hang.y / mass_p;
         gb[r0 + 2] = zs[Z_H + 5] - hang.z / mass_p;
       }
-      r0 = grow(C, HB_KF_FEET_DIST, k, 0);
+      r0 = grow(T, HB_KF_FEET_DIST, k, 0);
       if (r0 >= 0) gb[r0] = feet_y;
     }
   }
@@ -907,7 +910,7 @@ __global__ void __launch_bounds__(128, WITH_HESS ? KIN_H_MIN_BLOCKS : 3) kino_ki
     em.stage = (WITH_HESS ? HB_KIN_STAGE : HB_KIN_STAGE_F) ? sm + L.stage : nullptr;
     em.init_bases();
     D3 n0, w0, v0;
-    kin_backward<double>(C, sb, zs, nodir, S, xc, xcd, slot, em, n0, w0, v0);
+    kin_backward<double>(T, sb, zs, nodir, S, xc, xcd, slot, em, n0, w0, v0);
     // base chain rule
     D3 gq[4], uq[4], wq[4];
     const double qraw[4] = {q0, q1, q2, q3};
@@ -1015,24 +1018,24 @@ __global__ void __launch_bounds__(128, WITH_HESS ? KIN_H_MIN_BLOCKS : 3) kino_ki
       const St<Dual> s = load_state(sb, l, dir, Dual());
       const V3<Dual> c = s.o + s.d;
       const V3<Dual> cd = s.v + cross(s.w, s.d);
-      const double m = C.body[l].mass;
+      const double m = T.mass[l];
       tP = tP + scale(m, v3<double>(c.x.d, c.y.d, c.z.d));
       tPd = tPd + scale(m, v3<double>(cd.x.d, cd.y.d, cd.z.d));
       if (fwd_jac) th = th + tangent_of(cross(scale(m, c), cd) + iw_omega(sb, l, dir, s));
     }
     const V3<Dual> xcD = lift<Dual>(xc, scale(1.0 / M, tP));
     const V3<Dual> xdD = lift<Dual>(xcd, scale(1.0 / M, tPd));
-    const double inL = ((dir.mask >> C.foot_body[0]) & 1u) ? 1.0 : 0.0;
-    const double inR = ((dir.mask >> C.foot_body[1]) & 1u) ? 1.0 : 0.0;
-    const double inC = ((dir.mask >> C.chest_body) & 1u) ? 1.0 : 0.0;
+    const double inL = ((dir.mask >> T.foot_body[0]) & 1u) ? 1.0 : 0.0;
+    const double inR = ((dir.mask >> T.foot_body[1]) & 1u) ? 1.0 : 0.0;
+    const double inC = ((dir.mask >> T.chest_body) & 1u) ? 1.0 : 0.0;
     double ty_lane = 0.0, tphi_lane = 0.0;  // tangents of the feet distance and of trace(G) along this direction
     Seeds<Dual> S;
     S.footF[0] = S.footF[1] = S.footN[0] = S.footN[1] = vzero<Dual>();
     {
-      const int r0 = grow(C, HB_KF_COM_KIN, k, 0);
+      const int r0 = grow(T, HB_KF_COM_KIN, k, 0);
       const D3 lc = r0 >= 0 ? v3<double>(lb[r0], lb[r0 + 1], lb[r0 + 2]) : v3<double>(0.0, 0.0, 0.0);
       S.wc = scale(-1.0 / M, lc);
-      const int r1 = grow(C, HB_KF_MOM_KIN, k, 0);
+      const int r1 = grow(T, HB_KF_MOM_KIN, k, 0);
       const D3 lh = r1 >= 0 ? v3<double>(lb[r1], lb[r1 + 1], lb[r1 + 2]) : v3<double>(0.0, 0.0, 0.0);
       S.hb = scale(-1.0 / mass_p, lh);
       // stage I^w hbar (same for every lane of the dual sweep)
@@ -1042,7 +1045,7 @@ __global__ void __launch_bounds__(128, WITH_HESS ? KIN_H_MIN_BLOCKS : 3) kino_ki
 #pragma unroll
     for (int pt = 0; pt < 8; ++pt) {
       const int f = pt >> 2;
-      const int r0 = grow(C, pt * HB_KF_PT_COUNT + HB_KF_PT_FK, k, 0);
+      const int r0 = grow(T, pt * HB_KF_PT_COUNT + HB_KF_PT_FK, k, 0);
       if (r0 < 0) continue;
       const D3 frc = v3<double>(-lb[r0], -lb[r0 + 1], -lb[r0 + 2]);
       const D3 a = ld3(sm + L.arms + 3 * pt);
@@ -1052,10 +1055,10 @@ __global__ void __launch_bounds__(128, WITH_HESS ? KIN_H_MIN_BLOCKS : 3) kino_ki
       S.footN[f] = S.footN[f] + cross(aD, frc);
     }
     {
-      const int r0 = grow(C, HB_KF_FEET_DIST, k, 0);
+      const int r0 = grow(T, HB_KF_FEET_DIST, k, 0);
       const double kd = r0 >= 0 ? lb[r0] : 0.0;
-      const St<Dual> sL = load_state(sb, C.foot_body[0], dir, Dual());
-      const St<Dual> sR = load_state(sb, C.foot_body[1], dir, Dual());
+      const St<Dual> sL = load_state(sb, T.foot_body[0], dir, Dual());
+      const St<Dual> sR = load_state(sb, T.foot_body[1], dir, Dual());
       const V3<Dual> uD = lift<Dual>(fdu, scale(inR, cross(dir.alpha, fdu)));
       const V3<Dual> alD = lift<Dual>(fdal, scale(inL, cross(dir.alpha, fdal)));
       const V3<Dual> arD = lift<Dual>(fdar, scale(inR, cross(dir.alpha, fdar)));
@@ -1101,7 +1104,7 @@ __global__ void __launch_bounds__(128, WITH_HESS ? KIN_H_MIN_BLOCKS : 3) kino_ki
           for (int pt = 0; pt < 8; ++pt) {
             const int f = pt >> 2;
             const double in = f == 0 ? inL : inR;
-            const D3 r = (ld3(sb + C.foot_body[f] * SB_STRIDE + SB_O) - dir.pi) + ld3(sm + L.arms + 3 * pt);
+            const D3 r = (ld3(sb + T.foot_body[f] * SB_STRIDE + SB_O) - dir.pi) + ld3(sm + L.arms + 3 * pt);
             const D3 t = scale(-in, cross(dir.alpha, r));
             stg[4 + (3 * pt) * 27 + lane] = t.x;
             stg[4 + (3 * pt + 1) * 27 + lane] = t.y;
@@ -1137,7 +1140,7 @@ __global__ void __launch_bounds__(128, WITH_HESS ? KIN_H_MIN_BLOCKS : 3) kino_ki
             const D3 o = ld3(bl + SB_O), d = ld3(bl + SB_D);
             const D3 Al = scale(((vm >> l) & 1u) ? 1.0 : 0.0, A);
             const D3 tcd = cross(Al, (o - piv) + d) + B;
-            const double m = C.body[l].mass;
+            const double m = T.mass[l];
             pv = pv + scale(m, tcd);
             hv = hv + cross(scale(m, o + d), tcd) + symmul(bl + SB_I, Al);
           }
@@ -1196,7 +1199,7 @@ __global__ void __launch_bounds__(128, WITH_HESS ? KIN_H_MIN_BLOCKS : 3) kino_ki
     V3<Dual> n0, w0, v0;
 #ifdef HB_DUAL_SWEEP
     // reference implementation: the whole adjoint sweep in dual arithmetic on every lane
-    kin_backward<Dual>(C, sb, zs, dir, S, xcD, xdD, slot, em, n0, w0, v0);
+    kin_backward<Dual>(T, sb, zs, dir, S, xcD, xdD, slot, em, n0, w0, v0);
 #else
     {
       SeedsP SP;
@@ -1213,9 +1216,9 @@ __global__ void __launch_bounds__(128, WITH_HESS ? KIN_H_MIN_BLOCKS : 3) kino_ki
       SP.chestN = primal_of(S.chestN);
       ST.chestN = tangent_of(S.chestN);
       __syncwarp();
-      primal_adjoint_pass(C, sb, zs, SP, xc, xcd);
+      primal_adjoint_pass(C, T, sb, zs, SP, xc, xcd);
       D3 tn0, tw0, tv0;
-      kin_tangent_sweep(C, sb, zs, dir, S.hb, ST, tangent_of(xcD), tangent_of(xdD), slot, em, tn0, tw0, tv0);
+      kin_tangent_sweep(T, sb, zs, dir, S.hb, ST, tangent_of(xcD), tangent_of(xdD), slot, em, tn0, tw0, tv0);
       n0 = lift<Dual>(ld3(sb + SB_ACC), tn0);
       w0 = lift<Dual>(ld3(sb + SB_ACC + 6), tw0);
       v0 = lift<Dual>(ld3(sb + SB_ACC + 9), tv0);
@@ -1225,7 +1228,7 @@ __global__ void __launch_bounds__(128, WITH_HESS ? KIN_H_MIN_BLOCKS : 3) kino_ki
       em.put(0, v0.x.d);
       em.put(1, v0.y.d);
       em.put(2, v0.z.d);
-      const int ru = grow(C, HB_KF_UNIT_QUAT, k, 0);
+      const int ru = grow(T, HB_KF_UNIT_QUAT, k, 0);
       const double lu = ru >= 0 ? lb[ru] : 0.0;
       // dual quaternion maps, rebuilt from shared memory after the sweep (see above)
       Dual qD[4];
@@ -1271,11 +1274,11 @@ __global__ void __launch_bounds__(128, WITH_HESS ? KIN_H_MIN_BLOCKS : 3) kino_ki
   }
 }
 
-template __global__ void kino_kin_kernel<true>(const KinoConst*, unsigned, const double*, const double*, long,
-                                               const double*, const double*, double*, double*, double*, double*,
-                                               double*, long);
-template __global__ void kino_kin_kernel<false>(const KinoConst*, unsigned, const double*, const double*, long,
-                                                const double*, const double*, double*, double*, double*, double*,
-                                                double*, long);
+template __global__ void kino_kin_kernel<true>(const __grid_constant__ KinTopo, const KinoConst*, unsigned, const double*,
+                                               const double*, long, const double*, const double*, double*, double*,
+                                               double*, double*, double*, long);
+template __global__ void kino_kin_kernel<false>(const __grid_constant__ KinTopo, const KinoConst*, unsigned,
+                                                const double*, const double*, long, const double*, const double*,
+                                                double*, double*, double*, double*, double*, long);
 
 }  // namespace hb
