@@ -34,7 +34,7 @@ struct KinoConst {
   int po_fq, po_bq, po_bqv, po_jr, ref_stride;  // reference parameters of the kinematics costs
   short zmap[192];
   int nb, foot_body[2], chest_body, max_depth, n_slots, max_sib;
-  int fam[HB_KF_COUNT][4];
+  alignas(16) int fam[HB_KF_COUNT][4];  // {first row, rows per knot, first knot, last knot}; read as one int4
   unsigned sub_mask[HB_MAX_BODIES];  // bit l: body l is in the subtree rooted at this body
   double w_swing, w_u, w_fd, w_centroid, w_comvel[3], w_frame, w_bq, w_bqv, w_joint, w_ratio, w_yaw;
   double wj[HB_N_JOINTS];
@@ -72,6 +72,12 @@ __device__ __forceinline__ int grow(const Tab& C, int fam, int k, int r) {
   const int base = C.fam[fam][0];
   if (base < 0 || k < C.fam[fam][2] || k > C.fam[fam][3]) return -1;
   return base + (k - C.fam[fam][2]) * C.fam[fam][1] + r;
+}
+// global table (lane-indexed families): one 16-byte load for {base, rows, k0, k1}
+__device__ __forceinline__ int grow(const KinoConst& C, int fam, int k, int r) {
+  const int4 f = __ldg(reinterpret_cast<const int4*>(C.fam[fam]));
+  if (f.x < 0 || k < f.z || k > f.w) return -1;
+  return f.x + (k - f.z) * f.y + r;
 }
 
 // reference sub-offsets (variables.py:13-116)

@@ -161,6 +161,28 @@ __global__ void __launch_bounds__(128) kino_contact_kernel(const KinoConst* __re
     const int row = grow(C, fam, kk, r);
     return row >= 0 ? lb[row] : 0.0;
   };
+  // Multipliers of this lane's contact-point rows and of the momentum dynamics, requested here so that
+  // their DRAM latency overlaps the g / Jacobian work (they are consumed in the Hessian section).
+  double lam_pl[3] = {0.0, 0.0, 0.0}, lam_dcc = 0.0, lam_h = 0.0, lam_n = 0.0, lam_fr = 0.0, La[3] = {0.0, 0.0, 0.0};
+  if (want_hess && lane < 8) {
+    const int fb_ = lane * HB_KF_PT_COUNT;
+    const int rp = grow(C, fb_ + HB_KF_PT_PLANAR, k, 0), rd = grow(C, fb_ + HB_KF_PT_DCC, k, 0);
+    const int rf = grow(C, fb_ + HB_KF_PT_FRICTION, k, 0);
+    const int ra = grow(C, HB_KF_H_DYN, k, 3), rb = grow(C, HB_KF_H_DYN, k + 1, 3);
+    if (rp >= 0) {
+      lam_pl[0] = lb[rp];
+      lam_pl[1] = lb[rp + 1];
+      lam_pl[2] = lb[rp + 2];
+    }
+    if (rd >= 0) lam_dcc = lb[rd];
+    if (rf >= 0) lam_fr = lb[rf];
+    if constexpr (TERRAIN == 1) {
+      lam_h = lamrow(fb_ + HB_KF_PT_HEIGHT, k, 0);
+      lam_n = lamrow(fb_ + HB_KF_PT_NORMAL, k, 0);
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) La[c] = (ra >= 0 ? lb[ra + c] : 0.0) + (rb >= 0 ? lb[rb + c] : 0.0);
+  }
 
   // ------------------------------------------------------------------ per-point quantities (lanes 0..7)
   const int pi_ = lane & 7;
@@ -315,11 +337,9 @@ __global__ void __launch_bounds__(128) kino_contact_kernel(const KinoConst* __re
         jput(pb0 + 42, fric.c[2]);
       }
       if (want_hess) {
-        const double lpl[3] = {lamrow(fb_ + HB_KF_PT_PLANAR, k, 0), lamrow(fb_ + HB_KF_PT_PLANAR, k, 1),
-                               lamrow(fb_ + HB_KF_PT_PLANAR, k, 2)};
+        const double lpl[3] = {lam_pl[0], lam_pl[1], lam_pl[2]};
         const D3 lplv = v3<double>(lpl[0], lpl[1], lpl[2]);
-        const double ld = lamrow(fb_ + HB_KF_PT_DCC, k, 0), lh = lamrow(fb_ + HB_KF_PT_HEIGHT, k, 0);
-        const double ln = lamrow(fb_ + HB_KF_PT_NORMAL, k, 0), lfr = lamrow(fb_ + HB_KF_PT_FRICTION, k, 0);
+        const double ld = lam_dcc, lh = lam_h, ln = lam_n, lfr = lam_fr;
         const double sws = k1 ? sg * C.w_swing : 0.0;
         const TJ Lp = lpl[0] * planar[0] + lpl[1] * planar[1] + lpl[2] * planar[2] + ld * margin + lh * F.h + ln * Nn +
                       lfr * fric + sws * swing;
@@ -551,23 +571,89 @@ __global__ void __launch_bounds__(128) kino_contact_kernel(const KinoConst* __re
       cost += w * r * r;
     }
     __syncwarp();
-    for (int row = 0; row < LS_ROWS; ++row) {
-      const int n = ls_n[row];
-      const double w = ls_w[row];
-      const int* var = ls_var + row * LS_MAXV;
-      const double* cf = ls_coef + row * LS_MAXV;
-      if (lane < n) gbuf[var[lane]] += 2.0 * w * ls_r[row] * cf[lane];
-      if (want_hess) {
-        const int npairs = n * (n + 1) / 2;
-        for (int t = lane; t < npairs; t += 32) {
-          int a = 0, tt = t;
-          while (tt >= n - a) {
-            tt -= n - a;
-            ++a;
-          }
-          const int c = a + tt;
-          hadd(var[a], var[c], 2.0 * sg * w * cf[a] * cf[c]);
+    // Rows are grouped in phases whose rows touch disjoint variables, so a phase is one parallel
+    // read-modify-write and the order of the additions into every entry is fixed (deterministic):
+    //   A   centroid rows 0..2 (one per component)            8 variables each
+    //   B/C yaw rows of side 0 / side 1 (one per foot)        4 variables each
+    //   D_i force-ratio rows of point i (one per foot, comp.) 4 variables each, i = 0..3
+    // (ncu, previous version: the 31 rows processed one after the other, each waiting for its own
+    // hc_index load, were 20 % of this kernel's stall samples.)
+    auto ls_row = [](int phase, int grp) {  // phase 0: A, 1: B, 2: C, 3 + i: D_i
+      if (phase == 0) return grp;
+      if (phase < 3) return 3 + 2 * grp + (phase - 1);
+      return 7 + (grp / 3) * 12 + (phase - 3) * 3 + grp % 3;
+    };
+    if (want_grad) {
+#pragma unroll 1
+      for (int phase = 0; phase < 7; ++phase) {
+        const int nv = phase == 0 ? 8 : 4;
+        const int ngrp = phase == 0 ? 3 : (phase < 3 ? 2 : 6);
+        const int grp = lane / nv, j = lane % nv;
+        if (grp < ngrp) {
+          const int row = ls_row(phase, grp);
+          gbuf[ls_var[row * LS_MAXV + j]] += 2.0 * ls_w[row] * ls_r[row] * ls_coef[row * LS_MAXV + j];
         }
+        __syncwarp();
+      }
+    }
+    if (want_hess) {
+      // pair (a, c), a <= c, number q of an n-variable row, row-major upper triangle
+      auto pair_of = [](int q, int n, int& a, int& c) {
+        a = 0;
+        while (q >= n - a) {
+          q -= n - a;
+          ++a;
+        }
+        c = a + q;
+      };
+      // every lane prepares its (at most 8) items, loads their local entries together, then adds by phase
+      int it_idx[8];
+      double it_val[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        it_idx[u] = -1;
+        it_val[u] = 0.0;
+        int row = -1, q = 0, n = 4;
+        if (u < 4) {  // A: 3 rows x 36 pairs
+          const int t = lane + 32 * u;
+          if (t < 108) {
+            row = t / 36;
+            q = t % 36;
+            n = 8;
+          }
+        } else if (u < 6) {  // B (u = 4), C (u = 5): 2 rows x 10 pairs
+          if (lane < 20) {
+            row = ls_row(u - 3, lane / 10);
+            q = lane % 10;
+          }
+        } else {  // D: 6 (foot, component) groups x 10 pairs, the 4 rows of a group summed here
+          const int t = lane + 32 * (u - 6);
+          if (t < 60) {
+            row = ls_row(3, t / 10);
+            q = t % 10;
+          }
+        }
+        if (row >= 0) {
+          int a, c;
+          pair_of(q, n, a, c);
+          const int* var = ls_var + row * LS_MAXV;
+          it_idx[u] = var[a] * NCV + var[c];
+          double v = 0.0;
+          const int reps = u < 6 ? 1 : 4;
+          for (int i = 0; i < reps; ++i) {  // D: rows of points i = 0..3 are 3 rows apart
+            const double* cf = ls_coef + (row + 3 * i) * LS_MAXV;
+            v += 2.0 * sg * ls_w[row + 3 * i] * cf[a] * cf[c];
+          }
+          it_val[u] = v;
+        }
+      }
+      int it_e[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) it_e[u] = it_idx[u] >= 0 ? (int)C.hc_index[it_idx[u]] : -1;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        if (it_e[u] >= 0) hbuf[it_e[u]] += it_val[u];
+        if (u >= 3 && u < 6) __syncwarp();  // phase boundaries: A | B | C | D
       }
       __syncwarp();
     }
@@ -675,42 +761,56 @@ __global__ void __launch_bounds__(128) kino_contact_kernel(const KinoConst* __re
   // ------------------------------------------------------------------ Hessian of the Lagrangian, contact block
   if (want_hess) {
     if (lane < 8) {
-      const int fb_ = lane * HB_KF_PT_COUNT;
       const int o = 15 * lane;
-      const double l0 = lamrow(fb_ + HB_KF_PT_PLANAR, k, 0), l1 = lamrow(fb_ + HB_KF_PT_PLANAR, k, 1);
-      const double ld = lamrow(fb_ + HB_KF_PT_DCC, k, 0), lf = lamrow(fb_ + HB_KF_PT_FRICTION, k, 0);
+      // The contributions of this point are listed first, their local entries loaded together, and only
+      // then accumulated: a hadd() per term serialises "index load -> shared read-modify-write" (the
+      // compiler cannot move the next index load above the previous shared store).
+      constexpr int NT = (TERRAIN == 0 ? 11 : 0) + 6 + 12;
+      int ti[NT];
+      double tv[NT];
+      int n = 0;
+      auto term = [&](int vi, int vj, double v) {
+        ti[n] = vi * NCV + vj;
+        tv[n] = v;
+        ++n;
+      };
+      const double kk1 = k1 ? 1.0 : 0.0;  // cost terms and the friction row exist from knot 1 on
       if constexpr (TERRAIN == 0) {
-        hadd(o + Z_P + 2, o + Z_P + 2, -(l0 * pu.x + l1 * pu.y) * ddtau + (k1 ? sg * C.w_swing : 0.0));
-        hadd(o + Z_P + 2, o + Z_U, -l0 * dtau);
-        hadd(o + Z_P + 2, o + Z_U + 1, -l1 * dtau);
-        hadd(o + Z_P + 2, o + Z_F + 2, -ld * kbs);
-        hadd(o + Z_V + 2, o + Z_F + 2, -ld);
-        hadd(o + Z_FD + 2, o + Z_P + 2, -ld);
-        if (k1) {
-          hadd(o + Z_V, o + Z_V, sg * C.w_swing);
-          hadd(o + Z_V + 1, o + Z_V + 1, sg * C.w_swing);
-          hadd(o + Z_F, o + Z_F, -2.0 * lf);
-          hadd(o + Z_F + 1, o + Z_F + 1, -2.0 * lf);
-          hadd(o + Z_F + 2, o + Z_F + 2, 2.0 * mu * mu * lf);
-        }
+        const double l0 = lam_pl[0], l1 = lam_pl[1], ld = lam_dcc, lf = kk1 * lam_fr;
+        term(o + Z_P + 2, o + Z_P + 2, -(l0 * pu.x + l1 * pu.y) * ddtau + kk1 * sg * C.w_swing);
+        term(o + Z_P + 2, o + Z_U, -l0 * dtau);
+        term(o + Z_P + 2, o + Z_U + 1, -l1 * dtau);
+        term(o + Z_P + 2, o + Z_F + 2, -ld * kbs);
+        term(o + Z_V + 2, o + Z_F + 2, -ld);
+        term(o + Z_FD + 2, o + Z_P + 2, -ld);
+        term(o + Z_V, o + Z_V, kk1 * sg * C.w_swing);
+        term(o + Z_V + 1, o + Z_V + 1, kk1 * sg * C.w_swing);
+        term(o + Z_F, o + Z_F, -2.0 * lf);
+        term(o + Z_F + 1, o + Z_F + 1, -2.0 * lf);
+        term(o + Z_F + 2, o + Z_F + 2, 2.0 * mu * mu * lf);
       }
-      if (k1) {
-        for (int c = 0; c < 3; ++c) {
-          hadd(o + Z_U + c, o + Z_U + c, 2.0 * sg * C.w_u);
-          hadd(o + Z_FD + c, o + Z_FD + c, 2.0 * sg * C.w_fd);
-        }
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        term(o + Z_U + c, o + Z_U + c, kk1 * 2.0 * sg * C.w_u);
+        term(o + Z_FD + c, o + Z_FD + c, kk1 * 2.0 * sg * C.w_fd);
       }
       // centroidal momentum dynamics: -(dt/2) (lam_k + lam_{k+1})_ang . ((p - x) x f)
-      double La[3];
-      for (int c = 0; c < 3; ++c) La[c] = lamrow(HB_KF_H_DYN, k, 3 + c) + lamrow(HB_KF_H_DYN, k + 1, 3 + c);
+#pragma unroll
       for (int a = 0; a < 3; ++a)
+#pragma unroll
         for (int bb = 0; bb < 3; ++bb) {
           if (a == bb) continue;
           const int c = 3 - a - bb;
           const double v = -hdt * eps3(a, bb) * La[c];
-          hadd(o + Z_P + a, o + Z_F + bb, v);
-          hadd(CV_COM + a, o + Z_F + bb, -v);
+          term(o + Z_P + a, o + Z_F + bb, v);
+          term(CV_COM + a, o + Z_F + bb, -v);
         }
+      int te[NT];
+#pragma unroll
+      for (int u = 0; u < NT; ++u) te[u] = C.hc_index[ti[u]];
+#pragma unroll
+      for (int u = 0; u < NT; ++u)
+        if (te[u] >= 0) hbuf[te[u]] += tv[u];
     }
     __syncwarp();
     const int* hmap = C.hc_map + (size_t)k * C.n_hc;
