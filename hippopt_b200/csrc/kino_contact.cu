@@ -95,8 +95,13 @@ __device__ __forceinline__ void linear_state(int j, int& so, int& ro, int& fam_d
 }
 
 // TERRAIN: 0 = PlanarTerrain, 1 = sum of two smooth steps (kino_smooth.cuh)
+// Measured on B200 (planar terrain, full mask): unconstrained 162 registers / 3 CTAs per SM 0.471 ms,
+// 5 CTAs (96 registers) 0.431 ms, 6 CTAs (80 registers, spills) 0.455 ms.
+#ifndef CONTACT_MIN_BLOCKS
+#define CONTACT_MIN_BLOCKS 5
+#endif
 template <int TERRAIN>
-__global__ void __launch_bounds__(128) kino_contact_kernel(const KinoConst* __restrict__ Cp, unsigned mask,
+__global__ void __launch_bounds__(128, TERRAIN == 0 ? CONTACT_MIN_BLOCKS : 1) kino_contact_kernel(const KinoConst* __restrict__ Cp, unsigned mask,
                                                            const double* __restrict__ x, const double* __restrict__ p,
                                                            long p_stride, const double* __restrict__ lam,
                                                            const double* __restrict__ sigma, double* __restrict__ fpart,
@@ -815,10 +820,14 @@ __global__ void __launch_bounds__(128) kino_contact_kernel(const KinoConst* __re
     __syncwarp();
     const int* hmap = C.hc_map + (size_t)k * C.n_hc;
     double* hb_ = hess + b * C.nnz_h;
-#pragma unroll 4
-    for (int e = lane; e < C.n_hc; e += 32) {
-      const int slot = hmap[e];
-      if (slot >= 0) hb_[slot] = hbuf[e];
+    const int n_hc = C.n_hc;
+    for (int eb = lane; eb < n_hc; eb += 256) {  // 8 map loads in flight before the dependent stores
+      int sl[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) sl[u] = (eb + 32 * u) < n_hc ? hmap[eb + 32 * u] : -1;
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        if (sl[u] >= 0) hb_[sl[u]] = hbuf[eb + 32 * u];
     }
   }
 }
