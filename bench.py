@@ -216,6 +216,7 @@ def main():
     fence()
     t1 = time.perf_counter()
     ms_total = e0.elapsed_time(e1)
+    launches_per_step = ev.last_launch_count()  # kernels one hb_eval of the timed region enqueued
     kernel_ms, n_evals = ev.profile_read()
     ev.profile(False)
     clocks = sampler.stop(t0, t1) if rank == 0 else None
@@ -304,6 +305,31 @@ def main():
                            "config 5: walking on stairs (two smooth steps, randomised heights), 512-instance shard, horizon 50"))
         del pev, ev4, ev5
 
+    # ---- row f2: the Newton (KKT) system of the same workload, stage-wise on the GPU
+    kkt_line = None
+    if world == 1 and not args.no_cpu_baseline:
+        from hippopt_b200.kkt import StageKKT
+
+        nk = min(B, 2 * torch.cuda.get_device_properties(dev).multi_processor_count)
+        lbk, ubk = lay.bounds(host[1][:1].cpu().numpy())
+        kkt, eqr, iner = StageKKT.for_evaluator(ev, lbk[0], ubk[0], device=dev)
+        vals = ev.eval(ALL, *(a[:nk].contiguous() for a in sets[0]))
+        gk = torch.Generator().manual_seed(0)
+        sig = (torch.rand((nk, len(iner)), generator=gk, dtype=torch.float64) * 10.0).to(dev)
+        dlt = torch.full((nk,), 1e-2, dtype=torch.float64, device=dev)
+        rxk = torch.randn((nk, lay.n_x), generator=gk, dtype=torch.float64).to(dev)
+        rEk = torch.randn((nk, len(eqr)), generator=gk, dtype=torch.float64).to(dev)
+        for _ in range(2):
+            torch.cuda.synchronize(dev)
+            tk = time.perf_counter()
+            kkt.solve(vals["hess"], vals["jac"], sig, dlt, 1e-9, rxk, rEk)
+            torch.cuda.synchronize(dev)
+            tk = time.perf_counter() - tk
+        kkt_line = {"workload": f"Newton system of config 3 (n_x + m_E = {lay.n_x + len(eqr)}), {nk} instances: block-"
+                                f"tridiagonal sweep over 30 stage blocks of {kkt.nb}^2, batched LU kernels (csrc/lu.cu)",
+                    "ms_per_batched_solve": tk * 1e3, "kkt_solves_per_s": nk / tk}
+        del kkt, vals
+
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
         from oracle.cpu_baseline import OraclePool
@@ -331,7 +357,7 @@ def main():
                 "path": "hb_eval_host (C ABI, host pointers): pinned host x/lam/sigma -> device, kernels, all five "
                         "outputs -> pinned host; 128-instance chunks over 3 internal streams",
                 "checksum_f": checksum},
-        "gpu_launches": ev.last_launch_count() * args.steps,
+        "gpu_launches": launches_per_step * args.steps,
         "kernel_ms_per_step": {k: v / max(n_evals, 1) for k, v in kernel_ms.items()},
         "roofline": {"bound": "hbm", "kernel": "kino_kin_kernel<true>", "achieved": achieved_gbs, "peak": hbm_peak,
                      "unit": "GB/s", "frac": achieved_gbs / hbm_peak, "traffic": traffic, "peak_source": hbm_src,
@@ -340,6 +366,7 @@ def main():
         "roofline_fp64": roofline_fp64,
         "cpu_baseline": cpu_baseline,
         "other_configs": other,
+        "kkt": kkt_line,
     }
     print(json.dumps(line))
     if world > 1:

@@ -93,6 +93,10 @@ def lib() -> ctypes.CDLL:
     L.hb_host_alloc.argtypes = [ctypes.POINTER(vp), ctypes.c_int64]
     L.hb_host_free.restype = ctypes.c_int
     L.hb_host_free.argtypes = [vp]
+    L.hb_lu_factor_batched.restype = ctypes.c_int
+    L.hb_lu_factor_batched.argtypes = [vp, vp, vp, ctypes.c_int64, ctypes.c_int64, vp]
+    L.hb_lu_solve_batched.restype = ctypes.c_int
+    L.hb_lu_solve_batched.argtypes = [vp, vp, vp, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, vp]
     L.hb_last_launch_count.restype = ctypes.c_int
     L.hb_last_launch_count.argtypes = [vp]
     L.hb_last_error.restype = ctypes.c_char_p
@@ -111,6 +115,7 @@ EXPORTED_SYMBOLS = [
     "hb_kino_create", "hb_toy_create", "hb_destroy", "hb_dims", "hb_pattern_jac", "hb_pattern_hess", "hb_eval",
     "hb_last_launch_count", "hb_last_error", "hb_probe_fp64_tflops", "hb_profile_enable", "hb_profile_read",
     "hb_host_set_parameters", "hb_eval_host", "hb_host_last_traffic", "hb_host_alloc", "hb_host_free",
+    "hb_lu_factor_batched", "hb_lu_solve_batched",
 ]
 
 

@@ -561,6 +561,44 @@ extern "C" int hb_host_free(void* ptr) {
   return HB_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// batched LU of the KKT stage blocks (lu.cu)
+extern "C" int hb_lu_factor_batched(double* A, int32_t* piv, int32_t* info, int64_t n, int64_t batch, void* stream) {
+  if (!A || !piv || !info) return fail(HB_ERR_INVALID, "hb_lu_factor_batched: null argument");
+  if (n <= 0 || n > 768 || batch <= 0) return fail(HB_ERR_INVALID, "hb_lu_factor_batched: need 0 < n <= 768, batch > 0");
+  const size_t smem = hb::lu_factor_smem((int)n);
+  static bool attr = false;
+  if (!attr) {
+    CUDA_TRY(cudaFuncSetAttribute(hb::lu_factor_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
+    CUDA_TRY(cudaFuncSetAttribute(hb::lu_factor_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
+    CUDA_TRY(cudaFuncSetAttribute(hb::lu_factor_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
+    attr = true;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n <= hb::LU_THREADS) hb::lu_factor_kernel<1><<<(unsigned)batch, hb::LU_THREADS, smem, st>>>(A, piv, info, (int)n);
+  else if (n <= 2 * hb::LU_THREADS) hb::lu_factor_kernel<2><<<(unsigned)batch, hb::LU_THREADS, smem, st>>>(A, piv, info, (int)n);
+  else hb::lu_factor_kernel<3><<<(unsigned)batch, hb::LU_THREADS, smem, st>>>(A, piv, info, (int)n);
+  CUDA_TRY(cudaGetLastError());
+  return HB_OK;
+}
+
+extern "C" int hb_lu_solve_batched(const double* LU, const int32_t* piv, double* Bm, int64_t n, int64_t nrhs,
+                                   int64_t batch, void* stream) {
+  if (!LU || !piv || !Bm) return fail(HB_ERR_INVALID, "hb_lu_solve_batched: null argument");
+  if (n <= 0 || n > 768 || batch <= 0 || nrhs <= 0)
+    return fail(HB_ERR_INVALID, "hb_lu_solve_batched: need 0 < n <= 768, batch > 0, nrhs > 0");
+  const size_t smem = (size_t)n * (hb::LU_RC + 1) * sizeof(double);
+  static bool attr = false;
+  if (!attr) {
+    CUDA_TRY(cudaFuncSetAttribute(hb::lu_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
+    attr = true;
+  }
+  const dim3 grid((unsigned)batch, (unsigned)((nrhs + hb::LU_RC - 1) / hb::LU_RC));
+  hb::lu_solve_kernel<<<grid, hb::LU_THREADS, smem, (cudaStream_t)stream>>>(LU, piv, Bm, (int)n, (int)nrhs);
+  CUDA_TRY(cudaGetLastError());
+  return HB_OK;
+}
+
 extern "C" int hb_profile_enable(hb_handle h, int enable) {
   if (!h) return fail(HB_ERR_INVALID, "hb_profile_enable: null handle");
   for (cudaEvent_t e : h->prof_ev) cudaEventDestroy(e);

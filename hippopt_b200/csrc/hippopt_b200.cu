@@ -3,4 +3,5 @@
 #include "kino_contact.cu"
 #include "pose_contact.cu"
 #include "toy.cu"
+#include "lu.cu"
 #include "api.cu"

@@ -1,0 +1,408 @@
+// lu.cu -- batched dense LU with partial pivoting for the stage blocks of the KKT sweep.
+//
+// What it replaces: the sparse symmetric indefinite factorisation IPOPT calls once per iteration (MUMPS
+// [ext], reached from /root/reference/src/hippopt/base/opti_solver.py:479).  hippopt_b200/kkt.py orders the
+// Newton system by stage, which leaves one dense (n_k + m_E,k)-square block (337 for the kinodynamic OCP)
+// per knot and instance; this file factors and solves those blocks, one CTA per matrix.
+//
+// The blocks are too large for shared memory (908 KB) and too small for one-matrix-per-launch BLAS
+// (cuSOLVER through torch.linalg: ~1 TFLOP/s on 256 blocks of 337^2 on B200).  Here a CTA
+//   * factors the current 16-column panel with its rows held in REGISTERS (thread t owns rows t, t+256,
+//     t+512): two barriers per column (pivot search, pivot-row exchange);
+//   * applies the panel's 16 interchanges to a trailing column as ONE gather (the composed permutation
+//     touches <= 32 rows), then U12 = L11^{-1} A12 in registers;
+//   * updates the trailing matrix A22 -= L21 U12 from shared memory with 4x4 register tiles, the A22
+//     tile being requested before the products so that its L2 latency overlaps them.
+//
+// Storage: column-major n x n, leading dimension n (a symmetric matrix can be passed as is).
+// Pivoting: rows are interchanged inside the panel and in the trailing columns, NOT in the columns to
+// the left (LINPACK-style across panels, LAPACK-style inside one), and lu_solve applies the interchanges
+// panel by panel in the same order; piv[j] is the row (>= j) exchanged with row j.
+#include <cstdint>
+
+namespace hb {
+
+constexpr int LU_NB = 16;
+// Measured on B200, 148 blocks of 337^2 (one wave): 256 threads + A22 prefetch 0.98 ms; 256 threads without
+// prefetch 1.98 ms; 512 threads (128 registers, spills) 1.22 ms with / 1.58 ms without prefetch.
+#ifndef HB_LU_THREADS
+#define HB_LU_THREADS 256
+#endif
+#ifndef HB_LU_PREFETCH
+#define HB_LU_PREFETCH 1  // request the A22 tile before the products: its L2 latency overlaps them
+#endif
+constexpr int LU_THREADS = HB_LU_THREADS;
+constexpr int LU_MAXN = 768;
+
+__host__ __device__ inline int lu_ldp(int n) { return (n + 3) & ~3; }
+// dynamic shared memory of the factor kernel: panel + U strip (+ slack: the last vector loads of a tile may
+// run past the strip; what they read is never stored)
+__host__ __device__ inline size_t lu_factor_smem(int n) { return ((size_t)2 * LU_NB * lu_ldp(n) + 256) * sizeof(double); }
+
+// RPT = panel rows per thread: n <= RPT * LU_THREADS
+template <int RPT>
+__global__ void __launch_bounds__(LU_THREADS) lu_factor_kernel(double* __restrict__ Aall, int* __restrict__ pivall,
+                                                               int* __restrict__ infoall, int n) {
+  extern __shared__ __align__(16) double lu_sm[];
+  double* A = Aall + (size_t)blockIdx.x * n * n;
+  int* piv = pivall + (size_t)blockIdx.x * n;
+  const int tid = threadIdx.x;
+  constexpr int nt = LU_THREADS;
+  const int ldp = lu_ldp(n);     // shared-memory stride, a multiple of 4 doubles (16-byte vector loads)
+  double* P = lu_sm;             // factored panel, column c at P + c * ldp, local row i = global row j0 + i
+  double* U = P + LU_NB * ldp;   // U strip: row k at U + k * ldp, entry jj = global column j0 + nbw + jj
+  __shared__ double red_v[nt / 32];
+  __shared__ int red_i[nt / 32];
+  __shared__ double rowbuf[2][LU_NB];
+  __shared__ int s_piv[LU_NB];
+  __shared__ int aff_dst[2 * LU_NB], aff_src[2 * LU_NB], aff_n;
+  __shared__ int s_info;
+  if (tid == 0) s_info = 0;
+  for (int j0 = 0; j0 < n; j0 += LU_NB) {
+    const int nbw = min(LU_NB, n - j0);
+    const int m = n - j0;
+    // ---- panel rows into registers: slot s of this thread is local row tid + s * nt
+    double row[RPT][LU_NB];
+#pragma unroll
+    for (int s = 0; s < RPT; ++s) {
+      const int i = tid + s * nt;
+#pragma unroll
+      for (int c = 0; c < LU_NB; ++c) row[s][c] = (i < m && c < nbw) ? A[(size_t)(j0 + c) * n + j0 + i] : 0.0;
+    }
+#pragma unroll
+    for (int c = 0; c < LU_NB; ++c) {
+      if (c < nbw) {  // uniform
+        // pivot search over local rows >= c
+        double bv = -1.0;
+        int bi = c;
+#pragma unroll
+        for (int s = 0; s < RPT; ++s) {
+          const int i = tid + s * nt;
+          const double v = fabs(row[s][c]);
+          if (i >= c && i < m && v > bv) {
+            bv = v;
+            bi = i;
+          }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {  // ties go to the lowest row: independent of the schedule
+          const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+          const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+          if (ov > bv || (ov == bv && oi < bi)) {
+            bv = ov;
+            bi = oi;
+          }
+        }
+        if ((tid & 31) == 0) {
+          red_v[tid >> 5] = bv;
+          red_i[tid >> 5] = bi;
+        }
+        __syncthreads();
+        bv = red_v[0];
+        bi = red_i[0];
+#pragma unroll
+        for (int w = 1; w < nt / 32; ++w)
+          if (red_v[w] > bv || (red_v[w] == bv && red_i[w] < bi)) {
+            bv = red_v[w];
+            bi = red_i[w];
+          }
+        if (tid == 0) {
+          s_piv[c] = bi;
+          piv[j0 + c] = j0 + bi;
+          if (!(bv > 0.0) && s_info == 0) s_info = j0 + c + 1;  // exactly singular (or NaN) pivot column
+        }
+        // exchange rows c and bi through shared memory (their owners publish them)
+#pragma unroll
+        for (int s = 0; s < RPT; ++s) {
+          const int i = tid + s * nt;
+          if (i == c)
+#pragma unroll
+            for (int cc = 0; cc < LU_NB; ++cc) rowbuf[0][cc] = row[s][cc];
+          if (i == bi)
+#pragma unroll
+            for (int cc = 0; cc < LU_NB; ++cc) rowbuf[1][cc] = row[s][cc];
+        }
+        __syncthreads();
+#pragma unroll
+        for (int s = 0; s < RPT; ++s) {
+          const int i = tid + s * nt;
+          if (i == c && bi != c)
+#pragma unroll
+            for (int cc = 0; cc < LU_NB; ++cc) row[s][cc] = rowbuf[1][cc];
+          else if (i == bi && bi != c)
+#pragma unroll
+            for (int cc = 0; cc < LU_NB; ++cc) row[s][cc] = rowbuf[0][cc];
+        }
+        const double pv = rowbuf[1][c];
+        const double inv = pv != 0.0 ? 1.0 / pv : 0.0;
+#pragma unroll
+        for (int s = 0; s < RPT; ++s) {
+          const int i = tid + s * nt;
+          if (i > c && i < m) {
+            const double l = row[s][c] * inv;
+            row[s][c] = l;
+#pragma unroll
+            for (int cc = c + 1; cc < LU_NB; ++cc) row[s][cc] -= l * rowbuf[1][cc];
+          }
+        }
+      }
+    }
+    // ---- panel back to global memory and into shared memory (L11 / L21 for the trailing phases)
+#pragma unroll
+    for (int s = 0; s < RPT; ++s) {
+      const int i = tid + s * nt;
+      if (i < m)
+#pragma unroll
+        for (int c = 0; c < LU_NB; ++c)
+          if (c < nbw) {
+            A[(size_t)(j0 + c) * n + j0 + i] = row[s][c];
+            P[c * ldp + i] = row[s][c];
+          }
+    }
+    const int nrem = n - j0 - nbw;  // trailing columns (and rows below the panel's square)
+    if (nrem <= 0) break;
+    // ---- the panel's interchanges composed into one gather: new[aff_dst[t]] = old[aff_src[t]]
+    if (tid == 0) {
+      int rows[2 * LU_NB], content[2 * LU_NB], cnt = nbw;
+      for (int c = 0; c < nbw; ++c) rows[c] = content[c] = c;
+      for (int c = 0; c < nbw; ++c) {
+        const int r = s_piv[c];  // s_piv writes are ordered by the barriers of the column loop
+        int pos = -1;
+        for (int t = 0; t < cnt; ++t)
+          if (rows[t] == r) pos = t;
+        if (pos < 0) {
+          pos = cnt++;
+          rows[pos] = content[pos] = r;
+        }
+        const int tmp = content[c];
+        content[c] = content[pos];
+        content[pos] = tmp;
+      }
+      for (int t = 0; t < cnt; ++t) {
+        aff_dst[t] = rows[t];
+        aff_src[t] = content[t];
+      }
+      aff_n = cnt;
+    }
+    __syncthreads();
+    // ---- trailing columns: interchanges, then U12 = L11^{-1} A12 (one thread per column)
+    for (int jj = tid; jj < nrem; jj += nt) {
+      double* col = A + (size_t)(j0 + nbw + jj) * n + j0;
+      const int na = aff_n;
+      double vals[2 * LU_NB];
+#pragma unroll
+      for (int t = 0; t < 2 * LU_NB; ++t) vals[t] = t < na ? col[aff_src[t]] : 0.0;
+#pragma unroll
+      for (int t = LU_NB; t < 2 * LU_NB; ++t)
+        if (t < na) col[aff_dst[t]] = vals[t];
+      if (nbw < LU_NB) {  // last, narrow panel: entries nbw..na-1 are pivot rows as well
+#pragma unroll
+        for (int t = 0; t < LU_NB; ++t)
+          if (t >= nbw && t < na) col[aff_dst[t]] = vals[t];
+      }
+      // rows 0..nbw-1 of the strip are vals[0..nbw-1] (aff_dst[t] = t for t < nbw)
+#pragma unroll
+      for (int k = 0; k < LU_NB; ++k)
+#pragma unroll
+        for (int i = k + 1; i < LU_NB; ++i)
+          if (i < nbw) vals[i] -= P[k * ldp + i] * vals[k];
+#pragma unroll
+      for (int k = 0; k < LU_NB; ++k)
+        if (k < nbw) {
+          col[k] = vals[k];
+          U[k * ldp + jj] = vals[k];
+        }
+    }
+    __syncthreads();
+    // ---- trailing update A22 -= L21 U12: CTA tile 128 rows x 32 columns, thread tile 4 x 4 (rows strided
+    // by 32 so that every A22 access is a coalesced 256-byte row segment; contiguous rows per thread were
+    // 20 % slower); per k four shared loads of L21 and two 16-byte broadcast loads of U12 feed 16 FMAs
+    {
+      const int tx = tid & 31, ty = tid >> 5;
+      const double* L21 = P + nbw;  // local row i of L21 = panel row nbw + i
+      for (int jt = 0; jt < nrem; jt += (nt / 32) * 4)
+        for (int it = 0; it < nrem; it += 128) {
+          double acc[4][4];
+#if HB_LU_PREFETCH
+          double a22[4][4];
+#endif
+          int ii[4], jc[4];
+#pragma unroll
+          for (int a = 0; a < 4; ++a) ii[a] = it + tx + 32 * a;  // lane = row: coalesced A22 accesses
+#pragma unroll
+          for (int b = 0; b < 4; ++b) jc[b] = jt + ty * 4 + b;
+#pragma unroll
+          for (int b = 0; b < 4; ++b) {
+            const double* col = A + (size_t)(j0 + nbw + jc[b]) * n + j0 + nbw;
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {
+#if HB_LU_PREFETCH
+              a22[a][b] = (jc[b] < nrem && ii[a] < nrem) ? col[ii[a]] : 0.0;
+#else
+              (void)col;
+#endif
+              acc[a][b] = 0.0;
+            }
+          }
+#pragma unroll 4
+          for (int k = 0; k < nbw; ++k) {
+            // entries past nrem are whatever the strip holds (the slack keeps the loads in bounds); the
+            // products they feed are never stored
+            const double* lp = L21 + k * ldp + it + tx;
+            const double2* up = reinterpret_cast<const double2*>(U + k * ldp + jt + ty * 4);
+            const double2 u01 = up[0], u23 = up[1];
+            const double l[4] = {lp[0], lp[32], lp[64], lp[96]}, uu[4] = {u01.x, u01.y, u23.x, u23.y};
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+              for (int b = 0; b < 4; ++b) acc[a][b] = fma(l[a], uu[b], acc[a][b]);
+          }
+#pragma unroll
+          for (int b = 0; b < 4; ++b)
+            if (jc[b] < nrem) {
+              double* col = A + (size_t)(j0 + nbw + jc[b]) * n + j0 + nbw;
+#pragma unroll
+              for (int a = 0; a < 4; ++a)
+#if HB_LU_PREFETCH
+                if (ii[a] < nrem) col[ii[a]] = a22[a][b] - acc[a][b];
+#else
+                if (ii[a] < nrem) col[ii[a]] -= acc[a][b];
+#endif
+            }
+        }
+    }
+    __syncthreads();
+  }
+  __syncthreads();
+  if (tid == 0) infoall[blockIdx.x] = s_info;
+}
+
+// Solve with the factors: B (n x nrhs, row-major, i.e. right-hand side c of row i at B[i * nrhs + c]) is
+// overwritten by the solution.  grid = (batch, ceil(nrhs / 32)); a CTA owns up to 32 right-hand sides,
+// kept in shared memory for the whole forward and backward substitution.  Rows outside the current
+// panel are updated with 4 x 8 register tiles (lane = row: coalesced reads of the factor).
+constexpr int LU_RC = 32;
+
+__device__ __forceinline__ void lu_rows_update(const double* __restrict__ A, double* b, int n, int ldb, int j0, int nbw,
+                                               int r0, int r1, int tid) {
+  // b[i][:] -= sum_k A[i, j0 + k] * b[j0 + k][:] for rows r0 <= i < r1
+  const int lane = tid & 31, w = tid >> 5;
+  const int cg = (w & 3) * 8;  // 8 right-hand sides per warp
+  for (int ib = r0 + (w >> 2) * 128; ib < r1; ib += LU_THREADS) {  // (warps / 4) row blocks of 128
+    double acc[4][8];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int c = 0; c < 8; ++c) acc[a][c] = 0.0;
+    for (int k = 0; k < nbw; ++k) {
+      double av[4];
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        const int i = ib + lane + 32 * a;
+        av[a] = i < r1 ? A[(size_t)(j0 + k) * n + i] : 0.0;
+      }
+      const double* bk = b + (j0 + k) * ldb + cg;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const double bv = bk[c];
+#pragma unroll
+        for (int a = 0; a < 4; ++a) acc[a][c] = fma(av[a], bv, acc[a][c]);
+      }
+    }
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      const int i = ib + lane + 32 * a;
+      if (i < r1)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) b[i * ldb + cg + c] -= acc[a][c];
+    }
+  }
+}
+
+__global__ void __launch_bounds__(LU_THREADS) lu_solve_kernel(const double* __restrict__ LUall,
+                                                              const int* __restrict__ pivall, double* __restrict__ Ball,
+                                                              int n, int nrhs) {
+  extern __shared__ __align__(16) double lu_sm[];
+  const double* A = LUall + (size_t)blockIdx.x * n * n;
+  const int* piv = pivall + (size_t)blockIdx.x * n;
+  double* Bg = Ball + (size_t)blockIdx.x * n * nrhs;
+  const int c0 = blockIdx.y * LU_RC;
+  const int nc = min(LU_RC, nrhs - c0);
+  const int tid = threadIdx.x;
+  constexpr int nt = LU_THREADS;
+  const int ldb = LU_RC + 1;
+  double* b = lu_sm;  // b[i * ldb + c]; columns >= nc are zero
+  __shared__ double tri[LU_NB][LU_NB + 1];  // diagonal block of the current panel, tri[k][i] = A[j0 + i, j0 + k]
+  __shared__ int s_piv[LU_NB];
+  for (int e = tid; e < n * LU_RC; e += nt) {
+    const int i = e / LU_RC, c = e - i * LU_RC;
+    b[i * ldb + c] = c < nc ? Bg[(size_t)i * nrhs + c0 + c] : 0.0;
+  }
+  // ---- forward: panel by panel -- interchanges of the panel, L11, then the rows below
+  for (int j0 = 0; j0 < n; j0 += LU_NB) {
+    const int nbw = min(LU_NB, n - j0);
+    if (tid < LU_NB * LU_NB) {
+      const int k = tid >> 4, i = tid & 15;
+      tri[k][i] = (k < nbw && i < nbw) ? A[(size_t)(j0 + k) * n + j0 + i] : 0.0;
+      if (tid < nbw) s_piv[tid] = piv[j0 + tid];
+    }
+    __syncthreads();
+    if (tid < LU_RC) {
+      for (int c = 0; c < nbw; ++c) {
+        const int r = s_piv[c];
+        if (r != j0 + c) {
+          const double t = b[(j0 + c) * ldb + tid];
+          b[(j0 + c) * ldb + tid] = b[r * ldb + tid];
+          b[r * ldb + tid] = t;
+        }
+      }
+      double y[LU_NB];
+#pragma unroll
+      for (int k = 0; k < LU_NB; ++k) y[k] = k < nbw ? b[(j0 + k) * ldb + tid] : 0.0;
+#pragma unroll
+      for (int k = 0; k < LU_NB; ++k)
+#pragma unroll
+        for (int i = k + 1; i < LU_NB; ++i) y[i] -= tri[k][i] * y[k];  // entries outside the block are zero
+#pragma unroll
+      for (int k = 0; k < LU_NB; ++k)
+        if (k < nbw) b[(j0 + k) * ldb + tid] = y[k];
+    }
+    __syncthreads();
+    lu_rows_update(A, b, n, ldb, j0, nbw, j0 + nbw, n, tid);
+    __syncthreads();
+  }
+  // ---- backward with U (panels aligned from the end; U is just upper triangular)
+  for (int j1 = n; j1 > 0; j1 -= LU_NB) {
+    const int j0 = max(0, j1 - LU_NB);
+    const int nbw = j1 - j0;
+    if (tid < LU_NB * LU_NB) {
+      const int k = tid >> 4, i = tid & 15;
+      tri[k][i] = (k < nbw && i < nbw) ? A[(size_t)(j0 + k) * n + j0 + i] : 0.0;
+    }
+    __syncthreads();
+    if (tid < LU_RC) {
+      double xv[LU_NB];
+#pragma unroll
+      for (int k = 0; k < LU_NB; ++k) xv[k] = k < nbw ? b[(j0 + k) * ldb + tid] : 0.0;
+#pragma unroll
+      for (int k = LU_NB - 1; k >= 0; --k)
+        if (k < nbw) {
+          xv[k] = xv[k] / tri[k][k];
+#pragma unroll
+          for (int i = 0; i < k; ++i) xv[i] -= tri[k][i] * xv[k];
+        }
+#pragma unroll
+      for (int k = 0; k < LU_NB; ++k)
+        if (k < nbw) b[(j0 + k) * ldb + tid] = xv[k];
+    }
+    __syncthreads();
+    lu_rows_update(A, b, n, ldb, j0, nbw, 0, j0, tid);
+    __syncthreads();
+  }
+  for (int e = tid; e < n * nc; e += nt) {
+    const int i = e / nc, c = e - i * nc;
+    Bg[(size_t)i * nrhs + c0 + c] = b[i * ldb + c];
+  }
+}
+
+}  // namespace hb

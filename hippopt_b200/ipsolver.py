@@ -17,6 +17,7 @@ stage-wise factorisation of row f2.
 from __future__ import annotations
 
 import dataclasses
+import time
 
 import numpy as np
 import torch
@@ -44,11 +45,78 @@ class BatchedOutput:
     evaluations: int = 0                  # batched hb_eval calls made
 
 
+class SparseOps:
+    """Products with jac_g / hess_l straight from the CCS value arrays the kernels write (one pattern shared by
+    all instances).  `index_add_` accumulates with atomics on CUDA: sums are reproducible to rounding only."""
+
+    def __init__(self, n_x, m, jac_sparsity, hess_sparsity, device):
+        colind, row = jac_sparsity
+        self.n, self.m = n_x, m
+        self.jr = torch.as_tensor(np.asarray(row), dtype=torch.long, device=device)
+        self.jc = torch.as_tensor(np.repeat(np.arange(n_x), np.diff(np.asarray(colind))), dtype=torch.long, device=device)
+        hcolind, hrow = hess_sparsity
+        self.hr = torch.as_tensor(np.asarray(hrow), dtype=torch.long, device=device)
+        self.hc = torch.as_tensor(np.repeat(np.arange(n_x), np.diff(np.asarray(hcolind))), dtype=torch.long, device=device)
+        self.hw = torch.where(self.hr == self.hc, 1.0, 2.0).to(torch.float64)  # upper triangle stored once
+
+    def J_mul(self, vals, x):
+        out = torch.zeros((vals.shape[0], self.m), dtype=vals.dtype, device=vals.device)
+        return out.index_add_(1, self.jr, vals * x[:, self.jc])
+
+    def Jt_mul(self, vals, lam):
+        out = torch.zeros((vals.shape[0], self.n), dtype=vals.dtype, device=vals.device)
+        return out.index_add_(1, self.jc, vals * lam[:, self.jr])
+
+    def W_quad(self, hvals, x):
+        return (hvals * x[:, self.hr] * x[:, self.hc] * self.hw).sum(dim=1)
+
+    def dense_jac(self, vals):
+        J = torch.zeros((vals.shape[0], self.m, self.n), dtype=vals.dtype, device=vals.device)
+        J[:, self.jr, self.jc] = vals
+        return J
+
+    def dense_hess(self, vals):
+        H = torch.zeros((vals.shape[0], self.n, self.n), dtype=vals.dtype, device=vals.device)
+        H[:, self.hr, self.hc] = vals
+        H[:, self.hc, self.hr] = vals
+        return H
+
+
+class DenseKKT:
+    """One dense (n_x + m_E)-square solve per instance (torch.linalg): the small NLPs (toy OCP, pose finder)."""
+
+    def __init__(self, ops: SparseOps, iE, iI):
+        self.ops, self.iE, self.iI = ops, iE, iI
+        self.K = None
+
+    def solve(self, hess_vals, jac_vals, sigma_I, delta, delta_c, rhs_x, rhs_E):
+        ops = self.ops
+        B, n, mE = hess_vals.shape[0], ops.n, len(self.iE)
+        J = ops.dense_jac(jac_vals)
+        JE, JI = J[:, self.iE, :], J[:, self.iI, :]
+        K = torch.zeros((B, n + mE, n + mE), dtype=hess_vals.dtype, device=hess_vals.device)
+        K[:, :n, :n] = ops.dense_hess(hess_vals) + torch.einsum("bin,bi,bik->bnk", JI, sigma_I, JI)
+        K[:, :n, :n] += delta[:, None, None] * torch.eye(n, dtype=K.dtype, device=K.device)
+        K[:, :n, n:] = JE.transpose(1, 2)
+        K[:, n:, :n] = JE
+        if mE and delta_c:
+            K[:, n:, n:] = -delta_c * torch.eye(mE, dtype=K.dtype, device=K.device)
+        self.K = K
+        rhs = torch.cat([rhs_x, rhs_E], dim=1)
+        try:
+            sol = torch.linalg.solve(K, rhs)
+        except RuntimeError:
+            sol = torch.full_like(rhs, float("nan"))
+        return sol[:, :n], sol[:, n:]
+
+
 class BatchedInteriorPoint:
     def __init__(self, ev, tol: float = 1e-8, max_iter: int = 300, mu_init: float = 0.1, kappa_eps: float = 10.0,
                  kappa_mu: float = 0.2, theta_mu: float = 1.5, tau_min: float = 0.99, eta: float = 1e-4,
                  max_backtrack: int = 16, delta_min: float = 1e-8, delta_max: float = 1e8, exact_inertia: bool = False,
-                 verbose: bool = False):
+                 verbose: bool = False, kkt: str = "dense", delta_c: float = 1e-11):
+        """kkt: "dense" (one dense factorisation per instance) or "stage" (block-tridiagonal sweep over the knots,
+        hippopt_b200.kkt.StageKKT -- the multiple-shooting OCPs of the kinodynamic planner)."""
         self.ev = ev
         self.exact_inertia = exact_inertia
         self.tol, self.max_iter, self.mu_init = tol, max_iter, mu_init
@@ -56,27 +124,10 @@ class BatchedInteriorPoint:
         self.tau_min, self.eta, self.max_backtrack = tau_min, eta, max_backtrack
         self.delta_min, self.delta_max = delta_min, delta_max
         self.verbose = verbose
-        colind, row = ev.jac_sparsity()
-        self._jr = torch.as_tensor(np.asarray(row), dtype=torch.long)
-        self._jc = torch.as_tensor(np.repeat(np.arange(ev.n_x), np.diff(colind)), dtype=torch.long)
-        hcolind, hrow = ev.hess_sparsity()
-        self._hr = torch.as_tensor(np.asarray(hrow), dtype=torch.long)
-        self._hc = torch.as_tensor(np.repeat(np.arange(ev.n_x), np.diff(hcolind)), dtype=torch.long)
-
-    # ------------------------------------------------------------------ dense assembly
-    def _dense_jac(self, vals):
-        B = vals.shape[0]
-        J = torch.zeros((B, self.ev.m, self.ev.n_x), dtype=vals.dtype, device=vals.device)
-        J[:, self._jr.to(vals.device), self._jc.to(vals.device)] = vals
-        return J
-
-    def _dense_hess(self, vals):
-        B = vals.shape[0]
-        H = torch.zeros((B, self.ev.n_x, self.ev.n_x), dtype=vals.dtype, device=vals.device)
-        r, c = self._hr.to(vals.device), self._hc.to(vals.device)
-        H[:, r, c] = vals
-        H[:, c, r] = vals
-        return H
+        if kkt not in ("dense", "stage"):
+            raise ValueError("kkt must be 'dense' or 'stage'")
+        self.kkt_kind, self.delta_c = kkt, delta_c
+        self.kkt_seconds = 0.0
 
     # ------------------------------------------------------------------ solve
     def solve(self, x0: torch.Tensor, p: torch.Tensor, lbg, ubg) -> BatchedOutput:
@@ -91,6 +142,16 @@ class BatchedInteriorPoint:
             raise ValueError("all instances must share the equality / inequality structure of their bounds")
         iE, iI = torch.nonzero(eq).ravel(), torch.nonzero(ine).ravel()
         mE, mI = len(iE), len(iI)
+        ops = SparseOps(n, m, ev.jac_sparsity(), ev.hess_sparsity(), dev)
+        if self.kkt_kind == "stage":
+            from .kkt import StageKKT
+
+            lay = ev.layout
+            jc_, jr_ = ev.jac_sparsity()
+            hc_, hr_ = ev.hess_sparsity()
+            backend = StageKKT(n, m, lay.N, 189, jc_, jr_, hc_, hr_, iE.cpu().numpy(), iI.cpu().numpy(), device=dev)
+        else:
+            backend = DenseKKT(ops, iE, iI)
         lb, ub = lbg[:, iI], ubg[:, iI]
         hasL, hasU = torch.isfinite(lb), torch.isfinite(ub)
         lbE = lbg[:, iE]
@@ -122,7 +183,10 @@ class BatchedInteriorPoint:
         done = torch.zeros(B, dtype=torch.bool, device=dev)
         iters = torch.zeros(B, dtype=torch.long, device=dev)
         err0 = torch.full((B,), float("inf"), dtype=torch.float64, device=dev)
-        eye = torch.eye(n, dtype=torch.float64, device=dev)
+        def rows_I(v):  # (B, m_I) values on the inequality rows -> (B, m) with zeros elsewhere
+            full = torch.zeros((B, m), dtype=torch.float64, device=dev)
+            full[:, iI] = v
+            return full
 
         def barrier(fv, ss, muv):
             t = torch.where(hasL, torch.log(ss - lbs), torch.zeros_like(ss)) + torch.where(hasU, torch.log(ubs - ss), torch.zeros_like(ss))
@@ -135,12 +199,10 @@ class BatchedInteriorPoint:
             out = evaluate(x, lam)
             n_eval += 1
             fv, grad, g = out["f"], out["grad_f"], out["g"]
-            J = self._dense_jac(out["jac"])
-            W = self._dense_hess(out["hess"])
-            JE, JI = J[:, iE, :], J[:, iI, :]
+            jv, hv = out["jac"], out["hess"]
             cE = g[:, iE] - lbE
             cI = g[:, iI] - s
-            rd = grad + torch.einsum("bmn,bm->bn", J, lam)
+            rd = grad + ops.Jt_mul(jv, lam)
             dL, dU = s - lbs, ubs - s
             compL = torch.where(hasL, dL * zL, torch.zeros_like(s))
             compU = torch.where(hasU, dU * zU, torch.zeros_like(s))
@@ -178,35 +240,31 @@ class BatchedInteriorPoint:
             SigU = torch.where(hasU, zU / dU, torch.zeros_like(s))
             Sig = SigL + SigU
             lamhat = torch.where(hasU, mu[:, None] / dU, torch.zeros_like(s)) - torch.where(hasL, mu[:, None] / dL, torch.zeros_like(s))
-            Hr = W + torch.einsum("bin,bi,bik->bnk", JI, Sig, JI)
-            rhs_x = -(grad + torch.einsum("bin,bi->bn", JI, lamhat + Sig * cI))
+            rhs_x = -(grad + ops.Jt_mul(jv, rows_I(lamhat + Sig * cI)))
             # solve with a per-instance Levenberg shift until the step has positive curvature
             dx = torch.zeros_like(x)
             lamE_new = lamE.clone()
             need = ~done
             for attempt in range(12):
-                K = torch.zeros((B, n + mE, n + mE), dtype=torch.float64, device=dev)
-                K[:, :n, :n] = Hr + delta[:, None, None] * eye
-                K[:, :n, n:] = JE.transpose(1, 2)
-                K[:, n:, :n] = JE
-                if mE and attempt > 0:  # delta_c only once a plain solve has failed (rank-deficient J_E)
-                    K[:, n:, n:] = -1e-11 * torch.eye(mE, dtype=torch.float64, device=dev)
-                rhs = torch.cat([rhs_x, -cE], dim=1)
-                try:
-                    sol = torch.linalg.solve(K, rhs)
-                except RuntimeError:
-                    sol = torch.full_like(rhs, float("nan"))
-                dxt, lamt = sol[:, :n], sol[:, n:]
-                dst = torch.einsum("bin,bn->bi", JI, dxt) + cI
+                # delta_c only once a plain solve has failed (rank-deficient J_E); the stage-wise sweep always
+                # carries it (its pivot blocks are the stage KKT matrices, not the whole one)
+                dc = self.delta_c if (attempt > 0 or self.kkt_kind == "stage") else 0.0
+                if dev.type == "cuda":
+                    torch.cuda.synchronize(dev)
+                t_k = time.perf_counter()
+                dxt, lamt = backend.solve(hv, jv, Sig, delta, dc, rhs_x, -cE)
+                if dev.type == "cuda":
+                    torch.cuda.synchronize(dev)
+                self.kkt_seconds += time.perf_counter() - t_k
+                dst = ops.J_mul(jv, dxt)[:, iI] + cI
                 # inertia test (IPOPT's criterion): the KKT matrix must have exactly n positive and mE negative
                 # eigenvalues, i.e. the reduced Hessian is positive definite on the null space of J_E
-                if self.exact_inertia and attempt < 11:
-                    inertia_ok = (torch.linalg.eigvalsh(K) < 0).sum(dim=1) == mE
+                if self.exact_inertia and attempt < 11 and self.kkt_kind == "dense":
+                    inertia_ok = (torch.linalg.eigvalsh(backend.K) < 0).sum(dim=1) == mE
                 else:  # cheap proxy: positive curvature of the barrier Lagrangian along the step
-                    curv = (torch.einsum("bn,bnk,bk->b", dxt, W, dxt) + delta * (dxt * dxt).sum(1)
-                            + (Sig * dst * dst).sum(1))
+                    curv = ops.W_quad(hv, dxt) + delta * (dxt * dxt).sum(1) + (Sig * dst * dst).sum(1)
                     inertia_ok = curv > 1e-12 * (dxt * dxt).sum(1)
-                ok = torch.isfinite(sol).all(dim=1) & inertia_ok
+                ok = torch.isfinite(dxt).all(dim=1) & torch.isfinite(lamt).all(dim=1) & inertia_ok
                 take = need & ok
                 dx = torch.where(take[:, None], dxt, dx)
                 lamE_new = torch.where(take[:, None], lamt, lamE_new)
@@ -214,7 +272,7 @@ class BatchedInteriorPoint:
                 if not bool(need.any()):
                     break
                 delta = torch.where(need, torch.clamp(torch.maximum(delta * 8.0, torch.full_like(delta, 1e-4)), max=self.delta_max), delta)
-            ds = torch.einsum("bin,bn->bi", JI, dx) + cI
+            ds = ops.J_mul(jv, dx)[:, iI] + cI
             lamI_new = lamhat + Sig * ds
             zL_new = torch.where(hasL, mu[:, None] / dL - SigL * ds, torch.zeros_like(s))
             zU_new = torch.where(hasU, mu[:, None] / dU + SigU * ds, torch.zeros_like(s))

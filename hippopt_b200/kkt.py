@@ -1,0 +1,310 @@
+"""Stage-wise solve of the primal-dual Newton (KKT) system of a multiple-shooting OCP.
+
+The step on the other side of the evaluation path: IPOPT hands `jac_g` / `hess_l` to a sparse symmetric
+indefinite solver (MUMPS [ext]) once per iteration.  For the problems of this repository the matrix
+
+        K = [ W + J_I^T Sigma J_I + delta I      J_E^T   ]        W   block diagonal per knot (hess_l)
+            [ J_E                             -delta_c I ]        J_I rows local to one knot
+                                                                  J_E rows touch knot k, or knots k-1 and k
+                                                                      (integrator defects)
+
+is block tridiagonal once unknowns are ordered by stage, u_k = (dx_k, dlam_E,k): the only coupling between
+stage k-1 and stage k are the defect rows of stage k acting on dx_{k-1}.  The solve is a block LU sweep
+over the stages (Riccati-like), batched over instances: per stage one dense LU of an
+(n_k + m_E,k)-square block and one solve with the ~87 coupling columns -- O(N) blocks instead of one
+(n_x + m_E)-square factorisation.  Dense block algebra is library code (torch.linalg -> cuSOLVER/cuBLAS);
+what this module owns is the structure: the assignment of rows to stages and the gather maps from the CCS
+value arrays the kernels write to the dense stage blocks.
+
+Checked against a dense solve of the same system (tests/test_kkt_cpu.py on random values in the real
+pattern, tests/test_gpu_solver.py on evaluated values).  Periodicity rows (knot 0 with knot N-1) make
+the matrix cyclic and are not supported here.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _capi
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def lu_factor(A: torch.Tensor, symmetric: bool = False):
+    """Batched LU with partial pivoting of A (B, n, n) on the GPU (csrc/lu.cu through the C ABI).
+    Returns (factors, piv, info); `factors` is only meaningful to ``lu_solve``.  symmetric=True skips the
+    transposition to the kernel's column-major storage (and factors A in place)."""
+    if not A.is_cuda or A.dtype != torch.float64 or A.dim() != 3 or A.shape[1] != A.shape[2]:
+        raise ValueError("lu_factor needs a (B, n, n) float64 CUDA tensor")
+    B, n = A.shape[0], A.shape[1]
+    F = A if (symmetric and A.is_contiguous()) else (A.contiguous() if symmetric else A.transpose(1, 2).contiguous())
+    piv = torch.empty((B, n), dtype=torch.int32, device=A.device)
+    info = torch.empty((B,), dtype=torch.int32, device=A.device)
+    st = torch.cuda.current_stream(A.device).cuda_stream
+    _capi.check(_capi.lib().hb_lu_factor_batched(_ptr(F), _ptr(piv), _ptr(info), n, B, ctypes.c_void_p(st)),
+                "hb_lu_factor_batched")
+    return F, piv, info
+
+
+def lu_solve(F: torch.Tensor, piv: torch.Tensor, rhs: torch.Tensor) -> torch.Tensor:
+    """Solve with the factors of ``lu_factor``; rhs (B, n, r) -> solution (B, n, r) (a new tensor)."""
+    if rhs.dim() != 3 or rhs.shape[0] != F.shape[0] or rhs.shape[1] != F.shape[1] or not rhs.is_cuda:
+        raise ValueError("lu_solve needs a (B, n, r) CUDA right-hand side matching the factors")
+    X = rhs.contiguous().clone()
+    st = torch.cuda.current_stream(F.device).cuda_stream
+    _capi.check(_capi.lib().hb_lu_solve_batched(_ptr(F), _ptr(piv), _ptr(X), F.shape[1], X.shape[2], F.shape[0],
+                                                ctypes.c_void_p(st)), "hb_lu_solve_batched")
+    return X
+
+
+class StageKKT:
+    def __init__(self, n_x: int, m: int, horizon: int, knot_size: int, jac_colind, jac_row, hess_colind, hess_row,
+                 eq_rows, ine_rows, device="cpu", linalg: str = "hb"):
+        """eq_rows / ine_rows: sorted global row indices of the equality / inequality constraints (the
+        ordering of the multiplier vectors handed to ``solve``).  Variables beyond horizon*knot_size
+        (initial-state decision variables) join stage 0.
+
+        linalg: "hb" = the batched LU kernels of this library (CUDA tensors only, no fallback);
+        "torch" = torch.linalg (cuSOLVER on the GPU, LAPACK on the CPU): the comparison baseline, and what
+        the CPU-side structural tests use."""
+        if linalg not in ("hb", "torch"):
+            raise ValueError("linalg must be 'hb' or 'torch'")
+        self.linalg = linalg
+        self.n_x, self.m, self.N, self.nz = n_x, m, horizon, knot_size
+        self.device = torch.device(device)
+        N, nz = horizon, knot_size
+        n_extra = n_x - N * nz
+        if n_extra < 0:
+            raise ValueError("n_x is smaller than horizon * knot_size")
+        self.nx = nx = nz + n_extra  # local variable slots of a stage (the extras are padding for k > 0)
+        jac_colind, jac_row = np.asarray(jac_colind), np.asarray(jac_row)
+        hess_colind, hess_row = np.asarray(hess_colind), np.asarray(hess_row)
+        eq_rows, ine_rows = np.asarray(eq_rows, dtype=np.int64), np.asarray(ine_rows, dtype=np.int64)
+        self.mE, self.mI = len(eq_rows), len(ine_rows)
+
+        def stage_of(c):
+            return np.where(c < N * nz, c // nz, 0)
+
+        def local_of(c):
+            return np.where(c < N * nz, c % nz, nz + (c - N * nz))
+
+        jcol = np.repeat(np.arange(n_x), np.diff(jac_colind))
+        jst = stage_of(jcol)
+        hi = np.full(m, -1)
+        lo = np.full(m, N + 1)
+        np.maximum.at(hi, jac_row, jst)
+        np.minimum.at(lo, jac_row, jst)
+        live = hi >= 0  # rows with an empty Jacobian (parameter-only rows) take no part in the Newton system
+        if np.any((hi - lo)[live] > 1):
+            raise NotImplementedError("a constraint row couples non-adjacent knots (periodicity): the KKT matrix is "
+                                      "cyclic, not block tridiagonal")
+        if np.any((hi - lo)[ine_rows][live[ine_rows]] > 0):
+            raise NotImplementedError("an inequality row couples two knots")
+        hcol = np.repeat(np.arange(n_x), np.diff(hess_colind))
+        if np.any(stage_of(hcol) != stage_of(hess_row)):
+            raise NotImplementedError("hess_l couples two knots")
+
+        # ---- rows -> stages
+        is_eq = np.zeros(m, dtype=bool)
+        is_eq[eq_rows] = True
+        pos_E = np.full(m, -1)
+        pos_E[eq_rows] = np.arange(self.mE)
+        pos_I = np.full(m, -1)
+        pos_I[ine_rows] = np.arange(self.mI)
+        self.eq_stage_rows, self.ine_stage_rows, self.cpl_local = [], [], []
+        for k in range(N):
+            e = eq_rows[(hi[eq_rows] == k)]
+            i = ine_rows[(hi[ine_rows] == k)]
+            self.eq_stage_rows.append(e)
+            self.ine_stage_rows.append(i)
+            self.cpl_local.append(np.nonzero(lo[e] < k)[0])  # positions (inside the stage's eq rows) of the defect rows
+        self.dead_eq = pos_E[eq_rows[~live[eq_rows]]]  # multipliers of empty rows: left at zero
+        self.mEk = max(len(e) for e in self.eq_stage_rows)
+        self.mIk = max(max(len(i) for i in self.ine_stage_rows), 1)
+        self.mCk = max(max(len(c) for c in self.cpl_local), 1)
+        self.nb = nb = nx + self.mEk
+        row_stage = hi
+        loc_E = np.full(m, -1)
+        loc_I = np.full(m, -1)
+        for k in range(N):
+            loc_E[self.eq_stage_rows[k]] = np.arange(len(self.eq_stage_rows[k]))
+            loc_I[self.ine_stage_rows[k]] = np.arange(len(self.ine_stage_rows[k]))
+        loc_C = np.full(m, -1)
+        for k in range(N):
+            loc_C[self.eq_stage_rows[k][self.cpl_local[k]]] = np.arange(len(self.cpl_local[k]))
+
+        dev = self.device
+
+        def t(a):
+            return torch.as_tensor(np.ascontiguousarray(a), dtype=torch.long, device=dev)
+
+        # ---- gather maps: for every stage, (value index, flat position in the dense block)
+        self.maps = []
+        hst = stage_of(hcol)
+        hr_l, hc_l = local_of(hess_row), local_of(hcol)
+        jc_l = local_of(jcol)
+        for k in range(N):
+            sel = np.nonzero(hst == k)[0]
+            w_idx, w_pos, w_pos_t = sel, hr_l[sel] * nb + hc_l[sel], hc_l[sel] * nb + hr_l[sel]
+            # equality rows of this stage, columns of this stage -> C (rows nx + loc_E) and its transpose
+            je = np.nonzero(is_eq[jac_row] & (row_stage[jac_row] == k) & (jst == k))[0]
+            c_pos = (nx + loc_E[jac_row[je]]) * nb + jc_l[je]
+            c_pos_t = jc_l[je] * nb + (nx + loc_E[jac_row[je]])
+            # equality rows of this stage, columns of stage k-1 -> A (mCk x nx)
+            ja = np.nonzero(is_eq[jac_row] & (row_stage[jac_row] == k) & (jst == k - 1))[0] if k > 0 else np.zeros(0, int)
+            a_pos = loc_C[jac_row[ja]] * nx + jc_l[ja]
+            # inequality rows -> J_I (mIk x nx)
+            ji = np.nonzero((~is_eq[jac_row]) & (pos_I[jac_row] >= 0) & (row_stage[jac_row] == k))[0]
+            i_pos = loc_I[jac_row[ji]] * nx + jc_l[ji]
+            var = (np.arange(nz) + k * nz) if k > 0 else np.concatenate([np.arange(nz), N * nz + np.arange(n_extra)])
+            self.maps.append({
+                "w_idx": t(w_idx), "w_pos": t(w_pos), "w_pos_t": t(w_pos_t),
+                "c_idx": t(je), "c_pos": t(c_pos), "c_pos_t": t(c_pos_t),
+                "a_idx": t(ja), "a_pos": t(a_pos),
+                "i_idx": t(ji), "i_pos": t(i_pos),
+                "var": t(var), "n_var": len(var),
+                "eq": t(pos_E[self.eq_stage_rows[k]]), "n_eq": len(self.eq_stage_rows[k]),
+                "ine": t(pos_I[self.ine_stage_rows[k]]), "n_ine": len(self.ine_stage_rows[k]),
+                "cpl": t(nx + self.cpl_local[k]), "n_cpl": len(self.cpl_local[k]),
+            })
+
+    @classmethod
+    def for_evaluator(cls, ev, lbg, ubg, device="cpu", linalg: str = "hb"):
+        """Kinodynamic evaluator (KinoEvaluator) + one instance's bounds -> solver and the (eq, ine) row lists."""
+        lbg, ubg = np.asarray(lbg, dtype=np.float64).ravel(), np.asarray(ubg, dtype=np.float64).ravel()
+        eq = np.nonzero(lbg == ubg)[0]
+        ine = np.nonzero((lbg != ubg) & ~(np.isinf(lbg) & np.isinf(ubg)))[0]
+        jc, jr = ev.jac_sparsity()
+        hc, hr = ev.hess_sparsity()
+        lay = ev.layout
+        return cls(ev.n_x, ev.m, lay.N, 189, jc, jr, hc, hr, eq, ine, device=device, linalg=linalg), eq, ine
+
+    # ------------------------------------------------------------------ dense block algebra
+    def _lu_factor(self, D):
+        if self.linalg == "hb":
+            F, piv, _ = lu_factor(D, symmetric=True)
+            return F, piv
+        lu, piv, _ = torch.linalg.lu_factor_ex(D)
+        return lu, piv
+
+    def _lu_solve(self, fac, rhs):
+        if self.linalg == "hb":
+            return lu_solve(fac[0], fac[1], rhs)
+        return torch.linalg.lu_solve(fac[0], fac[1], rhs)
+
+    # ------------------------------------------------------------------ solve
+    def solve(self, hess_vals, jac_vals, sigma_I, delta, delta_c, rhs_x, rhs_E, chunk: int | None = None):
+        """Solve K [dx; dlam_E] = [rhs_x; rhs_E] for every instance.
+
+        hess_vals (B, nnz_h), jac_vals (B, nnz_j): CCS value arrays as written by hb_eval;
+        sigma_I (B, m_I) >= 0: barrier diagonal of the inequality rows; delta (B,): Hessian shift;
+        delta_c: scalar >= 0 on the (2,2) block.  Returns dx (B, n_x), dlam_E (B, m_E).
+        Instances are processed `chunk` at a time: the forward sweep keeps, per stage, the substituted
+        right-hand side and the nb x 87 coupling solve for the back substitution (chunk * N * nb * 88 * 8
+        bytes, 1.8 GB for 256 instances of the 30-knot problem); the factors themselves live for one stage."""
+        B = hess_vals.shape[0]
+        if chunk is None:  # one CTA per stage block: whole waves of the factor kernel (1 CTA per SM)
+            chunk = 2 * torch.cuda.get_device_properties(hess_vals.device).multi_processor_count if hess_vals.is_cuda else 256
+        if B > chunk:
+            parts = [self.solve(hess_vals[i:i + chunk], jac_vals[i:i + chunk], sigma_I[i:i + chunk], delta[i:i + chunk],
+                                delta_c, rhs_x[i:i + chunk], rhs_E[i:i + chunk], chunk) for i in range(0, B, chunk)]
+            return torch.cat([a for a, _ in parts]), torch.cat([b for _, b in parts])
+        dev, dt = hess_vals.device, hess_vals.dtype
+        nx, nb, N = self.nx, self.nb, self.N
+        dx = torch.zeros((B, self.n_x), dtype=dt, device=dev)
+        dl = torch.zeros((B, self.mE), dtype=dt, device=dev)
+        Wv, Zs = [], []
+        w_prev = None
+
+        def coupling(kk):  # defect rows of stage kk with respect to the variables of stage kk - 1
+            mq = self.maps[kk]
+            Ak = torch.zeros((B, self.mCk * nx), dtype=dt, device=dev)
+            Ak[:, mq["a_pos"]] = jac_vals[:, mq["a_idx"]]
+            return Ak.view(B, self.mCk, nx)[:, :mq["n_cpl"], :]
+
+        A = Z = None
+        for k in range(N):
+            mp = self.maps[k]
+            D = torch.zeros((B, nb * nb), dtype=dt, device=dev)
+            D[:, mp["w_pos"]] = hess_vals[:, mp["w_idx"]]
+            D[:, mp["w_pos_t"]] = hess_vals[:, mp["w_idx"]]
+            D[:, mp["c_pos"]] = jac_vals[:, mp["c_idx"]]
+            D[:, mp["c_pos_t"]] = jac_vals[:, mp["c_idx"]]
+            D = D.view(B, nb, nb)
+            nv, ne = mp["n_var"], mp["n_eq"]
+            if mp["n_ine"]:
+                JI = torch.zeros((B, self.mIk * nx), dtype=dt, device=dev)
+                JI[:, mp["i_pos"]] = jac_vals[:, mp["i_idx"]]
+                JI = JI.view(B, self.mIk, nx)
+                sg = torch.zeros((B, self.mIk), dtype=dt, device=dev)
+                sg[:, :mp["n_ine"]] = sigma_I[:, mp["ine"]]
+                D[:, :nx, :nx] += torch.einsum("bin,bi,bik->bnk", JI, sg, JI)
+            idx = torch.arange(nb, device=dev)
+            diag = torch.zeros((B, nb), dtype=dt, device=dev)
+            diag[:, :nv] = delta[:, None]
+            diag[:, nv:nx] = 1.0             # padding variable slots
+            diag[:, nx:nx + ne] = -delta_c
+            diag[:, nx + ne:] = 1.0          # padding multiplier slots
+            D[:, idx, idx] += diag
+            b = torch.zeros((B, nb), dtype=dt, device=dev)
+            b[:, :nv] = rhs_x[:, mp["var"]]
+            b[:, nx:nx + ne] = rhs_E[:, mp["eq"]]
+            Zs.append(Z)
+            if Z is not None:  # Z = S_{k-1}^{-1} [A_k^T; 0] came out of the previous stage's solve
+                cp = mp["cpl"]
+                D[:, cp[:, None], cp[None, :]] -= torch.bmm(A, Z[:, :nx, :])
+                b[:, cp] -= torch.bmm(A, w_prev[:, :nx, None])[:, :, 0]
+            fac = self._lu_factor(D)  # the stage block is symmetric
+            # one solve per stage: the stage's right-hand side and the coupling columns of the next stage
+            if k + 1 < N and self.maps[k + 1]["n_cpl"]:
+                A = coupling(k + 1)
+                rhs = torch.zeros((B, nb, 1 + A.shape[1]), dtype=dt, device=dev)
+                rhs[:, :, 0] = b
+                rhs[:, :nx, 1:] = A.transpose(1, 2)
+                sol = self._lu_solve(fac, rhs)
+                w_prev, Z = sol[:, :, 0], sol[:, :, 1:]
+            else:
+                A = Z = None
+                w_prev = self._lu_solve(fac, b[:, :, None])[:, :, 0]
+            Wv.append(w_prev)
+        u_next = None
+        for k in range(N - 1, -1, -1):
+            mp = self.maps[k]
+            u = Wv[k]
+            if k < N - 1 and Zs[k + 1] is not None:
+                lam_c = u_next[:, self.maps[k + 1]["cpl"]]
+                u = u - torch.bmm(Zs[k + 1], lam_c[:, :, None])[:, :, 0]
+            dx[:, mp["var"]] = u[:, :mp["n_var"]]
+            dl[:, mp["eq"]] = u[:, nx:nx + mp["n_eq"]]
+            u_next = u
+        return dx, dl
+
+    # ------------------------------------------------------------------ reference: the same matrix, dense
+    def dense_matrix(self, hess_vals, jac_vals, sigma_I, delta, delta_c, eq_rows, ine_rows, jac_colind, jac_row,
+                     hess_colind, hess_row):
+        """(B, n_x + m_E, n_x + m_E) dense K for small problems (test oracle of ``solve``)."""
+        B = hess_vals.shape[0]
+        dev, dt = hess_vals.device, hess_vals.dtype
+        n, mE = self.n_x, self.mE
+        jcol = torch.as_tensor(np.repeat(np.arange(n), np.diff(np.asarray(jac_colind))), device=dev)
+        jrow = torch.as_tensor(np.asarray(jac_row), dtype=torch.long, device=dev)
+        hcol = torch.as_tensor(np.repeat(np.arange(n), np.diff(np.asarray(hess_colind))), device=dev)
+        hrow = torch.as_tensor(np.asarray(hess_row), dtype=torch.long, device=dev)
+        J = torch.zeros((B, self.m, n), dtype=dt, device=dev)
+        J[:, jrow, jcol] = jac_vals
+        W = torch.zeros((B, n, n), dtype=dt, device=dev)
+        W[:, hrow, hcol] = hess_vals
+        W[:, hcol, hrow] = hess_vals
+        eq_t = torch.as_tensor(np.asarray(eq_rows), dtype=torch.long, device=dev)
+        in_t = torch.as_tensor(np.asarray(ine_rows), dtype=torch.long, device=dev)
+        JE, JI = J[:, eq_t, :], J[:, in_t, :]
+        K = torch.zeros((B, n + mE, n + mE), dtype=dt, device=dev)
+        K[:, :n, :n] = W + torch.einsum("bin,bi,bik->bnk", JI, sigma_I, JI) + delta[:, None, None] * torch.eye(n, dtype=dt, device=dev)
+        K[:, :n, n:] = JE.transpose(1, 2)
+        K[:, n:, :n] = JE
+        K[:, n:, n:] = -delta_c * torch.eye(mE, dtype=dt, device=dev)
+        return K

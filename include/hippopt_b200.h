@@ -241,6 +241,22 @@ int hb_last_launch_count(hb_handle h);
 int hb_profile_enable(hb_handle h, int enable);
 int hb_profile_read(hb_handle h, double* ms3, int64_t* n_evals);
 
+/* Batched dense LU with partial pivoting for the stage blocks of the KKT sweep (hippopt_b200/kkt.py;
+ * SURVEY.md 8(f) row f2).  replaces: the numeric factorisation / solve IPOPT delegates to its sparse
+ * linear solver once per iteration (MUMPS [ext] below opti_solver.py:479), restricted to the dense
+ * per-knot blocks the stage ordering leaves.
+ *   A     device [batch][n*n]   column-major, leading dimension n; overwritten by L (unit, below) and U
+ *   piv   device [batch][n]     piv[j] = row (>= j) interchanged with row j.  Interchanges are applied to
+ *                               the panel and the trailing columns only (16-column panels); the factors are
+ *                               meant for hb_lu_solve_batched, not for LAPACK's getrs
+ *   info  device [batch]        0, or 1 + index of the first exactly-zero / NaN pivot column
+ *   Bm    device [batch][n*nrhs] row-major right-hand sides (entry (i, c) at i*nrhs + c), overwritten by X
+ * n <= 768 (panel and right-hand sides live in shared memory).  One CTA per matrix (and per 32
+ * right-hand sides). */
+int hb_lu_factor_batched(double* A, int32_t* piv, int32_t* info, int64_t n, int64_t batch, void* stream);
+int hb_lu_solve_batched(const double* LU, const int32_t* piv, double* Bm, int64_t n, int64_t nrhs, int64_t batch,
+                        void* stream);
+
 const char* hb_last_error(void);
 
 /* fp64 FMA throughput probe (TFLOP/s) used as roofline denominator when none is published */

@@ -1,0 +1,77 @@
+"""Stage-wise KKT solve against a dense solve of the same matrix, on the CPU:
+random values in the REAL sparsity patterns of the kinodynamic OCP (layout compiler), so the row -> stage
+assignment, the gather maps and the block recursion are all exercised without a GPU."""
+import numpy as np
+import pytest
+import torch
+
+from hippopt_b200.kino_layout import KinoLayout, KinoSettings
+from hippopt_b200.kkt import StageKKT
+from hippopt_b200.workloads import kino_parameters
+
+
+def _setup(model, N, final):
+    lay = KinoLayout(model, KinoSettings(horizon=N, final_state_constraint=final))
+    p = kino_parameters(lay, model, 1, np.random.default_rng(0))
+    lb, ub = lay.bounds(p)
+    eq = np.nonzero(lb[0] == ub[0])[0]
+    ine = np.nonzero(lb[0] != ub[0])[0]
+    kkt = StageKKT(lay.n_x, lay.m, N, 189, lay.jac_colind, lay.jac_row, lay.hess_colind, lay.hess_row, eq, ine,
+                   linalg="torch")  # LAPACK block algebra: this test is about the structure, on the CPU
+    return lay, kkt, eq, ine
+
+
+@pytest.mark.parametrize("N,final", [(2, False), (4, False), (3, True)])
+def test_stage_solve_matches_dense(model, N, final):
+    lay, kkt, eq, ine = _setup(model, N, final)
+    B = 3
+    g = torch.Generator().manual_seed(N)
+    hv = torch.randn((B, lay.nnz_h), generator=g, dtype=torch.float64)
+    jv = torch.randn((B, lay.nnz_j), generator=g, dtype=torch.float64)
+    sig = torch.rand((B, len(ine)), generator=g, dtype=torch.float64) * 3.0
+    delta = torch.tensor([40.0, 55.0, 70.0], dtype=torch.float64)  # random W is indefinite: shift it well positive
+    delta_c = 1e-6
+    rx = torch.randn((B, lay.n_x), generator=g, dtype=torch.float64)
+    rE = torch.randn((B, len(eq)), generator=g, dtype=torch.float64)
+    rE[:, kkt.dead_eq] = 0.0  # rows with an empty Jacobian are outside the Newton system
+    dx, dl = kkt.solve(hv, jv, sig, delta, delta_c, rx, rE)
+    K = kkt.dense_matrix(hv, jv, sig, delta, delta_c, eq, ine, lay.jac_colind, lay.jac_row, lay.hess_colind, lay.hess_row)
+    ref = torch.linalg.solve(K, torch.cat([rx, rE], dim=1))
+    u = torch.cat([dx, dl], dim=1)
+    scale = ref.abs().amax(dim=1, keepdim=True)
+    assert ((u - ref).abs() / scale).max().item() < 1e-9
+    res = torch.einsum("bij,bj->bi", K, u) - torch.cat([rx, rE], dim=1)
+    assert res.abs().max().item() < 1e-8 * max(1.0, float(scale.max()))
+    if final:
+        assert len(kkt.dead_eq) == 24  # parameter-only descriptor rows of the final-state constraint
+        assert dl[:, kkt.dead_eq].abs().max().item() == 0.0
+
+
+def test_stage_structure(model):
+    lay, kkt, eq, ine = _setup(model, 5, False)
+    assert [len(e) for e in kkt.eq_stage_rows] == [114, 142, 142, 142, 142]
+    assert [len(i) for i in kkt.ine_stage_rows] == [82, 132, 132, 132, 132]
+    assert [len(c) for c in kkt.cpl_local] == [0, 87, 87, 87, 87]  # 81 linear defects + 6 momentum rows
+    assert kkt.nb == 195 + 142
+
+
+def test_default_block_algebra_has_no_cpu_fallback(model):
+    """linalg="hb" (the default) is the CUDA kernels of this library: CPU tensors are refused, not rerouted."""
+    lay = KinoLayout(model, KinoSettings(horizon=2))
+    p = kino_parameters(lay, model, 1, np.random.default_rng(0))
+    lb, ub = lay.bounds(p)
+    eq, ine = np.nonzero(lb[0] == ub[0])[0], np.nonzero(lb[0] != ub[0])[0]
+    kkt = StageKKT(lay.n_x, lay.m, 2, 189, lay.jac_colind, lay.jac_row, lay.hess_colind, lay.hess_row, eq, ine)
+    z = lambda *s: torch.zeros(s, dtype=torch.float64)
+    with pytest.raises(ValueError, match="CUDA"):
+        kkt.solve(z(1, lay.nnz_h), z(1, lay.nnz_j), z(1, len(ine)), z(1), 1e-8, z(1, lay.n_x), z(1, len(eq)))
+
+
+def test_periodicity_is_rejected(model):
+    lay = KinoLayout(model, KinoSettings(horizon=3, periodicity_constraint=True))
+    p = kino_parameters(lay, model, 1, np.random.default_rng(0))
+    lb, ub = lay.bounds(p)
+    eq = np.nonzero(lb[0] == ub[0])[0]
+    ine = np.nonzero(lb[0] != ub[0])[0]
+    with pytest.raises(NotImplementedError):
+        StageKKT(lay.n_x, lay.m, 3, 189, lay.jac_colind, lay.jac_row, lay.hess_colind, lay.hess_row, eq, ine)
