@@ -270,7 +270,14 @@ def main():
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get("kinematics_dram_bytes_per_launch")
+        prof = json.load(open(tpath))
+        traffic = prof.get("kinematics_dram_bytes_per_launch")
+        if roofline_fp64 is not None:
+            # the honest utilisation figure: what ncu measured on the same kernel (committed capture)
+            roofline_fp64["pipe_fp64_active_pct_ncu"] = prof.get("kinematics_fp64_pipe_active_pct")
+            roofline_fp64["note"] += ("; frac can exceed 1: the kernel's closed-form tangents / composite moments "
+                                      "execute fewer fp64 operations than the oracle's tapes count -- "
+                                      "pipe_fp64_active_pct_ncu is the measured utilisation of the fp64 pipe")
 
     # ---- the other BASELINE configs (device-resident, 10 timed steps each; parity cases, not the headline)
     other = None
