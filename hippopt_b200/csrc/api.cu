@@ -250,6 +250,29 @@ extern "C" int hb_kino_create(const int32_t* icfg, const double* dcfg, const int
     T.max_depth = C.max_depth;
     T.n_slots = C.n_slots;
     T.max_sib = C.max_sib;
+    T.N = C.N;
+    T.n_x = C.n_x;
+    T.m = C.m;
+    T.nnz_j = C.nnz_j;
+    T.nnz_h = C.nnz_h;
+    T.n_jk = C.n_jk;
+    T.x_stride = C.x_stride;
+    T.cost_k0 = C.cost_k0;
+    T.joint_cost_kind = C.joint_cost_kind;
+    T.zmap_identity = 1;
+    for (int i = 0; i < 189; ++i) T.zmap_identity = T.zmap_identity && C.zmap[i] == i;
+    T.po_desc0 = C.po_desc0;
+    T.po_mass = C.po_mass;
+    T.po_fq = C.po_fq;
+    T.po_bq = C.po_bq;
+    T.po_bqv = C.po_bqv;
+    T.po_jr = C.po_jr;
+    T.ref_stride = C.ref_stride;
+    T.w_frame = C.w_frame;
+    T.w_bq = C.w_bq;
+    T.w_bqv = C.w_bqv;
+    T.w_joint = C.w_joint;
+    T.total_mass = C.total_mass;
   }
   const size_t N = C.N;
   cudaError_t e = cudaSuccess;

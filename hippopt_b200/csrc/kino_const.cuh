@@ -64,6 +64,11 @@ struct KinTopo {
   int n_steps;
   int fam[HB_KF_COUNT][4];
   int nb, foot_body[2], chest_body, max_depth, n_slots, max_sib;
+  // scalars of the kinematics kernel (offsets into x / p / g and weights): read from the constant bank, so
+  // that the first global load of a warp is its data, not the address of its data
+  int N, n_x, m, nnz_j, nnz_h, n_jk, x_stride, cost_k0, joint_cost_kind, zmap_identity;
+  int po_desc0, po_mass, po_fq, po_bq, po_bqv, po_jr, ref_stride;
+  double w_frame, w_bq, w_bqv, w_joint, total_mass;
 };
 
 // global g index of local row r of family `fam` at knot k, or -1 when the row does not exist

@@ -47,7 +47,7 @@ enum { HSTAGE = 27 * 57 };  // per-warp staging of the Hessian columns (and, bef
 #endif
 
 struct KinSmem {
-  int bodies, arms, fdu, fdal, fdar, G, z, gbuf, slot, stage, total;
+  int bodies, arms, fdu, fdal, fdar, G, z, gbuf, lamk, slot, stage, total;
 };
 __host__ __device__ inline KinSmem kin_smem_layout(int nb, int n_slots, bool with_hess) {
   KinSmem s;
@@ -68,6 +68,8 @@ __host__ __device__ inline KinSmem kin_smem_layout(int nb, int n_slots, bool wit
   o += NZ + 1;
   s.gbuf = o;
   o += 58;
+  s.lamk = o;  // multipliers of the 32 kinematic rows of the knot (Hessian variant)
+  o += with_hess ? 32 : 0;
   s.slot = o;
   o += n_slots * 32 * 12;  // fp64 sweep: adjoints; Hessian sweep: their tangents (primal totals are per body)
   s.stage = o;
@@ -598,7 +600,7 @@ __global__ void __launch_bounds__(128, WITH_HESS ? KIN_H_MIN_BLOCKS : 3) kino_ki
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const long wid = (long)blockIdx.x * (blockDim.x >> 5) + warp;
-  const int N = C.N;
+  const int N = T.N;
   if (wid >= batch * N) return;
   const long b = wid / N;
   const int k = (int)(wid % N);
@@ -607,14 +609,65 @@ __global__ void __launch_bounds__(128, WITH_HESS ? KIN_H_MIN_BLOCKS : 3) kino_ki
   double* sb = sm + L.bodies;
   double* zs = sm + L.z;
   double* gbuf = sm + L.gbuf;
-  const double* xb = x + b * C.n_x + (long)k * C.x_stride;
+  double* lamk = sm + L.lamk;
+  const double* xb = x + b * T.n_x + (long)k * T.x_stride;
   const double* pb_ = p + b * p_stride;
   const int nb = T.nb;
-  const bool k1 = k >= C.cost_k0;  // knots on which the "apply_to_first_elements=False" expressions exist
+  const bool k1 = k >= T.cost_k0;  // knots on which the "apply_to_first_elements=False" expressions exist
 
-  for (int i = lane; i < NZ; i += 32) {
-    const int zi = C.zmap[i];
-    zs[i] = zi >= 0 ? xb[zi] : 0.0;
+  // ---- every global input of this warp is requested here, addresses from the constant bank: the DRAM
+  // latencies of x, the parameter slices, the multipliers and the joint frames overlap each other and
+  // the forward kinematics instead of being exposed one by one at their points of use
+  if (T.zmap_identity) {
+    for (int i = lane; i < NZ; i += 32) zs[i] = xb[i];
+  } else {
+    for (int i = lane; i < NZ; i += 32) {
+      const int zi = C.zmap[i];
+      zs[i] = zi >= 0 ? xb[zi] : 0.0;
+    }
+  }
+  const double* rfq = pb_ + T.po_fq + T.ref_stride * k;
+  const double* rbq = pb_ + T.po_bq + T.ref_stride * k;
+  const double* rbqv = pb_ + T.po_bqv + T.ref_stride * k;
+  const double* rjr = pb_ + T.po_jr + T.ref_stride * k;
+  const D3 pre_desc = lane < 8 ? ld3(pb_ + T.po_desc0 + 24 * k + 3 * lane) : v3<double>(0.0, 0.0, 0.0);
+  double pre_fq[4] = {0.0, 0.0, 0.0, 1.0};
+  if (lane == 8) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) pre_fq[i] = rfq[i];
+  }
+  const double pre_bq[4] = {rbq[0], rbq[1], rbq[2], rbq[3]};
+  const double pre_bqv = lane < 4 ? rbqv[lane] : 0.0;
+  const double pre_jr = lane < HB_N_JOINTS ? rjr[lane] : 0.0;
+  const double mass_p = pb_[T.po_mass];
+  const bool with_l = WITH_HESS && (mask & HB_EVAL_HESS_L);
+  double sg = 0.0;
+  if (with_l) {
+    // multipliers of the 32 kinematic rows of this knot, one per lane, parked in shared memory
+    int row;
+    if (lane < 24) row = grow(C, (lane / 3) * HB_KF_PT_COUNT + HB_KF_PT_FK, k, lane % 3);
+    else if (lane < 27) row = grow(T, HB_KF_COM_KIN, k, lane - 24);
+    else if (lane < 30) row = grow(T, HB_KF_MOM_KIN, k, lane - 27);
+    else row = grow(T, lane == 30 ? HB_KF_FEET_DIST : HB_KF_UNIT_QUAT, k, 0);
+    lamk[lane] = row >= 0 ? lam[b * T.m + row] : 0.0;
+    sg = sigma[b];
+  }
+  // joint frame constants of this lane's body
+  const bool is_link = lane > 0 && lane < nb;
+  const int my_depth = is_link ? C.body[lane].depth : -1;
+  const int my_parent = is_link ? C.body[lane].parent : 0;
+  double bE[9], bEA[9], bEA2[9];
+  D3 b_r = v3<double>(0.0, 0.0, 0.0), b_axis = b_r;
+  if (is_link) {
+    const BodyC& bc = C.body[lane];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) {
+      bE[i] = bc.E[i];
+      bEA[i] = bc.EA[i];
+      bEA2[i] = bc.EA2[i];
+    }
+    b_r = ld3(bc.r);
+    b_axis = ld3(bc.axis);
   }
   for (int i = lane; i < 58; i += 32) gbuf[i] = 0.0;
   __syncwarp();
@@ -645,19 +698,23 @@ __global__ void __launch_bounds__(128, WITH_HESS ? KIN_H_MIN_BLOCKS : 3) kino_ki
   }
   __syncwarp();
   // ------------------------------------------------------------------ forward kinematics by depth
-  const int my_depth = (lane < nb && lane > 0) ? C.body[lane].depth : -1;
+  // the joint rotations do not depend on the parents: computed by all link lanes at once
+  double Rl[9];
+  double my_sd = 0.0;
+  if (is_link) {
+    const double s = zs[Z_S + lane - 1];
+    my_sd = zs[Z_SD + lane - 1];
+    double sn, cs;
+    sincos(s, &sn, &cs);
+    const double oc = 1.0 - cs;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) Rl[i] = bE[i] + sn * bEA[i] + oc * bEA2[i];
+  }
   for (int d = 1; d <= T.max_depth; ++d) {
     if (my_depth == d) {
-      const BodyC& bc = C.body[lane];
-      const double* bp = sb + bc.parent * SB_STRIDE;
+      const double* bp = sb + my_parent * SB_STRIDE;
       double* bl = sb + lane * SB_STRIDE;
-      const double s = zs[Z_S + lane - 1], sd = zs[Z_SD + lane - 1];
-      double sn, cs;
-      sincos(s, &sn, &cs);
-      const double oc = 1.0 - cs;
-      double Rl[9];
-#pragma unroll
-      for (int i = 0; i < 9; ++i) Rl[i] = bc.E[i] + sn * bc.EA[i] + oc * bc.EA2[i];
+      const double sd = my_sd;
       const double* Rp = bp + SB_R;
       double R[9];
 #pragma unroll
@@ -667,8 +724,8 @@ __global__ void __launch_bounds__(128, WITH_HESS ? KIN_H_MIN_BLOCKS : 3) kino_ki
 #pragma unroll
       for (int i = 0; i < 9; ++i) bl[SB_R + i] = R[i];
       const D3 op = ld3(bp + SB_O), wp = ld3(bp + SB_W), vp = ld3(bp + SB_V);
-      const D3 rho = matvec(Rp, ld3(bc.r));
-      const D3 ax = matvec(R, ld3(bc.axis));
+      const D3 rho = matvec(Rp, b_r);
+      const D3 ax = matvec(R, b_axis);
       st3(bl + SB_O, op + rho);
       st3(bl + SB_AX, ax);
       st3(bl + SB_W, wp + scale(sd, ax));
@@ -709,29 +766,24 @@ __global__ void __launch_bounds__(128, WITH_HESS ? KIN_H_MIN_BLOCKS : 3) kino_ki
     st3(bl + SB_L, Lw);
     hl = cross(mc, cd) + Lw;
   }
-  const double M = C.total_mass;
+  const double M = T.total_mass;
   const D3 Pm = v3<double>(warp_sum(mc.x), warp_sum(mc.y), warp_sum(mc.z));
   const D3 Pd = v3<double>(warp_sum(mcd.x), warp_sum(mcd.y), warp_sum(mcd.z));
   D3 hang = v3<double>(warp_sum(hl.x), warp_sum(hl.y), warp_sum(hl.z));
   hang = hang - scale(1.0 / M, cross(Pm, Pd));
   const D3 xc = scale(1.0 / M, Pm), xcd = scale(1.0 / M, Pd);
   // ------------------------------------------------------------------ frames
-  const int po_desc = C.po_desc0 + 24 * k;
   if (lane < 8) {
     const int f = lane >> 2;
     const double* Rf = C.foot_R[f];
-    const D3 r = ld3(pb_ + po_desc + 3 * lane);
+    const D3 r = pre_desc;
     const D3 bf = matvec(Rf, r) + ld3(C.foot_t[f]);
     const D3 a = matvec(sb + T.foot_body[f] * SB_STRIDE + SB_R, bf);
     st3(sm + L.arms + 3 * lane, a);
   }
-  const double* rfq = pb_ + C.po_fq + C.ref_stride * k;
-  const double* rbq = pb_ + C.po_bq + C.ref_stride * k;
-  const double* rbqv = pb_ + C.po_bqv + C.ref_stride * k;
-  const double* rjr = pb_ + C.po_jr + C.ref_stride * k;
   if (lane == 8) {
     // G = R_chest_body * (R_c * R(qd)^T), qd = desired frame quaternion (not normalised, kinematics.py:447)
-    const double vx = rfq[0], vy = rfq[1], vz = rfq[2], w = rfq[3];
+    const double vx = pre_fq[0], vy = pre_fq[1], vz = pre_fq[2], w = pre_fq[3];
     double Rd[9];
     Rd[0] = 1.0 - 2.0 * (vy * vy + vz * vz);
     Rd[1] = 2.0 * (vx * vy - w * vz);
@@ -770,11 +822,10 @@ __global__ void __launch_bounds__(128, WITH_HESS ? KIN_H_MIN_BLOCKS : 3) kino_ki
   const D3 oL = ld3(sb + T.foot_body[0] * SB_STRIDE + SB_O), oR = ld3(sb + T.foot_body[1] * SB_STRIDE + SB_O);
   const D3 fdDelta = (oL + fdal) - (oR + fdar);
   const double feet_y = dot(fdu, fdDelta);
-  const double mass_p = pb_[C.po_mass];
 
   // ------------------------------------------------------------------ values: g rows, costs, grad_f (simple terms)
   const bool want_g = (mask & HB_EVAL_G) != 0;
-  double* gb = g + b * C.m;
+  double* gb = g + b * T.m;
   if (want_g) {
     if (lane < 8 && k1) {
       const int f = lane >> 2;
@@ -810,7 +861,7 @@ __global__ void __launch_bounds__(128, WITH_HESS ? KIN_H_MIN_BLOCKS : 3) kino_ki
   // base-quaternion error e = qd^-1 (x) q - (0,0,0,1) = A q - e4 (quaternion.py:64-70); columns of A
   double Aq[4][4];
   {
-    const double dx = -rbq[0], dy = -rbq[1], dz = -rbq[2], dw = rbq[3];
+    const double dx = -pre_bq[0], dy = -pre_bq[1], dz = -pre_bq[2], dw = pre_bq[3];
     // (dw, dv) (x) (bw, bv): v = dw bv + bw dv + dv x bv ; w = dw bw - dv.bv ; column a: b = e_a
     // b = e_x
     Aq[0][0] = dw; Aq[1][0] = dz; Aq[2][0] = -dy; Aq[3][0] = -dx;
@@ -826,11 +877,11 @@ __global__ void __launch_bounds__(128, WITH_HESS ? KIN_H_MIN_BLOCKS : 3) kino_ki
     double cost = 0.0;
     // quaternion-velocity cost (all knots) and, for k >= 1, base quaternion / joint / frame costs
     if (lane < 4) {
-      const double e = qdv[lane] - rbqv[lane];
-      cost += C.w_bqv * e * e;
-      gbuf[3 + lane] += 2.0 * C.w_bqv * e;
+      const double e = qdv[lane] - pre_bqv;
+      cost += T.w_bqv * e * e;
+      gbuf[3 + lane] += 2.0 * T.w_bqv * e;
       if (k1) {
-        cost += C.w_bq * eq[lane] * eq[lane];
+        cost += T.w_bq * eq[lane] * eq[lane];
         double gq = 0.0;
 #pragma unroll
         for (int a = 0; a < 4; ++a) {
@@ -839,24 +890,24 @@ __global__ void __launch_bounds__(128, WITH_HESS ? KIN_H_MIN_BLOCKS : 3) kino_ki
           for (int i = 0; i < 4; ++i) t += Aq[i][a] * eq[i];
           if (a == lane) gq = t;
         }
-        gbuf[7 + lane] += 2.0 * C.w_bq * gq;
+        gbuf[7 + lane] += 2.0 * T.w_bq * gq;
       }
     }
     if (lane < HB_N_JOINTS && k1) {
-      const double sd = zs[Z_SD + lane], e = zs[Z_S + lane] - rjr[lane];
-      if (C.joint_cost_kind == 0) {
+      const double sd = zs[Z_SD + lane], e = zs[Z_S + lane] - pre_jr;
+      if (T.joint_cost_kind == 0) {
         // kinodynamic planner.py:506-520: sumsqr of the broadcast n x n matrix
         const double t = sd + C.wj[lane] * e;
-        cost += C.w_joint * ((HB_N_JOINTS - 1) * sd * sd + t * t);
-        gbuf[11 + lane] += C.w_joint * (2.0 * (HB_N_JOINTS - 1) * sd + 2.0 * t);
-        gbuf[34 + lane] += C.w_joint * 2.0 * C.wj[lane] * t;
+        cost += T.w_joint * ((HB_N_JOINTS - 1) * sd * sd + t * t);
+        gbuf[11 + lane] += T.w_joint * (2.0 * (HB_N_JOINTS - 1) * sd + 2.0 * t);
+        gbuf[34 + lane] += T.w_joint * 2.0 * C.wj[lane] * t;
       } else {
         // pose finder planner.py:584-588: e^T diag(w) e
-        cost += C.w_joint * (e * C.wj[lane]) * e;
-        gbuf[34 + lane] += C.w_joint * 2.0 * C.wj[lane] * e;
+        cost += T.w_joint * (e * C.wj[lane]) * e;
+        gbuf[34 + lane] += T.w_joint * 2.0 * C.wj[lane] * e;
       }
     }
-    if (lane == 31 && k1) cost += C.w_frame * frame_cost;
+    if (lane == 31 && k1) cost += T.w_frame * frame_cost;
     cost = warp_sum(cost);
     if (lane == 0 && (mask & HB_EVAL_F)) fpart[(b * N + k) * 2 + 1] = cost;
   }
@@ -900,12 +951,12 @@ __global__ void __launch_bounds__(128, WITH_HESS ? KIN_H_MIN_BLOCKS : 3) kino_ki
     }
     JacEmit em;
     em.C = Cp;
-    em.map = C.jk_map + (size_t)k * C.n_jk;
-    em.jac = jac + b * C.nnz_j;
+    em.map = C.jk_map + (size_t)k * T.n_jk;
+    em.jac = jac + b * T.nnz_j;
     em.gbuf = gbuf;
     em.lane = lane;
     em.k = k;
-    em.gscale = k1 ? 2.0 * C.w_frame * (phi - 3.0) : 0.0;
+    em.gscale = k1 ? 2.0 * T.w_frame * (phi - 3.0) : 0.0;
     em.write = want_jac;
     em.stage = (WITH_HESS ? HB_KIN_STAGE : HB_KIN_STAGE_F) ? sm + L.stage : nullptr;
     em.init_bases();
@@ -946,7 +997,7 @@ __global__ void __launch_bounds__(128, WITH_HESS ? KIN_H_MIN_BLOCKS : 3) kino_ki
     if (em.stage && want_jac) {
       // scatter the staged rows: coalesced map reads, no load->store dependency inside the sweep
       const double* st = sm + L.stage;
-      const int n = C.n_jk;
+      const int n = T.n_jk;
       for (int eb = lane; eb < n; eb += 256) {  // 8 map loads in flight before the dependent stores
         int sl[8];
 #pragma unroll
@@ -959,7 +1010,7 @@ __global__ void __launch_bounds__(128, WITH_HESS ? KIN_H_MIN_BLOCKS : 3) kino_ki
     }
     if (want_grad) {
       // gbuf order vb3 qd4 q4 sd23 s23 -> x offsets
-      double* gf = grad_f + b * C.n_x + (long)k * C.x_stride;
+      double* gf = grad_f + b * T.n_x + (long)k * T.x_stride;
       for (int i = lane; i < 57; i += 32) {
         int off;
         if (i < 3) off = Z_VB + i;
@@ -976,8 +1027,6 @@ __global__ void __launch_bounds__(128, WITH_HESS ? KIN_H_MIN_BLOCKS : 3) kino_ki
   if (!(mask & HB_EVAL_HESS_L)) return;
   // ------------------------------------------------------------------ adjoint sweep, dual: Hessian columns
   {
-    const double sg = sigma[b];
-    const double* lb = lam + b * C.m;
     const int dirj = lane < 27 ? lane : -1;
     Dir dir;
     dir.mask = 0u;
@@ -1094,12 +1143,9 @@ __global__ void __launch_bounds__(128, WITH_HESS ? KIN_H_MIN_BLOCKS : 3) kino_ki
     Seeds<Dual> S;
     S.footF[0] = S.footF[1] = S.footN[0] = S.footN[1] = vzero<Dual>();
     {
-      const int r0 = grow(T, HB_KF_COM_KIN, k, 0);
-      const D3 lc = r0 >= 0 ? v3<double>(lb[r0], lb[r0 + 1], lb[r0 + 2]) : v3<double>(0.0, 0.0, 0.0);
-      S.wc = scale(-1.0 / M, lc);
-      const int r1 = grow(T, HB_KF_MOM_KIN, k, 0);
-      const D3 lh = r1 >= 0 ? v3<double>(lb[r1], lb[r1 + 1], lb[r1 + 2]) : v3<double>(0.0, 0.0, 0.0);
-      S.hb = scale(-1.0 / mass_p, lh);
+      // multipliers from lamk (loaded at the top of the kernel; rows that do not exist hold 0)
+      S.wc = scale(-1.0 / M, ld3(lamk + 24));
+      S.hb = scale(-1.0 / mass_p, ld3(lamk + 27));
       // stage I^w hbar (same for every lane of the dual sweep)
       if (lane < nb) st3(sb + lane * SB_STRIDE + SB_IH, symmul(sb + lane * SB_STRIDE + SB_I, S.hb));
       __syncwarp();
@@ -1107,9 +1153,7 @@ __global__ void __launch_bounds__(128, WITH_HESS ? KIN_H_MIN_BLOCKS : 3) kino_ki
 #pragma unroll
     for (int pt = 0; pt < 8; ++pt) {
       const int f = pt >> 2;
-      const int r0 = grow(T, pt * HB_KF_PT_COUNT + HB_KF_PT_FK, k, 0);
-      if (r0 < 0) continue;
-      const D3 frc = v3<double>(-lb[r0], -lb[r0 + 1], -lb[r0 + 2]);
+      const D3 frc = v3<double>(-lamk[3 * pt], -lamk[3 * pt + 1], -lamk[3 * pt + 2]);
       const D3 a = ld3(sm + L.arms + 3 * pt);
       const double in = f == 0 ? inL : inR;
       const V3<Dual> aD = lift<Dual>(a, scale(in, cross(dir.alpha, a)));
@@ -1117,8 +1161,7 @@ __global__ void __launch_bounds__(128, WITH_HESS ? KIN_H_MIN_BLOCKS : 3) kino_ki
       S.footN[f] = S.footN[f] + cross(aD, frc);
     }
     {
-      const int r0 = grow(T, HB_KF_FEET_DIST, k, 0);
-      const double kd = r0 >= 0 ? lb[r0] : 0.0;
+      const double kd = lamk[30];
       const St<Dual> sL = load_state(sb, T.foot_body[0], dir, Dual());
       const St<Dual> sR = load_state(sb, T.foot_body[1], dir, Dual());
       const V3<Dual> uD = lift<Dual>(fdu, scale(inR, cross(dir.alpha, fdu)));
@@ -1146,7 +1189,7 @@ __global__ void __launch_bounds__(128, WITH_HESS ? KIN_H_MIN_BLOCKS : 3) kino_ki
       }
       const double tphi = tG[0] + tG[4] + tG[8];
       tphi_lane = tphi;
-      const double cw = k1 ? 2.0 * sg * C.w_frame : 0.0;
+      const double cw = k1 ? 2.0 * sg * T.w_frame : 0.0;
       const Dual kappa = mkdual(cw * (phi - 3.0), cw * tphi);
       const V3<Dual> mGD = lift<Dual>(mG, v3<double>(tG[5] - tG[7], tG[6] - tG[2], tG[1] - tG[3]));
       S.chestN = scale(kappa, mGD);
@@ -1193,12 +1236,12 @@ __global__ void __launch_bounds__(128, WITH_HESS ? KIN_H_MIN_BLOCKS : 3) kino_ki
       }
       // frame-orientation cost: d/dz w (phi - 3)^2 = 2 w (phi - 3) dphi/dz
       if (want_grad && lane < 27 && k1)
-        gbuf[lane < 4 ? 7 + lane : 34 + lane - 4] += 2.0 * C.w_frame * (phi - 3.0) * tphi_lane;
+        gbuf[lane < 4 ? 7 + lane : 34 + lane - 4] += 2.0 * T.w_frame * (phi - 3.0) * tphi_lane;
       __syncwarp();
       if (want_jac) {
-        const int* jmap = C.jk_map + (size_t)k * C.n_jk;
-        double* jb = jac + b * C.nnz_j;
-        const int n = C.n_jk;
+        const int* jmap = C.jk_map + (size_t)k * T.n_jk;
+        double* jb = jac + b * T.nnz_j;
+        const int n = T.n_jk;
         for (int eb = lane; eb < n; eb += 256) {  // 8 map loads in flight before the dependent stores
           int sl[8];
 #pragma unroll
@@ -1210,7 +1253,7 @@ __global__ void __launch_bounds__(128, WITH_HESS ? KIN_H_MIN_BLOCKS : 3) kino_ki
       }
       if (want_grad) {
         // gbuf order vb3 qd4 q4 sd23 s23 -> x offsets
-        double* gf = grad_f + b * C.n_x + (long)k * C.x_stride;
+        double* gf = grad_f + b * T.n_x + (long)k * T.x_stride;
         for (int i = lane; i < 57; i += 32) {
           int off;
           if (i < 3) off = Z_VB + i;
@@ -1227,14 +1270,14 @@ __global__ void __launch_bounds__(128, WITH_HESS ? KIN_H_MIN_BLOCKS : 3) kino_ki
 #endif
     HessEmit em;
     em.map = C.hk_map + (size_t)k * (27 * 57);
-    em.hess = hess + b * C.nnz_h;
+    em.hess = hess + b * T.nnz_h;
     em.stage = HB_KIN_STAGE ? sm + L.stage : nullptr;
     em.dirj = dirj;
     em.add_sd = em.add_s = 0.0;
     if (lane >= 4 && lane < 27 && k1) {
       const double wjl = C.wj[lane - 4];
-      em.add_sd = C.joint_cost_kind == 0 ? sg * C.w_joint * 2.0 * wjl : 0.0;
-      em.add_s = C.joint_cost_kind == 0 ? sg * C.w_joint * 2.0 * wjl * wjl : sg * C.w_joint * 2.0 * wjl;
+      em.add_sd = T.joint_cost_kind == 0 ? sg * T.w_joint * 2.0 * wjl : 0.0;
+      em.add_s = T.joint_cost_kind == 0 ? sg * T.w_joint * 2.0 * wjl * wjl : sg * T.w_joint * 2.0 * wjl;
     }
     V3<Dual> n0, w0, v0;
 #ifdef HB_DUAL_SWEEP
@@ -1268,8 +1311,7 @@ __global__ void __launch_bounds__(128, WITH_HESS ? KIN_H_MIN_BLOCKS : 3) kino_ki
       em.put(0, v0.x.d);
       em.put(1, v0.y.d);
       em.put(2, v0.z.d);
-      const int ru = grow(T, HB_KF_UNIT_QUAT, k, 0);
-      const double lu = ru >= 0 ? lb[ru] : 0.0;
+      const double lu = lamk[31];
       // dual quaternion maps, rebuilt from shared memory after the sweep (see above)
       Dual qD[4];
       double qdv2[4];
@@ -1282,12 +1324,12 @@ __global__ void __launch_bounds__(128, WITH_HESS ? KIN_H_MIN_BLOCKS : 3) kino_ki
       quat_maps<Dual>(qD, qdv2, gq, uq, wq);
       // Hessian of w_bq |qd^-1 (x) q - 1|^2 is 2 w_bq A^T A = 2 w_bq |qd|^2 I (left-multiplication matrix)
       const double nqd = rbq[0] * rbq[0] + rbq[1] * rbq[1] + rbq[2] * rbq[2] +
-                         rbq[3] * rbq[3];
+                         rbq[3] * rbq[3];  // re-read (L1/L2 hit by now) rather than kept live across the sweep
 #pragma unroll
       for (int a = 0; a < 4; ++a) {
         const Dual dq = dot(n0, gq[a]) + dot(w0, uq[a]);
         const Dual dqd = dot(w0, wq[a]);
-        const double extra = (a == lane && k1) ? 2.0 * sg * C.w_bq * nqd + 2.0 * lu : 0.0;
+        const double extra = (a == lane && k1) ? 2.0 * sg * T.w_bq * nqd + 2.0 * lu : 0.0;
         em.put(3 + a, dqd.d);
         em.put(30 + a, dq.d + extra);
       }
@@ -1309,7 +1351,7 @@ __global__ void __launch_bounds__(128, WITH_HESS ? KIN_H_MIN_BLOCKS : 3) kino_ki
     if (lane < 27) {
       const int slot2 = C.hk2_map[(size_t)k * 27 + lane];
       if (slot2 >= 0)
-        em.hess[slot2] = lane < 4 ? 2.0 * sg * C.w_bqv : sg * C.w_joint * 2.0 * HB_N_JOINTS;
+        em.hess[slot2] = lane < 4 ? 2.0 * sg * T.w_bqv : sg * T.w_joint * 2.0 * HB_N_JOINTS;
     }
   }
 }
