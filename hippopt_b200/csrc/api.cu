@@ -273,6 +273,29 @@ extern "C" int hb_kino_create(const int32_t* icfg, const double* dcfg, const int
     T.w_bqv = C.w_bqv;
     T.w_joint = C.w_joint;
     T.total_mass = C.total_mass;
+    T.n_jc = C.n_jc;
+    T.n_hc = C.n_hc;
+    T.has_final = C.has_final;
+    T.has_per = C.has_per;
+    T.h_init = C.h_init;
+    T.po_dt = C.po_dt;
+    T.po_gravity = C.po_gravity;
+    T.po_kt = C.po_kt;
+    T.po_kbs = C.po_kbs;
+    T.po_eps = C.po_eps;
+    T.po_mu = C.po_mu;
+    T.po_refs0 = C.po_refs0;
+    T.po_terrain = C.po_terrain;
+    for (int i = 0; i < 3; ++i) {
+      T.yaw[i] = C.yaw[i];
+      T.w_comvel[i] = C.w_comvel[i];
+    }
+    T.w_swing = C.w_swing;
+    T.w_u = C.w_u;
+    T.w_fd = C.w_fd;
+    T.w_centroid = C.w_centroid;
+    T.w_ratio = C.w_ratio;
+    T.w_yaw = C.w_yaw;
   }
   const size_t N = C.N;
   cudaError_t e = cudaSuccess;
@@ -288,6 +311,9 @@ extern "C" int hb_kino_create(const int32_t* icfg, const double* dcfg, const int
   C.hc_map = h->d_hc;
   C.hk_map = h->d_hk;
   C.hk2_map = h->d_hk2;
+  h->topo.jc_map = h->d_jc;
+  h->topo.hc_index = h->d_hci;
+  h->topo.hc_map = h->d_hc;
   if (e == cudaSuccess) e = upload(&h->dev, &C, 1);
   if (e != cudaSuccess) {
     hb_destroy(h);
@@ -428,13 +454,13 @@ extern "C" int hb_eval(hb_handle h, uint32_t mask, const double* x, const double
                                                                        d_fpart, grad_f, g, jac_vals, hess_vals,
                                                                        (long)batch);
     } else if (C.terrain == 0)
-      hb::kino_contact_kernel<0><<<grid, 32 * warps_per_block, smem, st>>>(h->dev, mask, x, p, (long)p_stride, lam_g,
-                                                                          sigma, d_fpart, grad_f, g, jac_vals, hess_vals,
-                                                                          (long)batch);
+      hb::kino_contact_kernel<0><<<grid, 32 * warps_per_block, smem, st>>>(h->topo, h->dev, mask, x, p, (long)p_stride,
+                                                                          lam_g, sigma, d_fpart, grad_f, g, jac_vals,
+                                                                          hess_vals, (long)batch);
     else
-      hb::kino_contact_kernel<1><<<grid, 32 * warps_per_block, smem, st>>>(h->dev, mask, x, p, (long)p_stride, lam_g,
-                                                                          sigma, d_fpart, grad_f, g, jac_vals, hess_vals,
-                                                                          (long)batch);
+      hb::kino_contact_kernel<1><<<grid, 32 * warps_per_block, smem, st>>>(h->topo, h->dev, mask, x, p, (long)p_stride,
+                                                                          lam_g, sigma, d_fpart, grad_f, g, jac_vals,
+                                                                          hess_vals, (long)batch);
     CUDA_TRY(cudaGetLastError());
     h->launches++;
   }

@@ -69,6 +69,14 @@ struct KinTopo {
   int N, n_x, m, nnz_j, nnz_h, n_jk, x_stride, cost_k0, joint_cost_kind, zmap_identity;
   int po_desc0, po_mass, po_fq, po_bq, po_bqv, po_jr, ref_stride;
   double w_frame, w_bq, w_bqv, w_joint, total_mass;
+  // ... and of the contact kernel
+  int n_jc, n_hc, has_final, has_per, h_init;
+  int po_dt, po_gravity, po_kt, po_kbs, po_eps, po_mu, po_refs0, po_terrain;
+  int yaw[3];
+  double w_swing, w_u, w_fd, w_centroid, w_comvel[3], w_ratio, w_yaw;
+  const int* jc_map;
+  const short* hc_index;
+  const int* hc_map;
 };
 
 // global g index of local row r of family `fam` at knot k, or -1 when the row does not exist

@@ -101,7 +101,8 @@ __device__ __forceinline__ void linear_state(int j, int& so, int& ro, int& fam_d
 #define CONTACT_MIN_BLOCKS 5
 #endif
 template <int TERRAIN>
-__global__ void __launch_bounds__(128, TERRAIN == 0 ? CONTACT_MIN_BLOCKS : 1) kino_contact_kernel(const KinoConst* __restrict__ Cp, unsigned mask,
+__global__ void __launch_bounds__(128, TERRAIN == 0 ? CONTACT_MIN_BLOCKS : 1) kino_contact_kernel(const __grid_constant__ KinTopo T,
+                                                           const KinoConst* __restrict__ Cp, unsigned mask,
                                                            const double* __restrict__ x, const double* __restrict__ p,
                                                            long p_stride, const double* __restrict__ lam,
                                                            const double* __restrict__ sigma, double* __restrict__ fpart,
@@ -109,7 +110,10 @@ __global__ void __launch_bounds__(128, TERRAIN == 0 ? CONTACT_MIN_BLOCKS : 1) ki
                                                            double* __restrict__ jac, double* __restrict__ hess,
                                                            long batch) {
   extern __shared__ double smem[];
-  const KinoConst& C = *Cp;
+  // C: warp-uniform scalars and tables from the constant bank (kernel parameter); G: the global copy, for
+  // row families indexed by the lane (one coalesced 16-byte load instead of a serialised constant fetch)
+  const KinTopo& C = T;
+  const KinoConst& G = *Cp;
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const long wid = (long)blockIdx.x * (blockDim.x >> 5) + warp;
@@ -163,7 +167,7 @@ __global__ void __launch_bounds__(128, TERRAIN == 0 ? CONTACT_MIN_BLOCKS : 1) ki
     if (e >= 0) hbuf[e] += v;
   };
   auto lamrow = [&](int fam, int kk, int r) -> double {
-    const int row = grow(C, fam, kk, r);
+    const int row = grow(G, fam, kk, r);
     return row >= 0 ? lb[row] : 0.0;
   };
   // Multipliers of this lane's contact-point rows and of the momentum dynamics, requested here so that
@@ -171,8 +175,8 @@ __global__ void __launch_bounds__(128, TERRAIN == 0 ? CONTACT_MIN_BLOCKS : 1) ki
   double lam_pl[3] = {0.0, 0.0, 0.0}, lam_dcc = 0.0, lam_h = 0.0, lam_n = 0.0, lam_fr = 0.0, La[3] = {0.0, 0.0, 0.0};
   if (want_hess && lane < 8) {
     const int fb_ = lane * HB_KF_PT_COUNT;
-    const int rp = grow(C, fb_ + HB_KF_PT_PLANAR, k, 0), rd = grow(C, fb_ + HB_KF_PT_DCC, k, 0);
-    const int rf = grow(C, fb_ + HB_KF_PT_FRICTION, k, 0);
+    const int rp = grow(G, fb_ +HB_KF_PT_PLANAR, k, 0), rd = grow(G, fb_ +HB_KF_PT_DCC, k, 0);
+    const int rf = grow(G, fb_ +HB_KF_PT_FRICTION, k, 0);
     const int ra = grow(C, HB_KF_H_DYN, k, 3), rb = grow(C, HB_KF_H_DYN, k + 1, 3);
     if (rp >= 0) {
       lam_pl[0] = lb[rp];
@@ -205,10 +209,10 @@ __global__ void __launch_bounds__(128, TERRAIN == 0 ? CONTACT_MIN_BLOCKS : 1) ki
       int so, ro, fd, fi, comp;
       linear_state(j, so, ro, fd, fi, comp);
       if (k1) {
-        const int r = grow(C, fd, k, comp);
+        const int r = grow(G, fd, k, comp);
         if (r >= 0) gb[r] = zs[so] - (zp[so] + hdt * (zp[ro] + zs[ro]));
       } else {
-        const int r = grow(C, fi, 0, comp);
+        const int r = grow(G, fi, 0, comp);
         if (r >= 0) gb[r] = zs[so];
       }
     }
@@ -285,19 +289,19 @@ __global__ void __launch_bounds__(128, TERRAIN == 0 ? CONTACT_MIN_BLOCKS : 1) ki
       const TJ DnTf0 = pf.x * F.Dn[0][0] + pf.y * F.Dn[1][0] + pf.z * F.Dn[2][0];
       const TJ DnTf1 = pf.x * F.Dn[0][1] + pf.y * F.Dn[1][1] + pf.z * F.Dn[2][1];
       if (want_g) {
-        int r = grow(C, fb_ + HB_KF_PT_PLANAR, k, 0);
+        int r = grow(G, fb_ +HB_KF_PT_PLANAR, k, 0);
         if (r >= 0) {
           gb[r] = planar[0].c[0];
           gb[r + 1] = planar[1].c[0];
           gb[r + 2] = planar[2].c[0];
         }
-        r = grow(C, fb_ + HB_KF_PT_DCC, k, 0);
+        r = grow(G, fb_ +HB_KF_PT_DCC, k, 0);
         if (r >= 0) gb[r] = margin.c[0];
-        r = grow(C, fb_ + HB_KF_PT_HEIGHT, k, 0);
+        r = grow(G, fb_ +HB_KF_PT_HEIGHT, k, 0);
         if (r >= 0) gb[r] = F.h.c[0];
-        r = grow(C, fb_ + HB_KF_PT_NORMAL, k, 0);
+        r = grow(G, fb_ +HB_KF_PT_NORMAL, k, 0);
         if (r >= 0) gb[r] = Nn.c[0];
-        r = grow(C, fb_ + HB_KF_PT_FRICTION, k, 0);
+        r = grow(G, fb_ +HB_KF_PT_FRICTION, k, 0);
         if (r >= 0) gb[r] = fric.c[0];
       }
       if (k1) {
@@ -412,28 +416,28 @@ __global__ void __launch_bounds__(128, TERRAIN == 0 ? CONTACT_MIN_BLOCKS : 1) ki
     if (want_g) {
       int r;
       if constexpr (TERRAIN == 0) {
-        r = grow(C, fb_ + HB_KF_PT_PLANAR, k, 0);
+        r = grow(G, fb_ +HB_KF_PT_PLANAR, k, 0);
         if (r >= 0) {
           gb[r] = pv.x - tau * pu.x;
           gb[r + 1] = pv.y - tau * pu.y;
           gb[r + 2] = pv.z - pu.z;
         }
-        r = grow(C, fb_ + HB_KF_PT_DCC, k, 0);
+        r = grow(G, fb_ +HB_KF_PT_DCC, k, 0);
         if (r >= 0) gb[r] = eps - kbs * (ppos.z * pf.z) - (pv.z * pf.z + ppos.z * pfd.z);
-        r = grow(C, fb_ + HB_KF_PT_HEIGHT, k, 0);
+        r = grow(G, fb_ +HB_KF_PT_HEIGHT, k, 0);
         if (r >= 0) gb[r] = ppos.z;
-        r = grow(C, fb_ + HB_KF_PT_NORMAL, k, 0);
+        r = grow(G, fb_ +HB_KF_PT_NORMAL, k, 0);
         if (r >= 0) gb[r] = pf.z;
-        r = grow(C, fb_ + HB_KF_PT_FRICTION, k, 0);
+        r = grow(G, fb_ +HB_KF_PT_FRICTION, k, 0);
         if (r >= 0) gb[r] = -(pf.x * pf.x) - pf.y * pf.y + mu * mu * (pf.z * pf.z);
       }
-      r = grow(C, fb_ + HB_KF_PT_U_BOUNDS, k, 0);
+      r = grow(G, fb_ +HB_KF_PT_U_BOUNDS, k, 0);
       if (r >= 0) {
         gb[r] = pu.x;
         gb[r + 1] = pu.y;
         gb[r + 2] = pu.z;
       }
-      r = grow(C, fb_ + HB_KF_PT_FD_BOUNDS, k, 0);
+      r = grow(G, fb_ +HB_KF_PT_FD_BOUNDS, k, 0);
       if (r >= 0) {
         gb[r] = pfd.x * mass;
         gb[r + 1] = pfd.y * mass;

@@ -321,14 +321,15 @@ struct SeedsT {
   D3 footF[2], footN[2], chestN;  // wc and hb are constants: zero tangent
 };
 
-__device__ __forceinline__ void primal_adjoint_pass(const KinoConst& C, const KinTopo& T, double* sb, const double* zs,
-                                                    const SeedsP& S, D3 xc, D3 xd) {
+__device__ __forceinline__ void primal_adjoint_pass(const KinTopo& T, double* sb, const double* zs, const SeedsP& S,
+                                                    D3 xc, D3 xd, int my_depth, int my_rank, int my_parent,
+                                                    double my_mass) {
   const int lane = threadIdx.x & 31;
   const int nb = T.nb;
   if (lane < nb) {
     double* bl = sb + lane * SB_STRIDE;
     const D3 o = ld3(bl + SB_O), d = ld3(bl + SB_D), w = ld3(bl + SB_W), v = ld3(bl + SB_V);
-    const double m = C.body[lane].mass;
+    const double m = my_mass;
     const D3 c = o + d;
     const D3 cd = v + cross(w, d);
     const D3 cbar = scale(m, cross(cd - xd, S.hb) + S.wc);
@@ -354,10 +355,6 @@ __device__ __forceinline__ void primal_adjoint_pass(const KinoConst& C, const Ki
     st3(bl + SB_CDB, cdbar);
   }
   __syncwarp();
-  // lane-indexed topology, read once (not inside the level loops)
-  const bool mine = lane > 0 && lane < nb;
-  const int my_depth = mine ? C.body[lane].depth : -1, my_rank = mine ? C.body[lane].sib_rank : -1;
-  const int my_parent = mine ? C.body[lane].parent : 0;
   // (depth, sibling rank) steps that have at least one body, deepest first: children of one parent are
   // serialised by rank so that the read-modify-write of the parent's totals needs no atomics
   for (int st = 0; st < T.n_steps; ++st) {
@@ -656,6 +653,15 @@ __global__ void __launch_bounds__(128, WITH_HESS ? KIN_H_MIN_BLOCKS : 3) kino_ki
   const bool is_link = lane > 0 && lane < nb;
   const int my_depth = is_link ? C.body[lane].depth : -1;
   const int my_parent = is_link ? C.body[lane].parent : 0;
+  const int my_rank = is_link ? C.body[lane].sib_rank : -1;
+  const double my_mass = lane < nb ? C.body[lane].mass : 0.0;
+  D3 b_com = v3<double>(0.0, 0.0, 0.0);
+  double b_I[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+  if (lane < nb) {
+    b_com = ld3(C.body[lane].com);
+#pragma unroll
+    for (int i = 0; i < 6; ++i) b_I[i] = C.body[lane].inertia[i];
+  }
   double bE[9], bEA[9], bEA2[9];
   D3 b_r = v3<double>(0.0, 0.0, 0.0), b_axis = b_r;
   if (is_link) {
@@ -737,14 +743,13 @@ __global__ void __launch_bounds__(128, WITH_HESS ? KIN_H_MIN_BLOCKS : 3) kino_ki
   // ------------------------------------------------------------------ per-body derived quantities + sums
   D3 mc = v3<double>(0.0, 0.0, 0.0), mcd = mc, hl = mc;
   if (lane < nb) {
-    const BodyC& bc = C.body[lane];
     double* bl = sb + lane * SB_STRIDE;
     const double* R = bl + SB_R;
-    const D3 d = matvec(R, ld3(bc.com));
+    const D3 d = matvec(R, b_com);
     st3(bl + SB_D, d);
     // I^w = R I R^T
     double RI[9];
-    const double* I = bc.inertia;
+    const double* I = b_I;
     const double Im[9] = {I[0], I[1], I[2], I[1], I[3], I[4], I[2], I[4], I[5]};
 #pragma unroll
     for (int i = 0; i < 3; ++i)
@@ -760,8 +765,8 @@ __global__ void __launch_bounds__(128, WITH_HESS ? KIN_H_MIN_BLOCKS : 3) kino_ki
     const D3 o = ld3(bl + SB_O), w = ld3(bl + SB_W), v = ld3(bl + SB_V);
     const D3 c = o + d;
     const D3 cd = v + cross(w, d);
-    mc = scale(bc.mass, c);
-    mcd = scale(bc.mass, cd);
+    mc = scale(my_mass, c);
+    mcd = scale(my_mass, cd);
     const D3 Lw = symmul(Iw, w);
     st3(bl + SB_L, Lw);
     hl = cross(mc, cd) + Lw;
@@ -1069,7 +1074,7 @@ __global__ void __launch_bounds__(128, WITH_HESS ? KIN_H_MIN_BLOCKS : 3) kino_ki
     double* comp = sm + L.stage;
     if (lane < nb) {
       const double* bl = sb + lane * SB_STRIDE;
-      const double m = C.body[lane].mass;
+      const double m = my_mass;
       const D3 c = ld3(bl + SB_O) + ld3(bl + SB_D);
       const D3 cd = ld3(bl + SB_V) + cross(ld3(bl + SB_W), ld3(bl + SB_D));
       const double* I = bl + SB_I;
@@ -1087,8 +1092,6 @@ __global__ void __launch_bounds__(128, WITH_HESS ? KIN_H_MIN_BLOCKS : 3) kino_ki
     }
     __syncwarp();
     {
-      const bool mine = lane > 0 && lane < nb;
-      const int my_rank = mine ? C.body[lane].sib_rank : -1, my_parent = mine ? C.body[lane].parent : 0;
       for (int st = 0; st < T.n_steps; ++st) {
         if (my_depth == T.step_depth[st] && my_rank == T.step_rank[st]) {
           const double* cl = comp + lane * CM_STRIDE;
@@ -1299,7 +1302,7 @@ __global__ void __launch_bounds__(128, WITH_HESS ? KIN_H_MIN_BLOCKS : 3) kino_ki
       SP.chestN = primal_of(S.chestN);
       ST.chestN = tangent_of(S.chestN);
       __syncwarp();
-      primal_adjoint_pass(C, T, sb, zs, SP, xc, xcd);
+      primal_adjoint_pass(T, sb, zs, SP, xc, xcd, my_depth, my_rank, my_parent, my_mass);
       D3 tn0, tw0, tv0;
       kin_tangent_sweep(T, sb, zs, dir, S.hb, ST, tangent_of(xcD), tangent_of(xdD), slot, em, tn0, tw0, tv0);
       n0 = lift<Dual>(ld3(sb + SB_ACC), tn0);
