@@ -139,14 +139,16 @@ __global__ void __launch_bounds__(128, TERRAIN == 0 ? CONTACT_MIN_BLOCKS : 1) ki
   const bool want_f = mask & HB_EVAL_F, want_grad = mask & HB_EVAL_GRAD_F, want_g = mask & HB_EVAL_G;
   const bool want_jac = mask & HB_EVAL_JAC_G, want_hess = mask & HB_EVAL_HESS_L;
 
-  for (int i = lane; i < NZ; i += 32) {
-    zs[i] = xb[i];
-    zp[i] = k1 ? xb[i - NZ] : 0.0;
+  // every global input is requested before the first shared-memory store: a store waits for its load and,
+  // in program order, would hold back the loads behind it (x, the parameters and the multipliers would
+  // each pay their DRAM latency in turn)
+  double xs_[6], xp_[6];
+#pragma unroll
+  for (int u = 0; u < 6; ++u) {
+    const int i = lane + 32 * u;
+    xs_[u] = i < NZ ? xb[i] : 0.0;
+    xp_[u] = (i < NZ && k1) ? xb[i - NZ] : 0.0;
   }
-  for (int i = lane; i < C.n_hc; i += 32) hbuf[i] = 0.0;
-  for (int i = lane; i < NCV; i += 32) gbuf[i] = 0.0;
-  if (lane < LS_ROWS) ls_n[lane] = 0;
-  __syncwarp();
 
   const double dt = pp[C.po_dt];
   const double hdt = 0.5 * dt;
@@ -192,6 +194,18 @@ __global__ void __launch_bounds__(128, TERRAIN == 0 ? CONTACT_MIN_BLOCKS : 1) ki
 #pragma unroll
     for (int c = 0; c < 3; ++c) La[c] = (ra >= 0 ? lb[ra + c] : 0.0) + (rb >= 0 ? lb[rb + c] : 0.0);
   }
+#pragma unroll
+  for (int u = 0; u < 6; ++u) {
+    const int i = lane + 32 * u;
+    if (i < NZ) {
+      zs[i] = xs_[u];
+      zp[i] = xp_[u];
+    }
+  }
+  for (int i = lane; i < C.n_hc; i += 32) hbuf[i] = 0.0;
+  for (int i = lane; i < NCV; i += 32) gbuf[i] = 0.0;
+  if (lane < LS_ROWS) ls_n[lane] = 0;
+  __syncwarp();
 
   // ------------------------------------------------------------------ per-point quantities (lanes 0..7)
   const int pi_ = lane & 7;
@@ -717,12 +731,12 @@ __global__ void __launch_bounds__(128, TERRAIN == 0 ? CONTACT_MIN_BLOCKS : 1) ki
       return hdt * eps3(a, bcol) * (c == 0 ? fsum.x : (c == 1 ? fsum.y : fsum.z));
     };
     auto emit_range = [&](int e0, int e1, auto value) {
-      for (int eb = e0 + lane; eb < e1; eb += 128) {
-        int sl[4];
+      for (int eb = e0 + lane; eb < e1; eb += 256) {
+        int sl[8];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) sl[u] = (eb + 32 * u) < e1 ? jmap[eb + 32 * u] : -1;
+        for (int u = 0; u < 8; ++u) sl[u] = (eb + 32 * u) < e1 ? jmap[eb + 32 * u] : -1;
 #pragma unroll
-        for (int u = 0; u < 4; ++u)
+        for (int u = 0; u < 8; ++u)
           if (sl[u] >= 0) jb[sl[u]] = value(eb + 32 * u);
       }
     };

@@ -45,6 +45,12 @@ enum { HSTAGE = 27 * 57 };  // per-warp staging of the Hessian columns (and, bef
 #if HB_FWD_JAC && !HB_KIN_STAGE
 #error "HB_FWD_JAC stages the Jacobian columns: it needs HB_KIN_STAGE"
 #endif
+#ifndef HB_SWEEP_PACKED
+#define HB_SWEEP_PACKED 1  // Hessian kernel: (direction, body) tasks packed on the lanes (kin_tangent_sweep_packed)
+#endif
+#if HB_SWEEP_PACKED && !HB_KIN_STAGE
+#error "HB_SWEEP_PACKED accumulates in the staged Hessian columns: it needs HB_KIN_STAGE"
+#endif
 
 struct KinSmem {
   int bodies, arms, fdu, fdal, fdar, G, z, gbuf, lamk, slot, stage, total;
@@ -470,6 +476,152 @@ __device__ __forceinline__ void kin_tangent_sweep(const KinTopo& C, const double
   v0 = cv;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Packed tangent sweep.  In kin_tangent_sweep lane d walks all the bodies although direction d only
+// moves its own sub-tree: of the 27 x 23 body steps 188 carry non-zero state tangents and 92 more are
+// pure propagation through the ancestors of the joint.  Here those (direction, body) steps are TASKS,
+// list-scheduled by the host (api.cu::build_sweep_schedule) on the 32 lanes in ~12 rounds instead of
+// 23: in every round a lane executes the task sched[round][lane] -- whatever direction it belongs to.
+//   * direction data (alpha, pivot, ...) and seed tangents stay in the registers of the OWNER lane d and
+//     are fetched with warp shuffles by the lane that executes a task of direction d;
+//   * a lane keeps the running adjoint of its chain in registers; where a chain ends it is added to a
+//     shared-memory slot of the body it feeds (the schedule never lets two chains hit one slot in the
+//     same round, so the order of the additions is fixed);
+//   * the coupling of ALL bodies through the total momentum, -hb.(P x Pdot)/M, is what would make every
+//     step non-zero; its Hessian is the rank-structured term -(1/M) hb.(dP_i x dPdot_j + dP_j x dPdot_i),
+//     written into the stage beforehand (cross_terms), and the sweep runs with d xc = d xdot_c = 0.
+struct DirData {
+  D3 alpha, pi, wpi, vpi, u;
+};
+__device__ __forceinline__ D3 shfl3(const D3& v, int src) {
+  return v3<double>(__shfl_sync(0xffffffffu, v.x, src), __shfl_sync(0xffffffffu, v.y, src),
+                    __shfl_sync(0xffffffffu, v.z, src));
+}
+
+__device__ __forceinline__ void kin_tangent_sweep_packed(const KinTopo& T, const double* sb, const double* zs,
+                                                         const double* qdat, const double* massv, const SeedsT& ownS,
+                                                         D3 hb, double* pslot, double* stage) {
+  const int lane = threadIdx.x & 31;
+  const D3 zero = v3<double>(0.0, 0.0, 0.0);
+  for (int i = lane; i < T.n_pslots * 12; i += 32) pslot[i] = 0.0;
+  __syncwarp();
+  D3 cn = zero, cF = zero, cw = zero, cv = zero;
+  unsigned t_next = (unsigned)T.sched[lane];
+  for (int r = 0; r < T.n_rounds; ++r) {
+    const unsigned t = t_next;
+    if (r + 1 < T.n_rounds) t_next = (unsigned)T.sched[(r + 1) * 32 + lane];
+    const bool valid = (t & KT_VALID) != 0;
+    const int l = (t >> KT_L_SHIFT) & 31, p = (t >> KT_P_SHIFT) & 31, d = (t >> KT_D_SHIFT) & 31;
+    const int src = valid ? d : lane;
+    // direction data: a joint direction is the axis / origin / twist of its body (already in shared
+    // memory); the four quaternion directions rotate everything about the base origin (qdat: g_a, u_a)
+    DirData dir;
+    {
+      const double* bd = sb + (d < 4 ? 0 : d - 3) * SB_STRIDE;
+      dir.wpi = ld3(bd + SB_W);
+      dir.vpi = ld3(bd + SB_V);
+      if (d < 4) {
+        dir.alpha = ld3(qdat + 6 * d);
+        dir.u = ld3(qdat + 6 * d + 3);
+        dir.pi = zero;
+      } else {
+        dir.alpha = ld3(bd + SB_AX);
+        dir.u = zero;
+        dir.pi = ld3(bd + SB_O);
+      }
+    }
+    const double m = massv[l];
+    SeedsT S;
+    S.footF[0] = S.footF[1] = S.footN[0] = S.footN[1] = S.chestN = zero;
+    if ((T.round_seed_mask >> r) & 1u) {  // warp-uniform
+      S.footF[0] = shfl3(ownS.footF[0], src);
+      S.footF[1] = shfl3(ownS.footF[1], src);
+      S.footN[0] = shfl3(ownS.footN[0], src);
+      S.footN[1] = shfl3(ownS.footN[1], src);
+      S.chestN = shfl3(ownS.chestN, src);
+    }
+    if (valid) {
+      if (t & KT_START) cn = cF = cw = cv = zero;
+      const double* bl = sb + l * SB_STRIDE;
+      const bool in = (t & KT_IN_L) != 0;
+      const D3 a = in ? dir.alpha : zero, uu = in ? dir.u : zero;
+      const D3 d_ = ld3(bl + SB_D), w = ld3(bl + SB_W), ax = ld3(bl + SB_AX);
+      const D3 rr = ld3(bl + SB_O) - dir.pi;
+      const D3 to = cross(a, rr);
+      const D3 td = cross(a, d_);
+      const D3 tw = cross(a, w - dir.wpi) + uu;
+      const D3 tv = cross(dir.wpi, to) + cross(a, (ld3(bl + SB_V) - dir.vpi) - cross(dir.wpi, rr)) + cross(uu, rr);
+      const D3 tax = cross(a, ax);
+      if (in) {  // local adjoints of body l move only with the sub-tree of the direction
+        const double* I = bl + SB_I;
+        const D3 cbar = ld3(bl + SB_CB), cdbar = ld3(bl + SB_CDB), Ih = ld3(bl + SB_IH), Iw = ld3(bl + SB_L);
+        const D3 tc = to + td;
+        const D3 tcd = tv + cross(tw, d_) + cross(w, td);
+        const D3 tcbar = scale(m, cross(tcd, hb));
+        const D3 tcdbar = scale(m, cross(hb, tc));
+        const D3 tIw = symmul(I, tw - cross(a, w)) + cross(a, Iw);
+        const D3 tIh = cross(a, Ih) - symmul(I, cross(a, hb));
+        cF = cF + tcbar;
+        cn = cn + cross(td, cbar) + cross(d_, tcbar) + cross(td, cross(cdbar, w)) +
+             cross(d_, cross(tcdbar, w) + cross(cdbar, tw)) + cross(tIw, hb) + cross(tIh, w) + cross(Ih, tw);
+        cv = cv + tcdbar;
+        cw = cw + cross(td, cdbar) + cross(d_, tcdbar) + tIh;
+      }
+      // seed tangents (zero where they do not apply).  The feet-distance row couples the two feet: a
+      // direction that moves one foot also changes the seed on the OTHER foot, which is why the schedule
+      // visits the other leg for such a direction
+      if (l == T.foot_body[0]) {
+        cF = cF + S.footF[0];
+        cn = cn + S.footN[0];
+      }
+      if (l == T.foot_body[1]) {
+        cF = cF + S.footF[1];
+        cn = cn + S.footN[1];
+      }
+      if (l == T.chest_body) cn = cn + S.chestN;
+      const int ls = (t >> KT_LOAD_SHIFT) & 63;
+      if (ls) {
+        const double* sl = pslot + (ls - 1) * 12;
+        cn = cn + ld3(sl);
+        cF = cF + ld3(sl + 3);
+        cw = cw + ld3(sl + 6);
+        cv = cv + ld3(sl + 9);
+      }
+      if (l != 0) {
+        const D3 np = ld3(bl + SB_ACC), Fp = ld3(bl + SB_ACC + 3), wp = ld3(bl + SB_ACC + 6), vp = ld3(bl + SB_ACC + 9);
+        double* col = stage + d * 57;
+        col[7 + l - 1] += dot(tax, wp) + dot(ax, cw);   // rows: vb3 qd4 sd23 q4 s23
+        col[34 + l - 1] += dot(tax, np) + dot(ax, cn);
+        const D3 rho = ld3(bl + SB_RHO), wpar = ld3(sb + p * SB_STRIDE + SB_W);
+        const bool inp = (t & KT_IN_P) != 0;
+        const D3 ap = inp ? dir.alpha : zero;
+        const D3 trho = cross(ap, rho);
+        const D3 twpar = cross(ap, wpar - dir.wpi) + (inp ? dir.u : zero);
+        const double sd = zs[Z_SD + l - 1];
+        cn = cn + cross(trho, Fp) + cross(rho, cF) + scale(sd, cross(tax, wp) + cross(ax, cw)) +
+             cross(trho, cross(vp, wpar)) + cross(rho, cross(cv, wpar) + cross(vp, twpar));
+        cw = cw + cross(trho, vp) + cross(rho, cv);
+      }
+      const int fs = (t >> KT_FLUSH_SHIFT) & 63;
+      if (fs) {
+        double* sl = pslot + (fs - 1) * 12;
+        if (t & KT_STORE) {
+          st3(sl, cn);
+          st3(sl + 3, cF);
+          st3(sl + 6, cw);
+          st3(sl + 9, cv);
+        } else {
+          st3(sl, ld3(sl) + cn);
+          st3(sl + 3, ld3(sl + 3) + cF);
+          st3(sl + 6, ld3(sl + 6) + cw);
+          st3(sl + 9, ld3(sl + 9) + cv);
+        }
+      }
+    }
+    __syncwarp();
+  }
+}
+
 // quaternion maps: g_a (rotation tangent of R(q/|q|) along q_a), u_a = d omega_0 / d q_a,
 // w_a = d omega_0 / d q_dot_a.
 template <class T>
@@ -558,10 +710,12 @@ struct HessEmit {
   int dirj;        // direction index 0..26, or -1 (idle lane)
   double add_sd, add_s;  // joint-regularisation terms on (sd_j, s_j), (s_j, s_j) for joint lanes
   double* stage;   // per-warp staging (HSTAGE doubles); scattered after the sweep
+  bool acc = false;  // packed sweep: the stage already holds the cross terms, entries are added
   __device__ __forceinline__ void prefetch(int) {}
   __device__ __forceinline__ void put(int row, double v) const {
     if (stage) {
-      stage[dirj * 57 + row] = v;
+      if (acc) stage[dirj * 57 + row] += v;
+      else stage[dirj * 57 + row] = v;
       return;
     }
     const int slot = map[dirj * 57 + row];
@@ -615,12 +769,19 @@ __global__ void __launch_bounds__(128, WITH_HESS ? KIN_H_MIN_BLOCKS : 3) kino_ki
   // ---- every global input of this warp is requested here, addresses from the constant bank: the DRAM
   // latencies of x, the parameter slices, the multipliers and the joint frames overlap each other and
   // the forward kinematics instead of being exposed one by one at their points of use
-  if (T.zmap_identity) {
-    for (int i = lane; i < NZ; i += 32) zs[i] = xb[i];
-  } else {
-    for (int i = lane; i < NZ; i += 32) {
-      const int zi = C.zmap[i];
-      zs[i] = zi >= 0 ? xb[zi] : 0.0;
+  // (loads first, shared-memory stores last: a store that waits for its load would hold back, in program
+  // order, every load behind it)
+  double xr[6];
+#pragma unroll
+  for (int u = 0; u < 6; ++u) {
+    const int i = lane + 32 * u;
+    xr[u] = 0.0;
+    if (i < NZ) {
+      if (T.zmap_identity) xr[u] = xb[i];
+      else {
+        const int zi = C.zmap[i];
+        if (zi >= 0) xr[u] = xb[zi];
+      }
     }
   }
   const double* rfq = pb_ + T.po_fq + T.ref_stride * k;
@@ -638,7 +799,7 @@ __global__ void __launch_bounds__(128, WITH_HESS ? KIN_H_MIN_BLOCKS : 3) kino_ki
   const double pre_jr = lane < HB_N_JOINTS ? rjr[lane] : 0.0;
   const double mass_p = pb_[T.po_mass];
   const bool with_l = WITH_HESS && (mask & HB_EVAL_HESS_L);
-  double sg = 0.0;
+  double sg = 0.0, lam_reg = 0.0;
   if (with_l) {
     // multipliers of the 32 kinematic rows of this knot, one per lane, parked in shared memory
     int row;
@@ -646,7 +807,7 @@ __global__ void __launch_bounds__(128, WITH_HESS ? KIN_H_MIN_BLOCKS : 3) kino_ki
     else if (lane < 27) row = grow(T, HB_KF_COM_KIN, k, lane - 24);
     else if (lane < 30) row = grow(T, HB_KF_MOM_KIN, k, lane - 27);
     else row = grow(T, lane == 30 ? HB_KF_FEET_DIST : HB_KF_UNIT_QUAT, k, 0);
-    lamk[lane] = row >= 0 ? lam[b * T.m + row] : 0.0;
+    lam_reg = row >= 0 ? lam[b * T.m + row] : 0.0;
     sg = sigma[b];
   }
   // joint frame constants of this lane's body
@@ -675,6 +836,11 @@ __global__ void __launch_bounds__(128, WITH_HESS ? KIN_H_MIN_BLOCKS : 3) kino_ki
     b_r = ld3(bc.r);
     b_axis = ld3(bc.axis);
   }
+  const unsigned my_submask = lane < nb ? C.sub_mask[lane] : 0u;
+#pragma unroll
+  for (int u = 0; u < 6; ++u)
+    if (lane + 32 * u < NZ) zs[lane + 32 * u] = xr[u];
+  if (WITH_HESS) lamk[lane] = lam_reg;
   for (int i = lane; i < 58; i += 32) gbuf[i] = 0.0;
   __syncwarp();
 
@@ -1092,15 +1258,24 @@ __global__ void __launch_bounds__(128, WITH_HESS ? KIN_H_MIN_BLOCKS : 3) kino_ki
     }
     __syncwarp();
     {
-      for (int st = 0; st < T.n_steps; ++st) {
-        if (my_depth == T.step_depth[st] && my_rank == T.step_rank[st]) {
-          const double* cl = comp + lane * CM_STRIDE;
-          double* cp = comp + my_parent * CM_STRIDE;
+      // lane = body: sum the rows of its sub-tree (every lane reads the same row: broadcast loads, no
+      // barriers; the leaf-to-root read-modify-write version of this pass took 12 % of the kernel)
+      double acc[16];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) cp[i] += cl[i];
-        }
-        __syncwarp();
+      for (int i = 0; i < 16; ++i) acc[i] = 0.0;
+      for (int l = 0; l < nb; ++l) {
+        const double in = ((my_submask >> l) & 1u) ? 1.0 : 0.0;
+        const double* cl = comp + l * CM_STRIDE;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) acc[i] = fma(in, cl[i], acc[i]);
       }
+      __syncwarp();
+      if (lane < nb) {
+        double* cm = comp + lane * CM_STRIDE;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) cm[i] = acc[i];
+      }
+      __syncwarp();
     }
     const bool fwd_jac = HB_FWD_JAC && want_jac;
     // tangents of P, P_dot, h (about the base origin) along this lane's (q, s) direction
@@ -1119,7 +1294,8 @@ __global__ void __launch_bounds__(128, WITH_HESS ? KIN_H_MIN_BLOCKS : 3) kino_ki
     // velocity directions (lanes 0..29 = vb, qd, sd): w_l += in_l A, v_l += in_l A x (o_l - pivot) + B;
     // momentum is linear in the velocities, so its column is again closed-form in the moments
     D3 vel_dh = v3<double>(0.0, 0.0, 0.0);
-    if (fwd_jac && lane < 30) {
+    D3 vel_pv = vel_dh;  // d Pdot / d (velocity variable of this lane), for the cross terms of the Hessian
+    if (lane < 30) {
       D3 A = v3<double>(0.0, 0.0, 0.0), B = A, piv = A;
       int lv = 0;
       if (lane < 3) B = v3<double>(lane == 0 ? 1.0 : 0.0, lane == 1 ? 1.0 : 0.0, lane == 2 ? 1.0 : 0.0);
@@ -1135,6 +1311,7 @@ __global__ void __launch_bounds__(128, WITH_HESS ? KIN_H_MIN_BLOCKS : 3) kino_ki
       const D3 pv = cross(A, P - scale(Ms, piv)) + scale(Ms, B);
       const D3 hv = symmul(cm + CM_J, A) - cross(P, cross(A, piv)) + cross(P, B);
       vel_dh = scale(-1.0 / mass_p, hv - scale(1.0 / M, cross(Pm, pv)));
+      vel_pv = pv;
     }
     __syncwarp();  // the stage is reused for the Jacobian columns below
     const V3<Dual> xcD = lift<Dual>(xc, scale(1.0 / M, tP));
@@ -1283,6 +1460,7 @@ __global__ void __launch_bounds__(128, WITH_HESS ? KIN_H_MIN_BLOCKS : 3) kino_ki
       em.add_s = T.joint_cost_kind == 0 ? sg * T.w_joint * 2.0 * wjl * wjl : sg * T.w_joint * 2.0 * wjl;
     }
     V3<Dual> n0, w0, v0;
+    const double lu_pre = lamk[31];  // read now: the slots of the packed sweep alias gbuf + lamk + slot
 #ifdef HB_DUAL_SWEEP
     // reference implementation: the whole adjoint sweep in dual arithmetic on every lane
     kin_backward<Dual>(T, sb, zs, dir, S, xcD, xdD, slot, em, n0, w0, v0);
@@ -1304,7 +1482,54 @@ __global__ void __launch_bounds__(128, WITH_HESS ? KIN_H_MIN_BLOCKS : 3) kino_ki
       __syncwarp();
       primal_adjoint_pass(T, sb, zs, SP, xc, xcd, my_depth, my_rank, my_parent, my_mass);
       D3 tn0, tw0, tv0;
+#if HB_SWEEP_PACKED
+      {
+        // Hessian of -hb.(P x Pdot)/M (see kin_tangent_sweep_packed) for every (direction, row), which also
+        // initialises the stage; rows: vb3 qd4 sd23 (velocity lane = row) q4 s23 (direction lane = row - 30)
+        double* stg = sm + L.stage;
+        double* pslot = sm + L.gbuf;  // gbuf + lamk + slot: 474 contiguous doubles, all dead by now
+        // tangents of P (rows q, s) and of Pdot (all rows) parked in the slot area for the cross terms;
+        // quaternion direction data and the masses in the part of z the kinematics no longer reads
+        double* xt = pslot;           // [57][6]: dP_r (zero for velocity rows), dPdot_r
+        double* qdat = zs;            // [4][6]: g_a, u_a
+        double* massv = zs + 24;      // [nb]
+        if (lane < 27) {
+          st3(xt + (30 + lane) * 6, tP);
+          st3(xt + (30 + lane) * 6 + 3, tPd);
+        }
+        if (lane < 30) {
+          st3(xt + lane * 6, v3<double>(0.0, 0.0, 0.0));
+          st3(xt + lane * 6 + 3, vel_pv);
+        }
+        if (lane < 4) {
+          st3(qdat + 6 * lane, dir.alpha);
+          st3(qdat + 6 * lane + 3, dir.u);
+        }
+        if (lane < nb) massv[lane] = my_mass;
+        __syncwarp();
+        if (lane < 27) {
+          const D3 hbv = S.hb;
+          const D3 a1 = cross(tPd, hbv), a2 = cross(hbv, tP);  // hb.(dP_r x dPdot_d) = dP_r.a1, hb.(dP_d x dPdot_r) = dPdot_r.a2
+          double* col = stg + lane * 57;
+          const double sM = -1.0 / M;
+#pragma unroll 3
+          for (int r = 0; r < 57; ++r) col[r] = sM * (dot(ld3(xt + 6 * r), a1) + dot(ld3(xt + 6 * r + 3), a2));
+          if (lane >= 4) {  // joint regularisation on (sd_j, s_j), (s_j, s_j)
+            col[7 + lane - 4] += em.add_sd;
+            col[34 + lane - 4] += em.add_s;
+          }
+        }
+        __syncwarp();
+        em.acc = true;
+        kin_tangent_sweep_packed(T, sb, zs, qdat, massv, ST, S.hb, pslot, stg);
+        const double* rs = pslot + (lane < 27 ? T.root_slot[lane] : 0) * 12;
+        tn0 = ld3(rs);
+        tw0 = ld3(rs + 6);
+        tv0 = ld3(rs + 9);
+      }
+#else
       kin_tangent_sweep(T, sb, zs, dir, S.hb, ST, tangent_of(xcD), tangent_of(xdD), slot, em, tn0, tw0, tv0);
+#endif
       n0 = lift<Dual>(ld3(sb + SB_ACC), tn0);
       w0 = lift<Dual>(ld3(sb + SB_ACC + 6), tw0);
       v0 = lift<Dual>(ld3(sb + SB_ACC + 9), tv0);
@@ -1314,7 +1539,7 @@ __global__ void __launch_bounds__(128, WITH_HESS ? KIN_H_MIN_BLOCKS : 3) kino_ki
       em.put(0, v0.x.d);
       em.put(1, v0.y.d);
       em.put(2, v0.z.d);
-      const double lu = lamk[31];
+      const double lu = lu_pre;
       // dual quaternion maps, rebuilt from shared memory after the sweep (see above)
       Dual qD[4];
       double qdv2[4];
