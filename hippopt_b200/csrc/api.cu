@@ -475,6 +475,16 @@ extern "C" int hb_kino_create(const int32_t* icfg, const double* dcfg, const int
   h->topo.hc_index = h->d_hci;
   h->topo.hc_map = h->d_hc;
   {
+    // 4 warps per CTA; the kinematics kernels keep one branch accumulator per body whose children do not
+    // directly follow it in the joint list (n_slots): an interleaved joint order does not fit
+    const size_t kin_smem = (size_t)hb::kin_smem_layout(C.nb, C.n_slots, true).total * sizeof(double) * 4;
+    if (kin_smem > 200 * 1024) {
+      hb_destroy(h);
+      return fail(HB_ERR_UNSUPPORTED,
+                  "hb_kino_create: this joint order needs " + std::to_string(C.n_slots) +
+                      " branch accumulators (" + std::to_string(kin_smem / 1024) +
+                      " KB of shared memory per CTA > 200 KB): list the joints of a limb consecutively");
+    }
     const SweepSchedule sch = build_sweep_schedule(C);
     if (sch.n_rounds <= 0 || sch.n_rounds > 32 || sch.n_slots > 62 || sch.n_slots * 12 > 58 + 32 + C.n_slots * 32 * 12) {
       hb_destroy(h);

@@ -395,3 +395,41 @@ def test_minimal_horizon(model, built_library):
     close(out["g"], nlp.eval_g(x, p))
     close(out["jac"], nlp.eval_jac(x, p))
     close(out["hess"], nlp.eval_hess(x, p, lam, sigma))
+
+
+def test_other_joint_orders(built_library):
+    """The kernels take the tree as data (parents, sub-tree masks, the host-built sweep schedule): a joint list
+    with the limbs in another order -- other body numbers, foot / chest bodies, branch slots -- must give the
+    same agreement with the oracle; an interleaved list, which would need a branch accumulator per body, is
+    refused at creation with a message, not at launch."""
+    from hippopt_b200 import _capi
+    from hippopt_b200.evaluator import KinoEvaluator
+    from hippopt_b200.kino_layout import KinoSettings
+    from hippopt_b200.robot_model import ERGOCUB_JOINTS, RobotModel, synthetic_ergocub_urdf
+    from hippopt_b200.workloads import kino_batch
+    from oracle import kinodynamic as kd
+
+    torso, l_arm, r_arm, l_leg, r_leg = (ERGOCUB_JOINTS[0:3], ERGOCUB_JOINTS[3:7], ERGOCUB_JOINTS[7:11],
+                                         ERGOCUB_JOINTS[11:17], ERGOCUB_JOINTS[17:23])
+    frames = ["l_sole", "r_sole", "chest"]
+    urdf = synthetic_ergocub_urdf(seed=7)
+    model2 = RobotModel.from_urdf(urdf, l_leg + r_leg + torso + r_arm + l_arm, "root_link", frames=frames)
+    assert list(model2.parent[:8]) == [-1, 0, 1, 2, 3, 4, 5, 0]
+    ev = KinoEvaluator(model2, KinoSettings(horizon=3, final_state_constraint=True))
+    nlp, _ = kd.build(model2, kd.Settings(horizon=3, final_state_constraint=True))
+    assert np.array_equal(ev.jac_sparsity()[1], nlp.jac_structure()[1])
+    assert np.array_equal(ev.hess_sparsity()[1], nlp.hess_structure()[1])
+    x, p, lam, sigma = kino_batch(ev.layout, model2, 3, seed=4, noise=0.2)
+    out = run(ev, x, p, lam, sigma)
+    close(out["f"], nlp.eval_f(x, p))
+    close(out["g"], nlp.eval_g(x, p))
+    close(out["grad_f"], nlp.eval_grad_f(x, p))
+    close(out["jac"], nlp.eval_jac(x, p))
+    close(out["hess"], nlp.eval_hess(x, p, lam, sigma))
+    jac_only = run(ev, x, p, lam, sigma, 8)
+    close(jac_only["jac"], out["jac"], rtol=1e-13)
+
+    interleaved = [j for grp in zip(l_leg, r_leg) for j in grp] + torso + [j for grp in zip(l_arm, r_arm) for j in grp]
+    model3 = RobotModel.from_urdf(urdf, interleaved, "root_link", frames=frames)
+    with pytest.raises(_capi.EvaluationError, match="branch accumulators"):
+        KinoEvaluator(model3, KinoSettings(horizon=2))
