@@ -159,3 +159,45 @@ def kino_batch(lay: KinoLayout, model: RobotModel, B: int, seed: int = 2, noise:
     lam = rng.normal(size=(B, lay.m))
     sigma = np.ones(B)
     return x, p, lam, sigma
+
+
+def standing_problem(lay: KinoLayout, model: RobotModel, pose: np.ndarray):
+    """Kinodynamic "keep standing" OCPs from pose-finder solutions (the pose finder is
+    what produces initial / final states in `main_periodic_step.py:192-327`).
+
+    pose: (B, 81) pose-finder solutions [p_i, f_i (8 points), p_b, q, s, com].  Returns (p, x0): parameters
+    whose initial state, final state and references are that pose, and the initial guess that repeats it at
+    every knot with zero velocities -- feasible by construction (the pose finder enforces the static
+    balance, the contact rows and the kinematic consistency the OCP asks for)."""
+    po, N, B = lay.po, lay.N, pose.shape[0]
+    p = kino_parameters(lay, model, B, np.random.default_rng(0), spread=0.0)
+    for base in (po.init, po.final):
+        for i in range(NPT):
+            p[:, base + po.st_pt(i, "p"):base + po.st_pt(i, "p") + 3] = pose[:, 6 * i:6 * i + 3]
+            p[:, base + po.st_pt(i, "f"):base + po.st_pt(i, "f") + 3] = pose[:, 6 * i + 3:6 * i + 6]
+        p[:, base + po.ST_PB:base + po.ST_PB + 3] = pose[:, 48:51]
+        p[:, base + po.ST_Q:base + po.ST_Q + 4] = pose[:, 51:55]
+        p[:, base + po.ST_S:base + po.ST_S + NJ] = pose[:, 55:78]
+        p[:, base + po.ST_COM:base + po.ST_COM + 3] = pose[:, 78:81]
+    centroid = np.stack([pose[:, 6 * i:6 * i + 3] for i in range(NPT)], axis=0).mean(axis=0)
+    for k in range(N):
+        r = po.refs0 + 55 * k
+        p[:, r + po.R_CC:r + po.R_CC + 3] = centroid
+        p[:, r + po.R_COMV:r + po.R_COMV + 3] = 0.0
+        p[:, r + po.R_SWING] = 0.0
+        p[:, r + po.R_YAW_L] = p[:, r + po.R_YAW_R] = 0.0
+        p[:, r + po.R_BQ:r + po.R_BQ + 4] = pose[:, 51:55]
+        p[:, r + po.R_FQ:r + po.R_FQ + 4] = [0.0, 0.0, 0.0, 1.0]
+        p[:, r + po.R_BQV:r + po.R_BQV + 4] = 0.0
+        p[:, r + po.R_JR:r + po.R_JR + NJ] = pose[:, 55:78]
+    x0 = np.zeros((B, lay.n_x))
+    for k in range(N):
+        z = x0[:, NZ * k:NZ * (k + 1)]
+        for i in range(NPT):
+            z[:, 15 * i + P:15 * i + P + 3] = pose[:, 6 * i:6 * i + 3]
+            z[:, 15 * i + F:15 * i + F + 3] = pose[:, 6 * i + 3:6 * i + 6]
+        z[:, PB:PB + 3] = pose[:, 48:51]
+        z[:, Q:Q + 4] = pose[:, 51:55]
+        z[:, S:S + NJ] = pose[:, 55:78]
+        z[:, COM:COM + 3] = pose[:, 78:81]
+    return p, x0

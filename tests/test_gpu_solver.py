@@ -46,3 +46,38 @@ def test_solver_reports_failure_like_the_reference(built_library):
     with pytest.raises(OptiFailure):
         BatchedInteriorPoint(ev, tol=1e-12, max_iter=2).solve(torch.zeros((1, ev.n_x), dtype=torch.float64, device=dev),
                                                               torch.tensor(p, device=dev), lb, ub)
+
+
+def test_standing_ocp_solves_with_the_stage_kkt(model, built_library):
+    """Rows f1 + f2 end to end on the real problem: pose-finder solutions (dense KKT) become "keep standing"
+    kinodynamic OCPs, solved with the stage-wise KKT sweep and the batched LU kernels.  No reference
+    trajectory exists for this (IPOPT is not available), so the checks are intrinsic: the guess is feasible
+    by construction, and what the solver returns satisfies the constraints and its own KKT test."""
+    from hippopt_b200.evaluator import G, KinoEvaluator, PoseEvaluator
+    from hippopt_b200.ipsolver import BatchedInteriorPoint
+    from hippopt_b200.kino_layout import KinoSettings
+    from hippopt_b200.workloads import pose_batch, standing_problem
+
+    dev = torch.device("cuda:0")
+    pev = PoseEvaluator(model)
+    x, p, lam, sigma = pose_batch(pev.layout, model, 96, seed=1, noise=0.02)
+    lb, ub = pev.bounds(p)
+    out = BatchedInteriorPoint(pev, tol=1e-8, max_iter=300).solve(torch.tensor(x, device=dev), torch.tensor(p, device=dev), lb, ub)
+    pose = out.values.cpu().numpy()[out.success.cpu().numpy()]
+    assert pose.shape[0] >= 4  # a minority converges (no restoration phase): enough poses to go on
+    ev = KinoEvaluator(model, KinoSettings(horizon=4))
+    lay = ev.layout
+    pk, x0 = standing_problem(lay, model, pose)
+    lbk, ubk = lay.bounds(pk)
+    P = torch.tensor(pk, device=dev)
+    g0 = ev.eval(G, torch.tensor(x0, device=dev), P)["g"].cpu().numpy()
+    assert (np.maximum(lbk - g0, 0) + np.maximum(g0 - ubk, 0)).max() < 1e-9  # feasible guess
+    sol = BatchedInteriorPoint(ev, tol=1e-6, max_iter=300, kkt="stage", delta_c=1e-9, mu_init=1e-3)
+    res = sol.solve(torch.tensor(x0, device=dev), P, lbk, ubk)
+    ok = res.success.cpu().numpy()
+    # the driver has no restoration phase: part of the instances stall; the rate is reported in DESIGN.md
+    assert ok.sum() >= max(1, pose.shape[0] // 6), f"{int(ok.sum())} of {pose.shape[0]} standing OCPs converged"
+    assert float(res.kkt_error[res.success].max()) <= 1e-6
+    gs = ev.eval(G, res.values, P)["g"].cpu().numpy()[ok]
+    assert (np.maximum(lbk[ok] - gs, 0) + np.maximum(gs - ubk[ok], 0)).max() < 1e-5
+    assert torch.isfinite(res.cost_value[res.success]).all()
