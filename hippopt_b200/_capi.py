@@ -99,6 +99,8 @@ def lib() -> ctypes.CDLL:
     L.hb_lu_solve_batched.argtypes = [vp, vp, vp, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, vp]
     L.hb_last_launch_count.restype = ctypes.c_int
     L.hb_last_launch_count.argtypes = [vp]
+    L.hb_set_option.restype = ctypes.c_int
+    L.hb_set_option.argtypes = [vp, ctypes.c_int32, ctypes.c_int32]
     L.hb_last_error.restype = ctypes.c_char_p
     L.hb_last_error.argtypes = []
     L.hb_profile_enable.restype = ctypes.c_int
@@ -115,7 +117,7 @@ EXPORTED_SYMBOLS = [
     "hb_kino_create", "hb_toy_create", "hb_destroy", "hb_dims", "hb_pattern_jac", "hb_pattern_hess", "hb_eval",
     "hb_last_launch_count", "hb_last_error", "hb_probe_fp64_tflops", "hb_profile_enable", "hb_profile_read",
     "hb_host_set_parameters", "hb_eval_host", "hb_host_last_traffic", "hb_host_alloc", "hb_host_free",
-    "hb_lu_factor_batched", "hb_lu_solve_batched",
+    "hb_lu_factor_batched", "hb_lu_solve_batched", "hb_set_option",
 ]
 
 

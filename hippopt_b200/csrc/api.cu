@@ -35,6 +35,7 @@ struct hb_problem_s {
   // per-knot cost partial sums, one scratch buffer per stream so that evaluations enqueued on
   // different streams (HostPipeline) do not share scratch
   std::map<cudaStream_t, std::pair<double*, int64_t>> fpart;
+  bool jac_adjoint = false;  // hb_set_option(HB_OPT_JAC_ADJOINT)
   // optional per-kernel timing (CUDA events on the launching stream)
   bool prof = false;
   std::vector<cudaEvent_t> prof_ev;  // 4 events per hb_eval: start, after contact, after kin, after reduce
@@ -614,7 +615,14 @@ extern "C" int hb_eval(hb_handle h, uint32_t mask, const double* x, const double
   const int warps_per_block = 4;
   const long total_warps = (long)batch * C.N;
   const unsigned grid = (unsigned)((total_warps + warps_per_block - 1) / warps_per_block);
-  const bool with_hess = (mask & HB_EVAL_HESS_L) != 0;
+  // The "Hessian" variant of the kinematics kernel also serves Jacobian / gradient requests: its forward-mode
+  // Jacobian (closed-form tangents, no sweep: 0.42 ms) beats the row-per-lane adjoint sweep of the lean
+  // variant (0.62 ms), which is left with f and g.  hb_set_option(HB_OPT_JAC_ADJOINT) or HB_JAC_ADJOINT=1
+  // select the adjoint sweep: an independent algorithm for the same numbers (tests, A/B timing).
+  static const bool jac_adjoint_env = getenv("HB_JAC_ADJOINT") != nullptr;
+  const bool jac_adjoint = jac_adjoint_env || h->jac_adjoint;
+  const bool with_hess = (mask & HB_EVAL_HESS_L) != 0 ||
+                         (!jac_adjoint && (mask & (HB_EVAL_JAC_G | HB_EVAL_GRAD_F)) != 0);
   auto mark = [&]() -> int {
     if (!h->prof) return HB_OK;
     cudaEvent_t e;
@@ -862,6 +870,15 @@ extern "C" int hb_profile_read(hb_handle h, double* ms, int64_t* n_evals) {
 }
 
 extern "C" int hb_last_launch_count(hb_handle h) { return h ? h->launches : 0; }
+
+extern "C" int hb_set_option(hb_handle h, int32_t option, int32_t value) {
+  if (!h) return fail(HB_ERR_INVALID, "hb_set_option: null handle");
+  if (option == HB_OPT_JAC_ADJOINT) {
+    h->jac_adjoint = value != 0;
+    return HB_OK;
+  }
+  return fail(HB_ERR_INVALID, "hb_set_option: unknown option");
+}
 
 extern "C" const char* hb_last_error(void) { return g_err.c_str(); }
 

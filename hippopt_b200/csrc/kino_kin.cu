@@ -1195,7 +1195,7 @@ __global__ void __launch_bounds__(128, WITH_HESS ? KIN_H_MIN_BLOCKS : 3) kino_ki
     }
   }
   if (!WITH_HESS) return;
-  if (!(mask & HB_EVAL_HESS_L)) return;
+  if (!with_l && !(HB_FWD_JAC && (want_jac || want_grad))) return;
   // ------------------------------------------------------------------ adjoint sweep, dual: Hessian columns
   {
     const int dirj = lane < 27 ? lane : -1;
@@ -1319,60 +1319,16 @@ __global__ void __launch_bounds__(128, WITH_HESS ? KIN_H_MIN_BLOCKS : 3) kino_ki
     const double inL = ((dir.mask >> T.foot_body[0]) & 1u) ? 1.0 : 0.0;
     const double inR = ((dir.mask >> T.foot_body[1]) & 1u) ? 1.0 : 0.0;
     const double inC = ((dir.mask >> T.chest_body) & 1u) ? 1.0 : 0.0;
-    double ty_lane = 0.0, tphi_lane = 0.0;  // tangents of the feet distance and of trace(G) along this direction
-    Seeds<Dual> S;
-    S.footF[0] = S.footF[1] = S.footN[0] = S.footN[1] = vzero<Dual>();
+    // tangents of the feet distance u.(pL - pR) and of trace(G) along this direction
+    double ty_lane, tphi_lane;
     {
-      // multipliers from lamk (loaded at the top of the kernel; rows that do not exist hold 0)
-      S.wc = scale(-1.0 / M, ld3(lamk + 24));
-      S.hb = scale(-1.0 / mass_p, ld3(lamk + 27));
-      // stage I^w hbar (same for every lane of the dual sweep)
-      if (lane < nb) st3(sb + lane * SB_STRIDE + SB_IH, symmul(sb + lane * SB_STRIDE + SB_I, S.hb));
-      __syncwarp();
-    }
-#pragma unroll
-    for (int pt = 0; pt < 8; ++pt) {
-      const int f = pt >> 2;
-      const D3 frc = v3<double>(-lamk[3 * pt], -lamk[3 * pt + 1], -lamk[3 * pt + 2]);
-      const D3 a = ld3(sm + L.arms + 3 * pt);
-      const double in = f == 0 ? inL : inR;
-      const V3<Dual> aD = lift<Dual>(a, scale(in, cross(dir.alpha, a)));
-      S.footF[f] = S.footF[f] + lift<Dual>(frc, v3<double>(0.0, 0.0, 0.0));
-      S.footN[f] = S.footN[f] + cross(aD, frc);
-    }
-    {
-      const double kd = lamk[30];
-      const St<Dual> sL = load_state(sb, T.foot_body[0], dir, Dual());
-      const St<Dual> sR = load_state(sb, T.foot_body[1], dir, Dual());
-      const V3<Dual> uD = lift<Dual>(fdu, scale(inR, cross(dir.alpha, fdu)));
-      const V3<Dual> alD = lift<Dual>(fdal, scale(inL, cross(dir.alpha, fdal)));
-      const V3<Dual> arD = lift<Dual>(fdar, scale(inR, cross(dir.alpha, fdar)));
-      const V3<Dual> dD = (sL.o + alD) - (sR.o + arD);
-      ty_lane = dot(uD, dD).d;
-      const V3<Dual> ku = scale(kd, uD);
-      S.footF[0] = S.footF[0] + ku;
-      S.footN[0] = S.footN[0] + cross(alD, ku);
-      S.footF[1] = S.footF[1] - ku;
-      S.footN[1] = S.footN[1] + scale(kd, cross(uD, dD)) - cross(arD, ku);
-    }
-    {
-      // kappa = 2 sigma w (phi - 3) with its tangent; m(G) with its tangent (columns of G rotate with alpha)
-      const D3 a = scale(inC, dir.alpha);
-      double tG[9];
-#pragma unroll
-      for (int j = 0; j < 3; ++j) {
-        const D3 col = v3<double>(G[j], G[3 + j], G[6 + j]);
-        const D3 t = cross(a, col);
-        tG[j] = t.x;
-        tG[3 + j] = t.y;
-        tG[6 + j] = t.z;
-      }
-      const double tphi = tG[0] + tG[4] + tG[8];
-      tphi_lane = tphi;
-      const double cw = k1 ? 2.0 * sg * T.w_frame : 0.0;
-      const Dual kappa = mkdual(cw * (phi - 3.0), cw * tphi);
-      const V3<Dual> mGD = lift<Dual>(mG, v3<double>(tG[5] - tG[7], tG[6] - tG[2], tG[1] - tG[3]));
-      S.chestN = scale(kappa, mGD);
+      const D3 a = dir.alpha;
+      const D3 tL = scale(inL, cross(a, (ld3(sb + T.foot_body[0] * SB_STRIDE + SB_O) - dir.pi) + fdal));
+      const D3 tR = scale(inR, cross(a, (ld3(sb + T.foot_body[1] * SB_STRIDE + SB_O) - dir.pi) + fdar));
+      ty_lane = dot(scale(inR, cross(a, fdu)), fdDelta) + dot(fdu, tL - tR);
+      const D3 ac = scale(inC, a);
+      tphi_lane = cross(ac, v3<double>(G[0], G[3], G[6])).x + cross(ac, v3<double>(G[1], G[4], G[7])).y +
+                  cross(ac, v3<double>(G[2], G[5], G[8])).z;
     }
 #if HB_FWD_JAC
     // ---------------------------------------------------------------- forward-mode Jacobian
@@ -1448,6 +1404,59 @@ __global__ void __launch_bounds__(128, WITH_HESS ? KIN_H_MIN_BLOCKS : 3) kino_ki
       __syncwarp();  // the Hessian columns reuse the stage
     }
 #endif
+    if (!with_l) return;  // Jacobian / gradient only: done
+    Seeds<Dual> S;
+    S.footF[0] = S.footF[1] = S.footN[0] = S.footN[1] = vzero<Dual>();
+    {
+      // multipliers from lamk (loaded at the top of the kernel; rows that do not exist hold 0)
+      S.wc = scale(-1.0 / M, ld3(lamk + 24));
+      S.hb = scale(-1.0 / mass_p, ld3(lamk + 27));
+      // stage I^w hbar (same for every lane of the dual sweep)
+      if (lane < nb) st3(sb + lane * SB_STRIDE + SB_IH, symmul(sb + lane * SB_STRIDE + SB_I, S.hb));
+      __syncwarp();
+    }
+#pragma unroll
+    for (int pt = 0; pt < 8; ++pt) {
+      const int f = pt >> 2;
+      const D3 frc = v3<double>(-lamk[3 * pt], -lamk[3 * pt + 1], -lamk[3 * pt + 2]);
+      const D3 a = ld3(sm + L.arms + 3 * pt);
+      const double in = f == 0 ? inL : inR;
+      const V3<Dual> aD = lift<Dual>(a, scale(in, cross(dir.alpha, a)));
+      S.footF[f] = S.footF[f] + lift<Dual>(frc, v3<double>(0.0, 0.0, 0.0));
+      S.footN[f] = S.footN[f] + cross(aD, frc);
+    }
+    {
+      const double kd = lamk[30];
+      const St<Dual> sL = load_state(sb, T.foot_body[0], dir, Dual());
+      const St<Dual> sR = load_state(sb, T.foot_body[1], dir, Dual());
+      const V3<Dual> uD = lift<Dual>(fdu, scale(inR, cross(dir.alpha, fdu)));
+      const V3<Dual> alD = lift<Dual>(fdal, scale(inL, cross(dir.alpha, fdal)));
+      const V3<Dual> arD = lift<Dual>(fdar, scale(inR, cross(dir.alpha, fdar)));
+      const V3<Dual> dD = (sL.o + alD) - (sR.o + arD);
+      const V3<Dual> ku = scale(kd, uD);
+      S.footF[0] = S.footF[0] + ku;
+      S.footN[0] = S.footN[0] + cross(alD, ku);
+      S.footF[1] = S.footF[1] - ku;
+      S.footN[1] = S.footN[1] + scale(kd, cross(uD, dD)) - cross(arD, ku);
+    }
+    {
+      // kappa = 2 sigma w (phi - 3) with its tangent; m(G) with its tangent (columns of G rotate with alpha)
+      const D3 a = scale(inC, dir.alpha);
+      double tG[9];
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        const D3 col = v3<double>(G[j], G[3 + j], G[6 + j]);
+        const D3 t = cross(a, col);
+        tG[j] = t.x;
+        tG[3 + j] = t.y;
+        tG[6 + j] = t.z;
+      }
+      const double tphi = tG[0] + tG[4] + tG[8];
+      const double cw = k1 ? 2.0 * sg * T.w_frame : 0.0;
+      const Dual kappa = mkdual(cw * (phi - 3.0), cw * tphi);
+      const V3<Dual> mGD = lift<Dual>(mG, v3<double>(tG[5] - tG[7], tG[6] - tG[2], tG[1] - tG[3]));
+      S.chestN = scale(kappa, mGD);
+    }
     HessEmit em;
     em.map = C.hk_map + (size_t)k * (27 * 57);
     em.hess = hess + b * T.nnz_h;

@@ -109,6 +109,10 @@ class _Evaluator:
     def last_launch_count(self) -> int:
         return int(_capi.lib().hb_last_launch_count(self._h))
 
+    def set_option(self, name: str, value: int) -> None:
+        """name: a HB_OPT_* constant of include/hippopt_b200.h without the prefix, e.g. "JAC_ADJOINT"."""
+        _capi.check(_capi.lib().hb_set_option(self._h, H["HB_OPT_" + name], int(value)), "hb_set_option")
+
     def profile(self, enable: bool) -> None:
         _capi.check(_capi.lib().hb_profile_enable(self._h, int(enable)), "hb_profile_enable")
 

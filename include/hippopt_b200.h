@@ -234,6 +234,13 @@ int hb_host_free(void* ptr);
 /* number of kernel launches the last hb_eval / hb_eval_host enqueued (for bench.py's gpu_launches claim) */
 int hb_last_launch_count(hb_handle h);
 
+/* Evaluator options.  HB_OPT_JAC_ADJOINT (default 0): when jac_g / grad_f are requested WITHOUT hess_l,
+ * compute the kinematic rows with the row-per-lane adjoint sweep instead of the forward-mode columns -- an
+ * independent algorithm for the same numbers (agreement to rounding is part of the GPU tests), 0.2 ms
+ * slower per 30 720 knot-evals. */
+enum { HB_OPT_JAC_ADJOINT = 1 };
+int hb_set_option(hb_handle h, int32_t option, int32_t value);
+
 /* Per-kernel device timing of the kinodynamic evaluator.  While enabled, every hb_eval records CUDA
  * events on its stream around the contact kernel, the kinematics kernel and the f reduction.
  * hb_profile_read sums the elapsed milliseconds {contact, kinematics, reduce} over the hb_eval calls

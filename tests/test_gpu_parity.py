@@ -198,13 +198,20 @@ def test_kino_edge_cases(model, built_library):
         assert np.array_equal(one[k][0], full[k][2]), k  # batching does not change results
     part = run(ev, x, p, lam, sigma, F | G)
     assert set(part) == {"f", "g"} and np.array_equal(part["g"], full["g"]) and np.array_equal(part["f"], full["f"])
-    # Without the Hessian bit the kinematic rows come from the row-per-lane adjoint sweep, with it from
-    # the forward tangents of the direction lanes: two algorithms, equal to rounding, not bit-identical.
+    # The kinematic rows of jac_g come from the forward tangents of the direction lanes whatever the mask ...
     jac_only = run(ev, x, p, lam, sigma, JAC_G)
-    close(jac_only["jac"], full["jac"], rtol=1e-13)
+    assert np.array_equal(jac_only["jac"], full["jac"])
     jac_grad = run(ev, x, p, lam, sigma, JAC_G | GRAD_F)
-    assert np.array_equal(jac_grad["jac"], jac_only["jac"])
-    close(jac_grad["grad_f"], full["grad_f"], rtol=1e-12)
+    assert np.array_equal(jac_grad["jac"], full["jac"]) and np.array_equal(jac_grad["grad_f"], full["grad_f"])
+    # ... and, as an option, from the row-per-lane adjoint sweep: two algorithms, equal to rounding
+    ev.set_option("JAC_ADJOINT", 1)
+    adj = run(ev, x, p, lam, sigma, JAC_G | GRAD_F)
+    ev.set_option("JAC_ADJOINT", 0)
+    assert not np.array_equal(adj["jac"], full["jac"])
+    close(adj["jac"], full["jac"], rtol=1e-13)
+    close(adj["grad_f"], full["grad_f"], rtol=1e-12)
+    with pytest.raises(_capi.EvaluationError):
+        _capi.check(_capi.lib().hb_set_option(ev._h, 99, 1), "hb_set_option")
     again = run(ev, x, p, lam, sigma)
     for k in full:
         assert np.array_equal(again[k], full[k]), k  # same mask: bit-reproducible
