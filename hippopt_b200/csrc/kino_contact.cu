@@ -327,37 +327,49 @@ __global__ void __launch_bounds__(128, TERRAIN == 0 ? CONTACT_MIN_BLOCKS : 1) ki
         }
       }
       if (want_jac) {
+        // the 58 entries of this point are listed first and their scatter slots loaded together: one
+        // jput() per entry waited for its own map load (19 % of this kernel's stall samples)
         const int pb0 = 846 + 58 * lane;
+        double jv[58];
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-          jput(pb0 + c, 1.0);
-          jput(pb0 + 3 + 3 * c + 0, -t0 * F.xh[c].c[0]);
-          jput(pb0 + 3 + 3 * c + 1, -t0 * F.yh[c].c[0]);
-          jput(pb0 + 3 + 3 * c + 2, -F.n[c].c[0]);
+          jv[c] = 1.0;
+          jv[3 + 3 * c + 0] = -t0 * F.xh[c].c[0];
+          jv[3 + 3 * c + 1] = -t0 * F.yh[c].c[0];
+          jv[3 + 3 * c + 2] = -F.n[c].c[0];
 #pragma unroll
-          for (int d = 0; d < 3; ++d) jput(pb0 + 12 + 3 * c + d, planar[c].c[1 + d]);
+          for (int d = 0; d < 3; ++d) jv[12 + 3 * c + d] = planar[c].c[1 + d];
         }
         const double h0 = F.h.c[0], N0 = Nn.c[0];
-        jput(pb0 + 21, -(F.gx.c[0] * N0 + h0 * DnTf0.c[0]));
-        jput(pb0 + 22, -(F.gy.c[0] * N0 + h0 * DnTf1.c[0]));
-        jput(pb0 + 23, -N0);
+        jv[21] = -(F.gx.c[0] * N0 + h0 * DnTf0.c[0]);
+        jv[22] = -(F.gy.c[0] * N0 + h0 * DnTf1.c[0]);
+        jv[23] = -N0;
 #pragma unroll
         for (int d = 0; d < 3; ++d) {
-          jput(pb0 + 24 + d, -h0 * F.n[d].c[0]);
-          jput(pb0 + 27 + d, margin.c[1 + d]);
-          jput(pb0 + 30 + d, -kbs * h0 * F.n[d].c[0] - hv.c[0] * F.n[d].c[0] - h0 * Dnv[d].c[0]);
-          jput(pb0 + 33 + d, F.h.c[1 + d]);
-          jput(pb0 + 38 + d, F.n[d].c[0]);
-          jput(pb0 + 43 + d, 2.0 * mu * mu * N0 * F.n[d].c[0] - 2.0 * X.c[0] * F.xh[d].c[0] - 2.0 * Y.c[0] * F.yh[d].c[0]);
-          jput(pb0 + 46 + d, 1.0);
-          jput(pb0 + 49 + d, mass);
-          jput(pb0 + 52 + d, 1.0);
-          jput(pb0 + 55 + d, -1.0);
+          jv[24 + d] = -h0 * F.n[d].c[0];
+          jv[27 + d] = margin.c[1 + d];
+          jv[30 + d] = -kbs * h0 * F.n[d].c[0] - hv.c[0] * F.n[d].c[0] - h0 * Dnv[d].c[0];
+          jv[33 + d] = F.h.c[1 + d];
+          jv[38 + d] = F.n[d].c[0];
+          jv[43 + d] = 2.0 * mu * mu * N0 * F.n[d].c[0] - 2.0 * X.c[0] * F.xh[d].c[0] - 2.0 * Y.c[0] * F.yh[d].c[0];
+          jv[46 + d] = 1.0;
+          jv[49 + d] = mass;
+          jv[52 + d] = 1.0;
+          jv[55 + d] = -1.0;
         }
-        jput(pb0 + 36, Nn.c[1]);
-        jput(pb0 + 37, Nn.c[2]);
-        jput(pb0 + 41, fric.c[1]);
-        jput(pb0 + 42, fric.c[2]);
+        jv[36] = Nn.c[1];
+        jv[37] = Nn.c[2];
+        jv[41] = fric.c[1];
+        jv[42] = fric.c[2];
+#pragma unroll
+        for (int c0 = 0; c0 < 58; c0 += 29) {
+          int sl[29];
+#pragma unroll
+          for (int u = 0; u < 29; ++u) sl[u] = jmap[pb0 + c0 + u];
+#pragma unroll
+          for (int u = 0; u < 29; ++u)
+            if (sl[u] >= 0) jb[sl[u]] = jv[c0 + u];
+        }
       }
       if (want_hess) {
         const double lpl[3] = {lam_pl[0], lam_pl[1], lam_pl[2]};
@@ -366,12 +378,20 @@ __global__ void __launch_bounds__(128, TERRAIN == 0 ? CONTACT_MIN_BLOCKS : 1) ki
         const double sws = k1 ? sg * C.w_swing : 0.0;
         const TJ Lp = lpl[0] * planar[0] + lpl[1] * planar[1] + lpl[2] * planar[2] + ld * margin + lh * F.h + ln * Nn +
                       lfr * fric + sws * swing;
+        // 63 contributions of this point: listed, their table entries loaded together, then accumulated
+        int ti[63], nterm = 0;
+        double tv[63];
+        auto term = [&](int vi, int vj, double v) {
+          ti[nterm] = vi * NCV + vj;
+          tv[nterm] = v;
+          ++nterm;
+        };
         {
           int e = 0;
 #pragma unroll
           for (int a = 0; a < 3; ++a)
 #pragma unroll
-            for (int bb = a; bb < 3; ++bb) hadd(o + Z_P + a, o + Z_P + bb, tj_hess(Lp, e++));
+            for (int bb = a; bb < 3; ++bb) term(o + Z_P + a, o + Z_P + bb, tj_hess(Lp, e++));
         }
         const TJ Gu[3] = {-(tauj * tj_dot(F.xh, lplv)), -(tauj * tj_dot(F.yh, lplv)), -tj_dot(F.n, lplv)};
 #pragma unroll
@@ -383,10 +403,10 @@ __global__ void __launch_bounds__(128, TERRAIN == 0 ? CONTACT_MIN_BLOCKS : 1) ki
                         lfr * ((2.0 * mu * mu) * (Nn * F.n[d]) - 2.0 * (X * F.xh[d]) - 2.0 * (Y * F.yh[d]));
 #pragma unroll
           for (int a = 0; a < 3; ++a) {
-            hadd(o + Z_P + a, o + Z_U + d, Gu[d].c[1 + a]);
-            hadd(o + Z_P + a, o + Z_V + d, Gv.c[1 + a]);
-            hadd(o + Z_P + a, o + Z_FD + d, Gfd.c[1 + a]);
-            hadd(o + Z_P + a, o + Z_F + d, Gf.c[1 + a]);
+            term(o + Z_P + a, o + Z_U + d, Gu[d].c[1 + a]);
+            term(o + Z_P + a, o + Z_V + d, Gv.c[1 + a]);
+            term(o + Z_P + a, o + Z_FD + d, Gfd.c[1 + a]);
+            term(o + Z_P + a, o + Z_F + d, Gf.c[1 + a]);
           }
         }
 #pragma unroll
@@ -395,14 +415,23 @@ __global__ void __launch_bounds__(128, TERRAIN == 0 ? CONTACT_MIN_BLOCKS : 1) ki
           for (int bb = 0; bb < 3; ++bb) {
             const double ga = a == 0 ? F.gx.c[0] : (a == 1 ? F.gy.c[0] : 1.0);
             const double dnba = a < 2 ? F.Dn[bb][a].c[0] : 0.0;
-            hadd(o + Z_V + a, o + Z_F + bb, -ld * (ga * F.n[bb].c[0] + F.h.c[0] * dnba));
+            term(o + Z_V + a, o + Z_F + bb, -ld * (ga * F.n[bb].c[0] + F.h.c[0] * dnba));
             if (bb >= a) {
-              hadd(o + Z_F + a, o + Z_F + bb,
+              term(o + Z_F + a, o + Z_F + bb,
                    lfr * (2.0 * mu * mu * F.n[a].c[0] * F.n[bb].c[0] - 2.0 * F.xh[a].c[0] * F.xh[bb].c[0] -
                           2.0 * F.yh[a].c[0] * F.yh[bb].c[0]));
-              hadd(o + Z_V + a, o + Z_V + bb, sws * (F.xh[a].c[0] * F.xh[bb].c[0] + F.yh[a].c[0] * F.yh[bb].c[0]));
+              term(o + Z_V + a, o + Z_V + bb, sws * (F.xh[a].c[0] * F.xh[bb].c[0] + F.yh[a].c[0] * F.yh[bb].c[0]));
             }
           }
+#pragma unroll
+        for (int c0 = 0; c0 < 63; c0 += 21) {
+          int te[21];
+#pragma unroll
+          for (int u = 0; u < 21; ++u) te[u] = C.hc_index[ti[c0 + u]];
+#pragma unroll
+          for (int u = 0; u < 21; ++u)
+            if (te[u] >= 0) hbuf[te[u]] += tv[c0 + u];
+        }
       }
     }
     if (lane == 8) {

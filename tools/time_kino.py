@@ -1,4 +1,5 @@
-"""Developer timing: kinodynamic evaluator at config-3 size, per-kernel CUDA-event times."""
+"""Developer timing: kinodynamic evaluator at config-3 size (or, with "stairs", the config-5 problem: smooth-step
+terrain, horizon 50, 512 instances), per-kernel CUDA-event times for the masks a solver uses."""
 import sys
 import time
 
@@ -11,12 +12,19 @@ from hippopt_b200.robot_model import synthetic_ergocub  # noqa: E402
 from hippopt_b200.workloads import kino_batch  # noqa: E402
 
 model = synthetic_ergocub()
-ev = KinoEvaluator(model, KinoSettings(horizon=30))
-B = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
+stairs = "stairs" in sys.argv
+nums = [int(a) for a in sys.argv[1:] if a.isdigit()]
+if stairs:
+    st, B = KinoSettings(horizon=50, terrain="smooth_steps", n_terrain_params=10, final_state_constraint=True), 512
+else:
+    st, B = KinoSettings(horizon=30), 1024
+B = nums[0] if nums else B
+ev = KinoEvaluator(model, st)
+N = ev.layout.N
 x, p, lam, sigma = kino_batch(ev.layout, model, B, seed=2)
 d = torch.device("cuda:0")
 X, P, L, S = (torch.tensor(a, device=d) for a in (x, p, lam, sigma))
-for mask, name in ((ALL, "f+g+grad+jac+hess"), (ALL & ~16, "f+g+grad+jac"), (1 | 4, "f+g")):
+for mask, name in ((ALL, "f+g+grad+jac+hess"), (ALL & ~16, "f+g+grad+jac"), (16, "hess"), (1 | 4, "f+g")):
     for _ in range(5):
         ev.eval(mask, X, P, L, S)
     torch.cuda.synchronize()
@@ -29,5 +37,5 @@ for mask, name in ((ALL, "f+g+grad+jac+hess"), (ALL & ~16, "f+g+grad+jac"), (1 |
     dt = (time.perf_counter() - t0) / reps
     ms, n = ev.profile_read()
     ev.profile(False)
-    print(f"{name:20s} {dt * 1e3:7.3f} ms  {B * 30 / dt:.3e} knot-evals/s   " +
+    print(f"{name:20s} {dt * 1e3:7.3f} ms  {B * N / dt:.3e} knot-evals/s   " +
           " ".join(f"{k}={v / n:.3f}" for k, v in ms.items()))
