@@ -75,3 +75,23 @@ def test_periodicity_is_rejected(model):
     ine = np.nonzero(lb[0] != ub[0])[0]
     with pytest.raises(NotImplementedError):
         StageKKT(lay.n_x, lay.m, 3, 189, lay.jac_colind, lay.jac_row, lay.hess_colind, lay.hess_row, eq, ine)
+
+
+def test_sparse_operators_match_dense(model):
+    """The interior-point driver never forms jac_g / hess_l: its products go straight through the CCS value
+    arrays (ipsolver.SparseOps).  Checked against dense algebra on the real patterns."""
+    from hippopt_b200.ipsolver import SparseOps
+
+    lay = KinoLayout(model, KinoSettings(horizon=3, final_state_constraint=True))
+    ops = SparseOps(lay.n_x, lay.m, (lay.jac_colind, lay.jac_row), (lay.hess_colind, lay.hess_row), "cpu")
+    g = torch.Generator().manual_seed(5)
+    B = 2
+    jv = torch.randn((B, lay.nnz_j), generator=g, dtype=torch.float64)
+    hv = torch.randn((B, lay.nnz_h), generator=g, dtype=torch.float64)
+    x = torch.randn((B, lay.n_x), generator=g, dtype=torch.float64)
+    lam = torch.randn((B, lay.m), generator=g, dtype=torch.float64)
+    J, W = ops.dense_jac(jv), ops.dense_hess(hv)
+    assert torch.allclose(ops.J_mul(jv, x), torch.einsum("bmn,bn->bm", J, x), rtol=1e-12, atol=1e-12)
+    assert torch.allclose(ops.Jt_mul(jv, lam), torch.einsum("bmn,bm->bn", J, lam), rtol=1e-12, atol=1e-12)
+    assert torch.allclose(ops.W_quad(hv, x), torch.einsum("bn,bnk,bk->b", x, W, x), rtol=1e-12, atol=1e-12)
+    assert torch.equal(W, W.transpose(1, 2))
