@@ -114,7 +114,7 @@ class BatchedInteriorPoint:
     def __init__(self, ev, tol: float = 1e-8, max_iter: int = 300, mu_init: float = 0.1, kappa_eps: float = 10.0,
                  kappa_mu: float = 0.2, theta_mu: float = 1.5, tau_min: float = 0.99, eta: float = 1e-4,
                  max_backtrack: int = 16, delta_min: float = 1e-8, delta_max: float = 1e8, exact_inertia: bool = False,
-                 verbose: bool = False, kkt: str = "dense", delta_c: float = 1e-11):
+                 verbose: bool = False, kkt: str = "dense", delta_c: float = 1e-11, f_type: bool = True):
         """kkt: "dense" (one dense factorisation per instance) or "stage" (block-tridiagonal sweep over the knots,
         hippopt_b200.kkt.StageKKT -- the multiple-shooting OCPs of the kinodynamic planner)."""
         self.ev = ev
@@ -126,7 +126,7 @@ class BatchedInteriorPoint:
         self.verbose = verbose
         if kkt not in ("dense", "stage"):
             raise ValueError("kkt must be 'dense' or 'stage'")
-        self.kkt_kind, self.delta_c = kkt, delta_c
+        self.kkt_kind, self.delta_c, self.f_type = kkt, delta_c, f_type
         self.kkt_seconds = 0.0
 
     # ------------------------------------------------------------------ solve
@@ -311,7 +311,15 @@ class BatchedInteriorPoint:
                 # progress in the constraint violation OR in the barrier objective
                 bart = barrier(ot["f"], st, mu)
                 filt = (ct <= (1.0 - 1e-5) * cnorm) | (bart <= bar0 - 1e-5 * cnorm)
-                good = torch.isfinite(phit) & (armijo | (filt & (cnorm > 1e-4 * torch.clamp(cnorm0, min=1.0))))
+                # f-type step (Waechter & Biegler, eq. 19-20): at an almost feasible iterate with a descent
+                # direction for the barrier objective, ask for Armijo decrease of THAT alone, letting the
+                # violation grow to a small multiple of theta_min.  Without it the l1 merit function
+                # rejects the full step whenever the curved constraints (quaternion, kinematics) give back a
+                # second-order violation -- the Maratos effect: 16 evaluations per iteration, tiny steps.
+                theta_min = 1e-4 * torch.clamp(cnorm0, min=1.0)
+                ftype = self.f_type & (cnorm <= theta_min) & (dbar < 0)
+                acc_f = ftype & (bart <= bar0 + self.eta * alpha * dbar) & (ct <= 10.0 * theta_min)
+                good = torch.isfinite(phit) & (armijo | (filt & (cnorm > theta_min)) | acc_f)
                 take = good & ~accepted
                 x_new = torch.where(take[:, None], xt, x_new)
                 s_new = torch.where(take[:, None], st, s_new)
