@@ -64,7 +64,8 @@ def test_standing_ocp_solves_with_the_stage_kkt(model, built_library):
     lb, ub = pev.bounds(p)
     out = BatchedInteriorPoint(pev, tol=1e-8, max_iter=300).solve(torch.tensor(x, device=dev), torch.tensor(p, device=dev), lb, ub)
     pose = out.values.cpu().numpy()[out.success.cpu().numpy()]
-    assert pose.shape[0] >= 4  # a minority converges (no restoration phase): enough poses to go on
+    assert pose.shape[0] >= 90  # 96/96 with the f-type step acceptance (36 % without: profiles/r01/solver_v8.txt)
+    assert int(out.iterations.max()) <= 150
     ev = KinoEvaluator(model, KinoSettings(horizon=4))
     lay = ev.layout
     pk, x0 = standing_problem(lay, model, pose)
@@ -75,8 +76,8 @@ def test_standing_ocp_solves_with_the_stage_kkt(model, built_library):
     sol = BatchedInteriorPoint(ev, tol=1e-6, max_iter=300, kkt="stage", delta_c=1e-9, mu_init=1e-3)
     res = sol.solve(torch.tensor(x0, device=dev), P, lbk, ubk)
     ok = res.success.cpu().numpy()
-    # the driver has no restoration phase: part of the instances stall; the rate is reported in DESIGN.md
-    assert ok.sum() >= max(1, pose.shape[0] // 6), f"{int(ok.sum())} of {pose.shape[0]} standing OCPs converged"
+    assert ok.sum() >= int(0.9 * pose.shape[0]), f"{int(ok.sum())} of {pose.shape[0]} standing OCPs converged"
+    assert int(res.iterations[res.success].median()) <= 60
     assert float(res.kkt_error[res.success].max()) <= 1e-6
     gs = ev.eval(G, res.values, P)["g"].cpu().numpy()[ok]
     assert (np.maximum(lbk[ok] - gs, 0) + np.maximum(gs - ubk[ok], 0)).max() < 1e-5
