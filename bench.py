@@ -337,6 +337,45 @@ def main():
                     "ms_per_batched_solve": tk * 1e3, "kkt_solves_per_s": nk / tk}
         del kkt, vals
 
+    # ---- row f1: complete solves with the evaluator in the loop (pose finder, then "keep standing" OCPs of the
+    # bench workload's size built from those poses); informational, failures are reported, not hidden
+    solves = None
+    if world == 1 and not args.no_cpu_baseline:
+        from hippopt_b200.evaluator import PoseEvaluator
+        from hippopt_b200.ipsolver import BatchedInteriorPoint
+        from hippopt_b200.workloads import pose_batch, standing_problem
+
+        try:
+            n_s = torch.cuda.get_device_properties(dev).multi_processor_count  # one wave of the LU kernels
+            pev = PoseEvaluator(model)
+            xq, pq, _, _ = pose_batch(pev.layout, model, n_s, seed=1, noise=0.02)
+            lbq, ubq = pev.bounds(pq)
+            torch.cuda.synchronize(dev)
+            ts = time.perf_counter()
+            po_out = BatchedInteriorPoint(pev, tol=1e-8, max_iter=300).solve(torch.tensor(xq, device=dev),
+                                                                             torch.tensor(pq, device=dev), lbq, ubq)
+            torch.cuda.synchronize(dev)
+            t_pose = time.perf_counter() - ts
+            okp = po_out.success.cpu().numpy()
+            pk, x0k = standing_problem(lay, model, po_out.values.cpu().numpy()[okp])
+            lbs_, ubs_ = lay.bounds(pk)
+            ip = BatchedInteriorPoint(ev, tol=1e-6, max_iter=300, kkt="stage", delta_c=1e-9, mu_init=1e-3)
+            ts = time.perf_counter()
+            st_out = ip.solve(torch.tensor(x0k, device=dev), torch.tensor(pk, device=dev), lbs_, ubs_)
+            torch.cuda.synchronize(dev)
+            t_ocp = time.perf_counter() - ts
+            n_ok = int(st_out.success.sum())
+            solves = {"pose_finder": {"instances": n_s, "converged": int(okp.sum()), "solves_per_s": int(okp.sum()) / t_pose,
+                                      "iterations_median": int(po_out.iterations.median())},
+                      "standing_ocp": {"workload": f"keep-standing OCP at the bench size (horizon {HORIZON}, n_x {lay.n_x}, "
+                                                   f"m {lay.m}) from the converged poses, stage-wise KKT",
+                                       "instances": int(okp.sum()), "converged": n_ok, "solves_per_s": n_ok / t_ocp,
+                                       "iterations_median": int(st_out.iterations[st_out.success].median()) if n_ok else None,
+                                       "seconds": t_ocp, "seconds_in_kkt": ip.kkt_seconds,
+                                       "batched_evaluations": st_out.evaluations}}
+        except Exception as exc:  # noqa: BLE001 -- a solver failure must not cost the throughput line
+            solves = {"error": f"{type(exc).__name__}: {exc}"}
+
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
         from oracle.cpu_baseline import OraclePool
@@ -374,6 +413,7 @@ def main():
         "cpu_baseline": cpu_baseline,
         "other_configs": other,
         "kkt": kkt_line,
+        "solves": solves,
     }
     print(json.dumps(line))
     if world > 1:

@@ -252,7 +252,16 @@ class BatchedInteriorPoint:
                 if dev.type == "cuda":
                     torch.cuda.synchronize(dev)
                 t_k = time.perf_counter()
-                dxt, lamt = backend.solve(hv, jv, Sig, delta, dc, rhs_x, -cE)
+                # only the instances that still need a step: converged ones (and those whose step was
+                # accepted in an earlier attempt) do not ride along -- the factorisation is what costs
+                idx = torch.nonzero(need).ravel()
+                if idx.numel() == B:
+                    dxt, lamt = backend.solve(hv, jv, Sig, delta, dc, rhs_x, -cE)
+                else:
+                    sub = backend.solve(hv[idx], jv[idx], Sig[idx], delta[idx], dc, rhs_x[idx], -cE[idx])
+                    dxt = torch.zeros_like(x)
+                    lamt = torch.zeros_like(lamE)
+                    dxt[idx], lamt[idx] = sub[0], sub[1]
                 if dev.type == "cuda":
                     torch.cuda.synchronize(dev)
                 self.kkt_seconds += time.perf_counter() - t_k
@@ -260,7 +269,8 @@ class BatchedInteriorPoint:
                 # inertia test (IPOPT's criterion): the KKT matrix must have exactly n positive and mE negative
                 # eigenvalues, i.e. the reduced Hessian is positive definite on the null space of J_E
                 if self.exact_inertia and attempt < 11 and self.kkt_kind == "dense":
-                    inertia_ok = (torch.linalg.eigvalsh(backend.K) < 0).sum(dim=1) == mE
+                    inertia_ok = torch.zeros(B, dtype=torch.bool, device=dev)
+                    inertia_ok[idx] = (torch.linalg.eigvalsh(backend.K) < 0).sum(dim=1) == mE
                 else:  # cheap proxy: positive curvature of the barrier Lagrangian along the step
                     curv = ops.W_quad(hv, dxt) + delta * (dxt * dxt).sum(1) + (Sig * dst * dst).sum(1)
                     inertia_ok = curv > 1e-12 * (dxt * dxt).sum(1)
