@@ -815,16 +815,32 @@ extern "C" int hb_lu_factor_batched(double* A, int32_t* piv, int32_t* info, int6
   if (n <= 0 || n > 768 || batch <= 0) return fail(HB_ERR_INVALID, "hb_lu_factor_batched: need 0 < n <= 768, batch > 0");
   const size_t smem = hb::lu_factor_smem((int)n);
   static bool attr = false;
+  static int sms = 0;
   if (!attr) {
-    CUDA_TRY(cudaFuncSetAttribute(hb::lu_factor_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
-    CUDA_TRY(cudaFuncSetAttribute(hb::lu_factor_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
-    CUDA_TRY(cudaFuncSetAttribute(hb::lu_factor_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
+    const int big = 210 * 1024;
+    CUDA_TRY(cudaFuncSetAttribute(hb::lu_factor_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CUDA_TRY(cudaFuncSetAttribute(hb::lu_factor_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CUDA_TRY(cudaFuncSetAttribute(hb::lu_factor_kernel<3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CUDA_TRY(cudaFuncSetAttribute(hb::lu_factor_kernel<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CUDA_TRY(cudaFuncSetAttribute(hb::lu_factor_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     attr = true;
   }
   cudaStream_t st = (cudaStream_t)stream;
-  if (n <= hb::LU_THREADS) hb::lu_factor_kernel<1><<<(unsigned)batch, hb::LU_THREADS, smem, st>>>(A, piv, info, (int)n);
-  else if (n <= 2 * hb::LU_THREADS) hb::lu_factor_kernel<2><<<(unsigned)batch, hb::LU_THREADS, smem, st>>>(A, piv, info, (int)n);
-  else hb::lu_factor_kernel<3><<<(unsigned)batch, hb::LU_THREADS, smem, st>>>(A, piv, info, (int)n);
+  const unsigned grid = (unsigned)batch;
+  // more than one block per SM and two of them fit (shared memory): the 128-register variant
+  const bool two = batch > sms && 2 * (smem + 2048) <= 227 * 1024;
+  if (n <= hb::LU_THREADS) {
+    if (two) hb::lu_factor_kernel<1, 2><<<grid, hb::LU_THREADS, smem, st>>>(A, piv, info, (int)n);
+    else hb::lu_factor_kernel<1, 1><<<grid, hb::LU_THREADS, smem, st>>>(A, piv, info, (int)n);
+  } else if (n <= 2 * hb::LU_THREADS) {
+    if (two) hb::lu_factor_kernel<2, 2><<<grid, hb::LU_THREADS, smem, st>>>(A, piv, info, (int)n);
+    else hb::lu_factor_kernel<2, 1><<<grid, hb::LU_THREADS, smem, st>>>(A, piv, info, (int)n);
+  } else {
+    hb::lu_factor_kernel<3, 1><<<grid, hb::LU_THREADS, smem, st>>>(A, piv, info, (int)n);
+  }
   CUDA_TRY(cudaGetLastError());
   return HB_OK;
 }

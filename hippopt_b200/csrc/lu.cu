@@ -40,8 +40,11 @@ __host__ __device__ inline int lu_ldp(int n) { return (n + 3) & ~3; }
 __host__ __device__ inline size_t lu_factor_smem(int n) { return ((size_t)2 * LU_NB * lu_ldp(n) + 256) * sizeof(double); }
 
 // RPT = panel rows per thread: n <= RPT * LU_THREADS
-template <int RPT>
-__global__ void __launch_bounds__(LU_THREADS) lu_factor_kernel(double* __restrict__ Aall, int* __restrict__ pivall,
+// MB = CTAs per SM the register allocation is tuned for.  Measured on B200 (blocks of 337^2): 148 blocks
+// 0.93 ms at MB = 1 (232 registers) vs 1.06 ms at MB = 2 (128 registers, 416 B of spills); 296 blocks 1.85 ms
+// vs 1.53 ms -- the host picks MB = 2 when the batch exceeds one CTA per SM.
+template <int RPT, int MB>
+__global__ void __launch_bounds__(LU_THREADS, MB) lu_factor_kernel(double* __restrict__ Aall, int* __restrict__ pivall,
                                                                int* __restrict__ infoall, int n) {
   extern __shared__ __align__(16) double lu_sm[];
   double* A = Aall + (size_t)blockIdx.x * n * n;
@@ -282,6 +285,13 @@ __global__ void __launch_bounds__(LU_THREADS) lu_factor_kernel(double* __restric
 // kept in shared memory for the whole forward and backward substitution.  Rows outside the current
 // panel are updated with 4 x 8 register tiles (lane = row: coalesced reads of the factor).
 constexpr int LU_RC = 32;
+#ifndef HB_LU_KD
+// panel columns whose factor entries are requested together in the substitution sweeps.  Measured on B200,
+// 148 / 296 blocks of 337^2 with 88 right-hand sides: a load per column 1.30 / 1.95 ms; 8 columns together
+// (254 registers, 1 CTA per SM) 0.94 / 1.88 ms; 4 columns and 2 CTAs per SM (128 registers) 0.81 / 1.23 ms
+#define HB_LU_KD 4
+#endif
+constexpr int LU_KD = HB_LU_KD;
 
 __device__ __forceinline__ void lu_rows_update(const double* __restrict__ A, double* b, int n, int ldb, int j0, int nbw,
                                                int r0, int r1, int tid) {
@@ -294,19 +304,26 @@ __device__ __forceinline__ void lu_rows_update(const double* __restrict__ A, dou
     for (int a = 0; a < 4; ++a)
 #pragma unroll
       for (int c = 0; c < 8; ++c) acc[a][c] = 0.0;
-    for (int k = 0; k < nbw; ++k) {
-      double av[4];
+    for (int k0 = 0; k0 < nbw; k0 += LU_KD) {
+      // the factor entries of 8 panel columns are requested together (32 loads in flight per thread):
+      // with a load per k the loop ran at the L2 latency
+      double av[LU_KD][4];
 #pragma unroll
-      for (int a = 0; a < 4; ++a) {
-        const int i = ib + lane + 32 * a;
-        av[a] = i < r1 ? A[(size_t)(j0 + k) * n + i] : 0.0;
-      }
-      const double* bk = b + (j0 + k) * ldb + cg;
+      for (int kk = 0; kk < LU_KD; ++kk)
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        const double bv = bk[c];
+        for (int a = 0; a < 4; ++a) {
+          const int i = ib + lane + 32 * a;
+          av[kk][a] = (k0 + kk < nbw && i < r1) ? A[(size_t)(j0 + k0 + kk) * n + i] : 0.0;
+        }
 #pragma unroll
-        for (int a = 0; a < 4; ++a) acc[a][c] = fma(av[a], bv, acc[a][c]);
+      for (int kk = 0; kk < LU_KD; ++kk) {
+        const double* bk = b + (j0 + min(k0 + kk, nbw - 1)) * ldb + cg;  // av is zero past the panel
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const double bv = bk[c];
+#pragma unroll
+          for (int a = 0; a < 4; ++a) acc[a][c] = fma(av[kk][a], bv, acc[a][c]);
+        }
       }
     }
 #pragma unroll
@@ -319,7 +336,10 @@ __device__ __forceinline__ void lu_rows_update(const double* __restrict__ A, dou
   }
 }
 
-__global__ void __launch_bounds__(LU_THREADS) lu_solve_kernel(const double* __restrict__ LUall,
+#ifndef HB_LU_SOLVE_MIN_BLOCKS
+#define HB_LU_SOLVE_MIN_BLOCKS 2
+#endif
+__global__ void __launch_bounds__(LU_THREADS, HB_LU_SOLVE_MIN_BLOCKS) lu_solve_kernel(const double* __restrict__ LUall,
                                                               const int* __restrict__ pivall, double* __restrict__ Ball,
                                                               int n, int nrhs) {
   extern __shared__ __align__(16) double lu_sm[];
