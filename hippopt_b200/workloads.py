@@ -201,3 +201,22 @@ def standing_problem(lay: KinoLayout, model: RobotModel, pose: np.ndarray):
         z[:, S:S + NJ] = pose[:, 55:78]
         z[:, COM:COM + 3] = pose[:, 78:81]
     return p, x0
+
+
+def transfer_problem(lay: KinoLayout, model: RobotModel, pose_a: np.ndarray, pose_b: np.ndarray):
+    """OCPs that go from pose A to pose B: initial state A, final state B (use a layout with
+    ``final_state_constraint``), references and initial guess interpolated linearly knot by knot -- the role of
+    `humanoid_state_interpolator` (`robot_planning/utilities/interpolators.py:396-448`) for states without a
+    contact-phase change (the quaternion is interpolated linearly and left to the unit-norm row, not slerped).
+    The guess has zero velocities, i.e. it violates the integrator rows by O(|B - A| / N)."""
+    pa, xa = standing_problem(lay, model, pose_a)
+    pb, xb = standing_problem(lay, model, pose_b)
+    po, N = lay.po, lay.N
+    n_state = po.ST_COM + 3  # one state block: points, base, joints, com
+    pa[:, po.final:po.final + n_state] = pb[:, po.final:po.final + n_state]
+    for k in range(N):
+        w = k / max(N - 1, 1)
+        r = po.refs0 + 55 * k
+        pa[:, r:r + 55] = (1 - w) * pa[:, r:r + 55] + w * pb[:, r:r + 55]
+        xa[:, NZ * k:NZ * (k + 1)] = (1 - w) * xa[:, NZ * k:NZ * (k + 1)] + w * xb[:, NZ * k:NZ * (k + 1)]
+    return pa, xa
