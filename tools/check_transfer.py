@@ -43,7 +43,8 @@ lbk, ubk = lay.bounds(pk)
 g0 = ev.eval(4, torch.tensor(x0, device=d), torch.tensor(pk, device=d))["g"].cpu().numpy()
 viol = np.maximum(lbk - g0, 0) + np.maximum(g0 - ubk, 0)
 print(f"interpolated guess: max constraint violation {viol.max():.2e}")
-sol = BatchedInteriorPoint(ev, tol=1e-6, max_iter=iters, verbose="-v" in sys.argv, kkt="stage", delta_c=1e-9, mu_init=1e-3)
+tol = float(sys.argv[sys.argv.index("-t") + 1]) if "-t" in sys.argv else 1e-6
+sol = BatchedInteriorPoint(ev, tol=tol, max_iter=iters, verbose="-v" in sys.argv, kkt="stage", delta_c=1e-9, mu_init=1e-3)
 t0 = time.perf_counter()
 try:
     res = sol.solve(torch.tensor(x0, device=d), torch.tensor(pk, device=d), lbk, ubk)
@@ -53,7 +54,7 @@ try:
     gs = ev.eval(4, res.values, torch.tensor(pk, device=d))["g"].cpu().numpy()
     vs = (np.maximum(lbk - gs, 0) + np.maximum(gs - ubk, 0))[okk]
     com_y = xs[:, [NZ * k + COM + 1 for k in range(N)]]
-    print(f"weight-shift OCP (N={N}, shift {shift} m): {int(okk.sum())}/{nB} converged to 1e-6, iterations median "
+    print(f"weight-shift OCP (N={N}, shift {shift} m): {int(okk.sum())}/{nB} converged to {tol:g}, iterations median "
           f"{int(res.iterations[res.success].median()) if okk.any() else -1}, {time.perf_counter() - t0:.1f} s; constraint violation "
           f"{vs.max() if okk.any() else float('nan'):.1e}; CoM y of instance 0 over the horizon: "
           f"{np.array2string(com_y[0], precision=4) if okk.any() else '-'}")
