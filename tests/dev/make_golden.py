@@ -1,13 +1,14 @@
 """Generate the golden fixtures under tests/golden/ from the CPU oracle (run in this container:
-`python tools/make_golden.py`).  The oracle itself is pinned by tests/test_oracle_*.py; these files
+`python tests/dev/make_golden.py`).  The oracle itself is pinned by tests/test_oracle_*.py; these files
 freeze its outputs so that the GPU parity tests do not depend on rebuilding the graphs, and so that a
-later CasADi dump can replace them file-for-file (same keys)."""
+later CasADi dump can replace them file-for-file (same keys).  Lives under tests/ because it imports
+oracle/ (test infrastructure only)."""
 import os
 import sys
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 
 from hippopt_b200.kino_layout import KinoLayout, KinoSettings  # noqa: E402
