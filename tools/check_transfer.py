@@ -44,7 +44,8 @@ g0 = ev.eval(4, torch.tensor(x0, device=d), torch.tensor(pk, device=d))["g"].cpu
 viol = np.maximum(lbk - g0, 0) + np.maximum(g0 - ubk, 0)
 print(f"interpolated guess: max constraint violation {viol.max():.2e}")
 tol = float(sys.argv[sys.argv.index("-t") + 1]) if "-t" in sys.argv else 1e-6
-sol = BatchedInteriorPoint(ev, tol=tol, max_iter=iters, verbose="-v" in sys.argv, kkt="stage", delta_c=1e-9, mu_init=1e-3)
+dc = float(sys.argv[sys.argv.index("-c") + 1]) if "-c" in sys.argv else 1e-9
+sol = BatchedInteriorPoint(ev, tol=tol, max_iter=iters, verbose="-v" in sys.argv, kkt="stage", delta_c=dc, mu_init=1e-3)
 t0 = time.perf_counter()
 try:
     res = sol.solve(torch.tensor(x0, device=d), torch.tensor(pk, device=d), lbk, ubk)
