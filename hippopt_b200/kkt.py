@@ -18,7 +18,8 @@ value arrays the kernels write to the dense stage blocks.
 
 Checked against a dense solve of the same system (tests/test_kkt_cpu.py on random values in the real
 pattern, tests/test_gpu_solver.py on evaluated values).  Periodicity rows (knot 0 with knot N-1) make
-the matrix cyclic and are not supported here.
+the matrix cyclic: they are kept as a border of the block-tridiagonal part and eliminated with a Schur
+complement (one sweep with 1 + 84 right-hand sides).
 """
 from __future__ import annotations
 
@@ -63,7 +64,7 @@ def lu_solve(F: torch.Tensor, piv: torch.Tensor, rhs: torch.Tensor) -> torch.Ten
 
 class StageKKT:
     def __init__(self, n_x: int, m: int, horizon: int, knot_size: int, jac_colind, jac_row, hess_colind, hess_row,
-                 eq_rows, ine_rows, device="cpu", linalg: str = "hb"):
+                 eq_rows, ine_rows, device="cpu", linalg: str = "hb", max_border: int = 128):
         """eq_rows / ine_rows: sorted global row indices of the equality / inequality constraints (the
         ordering of the multiplier vectors handed to ``solve``).  Variables beyond horizon*knot_size
         (initial-state decision variables) join stage 0.
@@ -99,11 +100,17 @@ class StageKKT:
         np.maximum.at(hi, jac_row, jst)
         np.minimum.at(lo, jac_row, jst)
         live = hi >= 0  # rows with an empty Jacobian (parameter-only rows) take no part in the Newton system
-        if np.any((hi - lo)[live] > 1):
-            raise NotImplementedError("a constraint row couples non-adjacent knots (periodicity): the KKT matrix is "
-                                      "cyclic, not block tridiagonal")
+        # rows that couple non-adjacent knots (periodicity: knot 0 with knot N-1) make the matrix cyclic; they
+        # are kept out of the stages and handled as a BORDER: K = [[K_bt, P^T], [P, -delta_c I]], solved with
+        # one block-tridiagonal sweep over 1 + n_border right-hand sides and a small Schur complement
+        far = live & ((hi - lo) > 1)
+        if np.any(far[ine_rows]):
+            raise NotImplementedError("an inequality row couples non-adjacent knots")
         if np.any((hi - lo)[ine_rows][live[ine_rows]] > 0):
             raise NotImplementedError("an inequality row couples two knots")
+        if far.sum() > max_border:
+            raise NotImplementedError(f"{int(far.sum())} constraint rows couple non-adjacent knots (limit {max_border})")
+        hi = np.where(far, -2, hi)  # not in any stage
         hcol = np.repeat(np.arange(n_x), np.diff(hess_colind))
         if np.any(stage_of(hcol) != stage_of(hess_row)):
             raise NotImplementedError("hess_l couples two knots")
@@ -123,6 +130,8 @@ class StageKKT:
             self.ine_stage_rows.append(i)
             self.cpl_local.append(np.nonzero(lo[e] < k)[0])  # positions (inside the stage's eq rows) of the defect rows
         self.dead_eq = pos_E[eq_rows[~live[eq_rows]]]  # multipliers of empty rows: left at zero
+        border = eq_rows[far[eq_rows]]
+        self.n_border = len(border)
         self.mEk = max(len(e) for e in self.eq_stage_rows)
         self.mIk = max(max(len(i) for i in self.ine_stage_rows), 1)
         self.mCk = max(max(len(c) for c in self.cpl_local), 1)
@@ -171,6 +180,11 @@ class StageKKT:
                 "ine": t(pos_I[self.ine_stage_rows[k]]), "n_ine": len(self.ine_stage_rows[k]),
                 "cpl": t(nx + self.cpl_local[k]), "n_cpl": len(self.cpl_local[k]),
             })
+        # ---- border rows: nnz index, local border row, global column; positions in the multiplier vector
+        loc_B = np.full(m, -1)
+        loc_B[border] = np.arange(self.n_border)
+        jb = np.nonzero(far[jac_row] & is_eq[jac_row])[0]
+        self.border = {"idx": t(jb), "row": t(loc_B[jac_row[jb]]), "col": t(jcol[jb]), "eq": t(pos_E[border])}
 
     @classmethod
     def for_evaluator(cls, ev, lbg, ubg, device="cpu", linalg: str = "hb"):
@@ -204,8 +218,12 @@ class StageKKT:
         sigma_I (B, m_I) >= 0: barrier diagonal of the inequality rows; delta (B,): Hessian shift;
         delta_c: scalar >= 0 on the (2,2) block.  Returns dx (B, n_x), dlam_E (B, m_E).
         Instances are processed `chunk` at a time: the forward sweep keeps, per stage, the substituted
-        right-hand side and the nb x 87 coupling solve for the back substitution (chunk * N * nb * 88 * 8
-        bytes, 1.8 GB for 256 instances of the 30-knot problem); the factors themselves live for one stage."""
+        right-hand sides and the nb x 87 coupling solve for the back substitution (chunk * N * nb * 88 * 8
+        bytes, 1.8 GB for 256 instances of the 30-knot problem); the factors themselves live for one stage.
+
+        Border rows (periodicity): K = [[K_bt, P^T], [P, -delta_c I]].  One sweep solves K_bt [y0 | Y] =
+        [rhs | P^T] (1 + n_border right-hand sides), then (-delta_c I - P Y) lam_p = rhs_p - P y0 and
+        u = y0 - Y lam_p."""
         B = hess_vals.shape[0]
         if chunk is None:  # one CTA per stage block: whole waves of the factor kernel (1 CTA per SM)
             chunk = 2 * torch.cuda.get_device_properties(hess_vals.device).multi_processor_count if hess_vals.is_cuda else 256
@@ -213,10 +231,37 @@ class StageKKT:
             parts = [self.solve(hess_vals[i:i + chunk], jac_vals[i:i + chunk], sigma_I[i:i + chunk], delta[i:i + chunk],
                                 delta_c, rhs_x[i:i + chunk], rhs_E[i:i + chunk], chunk) for i in range(0, B, chunk)]
             return torch.cat([a for a, _ in parts]), torch.cat([b for _, b in parts])
+        nbr = self.n_border
+        if nbr == 0:
+            DX, DL = self._sweep(hess_vals, jac_vals, sigma_I, delta, delta_c, rhs_x[:, :, None], rhs_E[:, :, None])
+            return DX[:, :, 0], DL[:, :, 0]
+        dev, dt = hess_vals.device, hess_vals.dtype
+        bd = self.border
+        pv = jac_vals[:, bd["idx"]]  # (B, nnz of P)
+        RX = torch.zeros((B, self.n_x, 1 + nbr), dtype=dt, device=dev)
+        RX[:, :, 0] = rhs_x
+        RX[:, bd["col"], 1 + bd["row"]] = pv  # P^T
+        RE = torch.zeros((B, self.mE, 1 + nbr), dtype=dt, device=dev)
+        RE[:, :, 0] = rhs_E
+        RE[:, bd["eq"], 0] = 0.0  # border rows are not part of K_bt
+        DX, DL = self._sweep(hess_vals, jac_vals, sigma_I, delta, delta_c, RX, RE)
+        # P X for X = [y0 | Y] (dx part only: P has no multiplier columns)
+        PX = torch.zeros((B, nbr, 1 + nbr), dtype=dt, device=dev)
+        PX.index_add_(1, bd["row"], pv[:, :, None] * DX[:, bd["col"], :])
+        S = -PX[:, :, 1:] - delta_c * torch.eye(nbr, dtype=dt, device=dev)
+        lam_p = torch.linalg.solve(S, (rhs_E[:, bd["eq"]] - PX[:, :, 0])[:, :, None])  # small (n_border^2) library solve
+        dx = DX[:, :, 0] - torch.bmm(DX[:, :, 1:], lam_p)[:, :, 0]
+        dl = DL[:, :, 0] - torch.bmm(DL[:, :, 1:], lam_p)[:, :, 0]
+        dl[:, bd["eq"]] = lam_p[:, :, 0]
+        return dx, dl
+
+    def _sweep(self, hess_vals, jac_vals, sigma_I, delta, delta_c, RX, RE):
+        """Block-tridiagonal part: K_bt [DX; DL] = [RX; RE] for R right-hand sides (B, n_x | m_E, R)."""
+        B, R = hess_vals.shape[0], RX.shape[2]
         dev, dt = hess_vals.device, hess_vals.dtype
         nx, nb, N = self.nx, self.nb, self.N
-        dx = torch.zeros((B, self.n_x), dtype=dt, device=dev)
-        dl = torch.zeros((B, self.mE), dtype=dt, device=dev)
+        DX = torch.zeros((B, self.n_x, R), dtype=dt, device=dev)
+        DL = torch.zeros((B, self.mE, R), dtype=dt, device=dev)
         Wv, Zs = [], []
         w_prev = None
 
@@ -250,38 +295,37 @@ class StageKKT:
             diag[:, nx:nx + ne] = -delta_c
             diag[:, nx + ne:] = 1.0          # padding multiplier slots
             D[:, idx, idx] += diag
-            b = torch.zeros((B, nb), dtype=dt, device=dev)
-            b[:, :nv] = rhs_x[:, mp["var"]]
-            b[:, nx:nx + ne] = rhs_E[:, mp["eq"]]
+            b = torch.zeros((B, nb, R), dtype=dt, device=dev)
+            b[:, :nv, :] = RX[:, mp["var"], :]
+            b[:, nx:nx + ne, :] = RE[:, mp["eq"], :]
             Zs.append(Z)
             if Z is not None:  # Z = S_{k-1}^{-1} [A_k^T; 0] came out of the previous stage's solve
                 cp = mp["cpl"]
                 D[:, cp[:, None], cp[None, :]] -= torch.bmm(A, Z[:, :nx, :])
-                b[:, cp] -= torch.bmm(A, w_prev[:, :nx, None])[:, :, 0]
+                b[:, cp, :] -= torch.bmm(A, w_prev[:, :nx, :])
             fac = self._lu_factor(D)  # the stage block is symmetric
-            # one solve per stage: the stage's right-hand side and the coupling columns of the next stage
+            # one solve per stage: the stage's right-hand sides and the coupling columns of the next stage
             if k + 1 < N and self.maps[k + 1]["n_cpl"]:
                 A = coupling(k + 1)
-                rhs = torch.zeros((B, nb, 1 + A.shape[1]), dtype=dt, device=dev)
-                rhs[:, :, 0] = b
-                rhs[:, :nx, 1:] = A.transpose(1, 2)
+                rhs = torch.zeros((B, nb, R + A.shape[1]), dtype=dt, device=dev)
+                rhs[:, :, :R] = b
+                rhs[:, :nx, R:] = A.transpose(1, 2)
                 sol = self._lu_solve(fac, rhs)
-                w_prev, Z = sol[:, :, 0], sol[:, :, 1:]
+                w_prev, Z = sol[:, :, :R], sol[:, :, R:]
             else:
                 A = Z = None
-                w_prev = self._lu_solve(fac, b[:, :, None])[:, :, 0]
+                w_prev = self._lu_solve(fac, b)
             Wv.append(w_prev)
         u_next = None
         for k in range(N - 1, -1, -1):
             mp = self.maps[k]
             u = Wv[k]
             if k < N - 1 and Zs[k + 1] is not None:
-                lam_c = u_next[:, self.maps[k + 1]["cpl"]]
-                u = u - torch.bmm(Zs[k + 1], lam_c[:, :, None])[:, :, 0]
-            dx[:, mp["var"]] = u[:, :mp["n_var"]]
-            dl[:, mp["eq"]] = u[:, nx:nx + mp["n_eq"]]
+                u = u - torch.bmm(Zs[k + 1], u_next[:, self.maps[k + 1]["cpl"], :])
+            DX[:, mp["var"], :] = u[:, :mp["n_var"], :]
+            DL[:, mp["eq"], :] = u[:, nx:nx + mp["n_eq"], :]
             u_next = u
-        return dx, dl
+        return DX, DL
 
     # ------------------------------------------------------------------ reference: the same matrix, dense
     def dense_matrix(self, hess_vals, jac_vals, sigma_I, delta, delta_c, eq_rows, ine_rows, jac_colind, jac_row,

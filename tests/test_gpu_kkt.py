@@ -52,14 +52,17 @@ def test_lu_pivots_like_partial_pivoting(built_library):
         lu_factor(torch.zeros((2, 3, 3), dtype=torch.float64))  # CPU tensor: no fallback
 
 
-def test_stage_sweep_on_evaluated_values(model, built_library):
+@pytest.mark.parametrize("periodic", [False, True])
+def test_stage_sweep_on_evaluated_values(model, built_library, periodic):
+    """periodic = BASELINE config 4's structure: the periodicity rows are a border of the block-tridiagonal
+    matrix (one sweep with 1 + 84 right-hand sides, then an 84 x 84 Schur complement)."""
     from hippopt_b200.evaluator import ALL, KinoEvaluator
     from hippopt_b200.kino_layout import KinoSettings
     from hippopt_b200.kkt import StageKKT
     from hippopt_b200.workloads import kino_batch
 
     N, B = 4, 5
-    ev = KinoEvaluator(model, KinoSettings(horizon=N, final_state_constraint=True))
+    ev = KinoEvaluator(model, KinoSettings(horizon=N, final_state_constraint=True, periodicity_constraint=periodic))
     x, p, lam, sigma = kino_batch(ev.layout, model, B, seed=3, noise=0.05)
     lb, ub = ev.bounds(p)
     d = dev()

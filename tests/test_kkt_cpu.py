@@ -10,8 +10,8 @@ from hippopt_b200.kkt import StageKKT
 from hippopt_b200.workloads import kino_parameters
 
 
-def _setup(model, N, final):
-    lay = KinoLayout(model, KinoSettings(horizon=N, final_state_constraint=final))
+def _setup(model, N, final, periodic=False):
+    lay = KinoLayout(model, KinoSettings(horizon=N, final_state_constraint=final, periodicity_constraint=periodic))
     p = kino_parameters(lay, model, 1, np.random.default_rng(0))
     lb, ub = lay.bounds(p)
     eq = np.nonzero(lb[0] == ub[0])[0]
@@ -21,9 +21,13 @@ def _setup(model, N, final):
     return lay, kkt, eq, ine
 
 
-@pytest.mark.parametrize("N,final", [(2, False), (4, False), (3, True)])
-def test_stage_solve_matches_dense(model, N, final):
-    lay, kkt, eq, ine = _setup(model, N, final)
+@pytest.mark.parametrize("N,final,periodic", [(2, False, False), (4, False, False), (3, True, False), (3, False, True),
+                                              (4, True, True), (2, True, True)])
+def test_stage_solve_matches_dense(model, N, final, periodic):
+    """periodic: the 84 periodicity rows couple knot 0 with knot N-1 (config 4): border + Schur complement for
+    N > 2, ordinary stage coupling for N = 2."""
+    lay, kkt, eq, ine = _setup(model, N, final, periodic)
+    assert kkt.n_border == (84 if periodic and N > 2 else 0)
     B = 3
     g = torch.Generator().manual_seed(N)
     hv = torch.randn((B, lay.nnz_h), generator=g, dtype=torch.float64)
@@ -67,14 +71,16 @@ def test_default_block_algebra_has_no_cpu_fallback(model):
         kkt.solve(z(1, lay.nnz_h), z(1, lay.nnz_j), z(1, len(ine)), z(1), 1e-8, z(1, lay.n_x), z(1, len(eq)))
 
 
-def test_periodicity_is_rejected(model):
+def test_border_limit(model):
+    """More far-coupling rows than the border is allowed to hold are refused at construction."""
     lay = KinoLayout(model, KinoSettings(horizon=3, periodicity_constraint=True))
     p = kino_parameters(lay, model, 1, np.random.default_rng(0))
     lb, ub = lay.bounds(p)
     eq = np.nonzero(lb[0] == ub[0])[0]
     ine = np.nonzero(lb[0] != ub[0])[0]
     with pytest.raises(NotImplementedError):
-        StageKKT(lay.n_x, lay.m, 3, 189, lay.jac_colind, lay.jac_row, lay.hess_colind, lay.hess_row, eq, ine)
+        StageKKT(lay.n_x, lay.m, 3, 189, lay.jac_colind, lay.jac_row, lay.hess_colind, lay.hess_row, eq, ine,
+                 linalg="torch", max_border=10)
 
 
 def test_sparse_operators_match_dense(model):
