@@ -249,7 +249,12 @@ class StageKKT:
         PX = torch.zeros((B, nbr, 1 + nbr), dtype=dt, device=dev)
         PX.index_add_(1, bd["row"], pv[:, :, None] * DX[:, bd["col"], :])
         S = -PX[:, :, 1:] - delta_c * torch.eye(nbr, dtype=dt, device=dev)
-        lam_p = torch.linalg.solve(S, (rhs_E[:, bd["eq"]] - PX[:, :, 0])[:, :, None])  # small (n_border^2) library solve
+        # small (n_border^2) library solve; a singular / non-finite Schur complement (a stage block that failed
+        # to factor) gives NaN for that instance, which the caller treats like any failed solve
+        S = torch.where(torch.isfinite(S), S, torch.zeros_like(S))
+        lam_p, info = torch.linalg.solve_ex(S, (rhs_E[:, bd["eq"]] - PX[:, :, 0])[:, :, None], check_errors=False)
+        bad = (info != 0) | ~torch.isfinite(PX).all(dim=2).all(dim=1)
+        lam_p = torch.where(bad[:, None, None], torch.full_like(lam_p, float("nan")), lam_p)
         dx = DX[:, :, 0] - torch.bmm(DX[:, :, 1:], lam_p)[:, :, 0]
         dl = DL[:, :, 0] - torch.bmm(DL[:, :, 1:], lam_p)[:, :, 0]
         dl[:, bd["eq"]] = lam_p[:, :, 0]

@@ -32,7 +32,8 @@ pose = out.values.cpu().numpy()[out.success.cpu().numpy()]
 B = pose.shape[0]
 print(f"pose finder: {B}/{B0} converged in {time.perf_counter() - t0:.1f} s")
 
-ev = KinoEvaluator(model, KinoSettings(horizon=N))
+periodic = "-p" in sys.argv  # BASELINE config 4's structure: final-state constraint + periodicity rows
+ev = KinoEvaluator(model, KinoSettings(horizon=N, final_state_constraint=periodic, periodicity_constraint=periodic))
 lay = ev.layout
 pk, x0 = standing_problem(lay, model, pose)
 lbk, ubk = lay.bounds(pk)
