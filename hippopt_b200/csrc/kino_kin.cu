@@ -13,13 +13,17 @@
 // is used directly).
 //   1. primal forward kinematics by depth level (lane = body), world transforms, twists, world
 //      inertias staged in shared memory; CoM / momentum sums by warp shuffles;
-//   2. one adjoint sweep over the tree per lane in fp64: lane r carries the seed of g-row r, so the
-//      sweep returns row r of the Jacobian (32 rows: 24 FK, 3 CoM, 3 momentum, feet distance and
-//      the frame-orientation trace whose gradient feeds grad_f);
-//   3. the same adjoint sweep in dual arithmetic: lane j carries the unit tangent of variable j
-//      (4 quaternion + 23 joint directions; tangents of every link state are closed-form in the
-//      staged primal state), seeds are the true multipliers, so the tangent part of the sweep is
-//      column j of the Lagrangian Hessian (q, s, and velocity rows).
+//   2. Jacobian by forward mode: lane j carries the unit tangent of variable j (4 quaternion + 23 joint
+//      directions).  A direction rotates one sub-tree rigidly about its joint, so the tangents of the
+//      contact points, of the CoM, of P_dot and of the angular momentum are closed-form in the staged
+//      primal state and in the composite (sub-tree) moments -- column j of the kinematic rows, no sweep;
+//   3. Hessian: the adjoints of the Lagrangian (true multipliers as seeds) once per warp, lane = body
+//      (primal_adjoint_pass); then only the TANGENT of those adjoints along every direction, as
+//      (direction, body) tasks packed on the lanes by a host-built schedule (kin_tangent_sweep_packed):
+//      column j of the Lagrangian Hessian restricted to (q, s) x (vb, qd, sd, q, s).
+//   The file also keeps the first algorithm for the Jacobian -- a row-per-lane adjoint sweep in fp64
+//   (kin_backward: 32 rows = 24 FK, 3 CoM, 3 momentum, feet distance, frame-orientation trace) -- as an
+//   option (hb_set_option) and cross-check, and the unpacked tangent sweep (HB_SWEEP_PACKED 0).
 #include "kino_const.cuh"
 
 namespace hb {
@@ -1277,7 +1281,6 @@ __global__ void __launch_bounds__(128, WITH_HESS ? KIN_H_MIN_BLOCKS : 3) kino_ki
       }
       __syncwarp();
     }
-    const bool fwd_jac = HB_FWD_JAC && want_jac;
     // tangents of P, P_dot, h (about the base origin) along this lane's (q, s) direction
     D3 tP, tPd, th;
     {

@@ -48,7 +48,8 @@ def test_solver_reports_failure_like_the_reference(built_library):
                                                               torch.tensor(p, device=dev), lb, ub)
 
 
-def test_standing_ocp_solves_with_the_stage_kkt(model, built_library):
+@pytest.mark.parametrize("periodic", [False, True])  # True: config 4's structure (final state + periodicity rows)
+def test_standing_ocp_solves_with_the_stage_kkt(model, built_library, periodic):
     """Rows f1 + f2 end to end on the real problem: pose-finder solutions (dense KKT) become "keep standing"
     kinodynamic OCPs, solved with the stage-wise KKT sweep and the batched LU kernels.  No reference
     trajectory exists for this (IPOPT is not available), so the checks are intrinsic: the guess is feasible
@@ -66,7 +67,7 @@ def test_standing_ocp_solves_with_the_stage_kkt(model, built_library):
     pose = out.values.cpu().numpy()[out.success.cpu().numpy()]
     assert pose.shape[0] >= 90  # 96/96 with the f-type step acceptance (36 % without: profiles/r01/solver_v8.txt)
     assert int(out.iterations.max()) <= 150
-    ev = KinoEvaluator(model, KinoSettings(horizon=4))
+    ev = KinoEvaluator(model, KinoSettings(horizon=4, final_state_constraint=periodic, periodicity_constraint=periodic))
     lay = ev.layout
     pk, x0 = standing_problem(lay, model, pose)
     lbk, ubk = lay.bounds(pk)
