@@ -359,7 +359,7 @@ def main():
             okp = po_out.success.cpu().numpy()
             pk, x0k = standing_problem(lay, model, po_out.values.cpu().numpy()[okp])
             lbs_, ubs_ = lay.bounds(pk)
-            ip = BatchedInteriorPoint(ev, tol=1e-6, max_iter=300, kkt="stage", delta_c=1e-9, mu_init=1e-3)
+            ip = BatchedInteriorPoint(ev, tol=1e-6, max_iter=150, kkt="stage", delta_c=1e-9, mu_init=1e-3)
             ts = time.perf_counter()
             st_out = ip.solve(torch.tensor(x0k, device=dev), torch.tensor(pk, device=dev), lbs_, ubs_)
             torch.cuda.synchronize(dev)

@@ -114,7 +114,8 @@ class BatchedInteriorPoint:
     def __init__(self, ev, tol: float = 1e-8, max_iter: int = 300, mu_init: float = 0.1, kappa_eps: float = 10.0,
                  kappa_mu: float = 0.2, theta_mu: float = 1.5, tau_min: float = 0.99, eta: float = 1e-4,
                  max_backtrack: int = 16, delta_min: float = 1e-8, delta_max: float = 1e8, exact_inertia: bool = False,
-                 verbose: bool = False, kkt: str = "dense", delta_c: float = 1e-11, f_type: bool = True):
+                 verbose: bool = False, kkt: str = "dense", delta_c: float = 1e-11, f_type: bool = True,
+                 max_fail: int = 8):
         """kkt: "dense" (one dense factorisation per instance) or "stage" (block-tridiagonal sweep over the knots,
         hippopt_b200.kkt.StageKKT -- the multiple-shooting OCPs of the kinodynamic planner)."""
         self.ev = ev
@@ -126,7 +127,7 @@ class BatchedInteriorPoint:
         self.verbose = verbose
         if kkt not in ("dense", "stage"):
             raise ValueError("kkt must be 'dense' or 'stage'")
-        self.kkt_kind, self.delta_c, self.f_type = kkt, delta_c, f_type
+        self.kkt_kind, self.delta_c, self.f_type, self.max_fail = kkt, delta_c, f_type, max_fail
         self.kkt_seconds = 0.0
 
     # ------------------------------------------------------------------ solve
@@ -181,6 +182,8 @@ class BatchedInteriorPoint:
         delta = torch.zeros(B, dtype=torch.float64, device=dev)
         nu = torch.ones(B, dtype=torch.float64, device=dev)
         done = torch.zeros(B, dtype=torch.bool, device=dev)
+        stalled = torch.zeros(B, dtype=torch.bool, device=dev)  # given up: max_fail line-search failures in a row
+        fails = torch.zeros(B, dtype=torch.long, device=dev)
         iters = torch.zeros(B, dtype=torch.long, device=dev)
         err0 = torch.full((B,), float("inf"), dtype=torch.float64, device=dev)
         def rows_I(v):  # (B, m_I) values on the inequality rows -> (B, m) with zeros elsewhere
@@ -226,9 +229,10 @@ class BatchedInteriorPoint:
                 print(f"it {it:3d} done {int(done.sum())}/{B} err0 med {err0.median().item():.2e} max {err0.max().item():.2e} "
                       f"mu med {mu.median().item():.1e} delta med {delta.median().item():.1e} max {delta.max().item():.1e} "
                       f"| dual med {(linf(rd) / sd).median().item():.2e} prim med {prim.median().item():.2e}")
-            if bool(done.all()):
+            inactive = done | stalled
+            if bool(inactive.all()):
                 break
-            iters += (~done).long()
+            iters += (~inactive).long()
             # barrier parameter update (possibly several reductions in one go)
             for _ in range(4):
                 dec = (~done) & (emu(mu) <= self.kappa_eps * mu) & (mu > self.tol / 10.0)
@@ -244,7 +248,7 @@ class BatchedInteriorPoint:
             # solve with a per-instance Levenberg shift until the step has positive curvature
             dx = torch.zeros_like(x)
             lamE_new = lamE.clone()
-            need = ~done
+            need = ~inactive
             for attempt in range(12):
                 # delta_c only once a plain solve has failed (rank-deficient J_E); the stage-wise sweep always
                 # carries it (its pivot blocks are the stage KKT matrices, not the whole one)
@@ -307,7 +311,7 @@ class BatchedInteriorPoint:
             if it == 0:
                 cnorm0 = cnorm.clone()
             alpha = a_p.clone()
-            accepted = done.clone()
+            accepted = inactive.clone()
             x_new, s_new = x.clone(), s.clone()
             for bt in range(self.max_backtrack):
                 xt = x + alpha[:, None] * dx
@@ -337,9 +341,13 @@ class BatchedInteriorPoint:
                 if bool(accepted.all()):
                     break
                 alpha = torch.where(accepted, alpha, alpha * 0.5)
-            moved = accepted & ~done
-            # instances whose line search failed get a larger Hessian shift and try again
+            moved = accepted & ~inactive
+            # instances whose line search failed get a larger Hessian shift and try again; after max_fail
+            # failures in a row an instance is given up (it would otherwise cost 16 evaluations and a KKT
+            # solve per iteration until max_iter: there is no restoration phase to send it to)
             failed = ~accepted
+            fails = torch.where(failed, fails + 1, torch.zeros_like(fails))
+            stalled |= fails >= self.max_fail
             delta = torch.where(failed, torch.clamp(torch.maximum(delta * 8.0, torch.full_like(delta, 1e-4)), max=self.delta_max),
                                 torch.where(moved, delta / 3.0, delta))
             delta = torch.where(delta < self.delta_min, torch.zeros_like(delta), delta)
