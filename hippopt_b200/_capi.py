@@ -97,6 +97,9 @@ def lib() -> ctypes.CDLL:
     L.hb_lu_factor_batched.argtypes = [vp, vp, vp, ctypes.c_int64, ctypes.c_int64, vp]
     L.hb_lu_solve_batched.restype = ctypes.c_int
     L.hb_lu_solve_batched.argtypes = [vp, vp, vp, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, vp]
+    i64 = ctypes.c_int64
+    L.hb_interpolate_humanoid_states.restype = ctypes.c_int
+    L.hb_interpolate_humanoid_states.argtypes = [i64, i64, i64, vp, vp, vp, vp, i64, i64, vp, i64, i64, vp, vp, i64, i64, vp]
     L.hb_last_launch_count.restype = ctypes.c_int
     L.hb_last_launch_count.argtypes = [vp]
     L.hb_set_option.restype = ctypes.c_int
@@ -117,7 +120,7 @@ EXPORTED_SYMBOLS = [
     "hb_kino_create", "hb_toy_create", "hb_destroy", "hb_dims", "hb_pattern_jac", "hb_pattern_hess", "hb_eval",
     "hb_last_launch_count", "hb_last_error", "hb_probe_fp64_tflops", "hb_profile_enable", "hb_profile_read",
     "hb_host_set_parameters", "hb_eval_host", "hb_host_last_traffic", "hb_host_alloc", "hb_host_free",
-    "hb_lu_factor_batched", "hb_lu_solve_batched", "hb_set_option",
+    "hb_lu_factor_batched", "hb_lu_solve_batched", "hb_set_option", "hb_interpolate_humanoid_states",
 ]
 
 

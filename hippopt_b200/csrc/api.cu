@@ -862,6 +862,29 @@ extern "C" int hb_lu_solve_batched(const double* LU, const int32_t* piv, double*
   return HB_OK;
 }
 
+extern "C" int hb_interpolate_humanoid_states(int64_t batch, int64_t n_points, int64_t n_joints, const double* initial,
+                                              const double* final_, const int32_t* schedule,
+                                              const double* phases_left, int64_t n_phases_left, int64_t stride_left,
+                                              const double* phases_right, int64_t n_phases_right,
+                                              int64_t stride_right, double* states, double* x, int64_t x_stride,
+                                              int64_t knot0, void* stream) {
+  if (!initial || !final_ || !schedule || !phases_left || !phases_right)
+    return fail(HB_ERR_INVALID, "hb_interpolate_humanoid_states: null argument");
+  if (!states && !x) return fail(HB_ERR_INVALID, "hb_interpolate_humanoid_states: no output requested");
+  if (batch <= 0 || batch > 65535 || n_points <= 0 || n_joints < 0 || n_phases_left <= 0 || n_phases_right <= 0)
+    return fail(HB_ERR_INVALID, "hb_interpolate_humanoid_states: need 0 < batch <= 65535, n_points > 0, phases > 0");
+  if (x && (n_joints != 23 || knot0 < 0 || x_stride < (knot0 + n_points) * hb::IZ_N))
+    return fail(HB_ERR_INVALID,
+                "hb_interpolate_humanoid_states: the guess layout has 23 joints and 189 variables per knot; "
+                "x_stride must cover knots knot0 .. knot0 + n_points - 1");
+  const dim3 grid((unsigned)n_points, (unsigned)batch);
+  hb::interp_states_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(
+      (int)n_points, (int)n_joints, initial, final_, schedule, phases_left, (long)stride_left, phases_right,
+      (long)stride_right, states, x, (long)x_stride, (int)knot0);
+  CUDA_TRY(cudaGetLastError());
+  return HB_OK;
+}
+
 extern "C" int hb_profile_enable(hb_handle h, int enable) {
   if (!h) return fail(HB_ERR_INVALID, "hb_profile_enable: null handle");
   for (cudaEvent_t e : h->prof_ev) cudaEventDestroy(e);

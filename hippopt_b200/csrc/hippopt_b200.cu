@@ -4,4 +4,5 @@
 #include "pose_contact.cu"
 #include "toy.cu"
 #include "lu.cu"
+#include "interp.cu"
 #include "api.cu"

@@ -264,6 +264,33 @@ int hb_lu_factor_batched(double* A, int32_t* piv, int32_t* info, int64_t n, int6
 int hb_lu_solve_batched(const double* LU, const int32_t* piv, double* Bm, int64_t n, int64_t nrhs, int64_t batch,
                         void* stream);
 
+/* Initial guesses / reference trajectories on the device.
+ * replaces: humanoid_state_interpolator (robot_planning/utilities/interpolators.py:396-448) with its callees
+ * linear_interpolator (:24-50), quaternion_slerp (:53-77), transform_interpolator (:80-103),
+ * feet_contact_points_interpolator (:312-337) and the per-point arithmetic of foot_contact_state_interpolator
+ * (:171-229), for `batch` instances at once.  The phase bookkeeping of foot_contact_state_interpolator
+ * (:106-169, :231-309) depends on times only; the caller passes its result as `schedule`
+ * (hippopt_b200/interpolators.py foot_contact_schedule builds it and raises the reference's ValueErrors).
+ *   initial, final   device [batch][82 + n_joints]  state blocks: 8 x (p[3], f[3], position_in_foot_frame[3]),
+ *                                                   base position[3], quaternion xyzw[4], joints, com[3]
+ *                                                   (points 0-3 left foot, 4-7 right; descriptors read from initial)
+ *   schedule         device [2][n_points][5] int32  per foot (left, right) and point: kind (0 stance of phase a,
+ *                                                   1 swing from a.transform to a.mid_swing_transform, 2 swing from
+ *                                                   a.mid_swing_transform to b.transform), a, b, sample j of n
+ *                                                   (np.linspace(0, 1, n)[j]); a, b are NOT range-checked on the device
+ *   phases_*         device [n_phases][17] doubles per instance, instances `stride_*` doubles apart (0: shared):
+ *                                                   transform position[3], quaternion[4], mid-swing position[3],
+ *                                                   quaternion[4], force[3]
+ *   states           device [batch][n_points][82 + n_joints] or NULL
+ *   x                device [batch][x_stride] or NULL: the same values written into the kinodynamic NLP's decision
+ *                    vector at knots knot0 .. knot0 + n_points - 1 (p, f of the points, base, joints, com; other
+ *                    entries untouched; n_joints must be 23) */
+int hb_interpolate_humanoid_states(int64_t batch, int64_t n_points, int64_t n_joints, const double* initial,
+                                   const double* final_, const int32_t* schedule, const double* phases_left,
+                                   int64_t n_phases_left, int64_t stride_left, const double* phases_right,
+                                   int64_t n_phases_right, int64_t stride_right, double* states, double* x,
+                                   int64_t x_stride, int64_t knot0, void* stream);
+
 const char* hb_last_error(void);
 
 /* fp64 FMA throughput probe (TFLOP/s) used as roofline denominator when none is published */

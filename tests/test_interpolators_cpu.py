@@ -1,0 +1,171 @@
+"""Row f3 on the CPU: the oracle's interpolators (oracle/interpolators.py) against closed-form properties, and the
+product's host-side phase bookkeeping (hippopt_b200.interpolators.foot_contact_schedule, one table for the whole
+batch) against the oracle's append-as-you-go restatement of
+/root/reference/src/hippopt/robot_planning/utilities/interpolators.py:106-309 on the reference's own call site
+(turnkey_planners/humanoid_kinodynamic/main_periodic_step.py:367-451) and on randomised phase timings."""
+import numpy as np
+import pytest
+
+from hippopt_b200.interpolators import (SWING_DOWN, SWING_UP, FootContactPhaseDescriptor, foot_contact_schedule)
+from oracle import interpolators as oi
+
+DESCRIPTOR = [[0.08, 0.03, 0.0], [0.08, -0.03, 0.0], [-0.08, -0.03, 0.0], [-0.08, 0.03, 0.0]]
+
+
+def rand_quat(rng):
+    q = rng.normal(size=4)
+    return q / np.linalg.norm(q)
+
+
+def periodic_step_phases(horizon, step_length=0.6):
+    """main_periodic_step.py:367-412 as oracle phase dicts: (left, right)."""
+    ident = np.array([0.0, 0.0, 0.0, 1.0])
+    f = np.array([0.0, 0.0, 100.0])
+
+    def phase(pos, mid, act, dea):
+        return {"position": np.array(pos), "quaternion": ident, "mid_position": None if mid is None else np.array(mid),
+                "mid_quaternion": None if mid is None else ident, "force": f, "activation_time": act,
+                "deactivation_time": dea}
+
+    left = [phase([0.0, 0.1, 0.0], [step_length / 2, 0.1, 0.05], None, horizon / 6.0),
+            phase([step_length, 0.1, 0.0], None, horizon / 3.0, None)]
+    right = [phase([step_length / 2, -0.1, 0.0], [step_length, -0.1, 0.05], None, horizon * 2.0 / 3.0),
+             phase([1.5 * step_length, -0.1, 0.0], None, horizon * 5.0 / 6.0, None)]
+    return left, right
+
+
+def to_product(phases):
+    return [FootContactPhaseDescriptor(position=p["position"], quaternion_xyzw=p["quaternion"],
+                                       mid_swing_position=p["mid_position"], mid_swing_quaternion_xyzw=p["mid_quaternion"],
+                                       force=p["force"], activation_time=p["activation_time"],
+                                       deactivation_time=p["deactivation_time"]) for p in phases]
+
+
+def evaluate_schedule(table, phases):
+    """Numpy evaluation of a schedule table with the oracle's transform_interpolator (what csrc/interp.cu does)."""
+    out = []
+    for kind, a, b, j, n in table.tolist():
+        A, B = phases[a], phases[b]
+        if kind in (SWING_UP, SWING_DOWN):
+            if A["mid_position"] is None:
+                mid = ((A["position"] + B["position"]) / 2, B["quaternion"])
+            else:
+                mid = (A["mid_position"], A["mid_quaternion"])
+            ends = ((A["position"], A["quaternion"]), mid) if kind == SWING_UP else (mid, (B["position"], B["quaternion"]))
+            out.append(oi.foot_state(DESCRIPTOR, oi.transform_interpolator(*ends, n)[j], np.zeros(3)))
+        else:
+            out.append(oi.foot_state(DESCRIPTOR, (A["position"], A["quaternion"]), A["force"]))
+    return out
+
+
+def same(a, b):
+    assert len(a) == len(b)
+    for (pa, fa), (pb, fb) in zip(a, b):
+        assert np.array_equal(pa, pb) and np.array_equal(fa, fb)
+
+
+def test_slerp_is_the_great_arc_at_constant_rate():
+    rng = np.random.default_rng(0)
+    for _ in range(20):
+        q0, q1 = rand_quat(rng), rand_quat(rng)
+        qs = oi.quaternion_slerp(q0, q1, 9)
+        assert np.allclose(qs[0], q0, atol=1e-15) and np.allclose(qs[-1], q1, atol=1e-14)
+        assert np.allclose([np.linalg.norm(q) for q in qs], 1.0, atol=1e-14)
+        total = np.arccos(np.dot(q0, q1))
+        steps = [np.arccos(np.clip(np.dot(qs[i], qs[i + 1]), -1, 1)) for i in range(8)]
+        assert np.allclose(steps, total / 8, atol=1e-7)  # acos near 1 loses half the digits
+    # below the reference's 1e-6 threshold, and for a dot product rounded above 1: the initial quaternion
+    q0 = rand_quat(rng)
+    assert all(np.array_equal(q, q0) for q in oi.quaternion_slerp(q0, q0, 4))
+    assert all(np.array_equal(q, q0) for q in oi.quaternion_slerp(q0, q0 * (1 + 1e-15), 3))
+
+
+def test_linear_interpolator_end_points_and_shape_error():
+    a, b = np.arange(5.0), np.arange(5.0) ** 2
+    out = oi.linear_interpolator(a, b, 7)
+    assert np.array_equal(out[0], a) and np.array_equal(out[-1], b) and np.allclose(out[3], (a + b) / 2)
+    assert len(oi.linear_interpolator(a, b, 1)) == 1 and np.array_equal(oi.linear_interpolator(a, b, 1)[0], a)
+    with pytest.raises(ValueError):
+        oi.linear_interpolator(a, b[:4], 3)
+
+
+def test_rotation_matrix_is_a_rotation():
+    rng = np.random.default_rng(1)
+    R = oi.rotation_matrix(rand_quat(rng))
+    assert np.allclose(R @ R.T, np.eye(3), atol=1e-14) and np.isclose(np.linalg.det(R), 1.0)
+    assert np.allclose(oi.rotation_matrix([0, 0, np.sin(0.3), np.cos(0.3)]) @ [1, 0, 0], [np.cos(0.6), np.sin(0.6), 0])
+
+
+@pytest.mark.parametrize("n, dt", [(30, 0.1), (15, 0.1), (31, 0.07)])
+def test_schedule_on_the_periodic_step_call_site(n, dt):
+    """The two halves of main_periodic_step.py:433-451 (second half with t0 in the middle of the plan)."""
+    horizon = n * dt
+    for foot in periodic_step_phases(horizon):
+        half = n // 2
+        for pts, t0 in ((half, 0.0), (n - half, half * dt), (n, 0.0)):
+            ref = oi.foot_contact_state_interpolator(foot, DESCRIPTOR, pts, dt, t0)
+            table = foot_contact_schedule(to_product(foot), pts, dt, t0)
+            assert table.shape == (pts, 5) and table.dtype == np.int32
+            same(evaluate_schedule(table, foot), ref)
+    # the shape of the left foot's plan: stance, swing up, swing down, stance of the second phase
+    kinds = foot_contact_schedule(to_product(periodic_step_phases(3.0)[0]), 30, 0.1)[:, 0].tolist()
+    assert kinds == [0] * 5 + [1] * 2 + [2] * 3 + [0] * 20
+
+
+def random_phases(rng, n_phases, t_start, span):
+    cuts = np.sort(rng.uniform(t_start, t_start + span, 2 * n_phases))
+    if n_phases > 1 and rng.random() < 0.3:  # touching phases: the swing in between has no points
+        cuts[2] = cuts[1]
+    phases = []
+    for i in range(n_phases):
+        phases.append({"position": rng.normal(size=3), "quaternion": rand_quat(rng),
+                       "mid_position": rng.normal(size=3) if rng.random() < 0.5 else None, "force": rng.normal(size=3),
+                       "activation_time": float(cuts[2 * i]), "deactivation_time": float(cuts[2 * i + 1])})
+        phases[-1]["mid_quaternion"] = rand_quat(rng) if phases[-1]["mid_position"] is not None else None
+    if rng.random() < 0.7:
+        phases[0]["activation_time"] = None
+    if rng.random() < 0.7:
+        phases[-1]["deactivation_time"] = None
+    return phases
+
+
+def test_schedule_on_random_phase_timings():
+    rng = np.random.default_rng(7)
+    raised = agreed = 0
+    for _ in range(400):
+        n_ph = int(rng.integers(1, 5))
+        dt = float(rng.choice([0.05, 0.1, 0.13]))
+        pts = int(rng.integers(1, 40))
+        t0 = float(rng.uniform(0.0, 1.5)) if rng.random() < 0.6 else 0.0
+        phases = random_phases(rng, n_ph, -0.5, 4.0)
+        try:
+            ref = oi.foot_contact_state_interpolator(phases, DESCRIPTOR, pts, dt, t0)
+        except ValueError:
+            with pytest.raises(ValueError):
+                foot_contact_schedule(to_product(phases), pts, dt, t0)
+            raised += 1
+            continue
+        same(evaluate_schedule(foot_contact_schedule(to_product(phases), pts, dt, t0), phases), ref)
+        agreed += 1
+    assert raised > 20 and agreed > 100  # both outcomes exercised
+
+
+def test_reference_errors():
+    ph = to_product(periodic_step_phases(3.0)[0])
+    ph[0].activation_time = 0.5
+    with pytest.raises(ValueError, match="first phase activation time"):
+        foot_contact_schedule(ph, 10, 0.1)
+    ph = to_product(periodic_step_phases(3.0)[0])
+    ph[1].activation_time = None
+    with pytest.raises(ValueError, match="no activation time"):
+        foot_contact_schedule(ph, 10, 0.1)
+    ph = to_product(periodic_step_phases(3.0)[0])
+    ph[1].deactivation_time = 2.0
+    with pytest.raises(ValueError, match="before the end time"):
+        foot_contact_schedule(ph, 30, 0.1)
+    ph = to_product(periodic_step_phases(3.0)[0])
+    ph[0].deactivation_time = 1.5
+    with pytest.raises(ValueError, match="greater than the activation time of the next phase"):
+        foot_contact_schedule(ph, 30, 0.1)
+    with pytest.raises(ValueError, match="given together"):
+        FootContactPhaseDescriptor(mid_swing_position=np.zeros(3))
