@@ -145,3 +145,49 @@ def test_interpolator_argument_errors(built_library):
     from hippopt_b200._capi import EvaluationError
     with pytest.raises(EvaluationError, match="x_stride must cover"):
         humanoid_state_interpolator(I, I, phases, 10, 0.1, x_out=torch.zeros((3, 500), dtype=torch.float64, device=dev))
+
+
+def test_periodic_step_setup_pipeline(model, built_library):
+    """main_periodic_step.py:365-478 for a batch: keyframes from the batched pose finder, guess from the device
+    interpolator, written into the decision vector and the parameters of the kinodynamic NLP."""
+    from hippopt_b200.evaluator import KinoEvaluator, PoseEvaluator
+    from hippopt_b200.initial_guess import periodic_step_guess
+    from hippopt_b200.kino_layout import COM, NZ, PB, Q, S, KinoSettings, F as ZF, P as ZP
+    from hippopt_b200.workloads import FOOT_CORNERS
+
+    B, N = 24, 12
+    L = np.random.default_rng(5).uniform(0.1, 0.3, B)
+    ev = KinoEvaluator(model, KinoSettings(horizon=N, final_state_constraint=True, periodicity_constraint=True))
+    gs = periodic_step_guess(model, PoseEvaluator(model), ev, L)
+    assert int(gs.ok.sum()) >= int(0.9 * B)
+    x, key, po = gs.x0.cpu().numpy(), gs.keyframes.cpu().numpy(), ev.layout.po
+    assert np.isfinite(x).all() and x.shape == (B, ev.layout.n_x)
+    z0, zl = x[:, :NZ], x[:, NZ * (N - 1):NZ * N]
+    # the base, joints and CoM go from the initial keyframe to the final one through the middle one
+    for zo, so, ln in ((PB, 72, 3), (S, 79, NJ), (COM, 79 + NJ, 3)):
+        assert np.array_equal(z0[:, zo:zo + ln], key[0][:, so:so + ln])
+        assert np.array_equal(zl[:, zo:zo + ln], key[2][:, so:so + ln])
+        zh = x[:, NZ * (N // 2):NZ * (N // 2 + 1)]
+        assert np.array_equal(zh[:, zo:zo + ln], key[1][:, so:so + ln])
+    qn = np.stack([np.linalg.norm(x[:, NZ * k + Q:NZ * k + Q + 4], axis=1) for k in range(N)])
+    assert np.abs(qn - 1.0).max() < 1e-12
+    # feet where the phases put them: left foot starts at x = 0 and ends at x = L, right foot from L/2 to 3L/2;
+    # planned force on the ground, none in the air
+    for i in range(8):
+        x_first, x_last = (0.0 * L, L) if i < 4 else (L / 2, 1.5 * L)
+        y = 0.1 if i < 4 else -0.1
+        assert np.allclose(z0[:, 15 * i + ZP:15 * i + ZP + 3], FOOT_CORNERS[i % 4] + np.stack([x_first, y + 0 * L, 0 * L], 1), atol=1e-15)
+        if i < 4:  # (the right foot is still in the air at the last knot of this short horizon)
+            assert np.allclose(zl[:, 15 * i + ZP:15 * i + ZP + 3], FOOT_CORNERS[i % 4] + np.stack([x_last, y + 0 * L, 0 * L], 1), atol=1e-15)
+    pz = np.stack([x[:, NZ * k + ZP + 2] for k in range(N)])  # height of the first left point over the knots
+    fz = np.stack([x[:, NZ * k + ZF + 2] for k in range(N)])
+    assert (pz.max(axis=0) > 0.03).all() and (fz[pz > 1e-12] == 0.0).all() and set(np.unique(fz)) == {0.0, 100.0}
+    # parameters: initial / final state = first / last keyframe; joint regularisation = the guess
+    p = gs.parameters
+    assert np.array_equal(p[:, po.init:po.init + 105], key[0]) and np.array_equal(p[:, po.final:po.final + 105], key[2])
+    for k in (0, N // 2, N - 1):
+        r = po.refs0 + 55 * k
+        assert np.array_equal(p[:, r + po.R_JR:r + po.R_JR + NJ], x[:, NZ * k + S:NZ * k + S + NJ])
+    # and the evaluator accepts the pair
+    g = ev.eval(4, gs.x0, torch.tensor(p, device=gs.x0.device))["g"]
+    assert torch.isfinite(g).all()
