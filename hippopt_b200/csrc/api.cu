@@ -871,15 +871,17 @@ extern "C" int hb_interpolate_humanoid_states(int64_t batch, int64_t n_points, i
   if (!initial || !final_ || !schedule || !phases_left || !phases_right)
     return fail(HB_ERR_INVALID, "hb_interpolate_humanoid_states: null argument");
   if (!states && !x) return fail(HB_ERR_INVALID, "hb_interpolate_humanoid_states: no output requested");
-  if (batch <= 0 || batch > 65535 || n_points <= 0 || n_joints < 0 || n_phases_left <= 0 || n_phases_right <= 0)
-    return fail(HB_ERR_INVALID, "hb_interpolate_humanoid_states: need 0 < batch <= 65535, n_points > 0, phases > 0");
+  if (batch <= 0 || n_points <= 0 || n_points > (1 << 20) || n_joints < 0 || n_phases_left <= 0 || n_phases_right <= 0)
+    return fail(HB_ERR_INVALID, "hb_interpolate_humanoid_states: need batch > 0, 0 < n_points <= 2^20, phases > 0");
   if (x && (n_joints != 23 || knot0 < 0 || x_stride < (knot0 + n_points) * hb::IZ_N))
     return fail(HB_ERR_INVALID,
                 "hb_interpolate_humanoid_states: the guess layout has 23 joints and 189 variables per knot; "
                 "x_stride must cover knots knot0 .. knot0 + n_points - 1");
-  const dim3 grid((unsigned)n_points, (unsigned)batch);
-  hb::interp_states_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(
-      (int)n_points, (int)n_joints, initial, final_, schedule, phases_left, (long)stride_left, phases_right,
+  const long total = (long)batch * n_points, per_cta = hb::IW_ITEMS * hb::IW_WARPS;
+  const size_t smem = (size_t)per_cta * (82 + n_joints) * sizeof(double);
+  if (smem > 48 * 1024) return fail(HB_ERR_INVALID, "hb_interpolate_humanoid_states: too many joints (n_joints <= 430)");
+  hb::interp_states_kernel<<<(unsigned)((total + per_cta - 1) / per_cta), 32 * hb::IW_WARPS, smem, (cudaStream_t)stream>>>(
+      total, (int)n_points, (int)n_joints, initial, final_, schedule, phases_left, (long)stride_left, phases_right,
       (long)stride_right, states, x, (long)x_stride, (int)knot0);
   CUDA_TRY(cudaGetLastError());
   return HB_OK;
