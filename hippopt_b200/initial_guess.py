@@ -11,7 +11,8 @@
 * the references of get_references (:330-352) and the initial / final state parameters (:470-478).
 
 Everything numeric runs on the GPU; the per-instance Python loop of the reference (one IPOPT solve after the other)
-is gone.  What is NOT claimed: that the plans built here are solved -- see DESIGN.md section 9 row f1."""
+is gone.  How far the interior-point driver gets on the plans built here (some converge, many do not) is recorded
+in DESIGN.md section 9, row (f), and profiles/r01/solver_v11.txt."""
 from __future__ import annotations
 
 import dataclasses

@@ -83,5 +83,17 @@ if "-s" in sys.argv:
         print(f"periodic-step OCP (n_x={lay.n_x}, m={lay.m}): {n_ok}/{len(sel)} converged in <= {iters} iterations "
               f"(median {int(res.iterations[res.success].median()) if n_ok else -1}), {time.perf_counter() - t0:.1f} s, "
               f"KKT error median {res.kkt_error.median().item():.2e}, best {res.kkt_error.min().item():.2e}")
+        if n_ok:
+            okk = res.success.cpu().numpy()
+            gsol = ev.eval(4, res.values, P[sel])["g"].cpu().numpy()
+            vs = (np.maximum(lb[sel] - gsol, 0) + np.maximum(gsol - ub[sel], 0))[okk]
+            xs = res.values.cpu().numpy()[okk]
+            zk = xs[:, :189 * N].reshape(-1, N, 189)
+            lift = zk[:, :, 6 + 2].max(axis=1)  # height of the first left contact point over the plan
+            moved = zk[:, -1, 6] - zk[:, 0, 6]
+            print(f"  solutions: constraint violation max {vs.max():.1e}; left foot travels {np.median(moved):.3f} m (median; planned "
+                  f"{np.median(L[sel][okk]):.3f}) and is lifted by {np.median(lift) * 1e3:.1f} mm (median, max over the knots); "
+                  f"cost median {res.cost_value[res.success].median().item():.3e}; {res.evaluations} batched evaluations, "
+                  f"{sol.kkt_seconds:.1f} s in the KKT sweep")
     except OptiFailure as e:
         print(f"periodic-step OCP: {e} ({time.perf_counter() - t0:.1f} s)")
