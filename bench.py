@@ -373,6 +373,28 @@ def main():
                                        "iterations_median": int(st_out.iterations[st_out.success].median()) if n_ok else None,
                                        "seconds": t_ocp, "seconds_in_kkt": ip.kkt_seconds,
                                        "batched_evaluations": st_out.evaluations}}
+            # row f3: set-up of periodic-step plans (3 keyframe pose solves per instance + device interpolation of
+            # the guess into the decision vector), hippopt_b200/initial_guess.py
+            try:
+                from hippopt_b200.evaluator import KinoEvaluator
+                from hippopt_b200.initial_guess import periodic_step_guess
+                from hippopt_b200.kino_layout import KinoSettings
+
+                pev4 = KinoEvaluator(model, KinoSettings(horizon=HORIZON, final_state_constraint=True,
+                                                         periodicity_constraint=True))
+                Ls = np.random.default_rng(5).uniform(0.1, 0.3, n_s)
+                periodic_step_guess(model, pev, pev4, Ls[:8])
+                torch.cuda.synchronize(dev)
+                ts = time.perf_counter()
+                gs = periodic_step_guess(model, pev, pev4, Ls)
+                torch.cuda.synchronize(dev)
+                t_set = time.perf_counter() - ts
+                solves["periodic_step_setup"] = {
+                    "workload": f"{n_s} plans of config 4's structure: contact phases, {3 * n_s} keyframe pose solves, guess "
+                                f"interpolated on the device into the decision vectors, parameters",
+                    "instances": n_s, "keyframe_triples_converged": int(gs.ok.sum()), "setups_per_s": n_s / t_set}
+            except Exception as exc:  # noqa: BLE001
+                solves["periodic_step_setup"] = {"error": f"{type(exc).__name__}: {exc}"}
         except Exception as exc:  # noqa: BLE001 -- a solver failure must not cost the throughput line
             solves = {"error": f"{type(exc).__name__}: {exc}"}
 

@@ -111,7 +111,7 @@ def periodic_step_guess(model, pose_evaluator, kino_evaluator, step_length: np.n
     N, po = lay.N, lay.po
     L = np.asarray(step_length, dtype=np.float64).reshape(-1)
     B = L.shape[0]
-    dev = torch.device("cuda:0")
+    dev = torch.device("cuda", torch.cuda.current_device())
     dt = 0.1
     phases = periodic_step_phases(L, N * dt, force_z=force_z)
     # keyframes: (left phase, right phase) of compute_initial_state / compute_middle_state / compute_final_state
