@@ -43,6 +43,7 @@ class BatchedOutput:
     iterations: torch.Tensor              # (B,) int
     kkt_error: torch.Tensor               # (B,) scaled optimality error at exit
     evaluations: int = 0                  # batched hb_eval calls made
+    acceptable: torch.Tensor = None       # (B,) bool: stopped at IPOPT's "acceptable level" (part of `success`)
 
 
 class SparseOps:
@@ -115,9 +116,30 @@ class BatchedInteriorPoint:
                  kappa_mu: float = 0.2, theta_mu: float = 1.5, tau_min: float = 0.99, eta: float = 1e-4,
                  max_backtrack: int = 16, delta_min: float = 1e-8, delta_max: float = 1e8, exact_inertia: bool = False,
                  verbose: bool = False, kkt: str = "dense", delta_c: float = 1e-11, f_type: bool = True,
-                 max_fail: int = 8):
+                 max_fail: int = 8, ipopt_options: dict | None = None):
         """kkt: "dense" (one dense factorisation per instance) or "stage" (block-tridiagonal sweep over the knots,
-        hippopt_b200.kkt.StageKKT -- the multiple-shooting OCPs of the kinodynamic planner)."""
+        hippopt_b200.kkt.StageKKT -- the multiple-shooting OCPs of the kinodynamic planner).
+
+        ipopt_options: the subset of IPOPT's termination / scaling options the reference's mains pass through
+        `casadi_solver_options` (e.g. main_periodic_step.py:111-134), with IPOPT's meaning: "tol", "max_iter",
+        "dual_inf_tol", "constr_viol_tol", "compl_inf_tol" (desired level: scaled error <= tol AND the three unscaled
+        measures below their tolerances), "acceptable_tol", "acceptable_iter", "acceptable_dual_inf_tol",
+        "acceptable_constr_viol_tol", "acceptable_compl_inf_tol", "acceptable_obj_change_tol" (stop after
+        acceptable_iter consecutive iterations at the acceptable level), "nlp_scaling_method" ("gradient-based":
+        objective scaled by min(1, nlp_scaling_max_gradient / |grad f(x0)|_inf); constraints are not rescaled;
+        "none", the default here).  Unknown keys are ignored, as options of parts this driver does not have."""
+        o = dict(ipopt_options or {})
+        tol, max_iter = float(o.get("tol", tol)), int(o.get("max_iter", max_iter))
+        self.dual_inf_tol, self.constr_viol_tol = o.get("dual_inf_tol"), o.get("constr_viol_tol")
+        self.compl_inf_tol = o.get("compl_inf_tol")
+        self.acceptable_tol = o.get("acceptable_tol")  # None: no acceptable-level termination
+        self.acceptable_iter = int(o.get("acceptable_iter", 15))
+        self.acceptable_dual_inf_tol = float(o.get("acceptable_dual_inf_tol", 1e10))
+        self.acceptable_constr_viol_tol = float(o.get("acceptable_constr_viol_tol", 1e-2))
+        self.acceptable_compl_inf_tol = float(o.get("acceptable_compl_inf_tol", 1e-2))
+        self.acceptable_obj_change_tol = float(o.get("acceptable_obj_change_tol", 1e20))
+        self.obj_scaling = o.get("nlp_scaling_method", "none") == "gradient-based"
+        self.scaling_max_gradient = float(o.get("nlp_scaling_max_gradient", 100.0))
         self.ev = ev
         self.exact_inertia = exact_inertia
         self.tol, self.max_iter, self.mu_init = tol, max_iter, mu_init
@@ -160,16 +182,27 @@ class BatchedInteriorPoint:
         ones = torch.ones(B, dtype=torch.float64, device=dev)
         zeros_m = torch.zeros((B, m), dtype=torch.float64, device=dev)
 
+        obj_scale = ones  # IPOPT's gradient-based objective scaling (set below); sigma of the Hessian carries it
+
         def evaluate(xx, lam=None, full=True):
-            out = ev.eval(ALL if full else (F | G), xx, p, lam if lam is not None else zeros_m, ones)
-            return {k: v.clone() for k, v in out.items()}
+            out = ev.eval(ALL if full else (F | G), xx, p, lam if lam is not None else zeros_m, obj_scale)
+            out = {k: v.clone() for k, v in out.items()}
+            if self.obj_scaling:
+                out["f"] = out["f"] * obj_scale
+                if "grad_f" in out:
+                    out["grad_f"] = out["grad_f"] * obj_scale[:, None]
+            return out
+
+        if self.obj_scaling:
+            g0 = ev.eval(ALL, x, p, zeros_m, ones)["grad_f"].abs().amax(dim=1)
+            obj_scale = torch.clamp(self.scaling_max_gradient / torch.clamp(g0, min=1e-300), max=1.0).contiguous()
 
         big = 1e300
         lbs = torch.where(hasL, lb, torch.full_like(lb, -big))
         ubs = torch.where(hasU, ub, torch.full_like(ub, big))
 
         out = evaluate(x, full=False)
-        n_eval = 1
+        n_eval = 2 if self.obj_scaling else 1
         gI = out["g"][:, iI]
         # push the slacks strictly inside their bounds (IPOPT bound_push / bound_frac)
         push = 1e-2
@@ -184,6 +217,9 @@ class BatchedInteriorPoint:
         done = torch.zeros(B, dtype=torch.bool, device=dev)
         stalled = torch.zeros(B, dtype=torch.bool, device=dev)  # given up: max_fail line-search failures in a row
         fails = torch.zeros(B, dtype=torch.long, device=dev)
+        acceptable = torch.zeros(B, dtype=torch.bool, device=dev)
+        acc_count = torch.zeros(B, dtype=torch.long, device=dev)
+        f_prev = torch.full((B,), float("inf"), dtype=torch.float64, device=dev)
         iters = torch.zeros(B, dtype=torch.long, device=dev)
         err0 = torch.full((B,), float("inf"), dtype=torch.float64, device=dev)
         def rows_I(v):  # (B, m_I) values on the inequality rows -> (B, m) with zeros elsewhere
@@ -223,7 +259,22 @@ class BatchedInteriorPoint:
                 return torch.maximum(torch.maximum(linf(rd) / sd, prim), torch.maximum(linf(cL), linf(cU)) / sd)
 
             err0 = torch.where(done, err0, emu(torch.zeros_like(mu)))
+            # IPOPT's termination tests: desired level = scaled error AND (optionally) the unscaled measures;
+            # acceptable level = the looser set, acceptable_iter times in a row
+            dual_u, compl_u = linf(rd) / obj_scale, torch.maximum(linf(compL), linf(compU))
             newly = (~done) & (err0 <= self.tol)
+            for limit, val in ((self.dual_inf_tol, dual_u), (self.constr_viol_tol, prim), (self.compl_inf_tol, compl_u)):
+                if limit is not None:
+                    newly &= val <= float(limit)
+            if self.acceptable_tol is not None:
+                acc = ((~done) & (err0 <= float(self.acceptable_tol)) & (dual_u <= self.acceptable_dual_inf_tol)
+                       & (prim <= self.acceptable_constr_viol_tol) & (compl_u <= self.acceptable_compl_inf_tol)
+                       & ((fv - f_prev).abs() / torch.clamp(fv.abs(), min=1.0) <= self.acceptable_obj_change_tol))
+                acc_count = torch.where(acc, acc_count + 1, torch.zeros_like(acc_count))
+                newly_acc = (acc_count >= self.acceptable_iter) & ~newly
+                acceptable |= newly_acc
+                newly |= newly_acc
+            f_prev = torch.where(done, f_prev, fv)
             done |= newly
             if self.verbose and it % 10 == 0:
                 print(f"it {it:3d} done {int(done.sum())}/{B} err0 med {err0.median().item():.2e} max {err0.max().item():.2e} "
@@ -371,5 +422,6 @@ class BatchedInteriorPoint:
         if not bool(done.any()):
             raise OptiFailure(f"no instance reached tol={self.tol} in {self.max_iter} iterations "
                               f"(best error {err0.min().item():.3e})")
-        return BatchedOutput(values=x, cost_value=final["f"], constraint_multipliers=lam, success=done, iterations=iters,
-                             kkt_error=err0, evaluations=n_eval)
+        # undo the objective scaling in what is reported (IPOPT: f / s_f, lam_g / s_f)
+        return BatchedOutput(values=x, cost_value=final["f"] / obj_scale, constraint_multipliers=lam / obj_scale[:, None],
+                             success=done, iterations=iters, kkt_error=err0, evaluations=n_eval, acceptable=acceptable)

@@ -34,6 +34,43 @@ def test_toy_ocp_solves_reach_the_reference_solution(built_library):
     assert int(out.iterations.max()) < 30
 
 
+def test_ipopt_termination_and_scaling_options(built_library):
+    """The IPOPT options the reference's mains pass (`main_periodic_step.py:111-134`): acceptable-level
+    termination, the extra desired-level tolerances and gradient-based objective scaling, with IPOPT's meaning."""
+    from hippopt_b200.evaluator import ToyEvaluator
+    from hippopt_b200.ipsolver import BatchedInteriorPoint
+
+    N, dt, B = 100, 0.01, 6
+    ev = ToyEvaluator(N, "euler", dt)
+    p = np.tile([-9.81, 1.0, 0.0], (B, 1))
+    lb, ub = ev.bounds(p)
+    dev = torch.device("cuda:0")
+    x0, P = torch.zeros((B, ev.n_x), dtype=torch.float64, device=dev), torch.tensor(p, device=dev)
+    tight = BatchedInteriorPoint(ev, tol=1e-8).solve(x0, P, lb, ub)
+    assert not bool(tight.acceptable.any())
+    # an unreachable desired tolerance: stops at the acceptable level after acceptable_iter iterations in a row
+    loose = BatchedInteriorPoint(ev, ipopt_options={"tol": 1e-300, "acceptable_tol": 1e-2, "acceptable_iter": 2,
+                                                    "max_iter": 60}).solve(x0, P, lb, ub)
+    assert bool(loose.success.all()) and bool(loose.acceptable.all())
+    assert int(loose.iterations.max()) < int(tight.iterations.max())
+    assert float(loose.kkt_error.max()) <= 1e-2 and (loose.values - tight.values).abs().max() < 1e-1
+    # a desired-level side condition that cannot hold keeps an otherwise converged instance running
+    never = BatchedInteriorPoint(ev, tol=1e-8, max_iter=40, ipopt_options={"constr_viol_tol": -1.0, "acceptable_tol": 1e-6,
+                                                                         "acceptable_iter": 3})
+    out = never.solve(x0, P, lb, ub)
+    assert bool(out.acceptable.all())  # ... until the acceptable level takes it
+    # gradient-based scaling (the objective gradient at x0 = 0 is zero here, at a shifted start it is ~ 6 N): same
+    # solution, and cost / multipliers are reported unscaled
+    x1 = torch.full_like(x0, 40.0)
+    a = BatchedInteriorPoint(ev, tol=1e-8).solve(x1, P, lb, ub)
+    b = BatchedInteriorPoint(ev, tol=1e-8, ipopt_options={"nlp_scaling_method": "gradient-based"}).solve(x1, P, lb, ub)
+    assert bool(a.success.all()) and bool(b.success.all())
+    assert (a.values - b.values).abs().max() < 1e-6
+    assert b.cost_value.cpu().numpy() == pytest.approx(a.cost_value.cpu().numpy(), rel=1e-8)
+    o = 2 * (N - 1) + 2 + 2 * N
+    assert b.constraint_multipliers[:, o:o + 3 * (N - 2)].cpu().numpy() == pytest.approx(-10.0, abs=1e-4)
+
+
 def test_solver_reports_failure_like_the_reference(built_library):
     """`OptiFailure` when nothing converges (base/opti_solver.py:28-37, test_optimization_problem.py:257-267)."""
     from hippopt_b200.evaluator import ToyEvaluator

@@ -1,7 +1,7 @@
 """Developer check of row f3 (+ f1/f2 on top of it): the set-up of main_periodic_step.py for a batch of step
 lengths -- keyframe poses by the batched pose finder, initial guess by the device interpolator -- and, with -s, an
 attempt to solve the resulting periodic-step OCPs (config 4's structure) with the stage-wise KKT sweep.
-Reports what happens, converged or not.   usage: check_periodic_step.py [-b BATCH] [-n HORIZON] [-s] [-i MAX_ITER] [-v] [--fz FORCE] [--lmin L] [--lmax L] [-m MU_INIT] [-t TOL]"""
+Reports what happens, converged or not.   usage: check_periodic_step.py [-b BATCH] [-n HORIZON] [-s] [-i MAX_ITER] [-v] [--fz FORCE] [--lmin L] [--lmax L] [-m MU_INIT] [-t TOL] [--ref-options]"""
 import sys
 import time
 
@@ -73,14 +73,19 @@ if "-k" in sys.argv:  # the interpolation kernel alone, at config 4's batch (409
               f"{written / 1e6:.0f} MB written")
 if "-s" in sys.argv:
     sel = np.nonzero(ok)[0]
+    # --ref-options: the termination / scaling options main_periodic_step.py:111-134 hands to IPOPT
+    ref_opts = {"tol": 1e-3, "dual_inf_tol": 1000.0, "compl_inf_tol": 1e-2, "constr_viol_tol": 1e-4, "acceptable_tol": 10,
+                "acceptable_iter": 2, "acceptable_compl_inf_tol": 1000.0, "acceptable_obj_change_tol": 1e0,
+                "nlp_scaling_method": "gradient-based"} if "--ref-options" in sys.argv else None
     sol = BatchedInteriorPoint(ev, tol=arg("-t", 1e-6), max_iter=iters, verbose="-v" in sys.argv, kkt="stage",
-                               delta_c=1e-9, mu_init=arg("-m", 1e-1))
+                               delta_c=1e-9, mu_init=arg("-m", 1e-1), ipopt_options=ref_opts)
     t0 = time.perf_counter()
     try:
         res = sol.solve(gs.x0[sel], P[sel], lb[sel], ub[sel])
         torch.cuda.synchronize()
         n_ok = int(res.success.sum())
-        print(f"periodic-step OCP (n_x={lay.n_x}, m={lay.m}): {n_ok}/{len(sel)} converged in <= {iters} iterations "
+        print(f"periodic-step OCP (n_x={lay.n_x}, m={lay.m}): {n_ok}/{len(sel)} converged ({int(res.acceptable.sum())} of them at "
+              f"IPOPT's acceptable level{', reference options' if ref_opts else ''}) in <= {iters} iterations "
               f"(median {int(res.iterations[res.success].median()) if n_ok else -1}), {time.perf_counter() - t0:.1f} s, "
               f"KKT error median {res.kkt_error.median().item():.2e}, best {res.kkt_error.min().item():.2e}")
         if n_ok:
