@@ -31,6 +31,9 @@ constexpr int LU_NB = 16;
 #ifndef HB_LU_PREFETCH
 #define HB_LU_PREFETCH 1  // request the A22 tile before the products: its L2 latency overlaps them
 #endif
+#ifndef HB_LU_TR
+#define HB_LU_TR 4  // rows of the trailing-update register tile when one CTA runs per SM (4 or 8)
+#endif
 constexpr int LU_THREADS = HB_LU_THREADS;
 constexpr int LU_MAXN = 768;
 
@@ -165,27 +168,29 @@ __global__ void __launch_bounds__(LU_THREADS, MB) lu_factor_kernel(double* __res
     const int nrem = n - j0 - nbw;  // trailing columns (and rows below the panel's square)
     if (nrem <= 0) break;
     // ---- the panel's interchanges composed into one gather: new[aff_dst[t]] = old[aff_src[t]]
-    if (tid == 0) {
-      int rows[2 * LU_NB], content[2 * LU_NB], cnt = nbw;
-      for (int c = 0; c < nbw; ++c) rows[c] = content[c] = c;
+    // (warp 0, entry t of the list on lane t: a serial version on one thread kept the other 255 waiting for
+    // ~2.5 us per panel)
+    if (tid < 32) {
+      int row_l = tid < nbw ? tid : -1, content_l = row_l, cnt = nbw;
       for (int c = 0; c < nbw; ++c) {
         const int r = s_piv[c];  // s_piv writes are ordered by the barriers of the column loop
-        int pos = -1;
-        for (int t = 0; t < cnt; ++t)
-          if (rows[t] == r) pos = t;
-        if (pos < 0) {
+        const unsigned hit = __ballot_sync(0xffffffffu, tid < cnt && row_l == r);
+        int pos;
+        if (hit) {
+          pos = __ffs(hit) - 1;
+        } else {
           pos = cnt++;
-          rows[pos] = content[pos] = r;
+          if (tid == pos) row_l = content_l = r;
         }
-        const int tmp = content[c];
-        content[c] = content[pos];
-        content[pos] = tmp;
+        const int at_c = __shfl_sync(0xffffffffu, content_l, c), at_pos = __shfl_sync(0xffffffffu, content_l, pos);
+        if (tid == c) content_l = at_pos;
+        else if (tid == pos) content_l = at_c;
       }
-      for (int t = 0; t < cnt; ++t) {
-        aff_dst[t] = rows[t];
-        aff_src[t] = content[t];
+      if (tid < cnt) {
+        aff_dst[tid] = row_l;
+        aff_src[tid] = content_l;
       }
-      aff_n = cnt;
+      if (tid == 0) aff_n = cnt;
     }
     __syncthreads();
     // ---- trailing columns: interchanges, then U12 = L11^{-1} A12 (one thread per column)
@@ -220,25 +225,27 @@ __global__ void __launch_bounds__(LU_THREADS, MB) lu_factor_kernel(double* __res
     // ---- trailing update A22 -= L21 U12: CTA tile 128 rows x 32 columns, thread tile 4 x 4 (rows strided
     // by 32 so that every A22 access is a coalesced 256-byte row segment; contiguous rows per thread were
     // 20 % slower); per k four shared loads of L21 and two 16-byte broadcast loads of U12 feed 16 FMAs
+#ifndef HB_LU_SKIP_TRAILING  // (timing experiments only: how much of a factorisation is the panel work)
     {
+      constexpr int TR = MB == 1 ? HB_LU_TR : 4;  // rows per thread tile: TR x 4, CTA tile 32 TR rows x 32 columns
       const int tx = tid & 31, ty = tid >> 5;
       const double* L21 = P + nbw;  // local row i of L21 = panel row nbw + i
       for (int jt = 0; jt < nrem; jt += (nt / 32) * 4)
-        for (int it = 0; it < nrem; it += 128) {
-          double acc[4][4];
+        for (int it = 0; it < nrem; it += 32 * TR) {
+          double acc[TR][4];
 #if HB_LU_PREFETCH
-          double a22[4][4];
+          double a22[TR][4];
 #endif
-          int ii[4], jc[4];
+          int ii[TR], jc[4];
 #pragma unroll
-          for (int a = 0; a < 4; ++a) ii[a] = it + tx + 32 * a;  // lane = row: coalesced A22 accesses
+          for (int a = 0; a < TR; ++a) ii[a] = it + tx + 32 * a;  // lane = row: coalesced A22 accesses
 #pragma unroll
           for (int b = 0; b < 4; ++b) jc[b] = jt + ty * 4 + b;
 #pragma unroll
           for (int b = 0; b < 4; ++b) {
             const double* col = A + (size_t)(j0 + nbw + jc[b]) * n + j0 + nbw;
 #pragma unroll
-            for (int a = 0; a < 4; ++a) {
+            for (int a = 0; a < TR; ++a) {
 #if HB_LU_PREFETCH
               a22[a][b] = (jc[b] < nrem && ii[a] < nrem) ? col[ii[a]] : 0.0;
 #else
@@ -249,14 +256,17 @@ __global__ void __launch_bounds__(LU_THREADS, MB) lu_factor_kernel(double* __res
           }
 #pragma unroll 4
           for (int k = 0; k < nbw; ++k) {
-            // entries past nrem are whatever the strip holds (the slack keeps the loads in bounds); the
-            // products they feed are never stored
+            // entries past nrem are whatever the panel / strip hold (the reads stay inside the shared-memory
+            // block: 15 ldp + nbw + nrem + 32 TR - 1 < 32 ldp); the products they feed are never stored
             const double* lp = L21 + k * ldp + it + tx;
             const double2* up = reinterpret_cast<const double2*>(U + k * ldp + jt + ty * 4);
             const double2 u01 = up[0], u23 = up[1];
-            const double l[4] = {lp[0], lp[32], lp[64], lp[96]}, uu[4] = {u01.x, u01.y, u23.x, u23.y};
+            const double uu[4] = {u01.x, u01.y, u23.x, u23.y};
+            double l[TR];
 #pragma unroll
-            for (int a = 0; a < 4; ++a)
+            for (int a = 0; a < TR; ++a) l[a] = lp[32 * a];
+#pragma unroll
+            for (int a = 0; a < TR; ++a)
 #pragma unroll
               for (int b = 0; b < 4; ++b) acc[a][b] = fma(l[a], uu[b], acc[a][b]);
           }
@@ -265,7 +275,7 @@ __global__ void __launch_bounds__(LU_THREADS, MB) lu_factor_kernel(double* __res
             if (jc[b] < nrem) {
               double* col = A + (size_t)(j0 + nbw + jc[b]) * n + j0 + nbw;
 #pragma unroll
-              for (int a = 0; a < 4; ++a)
+              for (int a = 0; a < TR; ++a)
 #if HB_LU_PREFETCH
                 if (ii[a] < nrem) col[ii[a]] = a22[a][b] - acc[a][b];
 #else
@@ -274,6 +284,7 @@ __global__ void __launch_bounds__(LU_THREADS, MB) lu_factor_kernel(double* __res
             }
         }
     }
+#endif
     __syncthreads();
   }
   __syncthreads();
