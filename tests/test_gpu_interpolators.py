@@ -191,3 +191,28 @@ def test_periodic_step_setup_pipeline(model, built_library):
     # and the evaluator accepts the pair
     g = ev.eval(4, gs.x0, torch.tensor(p, device=gs.x0.device))["g"]
     assert torch.isfinite(g).all()
+
+
+def test_kernel_matches_the_interpolator_fixture(built_library):
+    """Against the committed fixture (no oracle at run time): per-instance rotated foot transforms, both halves."""
+    from hippopt_b200.interpolators import FeetContactPhasesDescriptor, FootContactPhaseDescriptor, humanoid_state_interpolator
+    from test_interpolators_cpu import golden_interp
+
+    g, _ = golden_interp()
+    dev = torch.device("cuda:0")
+
+    def phases(side):
+        def t(v):
+            return None if np.isnan(v) else float(v)
+        return [FootContactPhaseDescriptor(
+            position=g[f"{side}_position"][:, i], quaternion_xyzw=g[f"{side}_quaternion"][:, i], force=g[f"{side}_force"][:, i],
+            mid_swing_position=g[f"{side}_mid_position"] if i == 0 else None,
+            mid_swing_quaternion_xyzw=g[f"{side}_mid_quaternion"] if i == 0 else None,
+            activation_time=t(g[f"{side}_times"][i, 0]), deactivation_time=t(g[f"{side}_times"][i, 1])) for i in range(2)]
+
+    ph = FeetContactPhasesDescriptor(left=phases("left"), right=phases("right"))
+    N, dt = int(g["n_points"]), float(g["dt"])
+    for h, (k0, k1, pts) in enumerate(((0, 1, N // 2), (1, 2, N - N // 2))):
+        out = humanoid_state_interpolator(torch.tensor(g[f"key_{k0}"], device=dev), torch.tensor(g[f"key_{k1}"], device=dev),
+                                          ph, pts, dt, float(g[f"t0_{h}"]))
+        check(out, g[f"states_{h}"])

@@ -169,3 +169,41 @@ def test_reference_errors():
         foot_contact_schedule(ph, 30, 0.1)
     with pytest.raises(ValueError, match="given together"):
         FootContactPhaseDescriptor(mid_swing_position=np.zeros(3))
+
+
+def golden_interp():
+    import os
+
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "interp_periodic_step.npz"))
+
+    def t(v):
+        return None if np.isnan(v) else float(v)
+
+    feet = {}
+    for side in ("left", "right"):
+        B = g[f"{side}_position"].shape[0]
+        feet[side] = [[{"position": g[f"{side}_position"][b, i], "quaternion": g[f"{side}_quaternion"][b, i],
+                        "force": g[f"{side}_force"][b, i],
+                        "mid_position": g[f"{side}_mid_position"][b] if i == 0 else None,
+                        "mid_quaternion": g[f"{side}_mid_quaternion"][b] if i == 0 else None,
+                        "activation_time": t(g[f"{side}_times"][i, 0]), "deactivation_time": t(g[f"{side}_times"][i, 1])}
+                       for i in range(2)] for b in range(B)]
+    return g, feet
+
+
+def test_oracle_reproduces_the_interpolator_fixture():
+    """tests/golden/interp_periodic_step.npz (tests/dev/make_golden.py interp) guards the fixture against oracle drift;
+    a dump from the reference itself can replace it key for key."""
+    g, feet = golden_interp()
+    desc = (g["descriptor"].tolist(),) * 2
+    N, dt = int(g["n_points"]), float(g["dt"])
+    for h, (k0, k1, pts) in enumerate(((0, 1, N // 2), (1, 2, N - N // 2))):
+        for b in range(g["key_0"].shape[0]):
+            def unblock(v):
+                pts9 = v[:72].reshape(8, 9)
+                return {"p": pts9[:, :3], "f": pts9[:, 3:6], "base_position": v[72:75], "base_quaternion": v[75:79],
+                        "joints": v[79:102], "com": v[102:105]}
+            out = oi.humanoid_state_interpolator(unblock(g[f"key_{k0}"][b]), unblock(g[f"key_{k1}"][b]),
+                                                 (feet["left"][b], feet["right"][b]), desc, pts, dt, float(g[f"t0_{h}"]))
+            got = np.stack([oi.state_block(s, desc) for s in out])
+            assert np.array_equal(got, g[f"states_{h}"][b])
