@@ -30,5 +30,19 @@ tev.eval(ALL, torch.zeros((2, tev.n_x), dtype=torch.float64, device=d), torch.on
 A = torch.randn(3, 37, 37, dtype=torch.float64, device=d)
 Fm, piv, info = lu_factor(A.clone())
 lu_solve(Fm, piv, torch.randn(3, 37, 5, dtype=torch.float64, device=d))
+A = torch.randn(2, 337, 337, dtype=torch.float64, device=d)  # the KKT stage-block size: 22 panels, both register variants
+Fm, piv, info = lu_factor(A.clone())
+lu_solve(Fm, piv, torch.randn(2, 337, 40, dtype=torch.float64, device=d))
+# interpolation kernel: a plan with swings, per-instance phases, both outputs, a warp with fewer than three items
+from hippopt_b200.initial_guess import periodic_step_phases  # noqa: E402
+from hippopt_b200.interpolators import humanoid_state_interpolator  # noqa: E402
+
+B = 7
+ph = periodic_step_phases(np.linspace(0.1, 0.3, B), 1.0)
+s0, s1 = torch.randn(B, 105, dtype=torch.float64, device=d), torch.randn(B, 105, dtype=torch.float64, device=d)
+for q in (s0, s1):
+    q[:, 75:79] /= q[:, 75:79].norm(dim=1, keepdim=True)
+xo = torch.zeros((B, 189 * 12 + 6), dtype=torch.float64, device=d)
+humanoid_state_interpolator(s0, s1, ph, 10, 0.1, x_out=xo, knot0=1)
 torch.cuda.synchronize()
 print("sanitize workload done")
