@@ -28,8 +28,9 @@ from .evaluator import ALL, F, G
 class OptiFailure(Exception):
     """Mirror of `hippopt.OptiFailure` (`base/opti_solver.py:28-37`): raised when no instance converged."""
 
-    def __init__(self, message: str):
-        super().__init__("Opti failed to solve the problem. Message: " + message)
+    def __init__(self, message: str, callback_used: bool = False):
+        callback_info = " and the callback did not manage to save an intermediate solution" if callback_used else ""
+        super().__init__(f"Opti failed to solve the problem{callback_info}. Message: {message}")
 
 
 @dataclasses.dataclass
@@ -44,6 +45,8 @@ class BatchedOutput:
     kkt_error: torch.Tensor               # (B,) scaled optimality error at exit
     evaluations: int = 0                  # batched hb_eval calls made
     acceptable: torch.Tensor = None       # (B,) bool: stopped at IPOPT's "acceptable level" (part of `success`)
+    callback_iteration: torch.Tensor = None  # (B,) int: >= 0 where a FAILED instance returns the iterate its callback
+    #                                          criterion saved at that iteration (opti_solver.py:478-520), else -1
 
 
 class SparseOps:
@@ -116,7 +119,7 @@ class BatchedInteriorPoint:
                  kappa_mu: float = 0.2, theta_mu: float = 1.5, tau_min: float = 0.99, eta: float = 1e-4,
                  max_backtrack: int = 16, delta_min: float = 1e-8, delta_max: float = 1e8, exact_inertia: bool = False,
                  verbose: bool = False, kkt: str = "dense", delta_c: float = 1e-11, f_type: bool = True,
-                 max_fail: int = 8, ipopt_options: dict | None = None):
+                 max_fail: int = 8, ipopt_options: dict | None = None, callback_criterion=None):
         """kkt: "dense" (one dense factorisation per instance) or "stage" (block-tridiagonal sweep over the knots,
         hippopt_b200.kkt.StageKKT -- the multiple-shooting OCPs of the kinodynamic planner).
 
@@ -127,7 +130,13 @@ class BatchedInteriorPoint:
         "acceptable_constr_viol_tol", "acceptable_compl_inf_tol", "acceptable_obj_change_tol" (stop after
         acceptable_iter consecutive iterations at the acceptable level), "nlp_scaling_method" ("gradient-based":
         objective scaled by min(1, nlp_scaling_max_gradient / |grad f(x0)|_inf); constraints are not rescaled;
-        "none", the default here).  Unknown keys are ignored, as options of parts this driver does not have."""
+        "none", the default here).  Unknown keys are ignored, as options of parts this driver does not have.
+
+        callback_criterion: a hippopt_b200.opti_callback criterion (the reference's `OptiSolver(callback_criterion=)`,
+        opti_solver.py:109,451-520): after every iteration the iterate of each unfinished instance whose criterion
+        is satisfied is saved, and an instance that fails returns that iterate instead of its last one; OptiFailure
+        is raised only if no instance converged AND none has a saved iterate."""
+        self.callback_criterion = callback_criterion
         o = dict(ipopt_options or {})
         tol, max_iter = float(o.get("tol", tol)), int(o.get("max_iter", max_iter))
         self.dual_inf_tol, self.constr_viol_tol = o.get("dual_inf_tol"), o.get("constr_viol_tol")
@@ -221,6 +230,11 @@ class BatchedInteriorPoint:
         acc_count = torch.zeros(B, dtype=torch.long, device=dev)
         f_prev = torch.full((B,), float("inf"), dtype=torch.float64, device=dev)
         iters = torch.zeros(B, dtype=torch.long, device=dev)
+        best_it = torch.full((B,), -1, dtype=torch.long, device=dev)
+        if self.callback_criterion is not None:
+            self.callback_criterion.reset(B, dev)
+            best_x, best_lam = x.clone(), zeros_m.clone()
+            best_cost = torch.full((B,), float("inf"), dtype=torch.float64, device=dev)
         err0 = torch.full((B,), float("inf"), dtype=torch.float64, device=dev)
         def rows_I(v):  # (B, m_I) values on the inequality rows -> (B, m) with zeros elsewhere
             full = torch.zeros((B, m), dtype=torch.float64, device=dev)
@@ -275,6 +289,16 @@ class BatchedInteriorPoint:
                 acceptable |= newly_acc
                 newly |= newly_acc
             f_prev = torch.where(done, f_prev, fv)
+            if self.callback_criterion is not None:
+                # SaveBestUnsolvedVariablesCallback.call (opti_callback.py:342-373), per instance: runs for every
+                # instance that had not finished before this iteration, the converging iterate included
+                cost_u = fv / obj_scale
+                sat = self.callback_criterion.satisfied(cost_u, prim) & ~done & ~stalled & torch.isfinite(cost_u)
+                self.callback_criterion.update(sat, cost_u, prim)
+                best_x = torch.where(sat[:, None], x, best_x)
+                best_lam = torch.where(sat[:, None], lam, best_lam)
+                best_cost = torch.where(sat, cost_u, best_cost)
+                best_it = torch.where(sat, torch.full_like(best_it, it), best_it)
             done |= newly
             if self.verbose and it % 10 == 0:
                 print(f"it {it:3d} done {int(done.sum())}/{B} err0 med {err0.median().item():.2e} max {err0.max().item():.2e} "
@@ -419,9 +443,16 @@ class BatchedInteriorPoint:
         lam[:, iI] = zU - zL
         final = evaluate(x, full=False)
         n_eval += 1
-        if not bool(done.any()):
+        used = (~done) & (best_it >= 0)  # failed instances with an iterate saved by the callback criterion
+        if not bool(done.any()) and not bool(used.any()):
             raise OptiFailure(f"no instance reached tol={self.tol} in {self.max_iter} iterations "
-                              f"(best error {err0.min().item():.3e})")
+                              f"(best error {err0.min().item():.3e})", callback_used=self.callback_criterion is not None)
         # undo the objective scaling in what is reported (IPOPT: f / s_f, lam_g / s_f)
-        return BatchedOutput(values=x, cost_value=final["f"] / obj_scale, constraint_multipliers=lam / obj_scale[:, None],
-                             success=done, iterations=iters, kkt_error=err0, evaluations=n_eval, acceptable=acceptable)
+        cost, lam_out = final["f"] / obj_scale, lam / obj_scale[:, None]
+        if bool(used.any()):  # opti_solver.py:478-520: the saved intermediate solution instead of the last iterate
+            x = torch.where(used[:, None], best_x, x)
+            cost = torch.where(used, best_cost, cost)
+            lam_out = torch.where(used[:, None], best_lam / obj_scale[:, None], lam_out)
+        return BatchedOutput(values=x, cost_value=cost, constraint_multipliers=lam_out, success=done, iterations=iters,
+                             kkt_error=err0, evaluations=n_eval, acceptable=acceptable,
+                             callback_iteration=torch.where(used, best_it, torch.full_like(best_it, -1)))

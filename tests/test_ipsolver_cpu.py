@@ -136,3 +136,55 @@ def test_opti_failure_and_give_up():
     lbb[1, 0] = np.inf
     with pytest.raises(ValueError, match="share"):
         BatchedInteriorPoint(ev).solve(starts(), torch.zeros((3, 1), dtype=torch.float64), lbb, np.tile(ub, (3, 1)))
+
+
+def test_opti_callback_saves_an_intermediate_solution():
+    """/root/reference/test/test_optimization_problem.py:270-283: an infeasible problem (0 <= x <= 1, x^2 == 10) does
+    not raise when a callback criterion saved an iterate; without one it does (:257-267)."""
+    from hippopt_b200 import opti_callback
+
+    f = lambda v: (v * v).sum() * 0.0  # noqa: E731  (the reference's problem has no cost)
+    g = lambda v: torch.cat([v, v * v])  # noqa: E731
+    ev = TorchEvaluator(f, g, 1, 2)
+    lb, ub = np.array([0.0, 10.0]), np.array([1.0, 10.0])
+    x0, p = torch.tensor([[0.5], [0.9]], dtype=torch.float64), torch.zeros((2, 1), dtype=torch.float64)
+    with pytest.raises(OptiFailure, match="Opti failed to solve the problem. Message"):
+        BatchedInteriorPoint(ev, tol=1e-8, max_iter=40).solve(x0, p, lb, ub)
+    crit = opti_callback.BestCost() | opti_callback.BestPrimalInfeasibility()
+    out = BatchedInteriorPoint(ev, tol=1e-8, max_iter=40, callback_criterion=crit).solve(x0, p, lb, ub)
+    assert not bool(out.success.any()) and (out.callback_iteration >= 0).all()
+    # what comes back is the iterate with the smallest violation seen, x close to its upper bound
+    assert (out.values > 0.9).all() and (out.values <= 1.0 + 1e-6).all()
+    # a criterion that is never satisfied saves nothing: the failure says so, in the reference's words
+    never = opti_callback.AcceptablePrimalInfeasibility(1e-12)
+    with pytest.raises(OptiFailure, match="the callback did not manage to save an intermediate solution"):
+        BatchedInteriorPoint(ev, tol=1e-8, max_iter=40, callback_criterion=never).solve(x0, p, lb, ub)
+    with pytest.raises(TypeError):
+        opti_callback.BestCost() | 3
+    with pytest.raises(TypeError):
+        opti_callback.BestCost() & "x"
+
+
+def test_planner_criterion_per_instance():
+    """`BestCost() & AcceptablePrimalInfeasibility(tol)` (humanoid_kinodynamic/planner.py:57-63): each instance keeps
+    its own best cost; converged instances return their solution, cut-off ones the best acceptable iterate."""
+    from hippopt_b200 import opti_callback
+
+    f, g, lb, ub = hs071()
+    ev = TorchEvaluator(f, g, 4, 6)
+    x0, p = starts(), torch.zeros((3, 1), dtype=torch.float64)
+    full = BatchedInteriorPoint(ev, tol=1e-9).solve(x0, p, lb, ub)
+    cut = int(full.iterations.min())  # the fastest instance just converges, the others are cut off
+    crit = opti_callback.BestCost() & opti_callback.AcceptablePrimalInfeasibility(1e-1)
+    out = BatchedInteriorPoint(ev, tol=1e-9, max_iter=cut + 1, callback_criterion=crit).solve(x0, p, lb, ub)
+    ok = out.success.numpy()
+    assert ok.any() and not ok.all()
+    saved = out.callback_iteration >= 0  # (a cut-off instance whose violation never got below 0.1 has nothing saved)
+    assert (out.callback_iteration[out.success] == -1).all() and bool(saved.any()) and not bool((saved & out.success).any())
+    assert out.values.numpy()[ok] == pytest.approx(np.tile(HS071_X, (int(ok.sum()), 1)), abs=1e-6)
+    # saved iterates respect the acceptable violation and carry their own cost
+    xs = out.values[saved]
+    gv = torch.vmap(g)(xs).numpy()
+    assert (np.maximum(lb - gv, 0) + np.maximum(gv - ub, 0)).max() < 1e-1
+    assert out.cost_value[saved].numpy() == pytest.approx(torch.vmap(f)(xs).numpy(), rel=1e-12)
+    assert torch.equal(crit.lhs.best_cost[saved], out.cost_value[saved])  # per-instance state of the criterion
