@@ -85,6 +85,27 @@ def test_solver_reports_failure_like_the_reference(built_library):
                                                               torch.tensor(p, device=dev), lb, ub)
 
 
+def test_callback_criterion_with_the_cuda_evaluator(built_library):
+    """`OptiSolver(callback_criterion=...)` (opti_solver.py:451-520) on device tensors: a solve cut off after a few
+    iterations returns, per instance, the iterate its criterion saved instead of raising."""
+    from hippopt_b200 import opti_callback
+    from hippopt_b200.evaluator import G, ToyEvaluator
+    from hippopt_b200.ipsolver import BatchedInteriorPoint
+
+    ev = ToyEvaluator(20, "euler", 0.01)
+    B = 5
+    p = np.tile([-9.81, 1.0, 0.0], (B, 1))
+    lb, ub = ev.bounds(p)
+    dev = torch.device("cuda:0")
+    x0, P = torch.zeros((B, ev.n_x), dtype=torch.float64, device=dev), torch.tensor(p, device=dev)
+    crit = opti_callback.BestCost() | opti_callback.BestPrimalInfeasibility()
+    out = BatchedInteriorPoint(ev, tol=1e-12, max_iter=4, callback_criterion=crit).solve(x0, P, lb, ub)
+    assert not bool(out.success.any()) and (out.callback_iteration >= 0).all() and (out.callback_iteration <= 3).all()
+    g = ev.eval(G, out.values, P)["g"].cpu().numpy()
+    assert np.isfinite(g).all() and torch.isfinite(out.cost_value).all()
+    assert torch.equal(crit.rhs.best_primal_infeasibility.isfinite(), torch.ones(B, dtype=torch.bool, device=dev))
+
+
 @pytest.mark.parametrize("periodic", [False, True])  # True: config 4's structure (final state + periodicity rows)
 def test_standing_ocp_solves_with_the_stage_kkt(model, built_library, periodic):
     """Rows f1 + f2 end to end on the real problem: pose-finder solutions (dense KKT) become "keep standing"
