@@ -137,6 +137,9 @@ class BatchedInteriorPoint:
         is satisfied is saved, and an instance that fails returns that iterate instead of its last one; OptiFailure
         is raised only if no instance converged AND none has a saved iterate."""
         self.callback_criterion = callback_criterion
+        # instances x shifts factored per sweep (stage backend on a GPU: one CTA per SM); 0 disables the speculation
+        self.spec_wave = 0
+        self.speculative_shifts = True
         o = dict(ipopt_options or {})
         tol, max_iter = float(o.get("tol", tol)), int(o.get("max_iter", max_iter))
         self.dual_inf_tol, self.constr_viol_tol = o.get("dual_inf_tol"), o.get("constr_viol_tol")
@@ -182,6 +185,8 @@ class BatchedInteriorPoint:
             jc_, jr_ = ev.jac_sparsity()
             hc_, hr_ = ev.hess_sparsity()
             backend = StageKKT(n, m, lay.N, 189, jc_, jr_, hc_, hr_, iE.cpu().numpy(), iI.cpu().numpy(), device=dev)
+            if dev.type == "cuda" and self.speculative_shifts:
+                self.spec_wave = torch.cuda.get_device_properties(dev).multi_processor_count
         else:
             backend = DenseKKT(ops, iE, iI)
         lb, ub = lbg[:, iI], ubg[:, iI]
@@ -324,6 +329,9 @@ class BatchedInteriorPoint:
             dx = torch.zeros_like(x)
             lamE_new = lamE.clone()
             need = ~inactive
+            def next_delta(dv):  # IPOPT's growth of the Hessian perturbation (kappa_plus = 8, first trial 1e-4)
+                return torch.clamp(torch.maximum(dv * 8.0, torch.full_like(dv, 1e-4)), max=self.delta_max)
+
             for attempt in range(12):
                 # delta_c only once a plain solve has failed (rank-deficient J_E); the stage-wise sweep always
                 # carries it (its pivot blocks are the stage KKT matrices, not the whole one)
@@ -334,6 +342,38 @@ class BatchedInteriorPoint:
                 # only the instances that still need a step: converged ones (and those whose step was
                 # accepted in an earlier attempt) do not ride along -- the factorisation is what costs
                 idx = torch.nonzero(need).ravel()
+                # speculative shifts: the LU kernels are latency-bound below one CTA per SM, so while the active
+                # instances fill less than half a wave the next S - 1 shifts of the sequence are factored in the
+                # SAME sweep and the first one that passes the test is taken -- the shifts tried and the step
+                # chosen are those of the one-at-a-time loop, only the number of sweeps drops
+                S = max(1, min(4, self.spec_wave // max(1, idx.numel()))) if self.spec_wave else 1
+                if S > 1:
+                    cand = [delta[idx]]
+                    for _ in range(S - 1):
+                        cand.append(next_delta(cand[-1]))
+                    rep = idx.repeat(S)
+                    dl_all = torch.cat(cand)
+                    hv_r, jv_r, Sig_r, cI_r = hv[rep], jv[rep], Sig[rep], cI[rep]
+                    dxa, lama = backend.solve(hv_r, jv_r, Sig_r, dl_all, dc, rhs_x[rep], -cE[rep])
+                    if dev.type == "cuda":
+                        torch.cuda.synchronize(dev)
+                    self.kkt_seconds += time.perf_counter() - t_k
+                    dsa = ops.J_mul(jv_r, dxa)[:, iI] + cI_r
+                    curv = ops.W_quad(hv_r, dxa) + dl_all * (dxa * dxa).sum(1) + (Sig_r * dsa * dsa).sum(1)
+                    oka = (torch.isfinite(dxa).all(dim=1) & torch.isfinite(lama).all(dim=1)
+                           & (curv > 1e-12 * (dxa * dxa).sum(1))).view(S, -1)
+                    first = torch.where(oka.any(dim=0), oka.to(torch.int8).argmax(dim=0), torch.full_like(idx, -1))
+                    got = first >= 0
+                    row = torch.clamp(first, min=0) * idx.numel() + torch.arange(idx.numel(), device=dev)
+                    sel = idx[got]
+                    dx[sel], lamE_new[sel] = dxa[row[got]], lama[row[got]]
+                    delta[sel] = dl_all[row[got]]
+                    delta[idx[~got]] = next_delta(cand[-1][~got])
+                    need = need.clone()
+                    need[sel] = False
+                    if not bool(need.any()):
+                        break
+                    continue
                 if idx.numel() == B:
                     dxt, lamt = backend.solve(hv, jv, Sig, delta, dc, rhs_x, -cE)
                 else:
@@ -360,7 +400,7 @@ class BatchedInteriorPoint:
                 need = need & ~ok
                 if not bool(need.any()):
                     break
-                delta = torch.where(need, torch.clamp(torch.maximum(delta * 8.0, torch.full_like(delta, 1e-4)), max=self.delta_max), delta)
+                delta = torch.where(need, next_delta(delta), delta)
             ds = ops.J_mul(jv, dx)[:, iI] + cI
             lamI_new = lamhat + Sig * ds
             zL_new = torch.where(hasL, mu[:, None] / dL - SigL * ds, torch.zeros_like(s))

@@ -188,3 +188,19 @@ def test_planner_criterion_per_instance():
     assert (np.maximum(lb - gv, 0) + np.maximum(gv - ub, 0)).max() < 1e-1
     assert out.cost_value[saved].numpy() == pytest.approx(torch.vmap(f)(xs).numpy(), rel=1e-12)
     assert torch.equal(crit.lhs.best_cost[saved], out.cost_value[saved])  # per-instance state of the criterion
+
+
+def test_speculative_hessian_shifts_take_the_same_steps():
+    """Several shifts of the regularisation sequence factored in one batched solve (the GPU default for the stage
+    backend) choose the shift the one-at-a-time loop would have chosen."""
+    f, g, lb, ub = hs071()
+    ev = TorchEvaluator(lambda v: -f(v), g, 4, 6)  # maximise: indefinite Hessians, shifts on most iterations
+    x0, p = starts(), torch.zeros((3, 1), dtype=torch.float64)
+    one = BatchedInteriorPoint(ev, tol=1e-8, delta_c=0.0)
+    a = one.solve(x0, p, lb, ub)
+    spec = BatchedInteriorPoint(ev, tol=1e-8, delta_c=0.0)
+    spec.spec_wave = 12  # 3 instances -> 4 shifts per solve
+    b = spec.solve(x0, p, lb, ub)
+    assert bool(a.success.all()) and torch.equal(a.iterations, b.iterations)
+    assert (a.values - b.values).abs().max() < 1e-9 and (a.constraint_multipliers - b.constraint_multipliers).abs().max() < 1e-7
+    assert b.evaluations == a.evaluations
