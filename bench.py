@@ -393,6 +393,32 @@ def main():
                     "workload": f"{n_s} plans of config 4's structure: contact phases, {3 * n_s} keyframe pose solves, guess "
                                 f"interpolated on the device into the decision vectors, parameters",
                     "instances": n_s, "keyframe_triples_converged": int(gs.ok.sum()), "setups_per_s": n_s / t_set}
+                # rows f3 + f1 + f2 on a plan with contact switches: 32 of those plans (planned force g/8 instead of
+                # the reference's 100) solved with the termination / scaling options the
+                # reference hands to IPOPT (main_periodic_step.py:111-134) -- loose on purpose: acceptable_tol = 10
+                n_p = 32
+                g2 = periodic_step_guess(model, pev, pev4, Ls[:n_p], force_z=9.80665 / 8.0)
+                lb4, ub4 = pev4.layout.bounds(g2.parameters)
+                ref_opts = {"tol": 1e-3, "dual_inf_tol": 1000.0, "compl_inf_tol": 1e-2, "constr_viol_tol": 1e-4,
+                            "acceptable_tol": 10, "acceptable_iter": 2, "acceptable_compl_inf_tol": 1000.0,
+                            "acceptable_obj_change_tol": 1e0, "nlp_scaling_method": "gradient-based", "max_iter": 200}
+                ip4 = BatchedInteriorPoint(pev4, kkt="stage", delta_c=1e-9, mu_init=1e-1, ipopt_options=ref_opts)
+                torch.cuda.synchronize(dev)
+                ts = time.perf_counter()
+                try:
+                    r4 = ip4.solve(g2.x0, torch.tensor(g2.parameters, device=dev), lb4, ub4)
+                    n4, a4 = int(r4.success.sum()), int(r4.acceptable.sum())
+                    it4 = int(r4.iterations[r4.success].median()) if n4 else None
+                except Exception as exc:  # noqa: BLE001 -- OptiFailure: nothing converged
+                    n4, a4, it4 = 0, 0, None
+                    solves["periodic_step_ocp_error"] = f"{type(exc).__name__}: {exc}"
+                torch.cuda.synchronize(dev)
+                t4 = time.perf_counter() - ts
+                solves["periodic_step_ocp"] = {
+                    "workload": f"{n_p} periodic-step plans (step length 0.1-0.3 m, horizon {HORIZON}, final-state and "
+                                f"periodicity rows), the reference's IPOPT termination options, <= 200 iterations",
+                    "instances": n_p, "converged": n4, "at_acceptable_level": a4, "iterations_median": it4,
+                    "seconds": t4, "plans_per_s": n4 / t4}
             except Exception as exc:  # noqa: BLE001
                 solves["periodic_step_setup"] = {"error": f"{type(exc).__name__}: {exc}"}
         except Exception as exc:  # noqa: BLE001 -- a solver failure must not cost the throughput line
