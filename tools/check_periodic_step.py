@@ -79,6 +79,10 @@ if "-s" in sys.argv:
                 "nlp_scaling_method": "gradient-based"} if "--ref-options" in sys.argv else None
     sol = BatchedInteriorPoint(ev, tol=arg("-t", 1e-6), max_iter=iters, verbose="-v" in sys.argv, kkt="stage",
                                delta_c=1e-9, mu_init=arg("-m", 1e-1), ipopt_options=ref_opts)
+    if "--callback" in sys.argv:  # the planner's criterion (humanoid_kinodynamic/planner.py:57-63)
+        from hippopt_b200 import opti_callback
+
+        sol.callback_criterion = opti_callback.BestCost() & opti_callback.AcceptablePrimalInfeasibility(arg("--callback", 1e-2))
     t0 = time.perf_counter()
     try:
         res = sol.solve(gs.x0[sel], P[sel], lb[sel], ub[sel])
@@ -88,6 +92,16 @@ if "-s" in sys.argv:
               f"IPOPT's acceptable level{', reference options' if ref_opts else ''}) in <= {iters} iterations "
               f"(median {int(res.iterations[res.success].median()) if n_ok else -1}), {time.perf_counter() - t0:.1f} s, "
               f"KKT error median {res.kkt_error.median().item():.2e}, best {res.kkt_error.min().item():.2e}")
+        if sol.callback_criterion is not None:
+            used = (res.callback_iteration >= 0).cpu().numpy()
+            if used.any():
+                gu = ev.eval(4, res.values, P[sel])["g"].cpu().numpy()
+                vu = (np.maximum(lb[sel] - gu, 0) + np.maximum(gu - ub[sel], 0))[used]
+                print(f"  callback: {int(used.sum())} of the {len(sel) - n_ok} unconverged plans return an iterate saved by BestCost & "
+                      f"AcceptablePrimalInfeasibility (iterations {res.callback_iteration[res.callback_iteration >= 0].tolist()}, "
+                      f"constraint violation max {vu.max():.1e})")
+            else:
+                print(f"  callback: none of the {len(sel) - n_ok} unconverged plans has a saved iterate")
         if n_ok:
             okk = res.success.cpu().numpy()
             gsol = ev.eval(4, res.values, P[sel])["g"].cpu().numpy()
