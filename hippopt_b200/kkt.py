@@ -185,6 +185,19 @@ class StageKKT:
         loc_B[border] = np.arange(self.n_border)
         jb = np.nonzero(far[jac_row] & is_eq[jac_row])[0]
         self.border = {"idx": t(jb), "row": t(loc_B[jac_row[jb]]), "col": t(jcol[jb]), "eq": t(pos_E[border])}
+        # two-sided elimination (_sweep_two_sided): halves the chain of stage steps; pays while twice the batch still
+        # fits a wave of the factor kernel.  Needs every stage after the first to couple through the same number of rows.
+        ncs = [mp["n_cpl"] for mp in self.maps]
+        self._two_sided_ok = N >= 4 and ncs[0] == 0 and ncs[1] > 0 and all(c == ncs[1] for c in ncs[1:])
+        # OFF by default: the bottom-up half eliminates through G = (S'^-1)[cp, cp], the multiplier block of the inverse,
+        # whose entries grow like 1 / delta_c -- on evaluated values (cond 1e11, delta_c = 1e-9) the relative residual
+        # is 2e-8 against 2e-15 for the one-sided sweep (tests/test_gpu_kkt.py).  Good enough for loose tolerances (the
+        # periodic-step plans with the reference's IPOPT options: 40 -> 34.5 s for 64 plans), not for 1e-6 and below;
+        # a stable version needs the coupling rows of the lower half assigned to the upper stage of each pair.
+        self.two_sided = False
+        # up to one CTA per SM on a B200 (148 SMs): 2 B <= 148 is free, up to 2 B = 296 the two-blocks-per-SM variant
+        # of the factor kernel still beats two separate waves
+        self.two_sided_max_batch = 148 if linalg == "hb" else 0
 
     @classmethod
     def for_evaluator(cls, ev, lbg, ubg, device="cpu", linalg: str = "hb"):
@@ -262,6 +275,8 @@ class StageKKT:
 
     def _sweep(self, hess_vals, jac_vals, sigma_I, delta, delta_c, RX, RE):
         """Block-tridiagonal part: K_bt [DX; DL] = [RX; RE] for R right-hand sides (B, n_x | m_E, R)."""
+        if self.two_sided and self._two_sided_ok and hess_vals.shape[0] <= self.two_sided_max_batch:
+            return self._sweep_two_sided(hess_vals, jac_vals, sigma_I, delta, delta_c, RX, RE)
         B, R = hess_vals.shape[0], RX.shape[2]
         dev, dt = hess_vals.device, hess_vals.dtype
         nx, nb, N = self.nx, self.nb, self.N
@@ -330,6 +345,121 @@ class StageKKT:
             DX[:, mp["var"], :] = u[:, :mp["n_var"], :]
             DL[:, mp["eq"], :] = u[:, nx:nx + mp["n_eq"], :]
             u_next = u
+        return DX, DL
+
+    # ------------------------------------------------------------------ two-sided sweep
+    def _assemble(self, k, hess_vals, jac_vals, sigma_I, delta, delta_c, RX, RE):
+        """Stage block D_k (B, nb, nb) and right-hand sides b_k (B, nb, R) without the coupling terms."""
+        B, R = hess_vals.shape[0], RX.shape[2]
+        dev, dt = hess_vals.device, hess_vals.dtype
+        nx, nb = self.nx, self.nb
+        mp = self.maps[k]
+        D = torch.zeros((B, nb * nb), dtype=dt, device=dev)
+        D[:, mp["w_pos"]] = hess_vals[:, mp["w_idx"]]
+        D[:, mp["w_pos_t"]] = hess_vals[:, mp["w_idx"]]
+        D[:, mp["c_pos"]] = jac_vals[:, mp["c_idx"]]
+        D[:, mp["c_pos_t"]] = jac_vals[:, mp["c_idx"]]
+        D = D.view(B, nb, nb)
+        nv, ne = mp["n_var"], mp["n_eq"]
+        if mp["n_ine"]:
+            JI = torch.zeros((B, self.mIk * nx), dtype=dt, device=dev)
+            JI[:, mp["i_pos"]] = jac_vals[:, mp["i_idx"]]
+            JI = JI.view(B, self.mIk, nx)
+            sg = torch.zeros((B, self.mIk), dtype=dt, device=dev)
+            sg[:, :mp["n_ine"]] = sigma_I[:, mp["ine"]]
+            D[:, :nx, :nx] += torch.einsum("bin,bi,bik->bnk", JI, sg, JI)
+        idx = torch.arange(nb, device=dev)
+        diag = torch.zeros((B, nb), dtype=dt, device=dev)
+        diag[:, :nv] = delta[:, None]
+        diag[:, nv:nx] = 1.0
+        diag[:, nx:nx + ne] = -delta_c
+        diag[:, nx + ne:] = 1.0
+        D[:, idx, idx] += diag
+        b = torch.zeros((B, nb, R), dtype=dt, device=dev)
+        b[:, :nv, :] = RX[:, mp["var"], :]
+        b[:, nx:nx + ne, :] = RE[:, mp["eq"], :]
+        return D, b
+
+    def _coupling(self, k, jac_vals):
+        """A_k (B, n_cpl, nx): the coupling rows of stage k with respect to the variable slots of stage k - 1."""
+        mq = self.maps[k]
+        B = jac_vals.shape[0]
+        Ak = torch.zeros((B, self.mCk * self.nx), dtype=jac_vals.dtype, device=jac_vals.device)
+        Ak[:, mq["a_pos"]] = jac_vals[:, mq["a_idx"]]
+        return Ak.view(B, self.mCk, self.nx)[:, :mq["n_cpl"], :]
+
+    def _sweep_two_sided(self, hess_vals, jac_vals, sigma_I, delta, delta_c, RX, RE):
+        """The same block-tridiagonal solve with the elimination running from both ends towards stage m = N // 2:
+        stages 0 .. m-1 top-down (Schur complement S_k = D_k - [A_k] S_{k-1}^{-1} [A_k]^T on the coupling rows, as in
+        `_sweep`), stages N-1 .. m+1 bottom-up (S'_k = D_k - A_{k+1}^T G_{k+1} A_{k+1} on the variable slots, with
+        G_{k+1} = (S'_{k+1}^{-1})[cp, cp] from a solve against the unit columns of the coupling rows).  Step j factors
+        stage j and stage N-1-j in ONE batched call, so the chain of latency-bound LU steps is N/2 + 1 long instead
+        of N -- worth it while 2 B matrices still fit a wave of the factor kernel."""
+        B, R = hess_vals.shape[0], RX.shape[2]
+        dev, dt = hess_vals.device, hess_vals.dtype
+        nx, nb, N = self.nx, self.nb, self.N
+        m = N // 2
+        nc = self.maps[1]["n_cpl"]
+        args = (hess_vals, jac_vals, sigma_I, delta, delta_c, RX, RE)
+        Wt, Zt = [None] * N, [None] * N      # top-down: w_k = S_k^{-1} b_k, Z_k = S_k^{-1} [A_{k+1}^T; 0]
+        Wb, Yb = [None] * N, [None] * N      # bottom-up: w'_k, Y_k = S'_k^{-1} P_cp
+        Acp = {k: self._coupling(k, jac_vals) for k in range(1, N)}
+
+        def unit_columns(k):
+            P = torch.zeros((B, nb, nc), dtype=dt, device=dev)
+            P[:, self.maps[k]["cpl"], torch.arange(nc, device=dev)] = 1.0
+            return P
+
+        for j in range(max(m, N - 1 - m)):
+            kt = j if j < m else None
+            kb = N - 1 - j if N - 1 - j > m else None
+            Ds, rhss = [], []
+            if kt is not None:
+                D, b = self._assemble(kt, *args)
+                if kt > 0:
+                    cp = self.maps[kt]["cpl"]
+                    D[:, cp[:, None], cp[None, :]] -= torch.bmm(Acp[kt], Zt[kt - 1][:, :nx, :])
+                    b[:, cp, :] -= torch.bmm(Acp[kt], Wt[kt - 1][:, :nx, :])
+                E = torch.zeros((B, nb, nc), dtype=dt, device=dev)
+                E[:, :nx, :] = Acp[kt + 1].transpose(1, 2)
+                Ds.append(D)
+                rhss.append(torch.cat([b, E], dim=2))
+            if kb is not None:
+                D, b = self._assemble(kb, *args)
+                if kb < N - 1:
+                    cpn = self.maps[kb + 1]["cpl"]
+                    An = Acp[kb + 1]
+                    G = Yb[kb + 1][:, cpn, :]
+                    D[:, :nx, :nx] -= torch.bmm(An.transpose(1, 2), torch.bmm(G, An))
+                    b[:, :nx, :] -= torch.bmm(An.transpose(1, 2), Wb[kb + 1][:, cpn, :])
+                Ds.append(D)
+                rhss.append(torch.cat([b, unit_columns(kb)], dim=2))
+            sol = self._lu_solve(self._lu_factor(torch.cat(Ds)), torch.cat(rhss))
+            if kt is not None:
+                Wt[kt], Zt[kt] = sol[:B, :, :R], sol[:B, :, R:]
+            if kb is not None:
+                Wb[kb], Yb[kb] = sol[-B:, :, :R], sol[-B:, :, R:]
+        # middle stage: both contributions
+        D, b = self._assemble(m, *args)
+        cp = self.maps[m]["cpl"]
+        D[:, cp[:, None], cp[None, :]] -= torch.bmm(Acp[m], Zt[m - 1][:, :nx, :])
+        b[:, cp, :] -= torch.bmm(Acp[m], Wt[m - 1][:, :nx, :])
+        if m < N - 1:
+            cpn, An = self.maps[m + 1]["cpl"], Acp[m + 1]
+            D[:, :nx, :nx] -= torch.bmm(An.transpose(1, 2), torch.bmm(Yb[m + 1][:, cpn, :], An))
+            b[:, :nx, :] -= torch.bmm(An.transpose(1, 2), Wb[m + 1][:, cpn, :])
+        U = [None] * N
+        U[m] = self._lu_solve(self._lu_factor(D), b)
+        for k in range(m - 1, -1, -1):
+            U[k] = Wt[k] - torch.bmm(Zt[k], U[k + 1][:, self.maps[k + 1]["cpl"], :])
+        for k in range(m + 1, N):
+            U[k] = Wb[k] - torch.bmm(Yb[k], torch.bmm(Acp[k], U[k - 1][:, :nx, :]))
+        DX = torch.zeros((B, self.n_x, R), dtype=dt, device=dev)
+        DL = torch.zeros((B, self.mE, R), dtype=dt, device=dev)
+        for k in range(N):
+            mp = self.maps[k]
+            DX[:, mp["var"], :] = U[k][:, :mp["n_var"], :]
+            DL[:, mp["eq"], :] = U[k][:, nx:nx + mp["n_eq"], :]
         return DX, DL
 
     # ------------------------------------------------------------------ reference: the same matrix, dense
