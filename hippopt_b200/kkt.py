@@ -195,9 +195,9 @@ class StageKKT:
         # periodic-step plans with the reference's IPOPT options: 40 -> 34.5 s for 64 plans), not for 1e-6 and below;
         # a stable version needs the coupling rows of the lower half assigned to the upper stage of each pair.
         self.two_sided = False
-        # up to one CTA per SM on a B200 (148 SMs): 2 B <= 148 is free, up to 2 B = 296 the two-blocks-per-SM variant
-        # of the factor kernel still beats two separate waves
-        self.two_sided_max_batch = 148 if linalg == "hb" else 0
+        # 2 B <= 148 (one CTA per SM on a B200) is free; measured: sweeps of 32 / 64 instances 29 / 37 ms against ~50 ms
+        # one-sided, but 148 instances 58 ms against 55 ms -- no gain once the pair no longer fits one wave
+        self.two_sided_max_batch = 74 if linalg == "hb" else 0
 
     @classmethod
     def for_evaluator(cls, ev, lbg, ubg, device="cpu", linalg: str = "hb"):
