@@ -3,16 +3,21 @@
 What sits directly above the evaluation path in the reference is IPOPT (`opti.solve()`,
 `/root/reference/src/hippopt/base/opti_solver.py:479`), one serial solve at a time.  Here B independent
 instances advance in lock-step on the GPU: every iteration makes ONE batched `hb_eval` call (f, grad_f,
-g, jac_g, hess_l for all instances) and one batched dense KKT solve.  The algorithm is the textbook
-line-search barrier method IPOPT implements (Waechter & Biegler 2006) reduced to what a dense batched
-solver needs: slacks on the inequality rows, monotone (Fiacco-McCormick) barrier update,
-fraction-to-boundary rule, l1 merit function with Armijo backtracking, and a Levenberg-type Hessian shift
-when the reduced Hessian is not positive along the step.  The dense KKT factorisation is a library
-call (torch.linalg); the evaluation kernels are the product.
+g, jac_g, hess_l for all instances) and one batched KKT solve for the instances that still need a step.
+The algorithm is the textbook line-search barrier method IPOPT implements (Waechter & Biegler 2006)
+reduced to what a batched solver needs: slacks on the inequality rows, monotone (Fiacco-McCormick)
+barrier update, fraction-to-boundary rule, l1 merit function with Armijo backtracking plus filter-type
+and f-type step acceptance, and a Levenberg-type Hessian shift when the reduced Hessian is not positive
+along the step (several shifts of the sequence per sweep while the batch is below a wave of the LU
+kernels).  There is no restoration phase: an instance whose line search fails `max_fail` times in a row
+is given up.
+
+KKT back ends: "dense" (torch.linalg, one (n_x + m_E)-square solve per instance: toy OCP, pose finder)
+and "stage" (hippopt_b200.kkt.StageKKT on the batched LU kernels: the kinodynamic OCPs).  Termination
+and scaling follow IPOPT's options (`ipopt_options`), failures the reference's `OptiFailure` and callback
+criteria (`callback_criterion`, hippopt_b200.opti_callback).
 
 Conventions follow IPOPT / CasADi: L = sigma f + lam^T g, lam > 0 on an active upper bound.
-Sized for the small NLPs (toy OCP, pose finder); the KKT systems of the 30-knot kinodynamic OCP need the
-stage-wise factorisation of row f2.
 """
 from __future__ import annotations
 
