@@ -12,12 +12,16 @@ is block tridiagonal once unknowns are ordered by stage, u_k = (dx_k, dlam_E,k):
 stage k-1 and stage k are the defect rows of stage k acting on dx_{k-1}.  The solve is a block LU sweep
 over the stages (Riccati-like), batched over instances: per stage one dense LU of an
 (n_k + m_E,k)-square block and one solve with the ~87 coupling columns -- O(N) blocks instead of one
-(n_x + m_E)-square factorisation.  Dense block algebra is library code (torch.linalg -> cuSOLVER/cuBLAS);
-what this module owns is the structure: the assignment of rows to stages and the gather maps from the CCS
-value arrays the kernels write to the dense stage blocks.
+(n_x + m_E)-square factorisation.  The stage blocks are factored and solved by this library's batched LU
+kernels (csrc/lu.cu through `lu_factor` / `lu_solve`, linalg="hb", CUDA only, no fallback) or, as the
+comparison baseline and for the CPU-side structural tests, by torch.linalg (linalg="torch"); the small
+products around them are torch calls.  What this module owns is the structure: the assignment of rows to
+stages and the gather maps from the CCS value arrays the kernels write to the dense stage blocks.  An
+opt-in two-sided variant of the sweep (`_sweep_two_sided`) halves the chain of stage steps at a loss of
+accuracy on ill-conditioned systems.
 
 Checked against a dense solve of the same system (tests/test_kkt_cpu.py on random values in the real
-pattern, tests/test_gpu_solver.py on evaluated values).  Periodicity rows (knot 0 with knot N-1) make
+pattern, tests/test_gpu_kkt.py on evaluated values).  Periodicity rows (knot 0 with knot N-1) make
 the matrix cyclic: they are kept as a border of the block-tridiagonal part and eliminated with a Schur
 complement (one sweep with 1 + 84 right-hand sides).
 """
