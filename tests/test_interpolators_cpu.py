@@ -207,3 +207,38 @@ def test_oracle_reproduces_the_interpolator_fixture():
                                                  (feet["left"][b], feet["right"][b]), desc, pts, dt, float(g[f"t0_{h}"]))
             got = np.stack([oi.state_block(s, desc) for s in out])
             assert np.array_equal(got, g[f"states_{h}"][b])
+
+
+def test_periodic_step_phases_and_pose_references(model):
+    """Host side of hippopt_b200.initial_guess: the contact phases of main_periodic_step.py:365-412 per instance and
+    the pose-finder references of compute_state (:192-258)."""
+    from hippopt_b200.initial_guess import DESIRED_JOINTS_DEG, periodic_step_phases, pose_problem
+    from hippopt_b200.pose_layout import PoseLayout, PoseSettings
+    from hippopt_b200.workloads import FOOT_CORNERS
+
+    L = np.array([0.6, 0.2])
+    ph = periodic_step_phases(L, 3.0)
+    ref_l, ref_r = periodic_step_phases_oracle(3.0)  # this file's transcription of the reference's call site
+    for mine, ref in ((ph.left, ref_l), (ph.right, ref_r)):
+        for a, b in zip(mine, ref):  # instance 0 is the reference's own step length
+            assert np.array_equal(a.position[0], b["position"]) and np.array_equal(a.force, b["force"])
+            assert a.activation_time == b["activation_time"] and a.deactivation_time == b["deactivation_time"]
+            assert (a.mid_swing_position is None) == (b["mid_position"] is None)
+            if b["mid_position"] is not None:
+                assert np.array_equal(a.mid_swing_position[0], b["mid_position"])
+    assert np.allclose(ph.left[1].position[1], [0.2, 0.1, 0.0]) and np.allclose(ph.right[1].position[1], [0.3, -0.1, 0.0])
+    lay = PoseLayout(model, PoseSettings())
+    lp, rp = ph.left[1].position, ph.right[0].position  # the middle keyframe (compute_middle_state, :292-308)
+    x, p = pose_problem(lay, model, lp, rp)
+    po = lay.po
+    com = p[:, po.ref + po.ST_COM:po.ref + po.ST_COM + 3]
+    assert np.allclose(com[:, :2], ((lp + rp) / 2)[:, :2]) and np.allclose(com[:, 2], 0.7)
+    assert np.allclose(p[:, po.ref + po.ST_S:po.ref + po.ST_S + 23], np.deg2rad(DESIRED_JOINTS_DEG))
+    for i in range(8):
+        foot = lp if i < 4 else rp
+        assert np.allclose(p[:, po.ref + 9 * i:po.ref + 9 * i + 3], foot + FOOT_CORNERS[i % 4])
+    assert x.shape == (2, lay.n_x) and np.array_equal(x[:, 78:81], com)
+
+
+def periodic_step_phases_oracle(horizon):
+    return periodic_step_phases(horizon)
