@@ -13,4 +13,7 @@ timeout 1200 ncu --set full --clock-control none --import-source on -k regex:kin
    python bench.py --steps 4 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full_kin.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:kino_contact_kernel -s 4 -c 1 -f -o gpurun_out/prof_contact \
    python bench.py --steps 4 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full_contact.log 2>&1
+# rows f1-f3: plan set-up rate + interpolation kernel timing, periodic-step plans with the reference's IPOPT options
+timeout 300 python tools/check_periodic_step.py -k 2>&1 | tail -4 | tee gpurun_out/setup.txt
+timeout 400 python tools/check_periodic_step.py -b 64 -s -i 300 --ref-options --fz 1.2258 2>&1 | tail -2 | tee gpurun_out/periodic_step.txt
 ls -la gpurun_out
