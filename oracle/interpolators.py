@@ -7,8 +7,9 @@ PARITY UNPINNED against the reference itself: interpolators.py imports casadi an
 installed here, and the reference ships no test or golden vector for these functions.  liecasadi (pinned by the
 reference's setup.cfg as `liecasadi`, no version) supplies `Quaternion.slerp_step` and `SO3.act`; their
 published definitions are restated below.  Anchors: the reference's own call site (main_periodic_step.py:367-451,
-reproduced in tests/test_interpolators_cpu.py) and closed-form properties (end points, unit norm, constant
-angular rate).
+reproduced in tests/test_interpolators_cpu.py), closed-form properties (end points, unit norm, constant
+angular rate) and an independent implementation: scipy's `Slerp` (same arc whenever q0 . q1 > 0) and
+`Rotation.as_matrix` agree with `quaternion_slerp` / `rotation_matrix` to 1e-12 / 1e-14.
 
 A state is a dict: p (8, 3), f (8, 3), base_position (3), base_quaternion (4), joints (n), com (3).
 A phase is a dict: position (3), quaternion (4), mid_position / mid_quaternion (or None), force (3),

@@ -242,3 +242,25 @@ def test_periodic_step_phases_and_pose_references(model):
 
 def periodic_step_phases_oracle(horizon):
     return periodic_step_phases(horizon)
+
+
+def test_slerp_and_rotation_against_scipy():
+    """An independent implementation as anchor (the reference's own dependency, liecasadi, is not installable here):
+    scipy's Slerp follows the shorter arc, liecasadi's formula the arc of acos(q0 . q1) -- the same one when the dot
+    product is positive; quaternion -> matrix must agree always (both xyzw)."""
+    from scipy.spatial.transform import Rotation, Slerp
+
+    rng = np.random.default_rng(3)
+    checked = 0
+    for _ in range(40):
+        q0, q1 = rand_quat(rng), rand_quat(rng)
+        assert np.allclose(oi.rotation_matrix(q0), Rotation.from_quat(q0).as_matrix(), atol=1e-14)
+        if np.dot(q0, q1) <= 0.05:
+            continue
+        ts = np.linspace(0.0, 1.0, 7)
+        ref = Slerp([0.0, 1.0], Rotation.from_quat([q0, q1]))(ts).as_quat()
+        got = np.stack(oi.quaternion_slerp(q0, q1, 7))
+        ref = ref * np.sign((ref * got).sum(axis=1, keepdims=True))  # q and -q are the same rotation
+        assert np.allclose(got, ref, atol=1e-12)
+        checked += 1
+    assert checked >= 10
