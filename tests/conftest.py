@@ -10,6 +10,8 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: test needs a CUDA device (run on the B200 box with -m gpu)")
+    # torch.func (used by the torch stand-in evaluator of tests/test_ipsolver_cpu.py) trips a deprecation notice inside torch
+    config.addinivalue_line("filterwarnings", "ignore:.*torch.jit.script.*:DeprecationWarning")
 
 
 @pytest.fixture(scope="session")
