@@ -478,7 +478,7 @@ extern "C" int hb_kino_create(const int32_t* icfg, const double* dcfg, const int
   {
     // 4 warps per CTA; the kinematics kernels keep one branch accumulator per body whose children do not
     // directly follow it in the joint list (n_slots): an interleaved joint order does not fit
-    const size_t kin_smem = (size_t)hb::kin_smem_layout(C.nb, C.n_slots, true).total * sizeof(double) * 4;
+    const size_t kin_smem = (size_t)hb::kin_smem_layout(C.nb, C.n_slots, true).total * sizeof(double) * (KIN_H_THREADS / 32);
     if (kin_smem > 200 * 1024) {
       hb_destroy(h);
       return fail(HB_ERR_UNSUPPORTED,
@@ -664,9 +664,12 @@ extern "C" int hb_eval(hb_handle h, uint32_t mask, const double* x, const double
   }
   if (mark() != HB_OK) return HB_ERR_CUDA;
   {
-    const size_t smem = (size_t)hb::kin_smem_layout(C.nb, C.n_slots, with_hess).total * sizeof(double) * warps_per_block;
+    // the Hessian variant has its own CTA shape (KIN_H_THREADS, kino_kin.cu): occupancy tuning
+    const int kin_warps = with_hess ? KIN_H_THREADS / 32 : warps_per_block;
+    const unsigned kin_grid = (unsigned)((total_warps + kin_warps - 1) / kin_warps);
+    const size_t smem = (size_t)hb::kin_smem_layout(C.nb, C.n_slots, with_hess).total * sizeof(double) * kin_warps;
     if (with_hess)
-      hb::kino_kin_kernel<true><<<grid, 32 * warps_per_block, smem, st>>>(h->topo, h->dev, mask, x, p, (long)p_stride,
+      hb::kino_kin_kernel<true><<<kin_grid, 32 * kin_warps, smem, st>>>(h->topo, h->dev, mask, x, p, (long)p_stride,
                                                                          lam_g, sigma, d_fpart, grad_f, g, jac_vals,
                                                                          hess_vals, (long)batch);
     else
@@ -972,3 +975,14 @@ extern "C" int hb_probe_fp64_tflops(double* tflops, void* stream) {
   *tflops = best;
   return HB_OK;
 }
+
+#ifdef HB_PHASE_CLOCK
+// developer build only (tools/phase_profile.py): read and reset the per-phase cycle sums
+extern "C" int hb_debug_phase_read(unsigned long long* out64) {
+  CUDA_TRY(cudaDeviceSynchronize());
+  CUDA_TRY(cudaMemcpyFromSymbol(out64, hb::hb_phase_acc, sizeof(unsigned long long) * 64));
+  static unsigned long long zero[64] = {0};
+  CUDA_TRY(cudaMemcpyToSymbol(hb::hb_phase_acc, zero, sizeof(zero)));
+  return HB_OK;
+}
+#endif

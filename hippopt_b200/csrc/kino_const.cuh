@@ -5,6 +5,23 @@
 
 namespace hb {
 
+// Developer instrumentation (tools/phase_profile.py builds a separate library with -DHB_PHASE_CLOCK; the shipped
+// library compiles these macros away): cycles per phase of the two evaluation kernels, summed over the warps.
+#ifdef HB_PHASE_CLOCK
+__device__ unsigned long long hb_phase_acc[2][32];
+#define HB_PHASE_INIT long long _pc = clock64();
+#define HB_PHASE(kern, i)                                                                     \
+  do {                                                                                        \
+    __syncwarp();                                                                             \
+    const long long _t = clock64();                                                           \
+    if ((threadIdx.x & 31) == 0) atomicAdd(&hb_phase_acc[kern][i], (unsigned long long)(_t - _pc)); \
+    _pc = _t;                                                                                 \
+  } while (0)
+#else
+#define HB_PHASE_INIT
+#define HB_PHASE(kern, i)
+#endif
+
 struct BodyC {
   double E[9];    // parent <- joint frame rotation
   double EA[9];   // E [a]x

@@ -135,6 +135,7 @@ __global__ void __launch_bounds__(128, TERRAIN == 0 ? CONTACT_MIN_BLOCKS : 1) ki
   const double* xinst = x + b * C.n_x;
   const double* xb = xinst + (long)k * NZ;
   const double* pp = p + b * p_stride;
+  HB_PHASE_INIT
   const bool k1 = k >= 1;
   const bool want_f = mask & HB_EVAL_F, want_grad = mask & HB_EVAL_GRAD_F, want_g = mask & HB_EVAL_G;
   const bool want_jac = mask & HB_EVAL_JAC_G, want_hess = mask & HB_EVAL_HESS_L;
@@ -206,6 +207,7 @@ __global__ void __launch_bounds__(128, TERRAIN == 0 ? CONTACT_MIN_BLOCKS : 1) ki
   for (int i = lane; i < NCV; i += 32) gbuf[i] = 0.0;
   if (lane < LS_ROWS) ls_n[lane] = 0;
   __syncwarp();
+  HB_PHASE(1, 0);  // inputs loaded and staged
 
   // ------------------------------------------------------------------ per-point quantities (lanes 0..7)
   const int pi_ = lane & 7;
@@ -569,6 +571,7 @@ __global__ void __launch_bounds__(128, TERRAIN == 0 ? CONTACT_MIN_BLOCKS : 1) ki
     }
   }
 
+  HB_PHASE(1, 1);  // g rows, per-point terms
   // ------------------------------------------------------------------ least-squares cost rows (k >= 1)
   if (k1 && (want_f || want_grad || want_hess)) {
     if (lane < LS_ROWS) {
@@ -711,6 +714,7 @@ __global__ void __launch_bounds__(128, TERRAIN == 0 ? CONTACT_MIN_BLOCKS : 1) ki
     }
   }
 
+  HB_PHASE(1, 2);  // least-squares rows
   // ------------------------------------------------------------------ f partial + grad_f
   if (want_f || want_grad) {
     const double total = warp_sum(cost);
@@ -726,6 +730,7 @@ __global__ void __launch_bounds__(128, TERRAIN == 0 ? CONTACT_MIN_BLOCKS : 1) ki
     if (k == 0 && lane < 6) grad_f[b * C.n_x + C.h_init + lane] = 0.0;
   }
 
+  HB_PHASE(1, 3);  // f, grad_f
   // ------------------------------------------------------------------ Jacobian values
   // The scatter slots are loaded in batches BEFORE the dependent stores (ncu: 25 % of the kernel's stall
   // samples sat on `jb[slot] = v` waiting for the map load when each store followed its own load).
@@ -810,6 +815,7 @@ __global__ void __launch_bounds__(128, TERRAIN == 0 ? CONTACT_MIN_BLOCKS : 1) ki
     }
   }
 
+  HB_PHASE(1, 4);  // Jacobian values + scatter
   // ------------------------------------------------------------------ Hessian of the Lagrangian, contact block
   if (want_hess) {
     if (lane < 8) {
@@ -864,6 +870,7 @@ __global__ void __launch_bounds__(128, TERRAIN == 0 ? CONTACT_MIN_BLOCKS : 1) ki
       for (int u = 0; u < NT; ++u)
         if (te[u] >= 0) hbuf[te[u]] += tv[u];
     }
+    HB_PHASE(1, 5);  // Hessian terms
     __syncwarp();
     const int* hmap = C.hc_map + (size_t)k * C.n_hc;
     double* hb_ = hess + b * C.nnz_h;

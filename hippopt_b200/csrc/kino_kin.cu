@@ -742,7 +742,10 @@ template <bool WITH_HESS>
 #ifndef KIN_H_MIN_BLOCKS
 #define KIN_H_MIN_BLOCKS 2
 #endif
-__global__ void __launch_bounds__(128, WITH_HESS ? KIN_H_MIN_BLOCKS : 3) kino_kin_kernel(const __grid_constant__ KinTopo T,
+#ifndef KIN_H_THREADS
+#define KIN_H_THREADS 128
+#endif
+__global__ void __launch_bounds__(WITH_HESS ? KIN_H_THREADS : 128, WITH_HESS ? KIN_H_MIN_BLOCKS : 3) kino_kin_kernel(const __grid_constant__ KinTopo T,
                                                        const KinoConst* __restrict__ Cp, unsigned mask,
                                                        const double* __restrict__ x, const double* __restrict__ p,
                                                        long p_stride, const double* __restrict__ lam,
@@ -769,6 +772,7 @@ __global__ void __launch_bounds__(128, WITH_HESS ? KIN_H_MIN_BLOCKS : 3) kino_ki
   const double* pb_ = p + b * p_stride;
   const int nb = T.nb;
   const bool k1 = k >= T.cost_k0;  // knots on which the "apply_to_first_elements=False" expressions exist
+  HB_PHASE_INIT
 
   // ---- every global input of this warp is requested here, addresses from the constant bank: the DRAM
   // latencies of x, the parameter slices, the multipliers and the joint frames overlap each other and
@@ -847,6 +851,7 @@ __global__ void __launch_bounds__(128, WITH_HESS ? KIN_H_MIN_BLOCKS : 3) kino_ki
   if (WITH_HESS) lamk[lane] = lam_reg;
   for (int i = lane; i < 58; i += 32) gbuf[i] = 0.0;
   __syncwarp();
+  HB_PHASE(0, 0);  // inputs loaded and staged
 
   // ------------------------------------------------------------------ base
   const double q0 = zs[Z_Q], q1 = zs[Z_Q + 1], q2 = zs[Z_Q + 2], q3 = zs[Z_Q + 3];
@@ -910,6 +915,7 @@ __global__ void __launch_bounds__(128, WITH_HESS ? KIN_H_MIN_BLOCKS : 3) kino_ki
     }
     __syncwarp();
   }
+  HB_PHASE(0, 1);  // forward kinematics by depth
   // ------------------------------------------------------------------ per-body derived quantities + sums
   D3 mc = v3<double>(0.0, 0.0, 0.0), mcd = mc, hl = mc;
   if (lane < nb) {
@@ -998,6 +1004,7 @@ __global__ void __launch_bounds__(128, WITH_HESS ? KIN_H_MIN_BLOCKS : 3) kino_ki
   const D3 fdDelta = (oL + fdal) - (oR + fdar);
   const double feet_y = dot(fdu, fdDelta);
 
+  HB_PHASE(0, 2);  // per-body quantities, sums, frames
   // ------------------------------------------------------------------ values: g rows, costs, grad_f (simple terms)
   const bool want_g = (mask & HB_EVAL_G) != 0;
   double* gb = g + b * T.m;
@@ -1088,6 +1095,7 @@ __global__ void __launch_bounds__(128, WITH_HESS ? KIN_H_MIN_BLOCKS : 3) kino_ki
   }
   __syncwarp();
 
+  HB_PHASE(0, 3);  // g rows, costs
   const bool want_jac = (mask & HB_EVAL_JAC_G) != 0, want_grad = (mask & HB_EVAL_GRAD_F) != 0;
   double* slot = sm + L.slot;
   Dir nodir;
@@ -1281,6 +1289,7 @@ __global__ void __launch_bounds__(128, WITH_HESS ? KIN_H_MIN_BLOCKS : 3) kino_ki
       }
       __syncwarp();
     }
+    HB_PHASE(0, 4);  // composite moments
     // tangents of P, P_dot, h (about the base origin) along this lane's (q, s) direction
     D3 tP, tPd, th;
     {
@@ -1333,6 +1342,7 @@ __global__ void __launch_bounds__(128, WITH_HESS ? KIN_H_MIN_BLOCKS : 3) kino_ki
       tphi_lane = cross(ac, v3<double>(G[0], G[3], G[6])).x + cross(ac, v3<double>(G[1], G[4], G[7])).y +
                   cross(ac, v3<double>(G[2], G[5], G[8])).z;
     }
+    HB_PHASE(0, 5);  // direction tangents of P, Pdot, h, feet distance, trace
 #if HB_FWD_JAC
     // ---------------------------------------------------------------- forward-mode Jacobian
     // The direction lanes already hold the tangent of every link state along q_a / s_j, so column j of
@@ -1376,6 +1386,7 @@ __global__ void __launch_bounds__(128, WITH_HESS ? KIN_H_MIN_BLOCKS : 3) kino_ki
       // frame-orientation cost: d/dz w (phi - 3)^2 = 2 w (phi - 3) dphi/dz
       if (want_grad && lane < 27 && k1)
         gbuf[lane < 4 ? 7 + lane : 34 + lane - 4] += 2.0 * T.w_frame * (phi - 3.0) * tphi_lane;
+      HB_PHASE(0, 6);  // Jacobian columns staged
       __syncwarp();
       if (want_jac) {
         const int* jmap = C.jk_map + (size_t)k * T.n_jk;
@@ -1407,6 +1418,7 @@ __global__ void __launch_bounds__(128, WITH_HESS ? KIN_H_MIN_BLOCKS : 3) kino_ki
       __syncwarp();  // the Hessian columns reuse the stage
     }
 #endif
+    HB_PHASE(0, 7);  // Jacobian scatter, grad_f
     if (!with_l) return;  // Jacobian / gradient only: done
     Seeds<Dual> S;
     S.footF[0] = S.footF[1] = S.footN[0] = S.footN[1] = vzero<Dual>();
@@ -1492,7 +1504,9 @@ __global__ void __launch_bounds__(128, WITH_HESS ? KIN_H_MIN_BLOCKS : 3) kino_ki
       SP.chestN = primal_of(S.chestN);
       ST.chestN = tangent_of(S.chestN);
       __syncwarp();
+      HB_PHASE(0, 8);  // seeds
       primal_adjoint_pass(T, sb, zs, SP, xc, xcd, my_depth, my_rank, my_parent, my_mass);
+      HB_PHASE(0, 9);  // primal adjoint pass
       D3 tn0, tw0, tv0;
 #if HB_SWEEP_PACKED
       {
@@ -1532,8 +1546,10 @@ __global__ void __launch_bounds__(128, WITH_HESS ? KIN_H_MIN_BLOCKS : 3) kino_ki
           }
         }
         __syncwarp();
+        HB_PHASE(0, 10);  // cross terms
         em.acc = true;
         kin_tangent_sweep_packed(T, sb, zs, qdat, massv, ST, S.hb, pslot, stg);
+        HB_PHASE(0, 11);  // packed tangent sweep
         const double* rs = pslot + (lane < 27 ? T.root_slot[lane] : 0) * 12;
         tn0 = ld3(rs);
         tw0 = ld3(rs + 6);
@@ -1574,6 +1590,7 @@ __global__ void __launch_bounds__(128, WITH_HESS ? KIN_H_MIN_BLOCKS : 3) kino_ki
         em.put(30 + a, dq.d + extra);
       }
     }
+    HB_PHASE(0, 12);  // root chain rule (dual quaternion maps)
     __syncwarp();
     if (em.stage) {
       // scatter the staged columns (27 directions x 57 rows) with coalesced map reads
@@ -1593,6 +1610,7 @@ __global__ void __launch_bounds__(128, WITH_HESS ? KIN_H_MIN_BLOCKS : 3) kino_ki
       if (slot2 >= 0)
         em.hess[slot2] = lane < 4 ? 2.0 * sg * T.w_bqv : sg * T.w_joint * 2.0 * HB_N_JOINTS;
     }
+    HB_PHASE(0, 13);  // Hessian scatter
   }
 }
 

@@ -27,8 +27,9 @@ struct ToyProblem {
   int *d_cptr = nullptr, *d_crow = nullptr;
   double* d_ccoef = nullptr;
   double *d_jvals = nullptr, *d_hvals = nullptr;  // constant CCS values
-  double* d_res = nullptr;
-  int64_t res_cap = 0;
+  // residual scratch PER STREAM: hb_eval_host pipelines the chunks of one handle over several streams, and a
+  // shared buffer would let one chunk overwrite the residuals another still reads (same idea as fpart in api.cu)
+  std::map<cudaStream_t, std::pair<double*, int64_t>> res;
   std::vector<int64_t> jac_colind, jac_row, hess_colind, hess_row;
 };
 
@@ -226,7 +227,7 @@ void toy_destroy(ToyProblem* P) {
   cudaFree(P->d_ccoef);
   cudaFree(P->d_jvals);
   cudaFree(P->d_hvals);
-  cudaFree(P->d_res);
+  for (auto& kv : P->res) cudaFree(kv.second.first);
   delete P;
 }
 
@@ -254,26 +255,31 @@ int toy_eval(ToyProblem* P, uint32_t mask, const double* x, const double* p, int
   const int T = 256;
   auto blocks = [&](int64_t n) { return (unsigned)((n + T - 1) / T); };
   const bool need_res = mask & (HB_EVAL_F | HB_EVAL_GRAD_F);
+  double* d_res = nullptr;
   if (need_res) {
     const int64_t need = batch * P->n_res;
-    if (need > P->res_cap) {
-      cudaFree(P->d_res);
-      if (cudaMalloc(&P->d_res, need * sizeof(double)) != cudaSuccess) return -1;
-      P->res_cap = need;
+    auto& slot = P->res[st];
+    if (need > slot.second) {
+      cudaFree(slot.first);  // synchronises with the work that may still read the old buffer
+      slot.first = nullptr;
+      slot.second = 0;
+      if (cudaMalloc(&slot.first, need * sizeof(double)) != cudaSuccess) return -1;
+      slot.second = need;
     }
+    d_res = slot.first;
   }
   if (need_res || (mask & HB_EVAL_G)) {
     toy_rows_kernel<<<blocks(batch * (P->m + P->n_res)), T, 0, st>>>(P->d_rowptr, P->d_col, P->d_coef, P->d_pc, P->m,
                                                                     need_res ? P->n_res : 0, P->n_x, x, p, (long)p_stride,
-                                                                    g, P->d_res, (mask & HB_EVAL_G) != 0, (long)batch);
+                                                                    g, d_res, (mask & HB_EVAL_G) != 0, (long)batch);
     ++launches;
   }
   if (mask & HB_EVAL_F) {
-    toy_f_kernel<<<blocks(batch), T, 0, st>>>(P->d_res, P->n_res, f, (long)batch);
+    toy_f_kernel<<<blocks(batch), T, 0, st>>>(d_res, P->n_res, f, (long)batch);
     ++launches;
   }
   if (mask & HB_EVAL_GRAD_F) {
-    toy_grad_kernel<<<blocks(batch * P->n_x), T, 0, st>>>(P->d_cptr, P->d_crow, P->d_ccoef, P->d_res, P->n_res, P->n_x,
+    toy_grad_kernel<<<blocks(batch * P->n_x), T, 0, st>>>(P->d_cptr, P->d_crow, P->d_ccoef, d_res, P->n_res, P->n_x,
                                                           grad_f, (long)batch);
     ++launches;
   }

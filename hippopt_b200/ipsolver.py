@@ -112,10 +112,9 @@ class DenseKKT:
             K[:, n:, n:] = -delta_c * torch.eye(mE, dtype=K.dtype, device=K.device)
         self.K = K
         rhs = torch.cat([rhs_x, rhs_E], dim=1)
-        try:
-            sol = torch.linalg.solve(K, rhs)
-        except RuntimeError:
-            sol = torch.full_like(rhs, float("nan"))
+        # a singular instance gets NaN (-> larger shift for THAT instance); the others keep their solution
+        sol, info = torch.linalg.solve_ex(K, rhs)
+        sol = torch.where((info != 0)[:, None], torch.full_like(sol, float("nan")), sol)
         return sol[:, :n], sol[:, n:]
 
 
@@ -186,10 +185,15 @@ class BatchedInteriorPoint:
         if self.kkt_kind == "stage":
             from .kkt import StageKKT
 
-            lay = ev.layout
+            lay = getattr(ev, "layout", None)
+            if lay is None or not hasattr(lay, "N") or not hasattr(lay, "knot_size"):
+                raise ValueError("kkt='stage' needs an evaluator with a multiple-shooting layout (layout.N knots of "
+                                 "layout.knot_size variables, e.g. KinoEvaluator); use kkt='dense' for "
+                                 f"{type(ev).__name__}")
             jc_, jr_ = ev.jac_sparsity()
             hc_, hr_ = ev.hess_sparsity()
-            backend = StageKKT(n, m, lay.N, 189, jc_, jr_, hc_, hr_, iE.cpu().numpy(), iI.cpu().numpy(), device=dev)
+            backend = StageKKT(n, m, lay.N, lay.knot_size, jc_, jr_, hc_, hr_, iE.cpu().numpy(), iI.cpu().numpy(),
+                               device=dev)
             if dev.type == "cuda" and self.speculative_shifts:
                 self.spec_wave = torch.cuda.get_device_properties(dev).multi_processor_count
         else:
@@ -224,9 +228,14 @@ class BatchedInteriorPoint:
         n_eval = 2 if self.obj_scaling else 1
         gI = out["g"][:, iI]
         # push the slacks strictly inside their bounds (IPOPT bound_push / bound_frac)
-        push = 1e-2
-        pl = torch.minimum(push * torch.clamp(lbs.abs(), min=1.0), 1e-2 * (ubs - lbs))
-        s = torch.minimum(torch.maximum(gI, lbs + pl), ubs - pl)
+        # (separate pushes per side, each only where that bound exists: a one-sided row must not inherit the
+        # 1e300 stand-in of its missing bound)
+        push, frac = 1e-2, 1e-2
+        width = torch.where(hasL & hasU, ub - lb, torch.full_like(lb, float("inf")))
+        pL = torch.minimum(push * torch.clamp(lb.abs(), min=1.0), frac * width)
+        pU = torch.minimum(push * torch.clamp(ub.abs(), min=1.0), frac * width)
+        s = torch.where(hasL, torch.maximum(gI, lb + pL), gI)
+        s = torch.where(hasU, torch.minimum(s, ub - pU), s)
         mu = torch.full((B,), self.mu_init, dtype=torch.float64, device=dev)
         zL = torch.where(hasL, mu[:, None] / (s - lbs), torch.zeros_like(s))
         zU = torch.where(hasU, mu[:, None] / (ubs - s), torch.zeros_like(s))
@@ -274,13 +283,17 @@ class BatchedInteriorPoint:
                 return t.abs().amax(dim=1) if t.shape[1] else torch.zeros(B, dtype=torch.float64, device=dev)
 
             # IPOPT's scaled optimality error E_mu
-            sd = torch.clamp((lam.abs().sum(1) + zL.sum(1) + zU.sum(1)) / max(1, m + 2 * mI) / 100.0, min=1.0)
+            # (Waechter & Biegler eq. 6: s_d from all multipliers -- constraint multipliers of the slack formulation
+            # and bound multipliers --, s_c from the bound multipliers alone; s_max = 100)
+            n_z = int(hasL[0].sum() + hasU[0].sum())
+            sd = torch.clamp((lam.abs().sum(1) + zL.sum(1) + zU.sum(1)) / max(1, m + n_z) / 100.0, min=1.0)
+            sc = torch.clamp((zL.sum(1) + zU.sum(1)) / max(1, n_z) / 100.0, min=1.0)
             prim = torch.maximum(linf(cE), linf(cI))
 
             def emu(muv):
                 cL = torch.where(hasL, compL - muv[:, None], torch.zeros_like(s))
                 cU = torch.where(hasU, compU - muv[:, None], torch.zeros_like(s))
-                return torch.maximum(torch.maximum(linf(rd) / sd, prim), torch.maximum(linf(cL), linf(cU)) / sd)
+                return torch.maximum(torch.maximum(linf(rd) / sd, prim), torch.maximum(linf(cL), linf(cU)) / sc)
 
             err0 = torch.where(done, err0, emu(torch.zeros_like(mu)))
             # IPOPT's termination tests: desired level = scaled error AND (optionally) the unscaled measures;
@@ -406,6 +419,7 @@ class BatchedInteriorPoint:
                 if not bool(need.any()):
                     break
                 delta = torch.where(need, next_delta(delta), delta)
+            no_step = need & ~inactive  # no shift of the sequence gave a usable step: counts as a failed line search
             ds = ops.J_mul(jv, dx)[:, iI] + cI
             lamI_new = lamhat + Sig * ds
             zL_new = torch.where(hasL, mu[:, None] / dL - SigL * ds, torch.zeros_like(s))
@@ -433,6 +447,7 @@ class BatchedInteriorPoint:
             alpha = a_p.clone()
             accepted = inactive.clone()
             x_new, s_new = x.clone(), s.clone()
+            blocked = no_step
             for bt in range(self.max_backtrack):
                 xt = x + alpha[:, None] * dx
                 st = s + alpha[:, None] * ds
@@ -454,11 +469,11 @@ class BatchedInteriorPoint:
                 ftype = self.f_type & (cnorm <= theta_min) & (dbar < 0)
                 acc_f = ftype & (bart <= bar0 + self.eta * alpha * dbar) & (ct <= 10.0 * theta_min)
                 good = torch.isfinite(phit) & (armijo | (filt & (cnorm > theta_min)) | acc_f)
-                take = good & ~accepted
+                take = good & ~accepted & ~blocked
                 x_new = torch.where(take[:, None], xt, x_new)
                 s_new = torch.where(take[:, None], st, s_new)
                 accepted |= take
-                if bool(accepted.all()):
+                if bool((accepted | blocked).all()):
                     break
                 alpha = torch.where(accepted, alpha, alpha * 0.5)
             moved = accepted & ~inactive

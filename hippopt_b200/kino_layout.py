@@ -129,6 +129,7 @@ class KinoLayout:
         self.model = model
         self.st = settings
         N = self.N = settings.horizon
+        self.knot_size = NZ  # variables per knot (stage size of the KKT sweep)
         self.n_x = NZ * N + 6
         self.po = ParamOffsets(N, settings.n_terrain_params)
         self.n_p = self.po.n_p

@@ -212,7 +212,9 @@ class StageKKT:
         jc, jr = ev.jac_sparsity()
         hc, hr = ev.hess_sparsity()
         lay = ev.layout
-        return cls(ev.n_x, ev.m, lay.N, 189, jc, jr, hc, hr, eq, ine, device=device, linalg=linalg), eq, ine
+        if not hasattr(lay, "knot_size"):
+            raise ValueError(f"{type(ev).__name__} has no multiple-shooting stage structure (layout.knot_size)")
+        return cls(ev.n_x, ev.m, lay.N, lay.knot_size, jc, jr, hc, hr, eq, ine, device=device, linalg=linalg), eq, ine
 
     # ------------------------------------------------------------------ dense block algebra
     def _lu_factor(self, D):

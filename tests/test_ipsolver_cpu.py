@@ -204,3 +204,29 @@ def test_speculative_hessian_shifts_take_the_same_steps():
     assert bool(a.success.all()) and torch.equal(a.iterations, b.iterations)
     assert (a.values - b.values).abs().max() < 1e-9 and (a.constraint_multipliers - b.constraint_multipliers).abs().max() < 1e-7
     assert b.evaluations == a.evaluations
+
+
+@pytest.mark.parametrize("form", ["upper", "lower", "two_sided"])
+def test_one_sided_inequalities(form):
+    """min (x0-2)^2 + (x1-2)^2 s.t. x0 + x1 <= 2 written with an upper bound only (what Opti's `<=` produces), a
+    lower bound only, and both: the slack push must use the bound that exists (advisor finding, round 1)."""
+    f = lambda v: ((v - 2.0) ** 2).sum()  # noqa: E731
+    if form == "lower":
+        g, lb, ub = (lambda v: -(v[0] + v[1]).reshape(1)), [-2.0], [np.inf]  # noqa: E731
+    else:
+        g, lb, ub = (lambda v: (v[0] + v[1]).reshape(1)), [-np.inf if form == "upper" else -50.0], [2.0]  # noqa: E731
+    ev = TorchEvaluator(f, g, 2, 1)
+    ip = BatchedInteriorPoint(ev, tol=1e-9, max_iter=60)
+    x0 = torch.tensor([[0.0, 0.0], [3.0, -1.0]], dtype=torch.float64)
+    out = ip.solve(x0, torch.zeros((2, 1), dtype=torch.float64), np.array(lb), np.array(ub))
+    assert bool(out.success.all())
+    assert torch.allclose(out.values, torch.ones((2, 2), dtype=torch.float64), atol=1e-6)
+    # active constraint: lam_g = +2 on an upper bound, -2 on a lower bound (IPOPT's sign)
+    assert torch.allclose(out.constraint_multipliers, torch.full((2, 1), -2.0 if form == "lower" else 2.0, dtype=torch.float64), atol=1e-5)
+
+
+def test_stage_backend_needs_a_stage_structure():
+    ev = TorchEvaluator(lambda v: (v * v).sum(), lambda v: v[:1], 2, 1)
+    ip = BatchedInteriorPoint(ev, kkt="stage")
+    with pytest.raises(ValueError, match="multiple-shooting layout"):
+        ip.solve(torch.zeros((1, 2), dtype=torch.float64), torch.zeros((1, 1), dtype=torch.float64), np.array([0.0]), np.array([0.0]))
