@@ -51,6 +51,37 @@ struct hb_problem_s {
   int64_t h2d_bytes = 0, d2h_bytes = 0;
 };
 
+
+// cudaFuncSetAttribute is per device: a process that drives several GPUs must opt every one of them in to the
+// large dynamic shared-memory carve-out (advisor finding, round 1).  Guarded by a mutex: cheap, and hb_eval may be
+// called from several host threads.
+#include <mutex>
+static int device_sms[64] = {0};
+static cudaError_t ensure_kernel_attributes(int dev) {
+  static std::mutex mu;
+  static bool done[64] = {false};
+  std::lock_guard<std::mutex> lock(mu);
+  if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+  if (done[dev]) return cudaSuccess;
+  const int big = 200 * 1024;
+  cudaError_t e;
+  if ((e = cudaFuncSetAttribute(hb::kino_contact_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(hb::kino_contact_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(hb::kino_kin_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(hb::kino_kin_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(hb::pose_contact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return e;
+  const int lu_big = 210 * 1024;
+  if ((e = cudaFuncSetAttribute(hb::lu_factor_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, lu_big)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(hb::lu_factor_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, lu_big)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(hb::lu_factor_kernel<3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, lu_big)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(hb::lu_factor_kernel<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, lu_big)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(hb::lu_factor_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, lu_big)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(hb::lu_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, lu_big)) != cudaSuccess) return e;
+  if ((e = cudaDeviceGetAttribute(&device_sms[dev], cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
+  done[dev] = true;
+  return cudaSuccess;
+}
+
 __global__ void reduce_f_kernel(const double* __restrict__ fpart, double* __restrict__ f, int n_terms, long batch) {
   const long b = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= batch) return;
@@ -634,20 +665,12 @@ extern "C" int hb_eval(hb_handle h, uint32_t mask, const double* x, const double
   if (mark() != HB_OK) return HB_ERR_CUDA;
   {
     const size_t smem = (size_t)hb::contact_smem_layout(C.n_hc).total * sizeof(double) * warps_per_block;
-    static bool attr_set = false;
-    if (!attr_set) {
-      CUDA_TRY(cudaFuncSetAttribute(hb::kino_contact_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-      CUDA_TRY(cudaFuncSetAttribute(hb::kino_contact_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-      CUDA_TRY(cudaFuncSetAttribute(hb::kino_kin_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-      CUDA_TRY(cudaFuncSetAttribute(hb::kino_kin_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-      attr_set = true;
+    {
+      int dev = 0;
+      CUDA_TRY(cudaGetDevice(&dev));
+      CUDA_TRY(ensure_kernel_attributes(dev));
     }
     if (C.kind == 1) {
-      static bool pose_attr = false;
-      if (!pose_attr) {
-        CUDA_TRY(cudaFuncSetAttribute(hb::pose_contact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        pose_attr = true;
-      }
       hb::pose_contact_kernel<<<grid, 32 * warps_per_block, smem, st>>>(h->dev, mask, x, p, (long)p_stride, lam_g, sigma,
                                                                        d_fpart, grad_f, g, jac_vals, hess_vals,
                                                                        (long)batch);
@@ -817,20 +840,10 @@ extern "C" int hb_lu_factor_batched(double* A, int32_t* piv, int32_t* info, int6
   if (!A || !piv || !info) return fail(HB_ERR_INVALID, "hb_lu_factor_batched: null argument");
   if (n <= 0 || n > 768 || batch <= 0) return fail(HB_ERR_INVALID, "hb_lu_factor_batched: need 0 < n <= 768, batch > 0");
   const size_t smem = hb::lu_factor_smem((int)n);
-  static bool attr = false;
-  static int sms = 0;
-  if (!attr) {
-    const int big = 210 * 1024;
-    CUDA_TRY(cudaFuncSetAttribute(hb::lu_factor_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-    CUDA_TRY(cudaFuncSetAttribute(hb::lu_factor_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-    CUDA_TRY(cudaFuncSetAttribute(hb::lu_factor_kernel<3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-    CUDA_TRY(cudaFuncSetAttribute(hb::lu_factor_kernel<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-    CUDA_TRY(cudaFuncSetAttribute(hb::lu_factor_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-    int dev = 0;
-    CUDA_TRY(cudaGetDevice(&dev));
-    CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    attr = true;
-  }
+  int dev = 0;
+  CUDA_TRY(cudaGetDevice(&dev));
+  CUDA_TRY(ensure_kernel_attributes(dev));
+  const int sms = device_sms[dev];
   cudaStream_t st = (cudaStream_t)stream;
   const unsigned grid = (unsigned)batch;
   // more than one block per SM and two of them fit (shared memory): the 128-register variant
@@ -854,10 +867,10 @@ extern "C" int hb_lu_solve_batched(const double* LU, const int32_t* piv, double*
   if (n <= 0 || n > 768 || batch <= 0 || nrhs <= 0)
     return fail(HB_ERR_INVALID, "hb_lu_solve_batched: need 0 < n <= 768, batch > 0, nrhs > 0");
   const size_t smem = (size_t)n * (hb::LU_RC + 1) * sizeof(double);
-  static bool attr = false;
-  if (!attr) {
-    CUDA_TRY(cudaFuncSetAttribute(hb::lu_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
-    attr = true;
+  {
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    CUDA_TRY(ensure_kernel_attributes(dev));
   }
   const dim3 grid((unsigned)batch, (unsigned)((nrhs + hb::LU_RC - 1) / hb::LU_RC));
   hb::lu_solve_kernel<<<grid, hb::LU_THREADS, smem, (cudaStream_t)stream>>>(LU, piv, Bm, (int)n, (int)nrhs);
@@ -973,6 +986,40 @@ extern "C" int hb_probe_fp64_tflops(double* tflops, void* stream) {
   cudaEventDestroy(e1);
   cudaFree(buf);
   *tflops = best;
+  return HB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// per-expression cost values (solution report)
+extern "C" int hb_eval_cost_terms(hb_handle h, const double* x, const double* p, int64_t p_stride, double* terms,
+                                  int64_t batch, void* stream) {
+  if (!h || !x || !p || !terms) return fail(HB_ERR_INVALID, "hb_eval_cost_terms: null argument");
+  if (batch <= 0) return fail(HB_ERR_INVALID, "hb_eval_cost_terms: batch must be positive");
+  if (h->kind != KIND_KINO || h->host.kind != 0)
+    return fail(HB_ERR_UNSUPPORTED, "hb_eval_cost_terms: kinodynamic OCP handles only");
+  const hb::KinoConst& C = h->host;
+  if (p_stride != 0 && p_stride != C.n_p) return fail(HB_ERR_INVALID, "hb_eval_cost_terms: p_stride must be 0 or n_p");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int wpb = 4;
+  const long total_warps = (long)batch * C.N;
+  const unsigned grid = (unsigned)((total_warps + wpb - 1) / wpb);
+  const unsigned mask = hb::HB_EVAL_COST_TERMS_BIT;
+  int dev = 0;
+  CUDA_TRY(cudaGetDevice(&dev));
+  CUDA_TRY(ensure_kernel_attributes(dev));
+  const size_t smem_c = (size_t)hb::contact_smem_layout(C.n_hc).total * sizeof(double) * wpb;
+  if (C.terrain == 0)
+    hb::kino_contact_kernel<0><<<grid, 32 * wpb, smem_c, st>>>(h->topo, h->dev, mask, x, p, (long)p_stride, nullptr, nullptr,
+                                                              terms, nullptr, nullptr, nullptr, nullptr, (long)batch);
+  else
+    hb::kino_contact_kernel<1><<<grid, 32 * wpb, smem_c, st>>>(h->topo, h->dev, mask, x, p, (long)p_stride, nullptr, nullptr,
+                                                              terms, nullptr, nullptr, nullptr, nullptr, (long)batch);
+  CUDA_TRY(cudaGetLastError());
+  const size_t smem_k = (size_t)hb::kin_smem_layout(C.nb, C.n_slots, false).total * sizeof(double) * wpb;
+  hb::kino_kin_kernel<false><<<grid, 32 * wpb, smem_k, st>>>(h->topo, h->dev, mask, x, p, (long)p_stride, nullptr, nullptr,
+                                                            terms, nullptr, nullptr, nullptr, nullptr, (long)batch);
+  CUDA_TRY(cudaGetLastError());
+  h->launches = 2;
   return HB_OK;
 }
 

@@ -22,6 +22,9 @@ __device__ unsigned long long hb_phase_acc[2][32];
 #define HB_PHASE(kern, i)
 #endif
 
+// internal evaluation bit (hb_eval_cost_terms): `fpart` then points to the [batch][N][HB_COST_TERMS] output
+enum { HB_EVAL_COST_TERMS_BIT = 32 };
+
 struct BodyC {
   double E[9];    // parent <- joint frame rotation
   double EA[9];   // E [a]x

@@ -139,6 +139,10 @@ __global__ void __launch_bounds__(128, TERRAIN == 0 ? CONTACT_MIN_BLOCKS : 1) ki
   const bool k1 = k >= 1;
   const bool want_f = mask & HB_EVAL_F, want_grad = mask & HB_EVAL_GRAD_F, want_g = mask & HB_EVAL_G;
   const bool want_jac = mask & HB_EVAL_JAC_G, want_hess = mask & HB_EVAL_HESS_L;
+  // solution report (hb_eval_cost_terms): fpart is the [batch][N][HB_COST_TERMS] table of named cost values
+  const bool want_terms = mask & HB_EVAL_COST_TERMS_BIT;
+  double* ct = want_terms ? fpart + (b * N + k) * HB_COST_TERMS : nullptr;
+  double c_swing = 0.0;  // swing-height cost of this lane's point (terrain-dependent block below)
 
   // every global input is requested before the first shared-memory store: a store waits for its load and,
   // in program order, would hold back the loads behind it (x, the parameters and the multipliers would
@@ -321,7 +325,8 @@ __global__ void __launch_bounds__(128, TERRAIN == 0 ? CONTACT_MIN_BLOCKS : 1) ki
         if (r >= 0) gb[r] = fric.c[0];
       }
       if (k1) {
-        cost += C.w_swing * swing.c[0];
+        c_swing = C.w_swing * swing.c[0];
+        cost += c_swing;
 #pragma unroll
         for (int a = 0; a < 3; ++a) {
           gbuf[o + Z_P + a] += C.w_swing * swing.c[1 + a];
@@ -495,13 +500,21 @@ __global__ void __launch_bounds__(128, TERRAIN == 0 ? CONTACT_MIN_BLOCKS : 1) ki
       if constexpr (TERRAIN == 0) {
         const double hd = ref[R_SWING];
         const double dh = ppos.z - hd;
-        cost += C.w_swing * 0.5 * (dh * dh + (pv.x * pv.x + pv.y * pv.y));
+        c_swing = C.w_swing * 0.5 * (dh * dh + (pv.x * pv.x + pv.y * pv.y));
+        cost += c_swing;
         gp[Z_P + 2] += C.w_swing * dh;
         gp[Z_V] += C.w_swing * pv.x;
         gp[Z_V + 1] += C.w_swing * pv.y;
       }
-      cost += C.w_u * (pu.x * pu.x + pu.y * pu.y + pu.z * pu.z);
-      cost += C.w_fd * (pfd.x * pfd.x + pfd.y * pfd.y + pfd.z * pfd.z);
+      const double c_u = C.w_u * (pu.x * pu.x + pu.y * pu.y + pu.z * pu.z);
+      const double c_fd = C.w_fd * (pfd.x * pfd.x + pfd.y * pfd.y + pfd.z * pfd.z);
+      cost += c_u;
+      cost += c_fd;
+      if (want_terms) {
+        ct[HB_CT_SWING0 + lane] = c_swing;
+        ct[HB_CT_UV0 + lane] = c_u;
+        ct[HB_CT_FDOT0 + lane] = c_fd;
+      }
       gp[Z_U] += 2.0 * C.w_u * pu.x;
       gp[Z_U + 1] += 2.0 * C.w_u * pu.y;
       gp[Z_U + 2] += 2.0 * C.w_u * pu.z;
@@ -510,7 +523,21 @@ __global__ void __launch_bounds__(128, TERRAIN == 0 ? CONTACT_MIN_BLOCKS : 1) ki
       gp[Z_FD + 2] += 2.0 * C.w_fd * pfd.z;
     }
   }
+  if (want_terms && !k1)  // expressions with apply_to_first_elements = False do not exist at knot 0
+    for (int i = lane; i < HB_CT_FRAME_QUAT; i += 32) ct[i] = 0.0;
+  __syncwarp();
   // CoM velocity cost (all knots): sum_c w_c (h_c - ref_c)^2
+  {
+    double c_cv = 0.0;
+    if (lane < 3) {
+      const double e = zs[Z_H + lane] - ref[R_COMV + lane];
+      c_cv = C.w_comvel[lane] * e * e;
+    }
+    if (want_terms) {
+      const double t = warp_sum(c_cv);
+      if (lane == 0) ct[HB_CT_COM_VELOCITY] = t;
+    }
+  }
   if (lane < 3) {
     const double e = zs[Z_H + lane] - ref[R_COMV + lane];
     cost += C.w_comvel[lane] * e * e;
@@ -573,7 +600,7 @@ __global__ void __launch_bounds__(128, TERRAIN == 0 ? CONTACT_MIN_BLOCKS : 1) ki
 
   HB_PHASE(1, 1);  // g rows, per-point terms
   // ------------------------------------------------------------------ least-squares cost rows (k >= 1)
-  if (k1 && (want_f || want_grad || want_hess)) {
+  if (k1 && (want_f || want_grad || want_hess || want_terms)) {
     if (lane < LS_ROWS) {
       int n = 0;
       int* var = ls_var + lane * LS_MAXV;
@@ -626,6 +653,17 @@ __global__ void __launch_bounds__(128, TERRAIN == 0 ? CONTACT_MIN_BLOCKS : 1) ki
       cost += w * r * r;
     }
     __syncwarp();
+    if (want_terms && lane < 11) {  // 1 centroid + 2 yaw + 8 force-ratio expressions
+      // rows of one named expression: centroid 0..2; yaw 3,4 (left) 5,6 (right); force ratio of point
+      // (foot, i): 7 + 12 foot + 3 i + c
+      int r0, n;
+      if (lane == 0) r0 = 0, n = 3;
+      else if (lane < 3) r0 = 3 + 2 * (lane - 1), n = 2;
+      else r0 = 7 + 3 * (lane - 3), n = 3;
+      double t = 0.0;
+      for (int i = 0; i < n; ++i) t += ls_w[r0 + i] * ls_r[r0 + i] * ls_r[r0 + i];
+      ct[lane == 0 ? HB_CT_CENTROID : (lane == 1 ? HB_CT_YAW_LEFT : (lane == 2 ? HB_CT_YAW_RIGHT : HB_CT_FRATIO0 + lane - 3))] = t;
+    }
     // Rows are grouped in phases whose rows touch disjoint variables, so a phase is one parallel
     // read-modify-write and the order of the additions into every entry is fixed (deterministic):
     //   A   centroid rows 0..2 (one per component)            8 variables each
@@ -718,7 +756,7 @@ __global__ void __launch_bounds__(128, TERRAIN == 0 ? CONTACT_MIN_BLOCKS : 1) ki
   // ------------------------------------------------------------------ f partial + grad_f
   if (want_f || want_grad) {
     const double total = warp_sum(cost);
-    if (lane == 0 && want_f) fpart[(b * N + k) * 2] = total;
+    if (lane == 0 && want_f && !want_terms) fpart[(b * N + k) * 2] = total;
   }
   __syncwarp();
   if (want_grad) {

@@ -1055,15 +1055,16 @@ __global__ void __launch_bounds__(WITH_HESS ? KIN_H_THREADS : 128, WITH_HESS ? K
 #pragma unroll
   for (int i = 0; i < 4; ++i) eq[i] = Aq[i][0] * q0 + Aq[i][1] * q1 + Aq[i][2] * q2 + Aq[i][3] * q3 - (i == 3 ? 1.0 : 0.0);
   const double frame_cost = (phi - 3.0) * (phi - 3.0);
-  if (mask & (HB_EVAL_F | HB_EVAL_GRAD_F)) {
-    double cost = 0.0;
+  const bool want_terms = (mask & HB_EVAL_COST_TERMS_BIT) != 0;
+  if (mask & (HB_EVAL_F | HB_EVAL_GRAD_F | HB_EVAL_COST_TERMS_BIT)) {
     // quaternion-velocity cost (all knots) and, for k >= 1, base quaternion / joint / frame costs
+    double c_bqv = 0.0, c_bq = 0.0, c_joint = 0.0, c_frame = 0.0;
     if (lane < 4) {
       const double e = qdv[lane] - pre_bqv;
-      cost += T.w_bqv * e * e;
+      c_bqv = T.w_bqv * e * e;
       gbuf[3 + lane] += 2.0 * T.w_bqv * e;
       if (k1) {
-        cost += T.w_bq * eq[lane] * eq[lane];
+        c_bq = T.w_bq * eq[lane] * eq[lane];
         double gq = 0.0;
 #pragma unroll
         for (int a = 0; a < 4; ++a) {
@@ -1080,18 +1081,31 @@ __global__ void __launch_bounds__(WITH_HESS ? KIN_H_THREADS : 128, WITH_HESS ? K
       if (T.joint_cost_kind == 0) {
         // kinodynamic planner.py:506-520: sumsqr of the broadcast n x n matrix
         const double t = sd + C.wj[lane] * e;
-        cost += T.w_joint * ((HB_N_JOINTS - 1) * sd * sd + t * t);
+        c_joint = T.w_joint * ((HB_N_JOINTS - 1) * sd * sd + t * t);
         gbuf[11 + lane] += T.w_joint * (2.0 * (HB_N_JOINTS - 1) * sd + 2.0 * t);
         gbuf[34 + lane] += T.w_joint * 2.0 * C.wj[lane] * t;
       } else {
         // pose finder planner.py:584-588: e^T diag(w) e
-        cost += T.w_joint * (e * C.wj[lane]) * e;
+        c_joint = T.w_joint * (e * C.wj[lane]) * e;
         gbuf[34 + lane] += T.w_joint * 2.0 * C.wj[lane] * e;
       }
     }
-    if (lane == 31 && k1) cost += T.w_frame * frame_cost;
-    cost = warp_sum(cost);
-    if (lane == 0 && (mask & HB_EVAL_F)) fpart[(b * N + k) * 2 + 1] = cost;
+    if (lane == 31 && k1) c_frame = T.w_frame * frame_cost;
+    if (want_terms) {
+      // solution report (hb_eval_cost_terms): one value per named cost expression of this knot
+      double* ct = fpart + (b * N + k) * HB_COST_TERMS;
+      const double t_frame = warp_sum(c_frame), t_bq = warp_sum(c_bq), t_bqv = warp_sum(c_bqv), t_j = warp_sum(c_joint);
+      if (lane == 0) {
+        ct[HB_CT_FRAME_QUAT] = t_frame;
+        ct[HB_CT_BASE_QUAT] = t_bq;
+        ct[HB_CT_BASE_QUAT_VEL] = t_bqv;
+        ct[HB_CT_JOINTS] = t_j;
+      }
+    } else {
+      double cost = (c_bqv + c_bq) + c_joint + c_frame;
+      cost = warp_sum(cost);
+      if (lane == 0 && (mask & HB_EVAL_F)) fpart[(b * N + k) * 2 + 1] = cost;
+    }
   }
   __syncwarp();
 

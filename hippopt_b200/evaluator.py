@@ -271,6 +271,20 @@ class KinoEvaluator(_Evaluator):
         self._read_dims()
         assert (self.n_x, self.n_p, self.m) == (lay.n_x, lay.n_p, lay.m)
 
+    def cost_terms(self, x: torch.Tensor, p: torch.Tensor) -> torch.Tensor:
+        """[B, N, HB_COST_TERMS] values of the named cost expressions (hb_eval_cost_terms; names: naming.py)."""
+        B = x.shape[0]
+        if x.shape != (B, self.n_x) or x.dtype != torch.float64 or not x.is_contiguous():
+            raise ValueError(f"x must be a contiguous float64 tensor of shape (B, {self.n_x})")
+        p_stride = 0 if p.dim() == 1 else self.n_p
+        if p.shape[-1] != self.n_p or (p.dim() == 2 and p.shape[0] != B) or not p.is_contiguous():
+            raise ValueError(f"p must be contiguous, of shape ({self.n_p},) or (B, {self.n_p})")
+        out = self._out("cost_terms", (B, self.layout.N, H["HB_COST_TERMS"]), x.device)
+        stream = torch.cuda.current_stream(x.device).cuda_stream
+        _capi.check(_capi.lib().hb_eval_cost_terms(self._h, _ptr(x), _ptr(p), p_stride, _ptr(out), B,
+                                                   ctypes.c_void_p(stream)), "hb_eval_cost_terms")
+        return out
+
     # patterns (CasADi-style compressed-column)
     def jac_sparsity(self):
         return self.layout.jac_colind, self.layout.jac_row

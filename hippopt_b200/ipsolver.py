@@ -154,6 +154,14 @@ class BatchedInteriorPoint:
         self.acceptable_constr_viol_tol = float(o.get("acceptable_constr_viol_tol", 1e-2))
         self.acceptable_compl_inf_tol = float(o.get("acceptable_compl_inf_tol", 1e-2))
         self.acceptable_obj_change_tol = float(o.get("acceptable_obj_change_tol", 1e20))
+        # warm start (IPOPT's warm_start_* options, main_single_step_flat_ground.py:120-125): used when solve() is
+        # given multipliers of a previous solution
+        self.warm_start = str(o.get("warm_start_init_point", "no")) == "yes"
+        self.ws_slack_push = float(o.get("warm_start_slack_bound_push", 1e-3))
+        self.ws_slack_frac = float(o.get("warm_start_slack_bound_frac", 1e-3))
+        self.ws_mult_push = float(o.get("warm_start_mult_bound_push", 1e-3))
+        if "mu_init" in o:
+            mu_init = float(o["mu_init"])
         self.obj_scaling = o.get("nlp_scaling_method", "none") == "gradient-based"
         self.scaling_max_gradient = float(o.get("nlp_scaling_max_gradient", 100.0))
         self.ev = ev
@@ -169,7 +177,12 @@ class BatchedInteriorPoint:
         self.kkt_seconds = 0.0
 
     # ------------------------------------------------------------------ solve
-    def solve(self, x0: torch.Tensor, p: torch.Tensor, lbg, ubg) -> BatchedOutput:
+    def solve(self, x0: torch.Tensor, p: torch.Tensor, lbg, ubg, lam0=None) -> BatchedOutput:
+        """lam0 (B, m), optional: constraint multipliers of a previous solution (IPOPT sign).  With them the solve is
+        warm-started as IPOPT does with warm_start_init_point = yes: slacks pushed by warm_start_slack_bound_push / _frac
+        only, equality multipliers taken over, bound multipliers = the given ones floored at
+        warm_start_mult_bound_push.  (Set "mu_init" low as well: a warm start from a solution with mu = 0.1 walks
+        back out along the central path.)"""
         ev, dev = self.ev, x0.device
         B, n, m = x0.shape[0], ev.n_x, ev.m
         lbg = torch.as_tensor(np.broadcast_to(np.asarray(lbg, dtype=np.float64), (B, m)).copy(), device=dev)
@@ -230,7 +243,12 @@ class BatchedInteriorPoint:
         # push the slacks strictly inside their bounds (IPOPT bound_push / bound_frac)
         # (separate pushes per side, each only where that bound exists: a one-sided row must not inherit the
         # 1e300 stand-in of its missing bound)
-        push, frac = 1e-2, 1e-2
+        warm = lam0 is not None
+        # warm start: IPOPT pushes by warm_start_slack_bound_push whatever mu_init is, which throws an active row of
+        # the previous solution (slack ~ mu / z) far back inside; capped here at a tenth of mu_init so that the
+        # start keeps the complementarity the previous solve ended with
+        push, frac = ((min(self.ws_slack_push, 0.1 * self.mu_init), min(self.ws_slack_frac, 0.1 * self.mu_init))
+                      if warm else (1e-2, 1e-2))
         width = torch.where(hasL & hasU, ub - lb, torch.full_like(lb, float("inf")))
         pL = torch.minimum(push * torch.clamp(lb.abs(), min=1.0), frac * width)
         pU = torch.minimum(push * torch.clamp(ub.abs(), min=1.0), frac * width)
@@ -240,6 +258,18 @@ class BatchedInteriorPoint:
         zL = torch.where(hasL, mu[:, None] / (s - lbs), torch.zeros_like(s))
         zU = torch.where(hasU, mu[:, None] / (ubs - s), torch.zeros_like(s))
         lamE = torch.zeros((B, mE), dtype=torch.float64, device=dev)
+        if warm:
+            lam0 = torch.as_tensor(np.asarray(lam0.cpu() if torch.is_tensor(lam0) else lam0, dtype=np.float64), device=dev)
+            lam0 = lam0.expand(B, m) * obj_scale[:, None]
+            lamE = lam0[:, iE].clone()
+            lI = lam0[:, iI]
+            # IPOPT floors the given bound multipliers at warm_start_mult_bound_push; here the floor is capped at
+            # 0.1 mu / slack, so that a constraint that is inactive at the previous solution does not come back with a
+            # complementarity of push * slack >> mu (which costs IPOPT-style warm starts a dozen iterations)
+            floorU = torch.minimum(torch.full_like(s, self.ws_mult_push), 0.1 * mu[:, None] / torch.clamp(ubs - s, min=1e-300))
+            floorL = torch.minimum(torch.full_like(s, self.ws_mult_push), 0.1 * mu[:, None] / torch.clamp(s - lbs, min=1e-300))
+            zU = torch.where(hasU, torch.maximum(lI, floorU), torch.zeros_like(s))
+            zL = torch.where(hasL, torch.maximum(-lI, floorL), torch.zeros_like(s))
         delta = torch.zeros(B, dtype=torch.float64, device=dev)
         nu = torch.ones(B, dtype=torch.float64, device=dev)
         done = torch.zeros(B, dtype=torch.bool, device=dev)
@@ -323,7 +353,7 @@ class BatchedInteriorPoint:
                 best_cost = torch.where(sat, cost_u, best_cost)
                 best_it = torch.where(sat, torch.full_like(best_it, it), best_it)
             done |= newly
-            if self.verbose and it % 10 == 0:
+            if self.verbose and it % getattr(self, "verbose_every", 10) == 0:
                 print(f"it {it:3d} done {int(done.sum())}/{B} err0 med {err0.median().item():.2e} max {err0.max().item():.2e} "
                       f"mu med {mu.median().item():.1e} delta med {delta.median().item():.1e} max {delta.max().item():.1e} "
                       f"| dual med {(linf(rd) / sd).median().item():.2e} prim med {prim.median().item():.2e}")

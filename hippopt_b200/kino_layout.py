@@ -124,6 +124,15 @@ def linear_states():
     return out
 
 
+def count_rows(horizon: int, final_state: bool, periodicity: bool) -> int:
+    """m of the kinodynamic OCP from its constraint families alone (no robot model needed): template matching."""
+    lay = KinoLayout.__new__(KinoLayout)
+    lay.N = horizon
+    lay.st = KinoSettings(horizon=horizon, final_state_constraint=final_state, periodicity_constraint=periodicity)
+    lay._families()
+    return lay.m
+
+
 class KinoLayout:
     def __init__(self, model: RobotModel, settings: KinoSettings):
         self.model = model
@@ -234,6 +243,45 @@ class KinoLayout:
         return out
 
     # ------------------------------------------------------------------ bounds (host side)
+    def simple_bound_rows(self, include_equalities: bool = False):
+        """Rows of g that are a bare decision variable, g_i = x_j -- the rows CasADi's nlpsol option
+        ``detect_simple_bounds`` (set by every main of the reference, e.g. main_single_step_flat_ground.py:106) turns
+        into lbx / ubx and removes from g [ext].  Returns (rows, x index of each row).
+
+        Planar terrain: control bounds u_v, joint position / velocity bounds, point height p_z, normal force f_z, CoM
+        height (720 + 667 + 690 + 232 + 232 + 29 = 2 570 of the 8 142 rows of config 3); on the smooth
+        terrain the height / normal-force / CoM-height rows are nonlinear and stay general.  Rows with a parametric
+        gain (f_dot * mass, h_ang * mass) are not bare variables and stay general.  ``include_equalities`` adds the
+        initial-condition rows x_j = parameter (lbx = ubx), which CasADi detects as well [ext] but IPOPT then treats
+        as fixed variables unless fixed_variable_treatment = relax_bounds."""
+        rows, cols = [], []
+
+        def add(name, k, xoff):
+            r0 = self.row(name, k)
+            if r0 >= 0:
+                for c, off in enumerate(xoff):
+                    rows.append(r0 + c)
+                    cols.append(NZ * k + off)
+
+        for k in range(self.N):
+            for i in range(NPT):
+                add(f"pt{i}.u_bounds", k, [15 * i + U + c for c in range(3)])
+                if not self.smooth:
+                    add(f"pt{i}.height", k, [15 * i + P + 2])
+                    add(f"pt{i}.normal", k, [15 * i + F + 2])
+                if include_equalities and k == 0:
+                    add(f"pt{i}.f_ic", 0, [15 * i + F + c for c in range(3)])
+                    add(f"pt{i}.p_ic", 0, [15 * i + P + c for c in range(3)])
+            if not self.smooth:
+                add("com_height", k, [COM + 2])
+            add("s_bounds", k, [S + j for j in range(NJ)])
+            add("sd_bounds", k, [SD + j for j in range(NJ)])
+            if include_equalities and k == 0:
+                for name, off, n in (("pb_ic", PB, 3), ("q_ic", Q, 4), ("s_ic", S, NJ), ("com_ic", COM, 3)):
+                    add(name, 0, [off + c for c in range(n)])
+        order = np.argsort(rows)
+        return np.asarray(rows, dtype=np.int64)[order], np.asarray(cols, dtype=np.int64)[order]
+
     def bounds(self, p: np.ndarray):
         """(lbg, ubg) for parameter vectors p of shape (B, n_p) -- canonical forms of the
         reference's constraints as CasADi Opti derives them [ext] (see oracle/kinodynamic.py)."""

@@ -211,6 +211,31 @@ int hb_eval(hb_handle h, uint32_t mask, const double* x, const double* p, int64_
             const double* lam_g, const double* sigma, double* f, double* grad_f, double* g,
             double* jac_vals, double* hess_vals, int64_t batch, void* stream);
 
+/* Per-expression cost values of the kinodynamic OCP, for the solution report (not an IPOPT callback).
+ * replaces: opti_solution.value(self._cost_expressions[name]) for every named cost, opti_solver.py:526-529
+ * (names: `name=` arguments of planner.py:215-895 + the "[k]" suffix of multiple_shooting_solver.py:810;
+ * hippopt_b200/naming.py maps the slots below to those names).
+ *   terms  device [batch][horizon][HB_COST_TERMS]: the value (multiplier included) of cost expression `slot` at
+ *          knot k, 0 where the expression does not exist (apply_to_first_elements = False at k = 0).
+ * The sum over slots and knots is f (up to the order of the additions). */
+enum {
+  HB_CT_SWING0 = 0,       /* 8: <point>.p_swing_height_regularization        planner.py:855-875 */
+  HB_CT_UV0 = 8,          /* 8: <point>.u_v_regularization                   planner.py:877-884 */
+  HB_CT_FDOT0 = 16,       /* 8: <point>.f_dot_regularization                 planner.py:886-893 */
+  HB_CT_FRATIO0 = 24,     /* 8: <point>.f_regularization (force ratio)       planner.py:756-771 */
+  HB_CT_COM_VELOCITY = 32,/* com_velocity_error                              planner.py:432-447 */
+  HB_CT_CENTROID,         /* contacts_centroid_cost                          planner.py:248-264 */
+  HB_CT_YAW_LEFT,         /* left_yaw_regularization                         planner.py:780-853 */
+  HB_CT_YAW_RIGHT,        /* right_yaw_regularization                                           */
+  HB_CT_FRAME_QUAT,       /* frame_quaternion_error                          planner.py:449-477 */
+  HB_CT_BASE_QUAT,        /* base_quaternion_error                           planner.py:479-491 */
+  HB_CT_BASE_QUAT_VEL,    /* base_quaternion_velocity_error                  planner.py:493-503 */
+  HB_CT_JOINTS,           /* joint_positions_error                           planner.py:505-520 */
+  HB_COST_TERMS
+};
+int hb_eval_cost_terms(hb_handle h, const double* x, const double* p, int64_t p_stride, double* terms,
+                       int64_t batch, void* stream);
+
 /* Host-buffer form of hb_eval: the call a CPU-side solver (IPOPT inside opti_solver.py:479) makes.
  * Every pointer is a HOST pointer (pinned memory from hb_host_alloc gives full copy/compute overlap;
  * pageable memory works, more slowly).  The batch is cut into chunks pipelined over internal CUDA

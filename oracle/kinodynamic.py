@@ -164,15 +164,18 @@ def build(model, st: Settings) -> tuple[NLP, Layout]:
 
     def add_linear_dynamics(n, name, state_off, rate_off, init_idx, init_is_var=False):
         t_ic = (ic_template_var if init_is_var else ic_template)(n, name + "_ic")
+        # names: multiple_shooting_solver.py:696-697 (x0_name = name + "[0]"), :728 (name + "[k]"); the dynamics
+        # are handed to Problem.add_expression as a generator over the state variables, which appends "{j}"
+        # (problem.py:105-110, 140-145) -- one state variable per call here, hence "{0}"
         if init_idx is not None:
-            nlp.subject_to(t_ic, _cat(lay.x(0, state_off, n), init_idx), name + "[0]")
+            nlp.subject_to(t_ic, _cat(lay.x(0, state_off, n), init_idx), name + "[0]{0}")
         t = trapezoid_linear(n, name)
         for k in range(N - 1):
             nlp.subject_to(
                 t,
                 _cat(lay.x(k, state_off, n), lay.x(k + 1, state_off, n), lay.x(k, rate_off, n),
                      lay.x(k + 1, rate_off, n), lay.dt),
-                f"{name}[{k + 1}]",
+                f"{name}[{k + 1}]{{0}}",
             )
 
     # ---------------------------------------------------------------- per-point templates
@@ -212,21 +215,22 @@ def build(model, st: Settings) -> tuple[NLP, Layout]:
     # ---------------------------------------------------------------- emission (planner.py:124-147)
     for i in range(NPT):
         frame = st.foot_frames[0] if i < 4 else st.foot_frames[1]
-        name = f"pt{i}"
+        # flattened symbol names (multiple_shooting_solver.py:292-337, 395-401): lists are flattened with "[k]"
+        name = f"system.contact_points.{'left' if i < 4 else 'right'}[{i % 4}]"
         # _add_point_dynamics (planner.py:721-744): dot(f) = f_dot, dot(p) = v
         add_linear_dynamics(3, name + ".f_dynamics", 15 * i + F, 15 * i + FD, lay.state_pt(lay.init, i, "f"))
         add_linear_dynamics(3, name + ".p_dynamics", 15 * i + P, 15 * i + V, lay.state_pt(lay.init, i, "p"))
         # _add_contact_point_feasibility (planner.py:634-719)
         for k in knots_all:
-            nlp.subject_to(t_planar, _cat(lay.pt(k, i), lay.kt, tp_idx), f"{name}.planar[{k}]")
+            nlp.subject_to(t_planar, _cat(lay.pt(k, i), lay.kt, tp_idx), f"{name}.p_planar_complementarity[{k}]")
         for k in knots_all:
-            nlp.subject_to(t_dcc, _cat(lay.pt(k, i), lay.k_bs, lay.eps, tp_idx), f"{name}.dcc[{k}]")
+            nlp.subject_to(t_dcc, _cat(lay.pt(k, i), lay.k_bs, lay.eps, tp_idx), f"{name}.p_dcc[{k}]")
         for k in knots_1:
-            nlp.subject_to(t_height, _cat(lay.pt(k, i), tp_idx), f"{name}.height[{k}]")
+            nlp.subject_to(t_height, _cat(lay.pt(k, i), tp_idx), f"{name}.p_height[{k}]")
         for k in knots_1:
-            nlp.subject_to(t_normal, _cat(lay.pt(k, i), tp_idx), f"{name}.normal[{k}]")
+            nlp.subject_to(t_normal, _cat(lay.pt(k, i), tp_idx), f"{name}.f_normal[{k}]")
         for k in knots_1:
-            nlp.subject_to(t_friction, _cat(lay.pt(k, i), lay.mu, tp_idx), f"{name}.friction[{k}]")
+            nlp.subject_to(t_friction, _cat(lay.pt(k, i), lay.mu, tp_idx), f"{name}.f_friction[{k}]")
         for k in knots_all:
             nlp.subject_to(t_ubounds, _cat(lay.pt(k, i), lay.rng(lay.max_u, 3)), f"{name}.u_v_bounds[{k}]")
         for k in knots_all:
@@ -234,15 +238,17 @@ def build(model, st: Settings) -> tuple[NLP, Layout]:
                            f"{name}.f_dot_bounds[{k}]")
         # _add_contact_kinematic_consistency (planner.py:590-632)
         for k in knots_1:
-            nlp.subject_to(t_fk[frame], _cat(lay.pt(k, i), kin_idx(k), lay.desc(k, i)), f"{name}.fk[{k}]")
+            nlp.subject_to(t_fk[frame], _cat(lay.pt(k, i), kin_idx(k), lay.desc(k, i)), f"{name}.p_kinematics_consistency[{k}]")
         # _add_contact_point_regularization (planner.py:855-895)
         for k in knots_1:
             nlp.minimize(t_swing, _cat(lay.pt(k, i), lay.ref(k, "swing_h"), tp_idx),
-                         st.swing_foot_height_cost_multiplier)
+                         st.swing_foot_height_cost_multiplier, f"{name}.p_swing_height_regularization[{k}]")
         for k in knots_1:
-            nlp.minimize(t_ureg, lay.pt(k, i), st.contact_velocity_control_cost_multiplier)
+            nlp.minimize(t_ureg, lay.pt(k, i), st.contact_velocity_control_cost_multiplier,
+                         f"{name}.u_v_regularization[{k}]")
         for k in knots_1:
-            nlp.minimize(t_fdreg, lay.pt(k, i), st.contact_force_control_cost_multiplier)
+            nlp.minimize(t_fdreg, lay.pt(k, i), st.contact_force_control_cost_multiplier,
+                         f"{name}.f_dot_regularization[{k}]")
 
     # ---------------------------------------------------------------- _add_robot_dynamics (:522-588)
     add_linear_dynamics(3, "base_position_dynamics", PB, VB, lay.state(lay.init, "pb"))
@@ -271,10 +277,10 @@ def build(model, st: Settings) -> tuple[NLP, Layout]:
 
     if not st.periodicity_constraint:  # planner.py:580-584
         nlp.subject_to(ic_template_var(6, "h_ic"), _cat(lay.x(0, H, 6), lay.rng(lay.h_init, 6)),
-                       "centroidal_momentum_dynamics[0]")
+                       "centroidal_momentum_dynamics[0]{0}")
     for k in range(N - 1):
         nlp.subject_to(t_hdyn, _cat(lay.x(k, H, 6), lay.x(k + 1, H, 6), hdyn_idx(k), hdyn_idx(k + 1),
-                                    lay.rng(lay.gravity, 6), lay.dt), f"centroidal_momentum_dynamics[{k + 1}]")
+                                    lay.rng(lay.gravity, 6), lay.dt), f"centroidal_momentum_dynamics[{k + 1}]{{0}}")
 
     # ---------------------------------------------------------------- _add_kinematics_constraints (:266-425)
     t_unit = Template("unitary_quaternion", _l(q), [sx.sumsqr(q)], lb=[1.0], ub=[1.0])
@@ -341,21 +347,25 @@ def build(model, st: Settings) -> tuple[NLP, Layout]:
     e = [hv[i] - cref[i] for i in range(3)]
     t_comvel = Template("com_velocity_error", _l(hv, cref), [_wquad(e, w)])
     for k in knots_all:
-        nlp.minimize(t_comvel, _cat(lay.x(k, H, 6), lay.ref(k, "comv")), st.com_linear_velocity_cost_multiplier)
+        nlp.minimize(t_comvel, _cat(lay.x(k, H, 6), lay.ref(k, "comv")), st.com_linear_velocity_cost_multiplier,
+                     f"com_velocity_error[{k}]")
 
     qdes = sx.syms("qdes", 4)
     E = ex.rotation_error_from_kinematics(model, st.frame_quaternion_cost_frame, pb, qn, s, qdes)
     t_frame = Template("frame_quaternion_error", _l(pb, q, s, qdes), [sx.sq((E[0, 0] + E[1, 1] + E[2, 2]) - 3.0)])
     for k in knots_1:
-        nlp.minimize(t_frame, _cat(kin_idx(k), lay.ref(k, "fq")), st.desired_frame_quaternion_cost_multiplier)
+        nlp.minimize(t_frame, _cat(kin_idx(k), lay.ref(k, "fq")), st.desired_frame_quaternion_cost_multiplier,
+                     f"frame_quaternion_error[{k}]")
 
     t_bq = Template("base_quaternion_error", _l(q, qdes), [sx.sumsqr(ex.quaternion_xyzw_error(q, qdes))])
     for k in knots_1:
-        nlp.minimize(t_bq, _cat(lay.x(k, Q, 4), lay.ref(k, "bq")), st.base_quaternion_cost_multiplier)
+        nlp.minimize(t_bq, _cat(lay.x(k, Q, 4), lay.ref(k, "bq")), st.base_quaternion_cost_multiplier,
+                     f"base_quaternion_error[{k}]")
 
     t_bqv = Template("base_quaternion_velocity_error", _l(qd, qdes), [sx.sumsqr([qd[i] - qdes[i] for i in range(4)])])
     for k in knots_all:
-        nlp.minimize(t_bqv, _cat(lay.x(k, QD, 4), lay.ref(k, "bqv")), st.base_quaternion_velocity_cost_multiplier)
+        nlp.minimize(t_bqv, _cat(lay.x(k, QD, 4), lay.ref(k, "bqv")), st.base_quaternion_velocity_cost_multiplier,
+                     f"base_quaternion_velocity_error[{k}]")
 
     # joint regularisation, planner.py:506-520.  ``diag(w) * error`` is an ELEMENT-WISE product of
     # an n x n matrix with an n x 1 vector; CasADi repeats the vector horizontally [ext], giving
@@ -371,7 +381,7 @@ def build(model, st: Settings) -> tuple[NLP, Layout]:
     t_joint = Template("joint_positions_error", _l(s, sd, jr), [acc])
     for k in knots_1:
         nlp.minimize(t_joint, _cat(lay.x(k, S, NJ), lay.x(k, SD, NJ), lay.ref(k, "jr")),
-                     st.joint_regularization_cost_multiplier)
+                     st.joint_regularization_cost_multiplier, f"joint_positions_error[{k}]")
 
     # ---------------------------------------------------------------- _add_contact_centroids_expressions (:215-264)
     pts = [sx.syms(f"p{i}", 3) for i in range(NPT)]
@@ -390,7 +400,7 @@ def build(model, st: Settings) -> tuple[NLP, Layout]:
     t_cent = Template("contacts_centroid_cost", _l(*pts, cc, cw), [_wquad(ce, cw)])
     for k in knots_1:
         nlp.minimize(t_cent, _cat(pts_idx(k), lay.ref(k, "cc"), lay.ref(k, "cw")),
-                     st.contacts_centroid_cost_multiplier)
+                     st.contacts_centroid_cost_multiplier, f"contacts_centroid_cost[{k}]")
 
     # ---------------------------------------------------------------- _add_foot_regularization x2 (:746-853)
     fs = [sx.syms(f"f{i}", 3) for i in range(4)]
@@ -411,13 +421,15 @@ def build(model, st: Settings) -> tuple[NLP, Layout]:
             for k in knots_1:
                 nlp.minimize(t_ratio[i], _cat(*[lay.x(k, 15 * (base + j) + F, 3) for j in range(4)],
                                               lay.ref(k, "ratio_l" if foot == 0 else "ratio_r")[i]),
-                             st.force_regularization_cost_multiplier)
+                             st.force_regularization_cost_multiplier,
+                             f"system.contact_points.{'left' if foot == 0 else 'right'}[{i}].f_regularization[{k}]")
         for k in knots_1:
             nlp.minimize(t_yaw, _cat(lay.x(k, 15 * (base + st.yaw_bottom_right) + P, 3),
                                      lay.x(k, 15 * (base + st.yaw_top_right) + P, 3),
                                      lay.x(k, 15 * (base + st.yaw_top_left) + P, 3),
                                      lay.ref(k, "yaw_l" if foot == 0 else "yaw_r")),
-                         st.foot_yaw_regularization_cost_multiplier)
+                         st.foot_yaw_regularization_cost_multiplier,
+                         f"{'left' if foot == 0 else 'right'}_yaw_regularization[{k}]")
 
     # ---------------------------------------------------------------- _add_periodicity_expression (:897-930)
     if st.periodicity_constraint:

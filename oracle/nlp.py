@@ -76,7 +76,9 @@ class NLP:
         self.m = 0
         self.row_apps: list[tuple[Template, np.ndarray, int]] = []
         self.cost_apps: list[tuple[Template, np.ndarray, float]] = []
-        self.row_names: list[str] = []
+        self.row_names: list[str] = []        # one per row: "<expression name>{i}"-style debugging labels
+        self.constraint_names: list[tuple[str, int, int]] = []  # (reference expression name, first row, rows)
+        self.cost_names: list[str] = []       # reference expression name of every cost application
         self._jac = None
         self._hess = None
         self._plans: dict = {}
@@ -89,12 +91,14 @@ class NLP:
         self.row_apps.append((template, binding, off))
         self.m += len(template.rows)
         self.row_names.extend([f"{name}{{{i}}}" for i in range(len(template.rows))])
+        self.constraint_names.append((name, off, len(template.rows)))
         return off
 
-    def minimize(self, template: Template, binding, scaling: float = 1.0) -> None:
+    def minimize(self, template: Template, binding, scaling: float = 1.0, name: str = "") -> None:
         binding = np.asarray(binding, dtype=np.int64)
         assert len(template.rows) == 1 and binding.shape == (len(template.inputs),)
         self.cost_apps.append((template, binding, float(scaling)))
+        self.cost_names.append(name)
 
     # -- helpers ----------------------------------------------------------------------
     @staticmethod

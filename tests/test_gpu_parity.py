@@ -435,3 +435,43 @@ def test_other_joint_orders(built_library):
     model3 = RobotModel.from_urdf(urdf, interleaved, "root_link", frames=frames)
     with pytest.raises(_capi.EvaluationError, match="branch accumulators"):
         KinoEvaluator(model3, KinoSettings(horizon=2))
+
+
+@pytest.mark.parametrize("smooth", [False, True])
+def test_named_cost_values_against_oracle(model, built_library, smooth):
+    """Row f4 / a30: `hb_eval_cost_terms` gives the value of every NAMED cost expression
+    (opti_solver.py:526-529); per name against the oracle's recording of the planner's minimize calls, and the
+    sum against f."""
+    from hippopt_b200 import naming
+    from hippopt_b200.evaluator import F, KinoEvaluator
+    from hippopt_b200.kino_layout import KinoSettings
+    from hippopt_b200.workloads import kino_batch
+    from oracle import expressions as ex
+    from oracle import kinodynamic as kd
+
+    N, B = 4, 3
+    ev = KinoEvaluator(model, KinoSettings(horizon=N, terrain="smooth_steps" if smooth else "planar",
+                                           n_terrain_params=10 if smooth else 0))
+    extra = dict(terrain=ex.TwoSmoothSteps(), terrain_params=10) if smooth else {}
+    nlp, _ = kd.build(model, kd.Settings(horizon=N, **extra))
+    x, p, lam, sigma = kino_batch(ev.layout, model, B, seed=21, noise=0.2)
+    X, P = (torch.tensor(a, device=dev()) for a in (x, p))
+    terms = ev.cost_terms(X, P).cpu().numpy()
+    f = ev.eval(F, X, P)["f"].cpu().numpy()
+    ref = nlp.eval_cost_terms(x, p)  # (B, applications), recording order
+    slots = naming.cost_slots(ev.layout)
+    assert set(slots) == set(nlp.cost_names)
+    scale = np.abs(ref).max(axis=1)
+    for j, name in enumerate(nlp.cost_names):
+        k, s = slots[name]
+        err = np.abs(terms[:, k, s] - ref[:, j]) / np.maximum(np.abs(ref[:, j]), 1e-300)
+        ok = (err <= RTOL) | (np.abs(terms[:, k, s] - ref[:, j]) <= 2.3e-16 * scale)
+        assert ok.all(), f"{name}: {terms[:, k, s]} vs {ref[:, j]}"
+    named = np.zeros_like(terms, dtype=bool)
+    for k, s in slots.values():
+        named[:, k, s] = True
+    assert np.all(terms[~named] == 0.0)  # expressions that do not exist at knot 0
+    assert np.allclose(terms.sum(axis=(1, 2)), f, rtol=1e-13, atol=0)
+    for b in range(B):
+        by_name = naming.cost_values(ev.layout, terms[b])
+        assert by_name["com_velocity_error[0]"] == terms[b, 0, 32]

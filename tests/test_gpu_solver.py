@@ -141,3 +141,73 @@ def test_standing_ocp_solves_with_the_stage_kkt(model, built_library, periodic):
     gs = ev.eval(G, res.values, P)["g"].cpu().numpy()[ok]
     assert (np.maximum(lbk[ok] - gs, 0) + np.maximum(gs - ubk[ok], 0)).max() < 1e-5
     assert torch.isfinite(res.cost_value[res.success]).all()
+
+
+def test_b200solver_behind_the_optimization_solver_interface(model, built_library):
+    """Row a30 / (b): the casadi-free solver object (hippopt_b200/plugin.py) drives a batch of standing OCPs through
+    the 16-method interface and returns per-name cost values and multipliers (opti_solver.py:522-537); a second
+    solve warm-started from the first one's solution (main_single_step_flat_ground.py:120-125) needs fewer iterations."""
+    from hippopt_b200 import naming, plugin
+    from hippopt_b200.evaluator import F, KinoEvaluator, PoseEvaluator
+    from hippopt_b200.ipsolver import BatchedInteriorPoint
+    from hippopt_b200.kino_layout import KinoSettings
+    from hippopt_b200.workloads import pose_batch, standing_problem
+
+    dev = torch.device("cuda:0")
+    pev = PoseEvaluator(model)
+    x, p, _, _ = pose_batch(pev.layout, model, 8, seed=4, noise=0.02)
+    lb, ub = pev.bounds(p)
+    pose = BatchedInteriorPoint(pev, tol=1e-8, max_iter=300).solve(torch.tensor(x, device=dev), torch.tensor(p, device=dev), lb, ub)
+    pose = pose.values.cpu().numpy()[pose.success.cpu().numpy()][:4]
+    B = pose.shape[0]
+    st = KinoSettings(horizon=4)
+    ev = KinoEvaluator(model, st)
+    pk, x0 = standing_problem(ev.layout, model, pose)
+    opts = {"tol": 1e-6, "max_iter": 300, "mu_init": 1e-3}
+    s = plugin.B200Solver(model=model, settings=st, batch=B, evaluator=ev, options_solver=opts,
+                          options_plugin={"expand": True, "detect_simple_bounds": True})
+    s.generate_optimization_objects({"x": x0, "p": pk})
+    s.register_problem("standing")
+    s.solve()
+    vals, costs, mult = s.get_values(), s.get_cost_values(), s.get_constraint_multipliers()
+    assert len(vals) == B and len(costs) == B and len(mult) == B
+    vec = s.get_solution_vectors()
+    f = ev.eval(F, torch.tensor(vec["x"], device=dev), torch.tensor(pk, device=dev))["f"].cpu().numpy()
+    assert s.get_cost_value() == pytest.approx(f, rel=1e-12)
+    for b in range(B):
+        assert sum(costs[b].values()) == pytest.approx(f[b], rel=1e-12)       # the named costs add up to f
+        assert set(mult[b]) == set(naming.constraint_rows(ev.layout))
+        assert np.array_equal(mult[b]["unitary_quaternion[2]"], vec["lam_g"][b][naming.constraint_rows(ev.layout)["unitary_quaternion[2]"]])
+        assert np.array_equal(vals[b]["system"][3]["kinematics"]["joints"]["positions"], vec["x"][b, 189 * 3 + 157:189 * 3 + 180])
+    cold_iters = int(s._last_output.iterations.max())
+    # warm start: previous solution and multipliers as the guess
+    w = plugin.B200Solver(model=model, settings=st, batch=B, evaluator=ev,
+                          options_solver=dict(opts, warm_start_init_point="yes", mu_init=1e-7))  # mu the cold solve ended with: tol / 10
+    w.generate_optimization_objects({"x": vec["x"], "p": pk, "lam_g": vec["lam_g"]})
+    w.solve()
+    assert int(w._last_output.iterations.max()) <= max(3, cold_iters // 3)
+    assert np.abs(w.get_solution_vectors()["x"] - vec["x"]).max() < 1e-4
+
+
+def test_oracle_cache_over_hb_eval_host(model, built_library):
+    """The shim's evaluation path with the real library: `HostEvaluator` (hb_eval_host, one instance, pinned
+    buffers) behind the x-keyed `OracleCache` -- values equal the device-pointer path bit for bit, two launches per
+    iterate."""
+    from hippopt_b200 import plugin
+    from hippopt_b200.evaluator import ALL, KinoEvaluator
+    from hippopt_b200.kino_layout import KinoSettings
+    from hippopt_b200.workloads import kino_batch
+
+    ev = KinoEvaluator(model, KinoSettings(horizon=5))
+    x, p, lam, sigma = kino_batch(ev.layout, model, 1, seed=8, noise=0.1)
+    dev = torch.device("cuda:0")
+    ref = {k: v.cpu().numpy()[0] for k, v in ev.eval(ALL, *(torch.tensor(a, device=dev) for a in (x, p, lam, sigma))).items()}
+    host = plugin.HostEvaluator(ev)
+    host.set_parameters(p[0])
+    cache = plugin.OracleCache(host, host.masks)
+    for name in ("f", "grad_f", "g", "jac", "g", "f"):
+        assert np.array_equal(np.ravel(cache.get(name, x[0])), np.ravel(ref[name])), name
+    assert np.array_equal(cache.hess(x[0], lam[0], sigma[0]), ref["hess"])
+    assert cache.launches == {"first_order": 1, "hess": 1}
+    cache.get("g", x[0] + 1e-3)
+    assert cache.launches["first_order"] == 2
