@@ -213,3 +213,82 @@ class Opti:
         if hasattr(expr, "par"):
             return self._p[expr.par[0]:expr.par[1]]
         raise KeyError(expr)
+
+
+# ---- generated oracle functions (tools/dump_casadi_golden.py): nlpsol(...).get_function("nlp_jac_g") etc. ----------
+class _OracleFunction:
+    """What CasADi generates from the symbolic problem, backed here by an object with the oracle NLP's interface
+    (eval_f / eval_grad_f / eval_g / eval_jac / eval_hess / jac_structure / hess_structure) attached to the Opti."""
+
+    def __init__(self, kind, nlp, keep_rows=None, jac_keep=None, jac_sp=None):
+        self.kind, self.nlp, self.keep_rows, self.jac_keep, self.jac_sp = kind, nlp, keep_rows, jac_keep, jac_sp
+
+    def sparsity_out(self, i):
+        n, m = self.nlp.n_x, self.nlp.m
+        if self.kind == "nlp_jac_g" and i == 1:
+            if self.jac_sp is not None:
+                return self.jac_sp
+            c, r = self.nlp.jac_structure()[:2]
+            return Sparsity(m, n, list(c), list(r))
+        if self.kind == "nlp_hess_l":
+            c, r = self.nlp.hess_structure()[:2]
+            return Sparsity(n, n, list(c), list(r))
+        raise KeyError((self.kind, i))
+
+    def __call__(self, *args):
+        a = [np.asarray(v, dtype=float).ravel() for v in args]
+        X, P = a[0][None], a[1][None]
+        RECORD.append(("oracle_call", self.kind))
+        if self.kind == "nlp_f":
+            return DM([self.nlp.eval_f(X, P)[0]])
+        if self.kind == "nlp_grad_f":
+            return [DM([self.nlp.eval_f(X, P)[0]]), DM(self.nlp.eval_grad_f(X, P)[0])]
+        if self.kind == "nlp_g":
+            return DM(self.nlp.eval_g(X, P)[0])
+        if self.kind == "nlp_jac_g":
+            vals = self.nlp.eval_jac(X, P)[0]
+            if self.jac_keep is not None:
+                vals = vals[self.jac_keep]
+            return [DM(self.nlp.eval_g(X, P)[0]), DM(self.sparsity_out(1), vals)]
+        if self.kind == "nlp_hess_l":
+            lam = a[3] if self.keep_rows is None else _scatter(a[3], self.keep_rows, self.nlp.m)
+            return DM(self.sparsity_out(0), self.nlp.eval_hess(X, P, lam[None], np.asarray([a[2][0]]))[0])
+        raise KeyError(self.kind)
+
+
+def _scatter(v, rows, m):
+    out = np.zeros(m)
+    out[rows] = v
+    return out
+
+
+def _nlpsol_get_function(self, name):
+    opti_nlp = self.nlp["f"].oracle if hasattr(self.nlp["f"], "oracle") else None
+    assert opti_nlp is not None, "attach an oracle to the fake Opti (Opti.attach_oracle)"
+    nlp, reduction = opti_nlp
+    if self.opts.get("detect_simple_bounds") and reduction is not None:
+        sp = Sparsity(reduction.m_reduced, nlp.n_x, list(reduction.jac_colind), list(reduction.jac_row))
+        return _OracleFunction(name, nlp, reduction.general, reduction.jac_keep, sp)
+    return _OracleFunction(name, nlp)
+
+
+def _nlpsol_simple_bounds(self, p):
+    nlp, reduction = self.nlp["f"].oracle
+    lb, ub = nlp.eval_bounds(np.asarray(p, dtype=float)[None])
+    _, _, lbx, ubx = reduction.bounds(lb[0], ub[0])
+    return reduction.general, lbx, ubx
+
+
+_Nlpsol.get_function = _nlpsol_get_function
+_Nlpsol.simple_bounds = _nlpsol_simple_bounds
+
+
+def _opti_attach_oracle(self, nlp, reduction=None):
+    """make `opti.f` carry the oracle so that nlpsol({... "f": opti.f ...}).get_function works; lbg / ubg become
+    functions of p"""
+    self.f.oracle = (nlp, reduction)
+    self.lbg.fn = lambda env: nlp.eval_bounds(env[id(self.p)][None])[0][0]
+    self.ubg.fn = lambda env: nlp.eval_bounds(env[id(self.p)][None])[1][0]
+
+
+Opti.attach_oracle = _opti_attach_oracle

@@ -7,6 +7,8 @@ import os
 
 import numpy as np
 import pytest
+
+from tests_support import golden_files
 import torch
 
 pytestmark = pytest.mark.gpu
@@ -52,7 +54,7 @@ def run(ev, x, p, lam, sigma, mask=None):
     return {k: v.cpu().numpy().copy() for k, v in out.items()}
 
 
-@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLD, "kino_*.npz"))))
+@pytest.mark.parametrize("path", golden_files("kino"))
 def test_kino_golden(model, built_library, path):
     from hippopt_b200.evaluator import KinoEvaluator
     from hippopt_b200.kino_layout import KinoSettings
@@ -68,7 +70,7 @@ def test_kino_golden(model, built_library, path):
     check(out, d, (d["jac_colind"], d["jac_row"]), (d["hess_colind"], d["hess_row"]), d["x"])
 
 
-@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLD, "toy_*.npz"))))
+@pytest.mark.parametrize("path", golden_files("toy"))
 def test_toy_golden(built_library, path):
     from hippopt_b200.evaluator import ToyEvaluator
 
@@ -320,7 +322,7 @@ def test_config4_periodic_step_full_size(model, built_library):
 def test_config5_stairs_full_size(model, built_library):
     """BASELINE config 5: walking on stairs, horizon 50, randomised step heights as runtime terrain
     parameters; one 512-instance shard: finite, deterministic, first-order consistent (J d vs central
-    differences of g)."""
+    differences of g), and four instances against the oracle at this size (f, g, grad_f, jac_g, hess_l)."""
     from hippopt_b200.evaluator import G, JAC_G, KinoEvaluator
     from hippopt_b200.kino_layout import KinoSettings
     from hippopt_b200.workloads import kino_batch
@@ -342,6 +344,73 @@ def test_config5_stairs_full_size(model, built_library):
     gm = run(ev, x - eps * d, p, lam, sigma, G)["g"]
     Jd = _spmv_ccs(lay.jac_colind, lay.jac_row, run(ev, x, p, lam, sigma, JAC_G)["jac"], d, lay.m)
     assert np.abs((gp - gm) / (2 * eps) - Jd).max() <= 1e-4 * max(1.0, np.abs(Jd).max())
+    # oracle samples AT THE FULL SIZE (N = 50, all five outputs): instances spread over the shard, incl. first / last
+    from oracle import expressions as ex
+    from oracle import kinodynamic as kd
+
+    nlp, _ = kd.build(model, kd.Settings(horizon=50, terrain=ex.TwoSmoothSteps(), terrain_params=10,
+                                         final_state_constraint=True))
+    assert np.array_equal(lay.jac_row, nlp.jac_structure()[1]) and np.array_equal(lay.jac_colind, nlp.jac_structure()[0])
+    assert np.array_equal(lay.hess_row, nlp.hess_structure()[1]) and np.array_equal(lay.hess_colind, nlp.hess_structure()[0])
+    idx = np.array([0, 137, 300, 511])
+    with np.errstate(all="ignore"):
+        from oracle import parity
+
+        ref = parity.reference_outputs(nlp, x[idx], p[idx], lam[idx], sigma[idx])
+    got = {}
+    for k, r in ref.items():
+        ok = np.isfinite(r)  # 0 * inf in the oracle's graph far from a step (see the smooth-terrain test above)
+        assert ok.mean() > 0.99, k
+        got[k], ref[k] = np.where(ok, out[k][idx], 0.0), np.where(ok, r, 0.0)
+    check(got, ref, nlp.jac_structure()[:2], nlp.hess_structure()[:2], x[idx], rtol=RTOL_SMOOTH)
+
+
+@pytest.mark.parametrize("config", [4, 5])
+def test_configs_4_and_5_at_their_stated_batch(model, built_library, config):
+    """BASELINE configs 4 and 5 at the stated batch of 4096 instances on ONE GPU (the bench shards them over 8):
+    every instance evaluated, shard-by-shard results identical to the whole batch (sharding by instance changes
+    nothing), oracle samples from the first, a middle and the last shard."""
+    from hippopt_b200.evaluator import KinoEvaluator
+    from hippopt_b200.kino_layout import KinoSettings
+    from hippopt_b200.sharding import shard_range
+    from hippopt_b200.workloads import kino_batch
+    from oracle import expressions as ex
+    from oracle import kinodynamic as kd
+    from oracle import parity
+
+    if config == 4:
+        st = KinoSettings(horizon=30, final_state_constraint=True, periodicity_constraint=True)
+        ks = kd.Settings(horizon=30, final_state_constraint=True, periodicity_constraint=True)
+    else:
+        st = KinoSettings(horizon=50, terrain="smooth_steps", n_terrain_params=10, final_state_constraint=True)
+        ks = kd.Settings(horizon=50, terrain=ex.TwoSmoothSteps(), terrain_params=10, final_state_constraint=True)
+    ev = KinoEvaluator(model, st)
+    B = 4096
+    x, p, lam, sigma = kino_batch(ev.layout, model, B, seed=40 + config)
+    X, P, L, S = (torch.tensor(a, device=dev()) for a in (x, p, lam, sigma))
+    from hippopt_b200.evaluator import ALL
+
+    out = ev.eval(ALL, X, P, L, S)
+    torch.cuda.synchronize()
+    whole = {k: v.clone() for k, v in out.items()}
+    for k, v in whole.items():
+        assert bool(torch.isfinite(v).all()), k
+    for r in (0, 3, 7):
+        lo, hi = shard_range(B, r, 8)
+        part = ev.eval(ALL, X[lo:hi].contiguous(), P[lo:hi].contiguous(), L[lo:hi].contiguous(), S[lo:hi].contiguous())
+        torch.cuda.synchronize()
+        for k, v in part.items():
+            assert torch.equal(v, whole[k][lo:hi]), (k, r)
+    idx = np.array([0, 2049, 4095])
+    nlp, _ = kd.build(model, ks)
+    with np.errstate(all="ignore"):
+        ref = parity.reference_outputs(nlp, x[idx], p[idx], lam[idx], sigma[idx])
+    got = {}
+    for k, r in ref.items():
+        ok = np.isfinite(r)
+        assert ok.mean() > 0.99, k
+        got[k], ref[k] = np.where(ok, whole[k][idx].cpu().numpy(), 0.0), np.where(ok, r, 0.0)
+    check(got, ref, nlp.jac_structure()[:2], nlp.hess_structure()[:2], x[idx], rtol=RTOL_SMOOTH)
 
 
 def test_config3_samples_against_oracle(model, config3):
