@@ -85,6 +85,9 @@ def lib() -> ctypes.CDLL:
     L.hb_eval.argtypes = [vp, ctypes.c_uint32, vp, vp, ctypes.c_int64, vp, vp, vp, vp, vp, vp, vp, ctypes.c_int64, vp]
     L.hb_eval_cost_terms.restype = ctypes.c_int
     L.hb_eval_cost_terms.argtypes = [vp, vp, vp, ctypes.c_int64, vp, ctypes.c_int64, vp]
+    L.hb_debug_sweep_schedule.restype = ctypes.c_int
+    L.hb_debug_sweep_schedule.argtypes = [ctypes.c_int32, i32p, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32,
+                                          ctypes.c_int32, i32p, i32p]
     L.hb_host_set_parameters.restype = ctypes.c_int
     L.hb_host_set_parameters.argtypes = [vp, vp, ctypes.c_int64, ctypes.c_int64]
     L.hb_eval_host.restype = ctypes.c_int
@@ -123,7 +126,7 @@ EXPORTED_SYMBOLS = [
     "hb_last_launch_count", "hb_last_error", "hb_probe_fp64_tflops", "hb_profile_enable", "hb_profile_read",
     "hb_host_set_parameters", "hb_eval_host", "hb_host_last_traffic", "hb_host_alloc", "hb_host_free",
     "hb_lu_factor_batched", "hb_lu_solve_batched", "hb_set_option", "hb_interpolate_humanoid_states",
-    "hb_eval_cost_terms",
+    "hb_eval_cost_terms", "hb_debug_sweep_schedule",
 ]
 
 

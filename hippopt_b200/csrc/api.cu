@@ -92,162 +92,46 @@ __global__ void reduce_f_kernel(const double* __restrict__ fpart, double* __rest
 }
 
 // ---------------------------------------------------------------------------------------------
-// Schedule of the packed tangent sweep (kino_kin.cu).  Direction d (0..3 base quaternion, 4 + j joint j)
-// only needs the bodies of its sub-tree (non-zero state tangents: "in") and the ancestors of its joint
-// (pure propagation).  Those bodies are cut into chains that walk from a leaf towards the root; a chain
-// ends where it meets a body that another chain of the same direction continues through, and flushes its
-// running adjoint into that body's slot.  Chains are list-scheduled on the 32 lanes, longest remaining
-// path first; a chain may start once every flush it will read has landed, and two chains never flush into
-// the same slot in the same round (the additions into a slot therefore happen in a fixed order).
-struct SweepSchedule {
-  std::vector<int> tasks;  // [round][32]
-  int n_rounds = 0, n_slots = 0;
-  unsigned seed_mask = 0;
-  int root_slot[32] = {0};
-};
+// Schedule of the packed tangent sweep: sweep_schedule.h (host-only, also reachable through
+// hb_debug_sweep_schedule for the CPU tests)
+static hb::SweepTopo sweep_topo_of(const hb::KinoConst& C) {
+  hb::SweepTopo T;
+  T.nb = C.nb;
+  for (int l = 0; l < 32; ++l) {
+    T.parent[l] = l < C.nb ? C.body[l].parent : -1;
+    T.sub_mask[l] = C.sub_mask[l];
+  }
+  T.foot_body[0] = C.foot_body[0];
+  T.foot_body[1] = C.foot_body[1];
+  T.chest_body = C.chest_body;
+  return T;
+}
 
-static SweepSchedule build_sweep_schedule(const hb::KinoConst& C) {
-  const int nb = C.nb, n_dir = 4 + (nb - 1);
-  struct Seg {
-    int d;
-    std::vector<int> bodies;  // leaf -> root order
-    int flush_body;           // body whose slot receives the chain's state (0: the root slot)
-    int crit = 0, done = -1, start = -1, lane = -1;
-  };
-  std::vector<Seg> segs;
-  std::vector<std::vector<int>> slot_of(n_dir, std::vector<int>(nb, -1));
-  std::vector<std::vector<char>> in_full(n_dir, std::vector<char>(nb, 0));
-  int n_slots = 0;
-  for (int d = 0; d < n_dir; ++d) {
-    const int ld = d < 4 ? 0 : d - 3;
-    std::vector<char> rel(nb, 0);
-    for (int l = 0; l < nb; ++l)
-      if ((C.sub_mask[ld] >> l) & 1u) in_full[d][l] = rel[l] = 1;
-    for (int a = C.body[ld].parent; a >= 0; a = C.body[a].parent) rel[a] = 1;
-    // the feet-distance row couples the feet: a direction that moves one foot changes the seed applied on
-    // the other, whose tangent then travels up the other leg
-    for (int f = 0; f < 2; ++f)
-      if (in_full[d][C.foot_body[f]])
-        for (int a = C.foot_body[1 - f]; a >= 0; a = C.body[a].parent) rel[a] = 1;
-    // longest relevant chain below every body -> main child
-    std::vector<int> height(nb, 0), main_child(nb, -1);
-    for (int l = nb - 1; l >= 1; --l) {
-      if (!rel[l]) continue;
-      const int p = C.body[l].parent;
-      if (rel[p] && height[l] + 1 > height[p]) {
-        height[p] = height[l] + 1;
-        main_child[p] = l;
-      }
-    }
-    slot_of[d][0] = n_slots++;  // the root slot doubles as the direction's result
-    for (int l = nb - 1; l >= 1; --l) {
-      if (!rel[l]) continue;
-      bool leaf = true;
-      for (int c = l + 1; c < nb; ++c)
-        if (rel[c] && C.body[c].parent == l) leaf = false;
-      if (!leaf) continue;
-      Seg s;
-      s.d = d;
-      int b = l;
-      for (;;) {
-        s.bodies.push_back(b);
-        const int p = C.body[b].parent;
-        if (p == 0 || main_child[p] != b) {
-          s.flush_body = p;
-          break;
-        }
-        b = p;
-      }
-      if (s.flush_body != 0 && slot_of[d][s.flush_body] < 0) slot_of[d][s.flush_body] = n_slots++;
-      segs.push_back(s);
-    }
-    Seg root;
-    root.d = d;
-    root.bodies.push_back(0);
-    root.flush_body = -1;
-    segs.push_back(root);
+extern "C" int hb_debug_sweep_schedule(int32_t nb, const int32_t* parent, int32_t foot_l, int32_t foot_r, int32_t chest,
+                                       int32_t typed, int32_t* tasks, int32_t* info) {
+  if (!parent || !tasks || !info || nb < 2 || nb > 28) return fail(HB_ERR_INVALID, "hb_debug_sweep_schedule: bad argument");
+  hb::SweepTopo T;
+  T.nb = nb;
+  for (int l = 0; l < 32; ++l) {
+    T.parent[l] = l < nb ? parent[l] : -1;
+    T.sub_mask[l] = 0u;
   }
-  const int ns = (int)segs.size();
-  // dependencies: (position inside the consumer, producer segment)
-  std::vector<std::vector<std::pair<int, int>>> dep(ns);
-  std::vector<int> consumer(ns, -1), consumer_pos(ns, 0);
-  for (int i = 0; i < ns; ++i)
-    for (int j = 0; j < ns; ++j) {
-      if (i == j || segs[i].d != segs[j].d || segs[j].flush_body < 0) continue;
-      for (size_t pos = 0; pos < segs[i].bodies.size(); ++pos)
-        if (segs[i].bodies[pos] == segs[j].flush_body) {
-          dep[i].push_back({(int)pos, j});
-          consumer[j] = i;
-          consumer_pos[j] = (int)pos;
-        }
-    }
-  // critical path (segments are created leaf-first per direction, consumers may come later: iterate to a fixpoint)
-  for (int i = 0; i < ns; ++i) segs[i].crit = (int)segs[i].bodies.size();
-  for (int it = 0; it < nb; ++it)
-    for (int j = 0; j < ns; ++j)
-      if (consumer[j] >= 0) {
-        const int v = (int)segs[j].bodies.size() + segs[consumer[j]].crit - consumer_pos[j];
-        if (v > segs[j].crit) segs[j].crit = v;
-      }
-  std::vector<int> order(ns);
-  for (int i = 0; i < ns; ++i) order[i] = i;
-  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return segs[a].crit > segs[b].crit; });
-  std::vector<int> lane_free(32, 0);
-  std::map<std::pair<int, int>, std::vector<int>> flush_rounds;  // (slot) -> rounds in use
-  int remaining = ns, n_rounds = 0;
-  for (int r = 0; remaining > 0 && r < 4 * nb; ++r) {
-    for (int oi = 0; oi < ns; ++oi) {
-      Seg& s = segs[order[oi]];
-      if (s.done >= 0) continue;
-      bool ready = true;
-      for (auto& pj : dep[order[oi]])
-        if (segs[pj.second].done < 0 || segs[pj.second].done >= r + pj.first) ready = false;
-      if (!ready) continue;
-      int lane = -1;
-      for (int L = 0; L < 32; ++L)
-        if (lane_free[L] <= r) {
-          lane = L;
-          break;
-        }
-      if (lane < 0) break;
-      const int end = r + (int)s.bodies.size() - 1;
-      if (s.flush_body >= 0) {
-        auto& used = flush_rounds[{s.d, s.flush_body}];
-        if (std::find(used.begin(), used.end(), end) != used.end()) continue;
-        used.push_back(end);
-      }
-      s.start = r;
-      s.done = end;
-      s.lane = lane;
-      lane_free[lane] = end + 1;
-      if (end + 1 > n_rounds) n_rounds = end + 1;
-      --remaining;
-    }
-  }
-  SweepSchedule out;
-  if (remaining > 0) return out;  // n_rounds = 0: the caller reports the failure
-  out.n_rounds = n_rounds;
-  out.n_slots = n_slots;
-  for (int d = 0; d < n_dir && d < 32; ++d) out.root_slot[d] = slot_of[d][0];
-  out.tasks.assign((size_t)n_rounds * 32, 0);
-  for (const Seg& s : segs)
-    for (size_t pos = 0; pos < s.bodies.size(); ++pos) {
-      const int l = s.bodies[pos], r = s.start + (int)pos;
-      const int p = l == 0 ? 31 : C.body[l].parent;
-      unsigned t = (unsigned)l << hb::KT_L_SHIFT | (unsigned)p << hb::KT_P_SHIFT | (unsigned)s.d << hb::KT_D_SHIFT |
-                   hb::KT_VALID;
-      if (pos == 0) t |= hb::KT_START;
-      if (in_full[s.d][l]) t |= hb::KT_IN_L;
-      if (l != 0 && in_full[s.d][p]) t |= hb::KT_IN_P;
-      if (slot_of[s.d][l] >= 0) t |= (unsigned)(slot_of[s.d][l] + 1) << hb::KT_LOAD_SHIFT;
-      if (pos + 1 == s.bodies.size()) {
-        if (l == 0) t |= (unsigned)(slot_of[s.d][0] + 1) << hb::KT_FLUSH_SHIFT | hb::KT_STORE;
-        else t |= (unsigned)(slot_of[s.d][s.flush_body] + 1) << hb::KT_FLUSH_SHIFT;
-      }
-      out.tasks[(size_t)r * 32 + s.lane] = (int)t;
-      if (l == C.foot_body[0] || l == C.foot_body[1] || l == C.chest_body) out.seed_mask |= 1u << r;
-    }
-  return out;
+  for (int l = 0; l < nb; ++l)
+    for (int b = l; b >= 0; b = T.parent[b]) T.sub_mask[b] |= 1u << l;
+  T.foot_body[0] = foot_l;
+  T.foot_body[1] = foot_r;
+  T.chest_body = chest;
+  const hb::SweepSchedule s = hb::build_sweep_schedule(T, typed != 0, typed >= 2 ? 0 : 1);
+  if (s.n_rounds <= 0) return fail(HB_ERR_UNSUPPORTED, "hb_debug_sweep_schedule: no schedule");
+  for (size_t i = 0; i < s.tasks.size() && i < 32 * 32; ++i) tasks[i] = s.tasks[i];
+  info[0] = s.n_rounds;
+  info[1] = s.n_slots;
+  info[2] = s.n_tasks;
+  info[3] = s.n_heavy_tasks;
+  info[4] = (int32_t)s.heavy_mask;
+  info[5] = (int32_t)s.seed_mask;
+  for (int d = 0; d < 27 && d < 4 + nb - 1; ++d) info[6 + d] = s.root_slot[d];
+  return HB_OK;
 }
 
 template <class T>
@@ -517,7 +401,9 @@ extern "C" int hb_kino_create(const int32_t* icfg, const double* dcfg, const int
                       " branch accumulators (" + std::to_string(kin_smem / 1024) +
                       " KB of shared memory per CTA > 200 KB): list the joints of a limb consecutively");
     }
-    const SweepSchedule sch = build_sweep_schedule(C);
+    static const bool untyped_env = getenv("HB_SWEEP_UNTYPED") != nullptr;  // A/B timing of the typed rounds
+    hb::SweepSchedule sch = hb::build_sweep_schedule(sweep_topo_of(C), !untyped_env);
+    if (sch.n_rounds <= 0 || sch.n_rounds > 32) sch = hb::build_sweep_schedule(sweep_topo_of(C), false);
     if (sch.n_rounds <= 0 || sch.n_rounds > 32 || sch.n_slots > 62 || sch.n_slots * 12 > 58 + 32 + C.n_slots * 32 * 12) {
       hb_destroy(h);
       return fail(HB_ERR_UNSUPPORTED, "hb_kino_create: no sweep schedule for this tree within the kernel's limits");
@@ -525,14 +411,15 @@ extern "C" int hb_kino_create(const int32_t* icfg, const double* dcfg, const int
     if (getenv("HB_DEBUG_SCHED")) {
       int n_tasks = 0;
       for (int t : sch.tasks) n_tasks += (t & hb::KT_VALID) ? 1 : 0;
-      fprintf(stderr, "hb_kino_create: packed sweep: %d tasks in %d rounds, %d slots, seed mask %#x\n", n_tasks,
-              sch.n_rounds, sch.n_slots, sch.seed_mask);
+      fprintf(stderr, "hb_kino_create: packed sweep: %d tasks (%d heavy) in %d rounds, %d slots, seed mask %#x, heavy mask %#x\n",
+              n_tasks, sch.n_heavy_tasks, sch.n_rounds, sch.n_slots, sch.seed_mask, sch.heavy_mask);
     }
     if (e == cudaSuccess) e = upload(&h->d_sched, sch.tasks.data(), sch.tasks.size());
     h->topo.sched = h->d_sched;
     h->topo.n_rounds = sch.n_rounds;
     h->topo.n_pslots = sch.n_slots;
     h->topo.round_seed_mask = sch.seed_mask;
+    h->topo.round_heavy_mask = sch.heavy_mask;
     for (int d = 0; d < 32; ++d) h->topo.root_slot[d] = (signed char)sch.root_slot[d];
   }
   if (e == cudaSuccess) e = upload(&h->dev, &C, 1);

@@ -110,6 +110,17 @@ template <class A, class B>
 __device__ __forceinline__ V3<typename Prom<A, B>::type> scale(A s, V3<B> a) {
   return v3<typename Prom<A, B>::type>(s * a.x, s * a.y, s * a.z);
 }
+// acc + a x b and acc - a x b with two fused multiply-adds per component (a cross product followed by an addition is
+// three operations per component: the multiply-add contraction only sees one product at a time)
+__device__ __forceinline__ V3<double> cadd(V3<double> acc, V3<double> a, V3<double> b) {
+  return v3<double>(fma(a.y, b.z, fma(-a.z, b.y, acc.x)), fma(a.z, b.x, fma(-a.x, b.z, acc.y)),
+                    fma(a.x, b.y, fma(-a.y, b.x, acc.z)));
+}
+__device__ __forceinline__ V3<double> csub(V3<double> acc, const double* I, V3<double> a);  // acc - I a (symmetric I)
+// acc + s v
+__device__ __forceinline__ V3<double> sadd(V3<double> acc, double s, V3<double> v) {
+  return v3<double>(fma(s, v.x, acc.x), fma(s, v.y, acc.y), fma(s, v.z, acc.z));
+}
 // combine a primal vector and a tangent vector into a V3<T>
 template <class T>
 __device__ __forceinline__ V3<T> lift(D3 p, D3 t) {
@@ -125,6 +136,11 @@ __device__ __forceinline__ void st3(double* p, D3 a) {
 __device__ __forceinline__ D3 symmul(const double* I, D3 a) {
   return v3<double>(I[0] * a.x + I[1] * a.y + I[2] * a.z, I[1] * a.x + I[3] * a.y + I[4] * a.z,
                     I[2] * a.x + I[4] * a.y + I[5] * a.z);
+}
+__device__ __forceinline__ V3<double> csub(V3<double> acc, const double* I, V3<double> a) {
+  return v3<double>(fma(-I[2], a.z, fma(-I[1], a.y, fma(-I[0], a.x, acc.x))),
+                    fma(-I[4], a.z, fma(-I[3], a.y, fma(-I[1], a.x, acc.y))),
+                    fma(-I[5], a.z, fma(-I[4], a.y, fma(-I[2], a.x, acc.z))));
 }
 // row-major 3x3 times vector
 __device__ __forceinline__ D3 matvec(const double* R, D3 a) {

@@ -2,6 +2,7 @@
 #pragma once
 #include "../../include/hippopt_b200.h"
 #include "hb_math.cuh"
+#include "sweep_schedule.h"  // KT_* task descriptor bits, host-side scheduler
 
 namespace hb {
 
@@ -102,12 +103,7 @@ struct KinTopo {
   signed char root_slot[32];  // slot that holds the root totals of direction d after the sweep
   int n_rounds, n_pslots;
   unsigned round_seed_mask;  // bit r: some task of round r sits on a foot / chest body (seed tangents needed)
-};
-
-// task descriptor of the packed tangent sweep
-enum {
-  KT_L_SHIFT = 0, KT_P_SHIFT = 5, KT_D_SHIFT = 10, KT_VALID = 1 << 15, KT_START = 1 << 16, KT_IN_L = 1 << 17,
-  KT_IN_P = 1 << 18, KT_LOAD_SHIFT = 19, KT_FLUSH_SHIFT = 25, KT_STORE = 1u << 31  // slot ids are stored + 1 (0: none)
+  unsigned round_heavy_mask;  // bit r: round r holds "in" tasks (sub-tree of the direction); else pure propagation
 };
 
 // global g index of local row r of family `fam` at knot k, or -1 when the row does not exist

@@ -517,24 +517,7 @@ __device__ __forceinline__ void kin_tangent_sweep_packed(const KinTopo& T, const
     const bool valid = (t & KT_VALID) != 0;
     const int l = (t >> KT_L_SHIFT) & 31, p = (t >> KT_P_SHIFT) & 31, d = (t >> KT_D_SHIFT) & 31;
     const int src = valid ? d : lane;
-    // direction data: a joint direction is the axis / origin / twist of its body (already in shared
-    // memory); the four quaternion directions rotate everything about the base origin (qdat: g_a, u_a)
-    DirData dir;
-    {
-      const double* bd = sb + (d < 4 ? 0 : d - 3) * SB_STRIDE;
-      dir.wpi = ld3(bd + SB_W);
-      dir.vpi = ld3(bd + SB_V);
-      if (d < 4) {
-        dir.alpha = ld3(qdat + 6 * d);
-        dir.u = ld3(qdat + 6 * d + 3);
-        dir.pi = zero;
-      } else {
-        dir.alpha = ld3(bd + SB_AX);
-        dir.u = zero;
-        dir.pi = ld3(bd + SB_O);
-      }
-    }
-    const double m = massv[l];
+    const bool heavy = (T.round_heavy_mask >> r) & 1u;  // warp-uniform (constant bank): typed rounds, sweep_schedule.h
     SeedsT S;
     S.footF[0] = S.footF[1] = S.footN[0] = S.footN[1] = S.chestN = zero;
     if ((T.round_seed_mask >> r) & 1u) {  // warp-uniform
@@ -547,29 +530,60 @@ __device__ __forceinline__ void kin_tangent_sweep_packed(const KinTopo& T, const
     if (valid) {
       if (t & KT_START) cn = cF = cw = cv = zero;
       const double* bl = sb + l * SB_STRIDE;
-      const bool in = (t & KT_IN_L) != 0;
-      const D3 a = in ? dir.alpha : zero, uu = in ? dir.u : zero;
-      const D3 d_ = ld3(bl + SB_D), w = ld3(bl + SB_W), ax = ld3(bl + SB_AX);
-      const D3 rr = ld3(bl + SB_O) - dir.pi;
-      const D3 to = cross(a, rr);
-      const D3 td = cross(a, d_);
-      const D3 tw = cross(a, w - dir.wpi) + uu;
-      const D3 tv = cross(dir.wpi, to) + cross(a, (ld3(bl + SB_V) - dir.vpi) - cross(dir.wpi, rr)) + cross(uu, rr);
-      const D3 tax = cross(a, ax);
-      if (in) {  // local adjoints of body l move only with the sub-tree of the direction
-        const double* I = bl + SB_I;
-        const D3 cbar = ld3(bl + SB_CB), cdbar = ld3(bl + SB_CDB), Ih = ld3(bl + SB_IH), Iw = ld3(bl + SB_L);
-        const D3 tc = to + td;
-        const D3 tcd = tv + cross(tw, d_) + cross(w, td);
-        const D3 tcbar = scale(m, cross(tcd, hb));
-        const D3 tcdbar = scale(m, cross(hb, tc));
-        const D3 tIw = symmul(I, tw - cross(a, w)) + cross(a, Iw);
-        const D3 tIh = cross(a, Ih) - symmul(I, cross(a, hb));
-        cF = cF + tcbar;
-        cn = cn + cross(td, cbar) + cross(d_, tcbar) + cross(td, cross(cdbar, w)) +
-             cross(d_, cross(tcdbar, w) + cross(cdbar, tw)) + cross(tIw, hb) + cross(tIh, w) + cross(Ih, tw);
-        cv = cv + tcdbar;
-        cw = cw + cross(td, cdbar) + cross(d_, tcdbar) + tIh;
+      const D3 ax = ld3(bl + SB_AX);
+      D3 tax = zero, trho = zero, twpar = zero;
+      const D3 rho = ld3(bl + SB_RHO), wpar = ld3(sb + p * SB_STRIDE + SB_W);
+      if (heavy) {
+        // direction data: a joint direction is the axis / origin / twist of its body (already in shared
+        // memory); the four quaternion directions rotate everything about the base origin (qdat: g_a, u_a)
+        DirData dir;
+        {
+          const double* bd = sb + (d < 4 ? 0 : d - 3) * SB_STRIDE;
+          dir.wpi = ld3(bd + SB_W);
+          dir.vpi = ld3(bd + SB_V);
+          if (d < 4) {
+            dir.alpha = ld3(qdat + 6 * d);
+            dir.u = ld3(qdat + 6 * d + 3);
+            dir.pi = zero;
+          } else {
+            dir.alpha = ld3(bd + SB_AX);
+            dir.u = zero;
+            dir.pi = ld3(bd + SB_O);
+          }
+        }
+        const double m = massv[l];
+        // with typed rounds every task of a heavy round lies in the sub-tree of its direction (KT_IN_L set); the
+        // untyped fallback schedule mixes both kinds, hence the select
+        const bool in = (t & KT_IN_L) != 0;
+        const D3 a = in ? dir.alpha : zero, uu = in ? dir.u : zero;
+        const D3 d_ = ld3(bl + SB_D), w = ld3(bl + SB_W);
+        const D3 rr = ld3(bl + SB_O) - dir.pi;
+        const D3 to = cross(a, rr);
+        const D3 td = cross(a, d_);
+        const D3 tw = cadd(uu, a, w - dir.wpi);
+        const D3 tv = cadd(cadd(cross(dir.wpi, to), a, (ld3(bl + SB_V) - dir.vpi) - cross(dir.wpi, rr)), uu, rr);
+        tax = cross(a, ax);
+        if (in) {  // local adjoints of body l move with the sub-tree of the direction
+          const double* I = bl + SB_I;
+          const D3 cbar = ld3(bl + SB_CB), cdbar = ld3(bl + SB_CDB), Ih = ld3(bl + SB_IH), Iw = ld3(bl + SB_L);
+          const D3 tc = to + td;
+          const D3 tcd = cadd(cadd(tv, tw, d_), w, td);
+          const D3 tcbar = scale(m, cross(tcd, hb));
+          const D3 tcdbar = scale(m, cross(hb, tc));
+          const D3 tIw = cadd(symmul(I, tw - cross(a, w)), a, Iw);
+          const D3 tIh = csub(cross(a, Ih), I, cross(a, hb));
+          cF = cF + tcbar;
+          // two accumulators keep the dependent chains short
+          D3 n1 = cadd(cadd(cadd(cn, td, cbar), d_, tcbar), td, cross(cdbar, w));
+          D3 n2 = cadd(cadd(cadd(cross(d_, cadd(cross(tcdbar, w), cdbar, tw)), tIw, hb), tIh, w), Ih, tw);
+          cn = n1 + n2;
+          cv = cv + tcdbar;
+          cw = cadd(cadd(cw, td, cdbar), d_, tcdbar) + tIh;
+        }
+        if (t & KT_IN_P) {  // the parent moves with the direction as well
+          trho = cross(dir.alpha, rho);
+          twpar = cadd(dir.u, dir.alpha, wpar - dir.wpi);
+        }
       }
       // seed tangents (zero where they do not apply).  The feet-distance row couples the two feet: a
       // direction that moves one foot also changes the seed on the OTHER foot, which is why the schedule
@@ -592,19 +606,24 @@ __device__ __forceinline__ void kin_tangent_sweep_packed(const KinTopo& T, const
         cv = cv + ld3(sl + 9);
       }
       if (l != 0) {
-        const D3 np = ld3(bl + SB_ACC), Fp = ld3(bl + SB_ACC + 3), wp = ld3(bl + SB_ACC + 6), vp = ld3(bl + SB_ACC + 9);
         double* col = stage + d * 57;
-        col[7 + l - 1] += dot(tax, wp) + dot(ax, cw);   // rows: vb3 qd4 sd23 q4 s23
-        col[34 + l - 1] += dot(tax, np) + dot(ax, cn);
-        const D3 rho = ld3(bl + SB_RHO), wpar = ld3(sb + p * SB_STRIDE + SB_W);
-        const bool inp = (t & KT_IN_P) != 0;
-        const D3 ap = inp ? dir.alpha : zero;
-        const D3 trho = cross(ap, rho);
-        const D3 twpar = cross(ap, wpar - dir.wpi) + (inp ? dir.u : zero);
         const double sd = zs[Z_SD + l - 1];
-        cn = cn + cross(trho, Fp) + cross(rho, cF) + scale(sd, cross(tax, wp) + cross(ax, cw)) +
-             cross(trho, cross(vp, wpar)) + cross(rho, cross(cv, wpar) + cross(vp, twpar));
-        cw = cw + cross(trho, vp) + cross(rho, cv);
+        if (heavy) {
+          const D3 np = ld3(bl + SB_ACC), Fp = ld3(bl + SB_ACC + 3), wp = ld3(bl + SB_ACC + 6), vp = ld3(bl + SB_ACC + 9);
+          col[7 + l - 1] += dot(tax, wp) + dot(ax, cw);   // rows: vb3 qd4 sd23 q4 s23
+          col[34 + l - 1] += dot(tax, np) + dot(ax, cn);
+          D3 n1 = cadd(cadd(cn, trho, Fp), rho, cF);
+          D3 n2 = cadd(scale(sd, cadd(cross(tax, wp), ax, cw)), trho, cross(vp, wpar));
+          cn = cadd(n1 + n2, rho, cadd(cross(cv, wpar), vp, twpar));
+          cw = cadd(cadd(cw, trho, vp), rho, cv);
+        } else {
+          // propagation through an ancestor of the joint: every state tangent is zero, the adjoint tangent moves
+          // towards the root with the primal coefficients only
+          col[7 + l - 1] += dot(ax, cw);
+          col[34 + l - 1] += dot(ax, cn);
+          cn = cadd(cadd(cn, rho, cF) + scale(sd, cross(ax, cw)), rho, cross(cv, wpar));
+          cw = cadd(cw, rho, cv);
+        }
       }
       const int fs = (t >> KT_FLUSH_SHIFT) & 63;
       if (fs) {

@@ -316,6 +316,13 @@ int hb_interpolate_humanoid_states(int64_t batch, int64_t n_points, int64_t n_jo
                                    int64_t n_phases_right, int64_t stride_right, double* states, double* x,
                                    int64_t x_stride, int64_t knot0, void* stream);
 
+/* Host-only: the (direction, body) task table of the kinematics kernel's packed tangent sweep for a tree
+ * (hippopt_b200/csrc/sweep_schedule.h), for the CPU tests of the scheduler.  parent[nb]; typed: homogeneous rounds.
+ *   tasks[32*32]  descriptor of (round, lane), 0 = idle
+ *   info[40]      n_rounds, n_slots, n_tasks, n_heavy_tasks, heavy_mask, seed_mask, root_slot[27] */
+int hb_debug_sweep_schedule(int32_t nb, const int32_t* parent, int32_t foot_l, int32_t foot_r, int32_t chest,
+                            int32_t typed, int32_t* tasks, int32_t* info);
+
 const char* hb_last_error(void);
 
 /* fp64 FMA throughput probe (TFLOP/s) used as roofline denominator when none is published */
