@@ -30,6 +30,7 @@ INSTANCES_PER_GPU = 1024
 METRIC = "knot_evals_per_s"
 UNIT = "knot-evals/s (f+grad_f+g+jac_g+hess_l)"
 WORKLOAD = "humanoid_kinodynamic single step flat ground (BASELINE config 3), horizon 30, 1024 instances per GPU"
+REFERENCE_BUDGET_S = 150.0  # wall-clock budget of the reference arm's timed + warm-up steps
 
 
 def parse():
@@ -91,6 +92,101 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def bind_to_gpu_numa_node(local_rank: int, world: int):
+    """Pin this rank's threads to the CPUs of the NUMA node its GPU hangs off, so that the pinned host buffers of
+    the end-to-end path are allocated (first touch) on that node and the copies of the ranks do not all cross one
+    memory controller.  Node from sysfs (PCI device of the GPU); when the platform reports none (-1: a virtualised
+    host) and several nodes exist, the ranks are spread evenly over them.  Returns a description for the JSON line."""
+    try:
+        nodes = sorted(int(d[4:]) for d in os.listdir("/sys/devices/system/node") if d.startswith("node") and d[4:].isdigit())
+    except OSError:
+        return {"nodes": 0, "bound": None}
+    if len(nodes) < 2:
+        return {"nodes": len(nodes), "bound": None}
+    node = -1
+    try:
+        import torch
+
+        bus = torch.cuda.get_device_properties(local_rank).pci_bus_id  # type: ignore[attr-defined]
+        node = int(open(f"/sys/bus/pci/devices/{str(bus).lower()}/numa_node").read())
+    except Exception:  # noqa: BLE001
+        node = -1
+    how = "sysfs"
+    if node < 0:
+        node, how = nodes[(local_rank * len(nodes)) // max(world, 1) % len(nodes)], "spread"
+    try:
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return {"nodes": len(nodes), "bound": node, "how": how, "cpus": len(cpus)}
+    except Exception as exc:  # noqa: BLE001
+        return {"nodes": len(nodes), "bound": None, "error": str(exc)}
+
+
+def sharded_solves(model, ev, dev, rank, world):
+    """Complete interior-point solves with the evaluator in the loop, one wave of instances per GPU: "keep standing"
+    OCPs of the bench workload's size built from batched pose-finder solutions (hippopt_b200.workloads), stage-wise
+    KKT on the GPU.  Returns (on every rank) the whole-job numbers: solves/s = converged instances of all ranks /
+    slowest rank's wall time; results are gathered with one NCCL all_gather."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from hippopt_b200.evaluator import PoseEvaluator
+    from hippopt_b200.ipsolver import BatchedInteriorPoint
+    from hippopt_b200.workloads import pose_batch, standing_problem
+
+    lay = ev.layout
+    try:
+        n_s = torch.cuda.get_device_properties(dev).multi_processor_count  # one wave of the LU kernels
+        pev = PoseEvaluator(model)
+        xq, pq, _, _ = pose_batch(pev.layout, model, n_s, seed=1 + 97 * rank, noise=0.02)
+        lbq, ubq = pev.bounds(pq)
+        po = BatchedInteriorPoint(pev, tol=1e-8, max_iter=300).solve(torch.tensor(xq, device=dev),
+                                                                     torch.tensor(pq, device=dev), lbq, ubq)
+        okp = po.success.cpu().numpy()
+        pk, x0k = standing_problem(lay, model, po.values.cpu().numpy()[okp])
+        lbs_, ubs_ = lay.bounds(pk)
+        ip = BatchedInteriorPoint(ev, tol=1e-6, max_iter=150, kkt="stage", delta_c=1e-9, mu_init=1e-3)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+        ts = time.perf_counter()
+        # end to end: host arrays in (guess, parameters), solution and multipliers back on the host
+        out = ip.solve(torch.tensor(x0k).pin_memory().to(dev, non_blocking=True), torch.tensor(pk).pin_memory().to(dev, non_blocking=True),
+                       lbs_, ubs_)
+        xs, lam = out.values.cpu(), out.constraint_multipliers.cpu()
+        torch.cuda.synchronize(dev)
+        secs = time.perf_counter() - ts
+        mine = torch.tensor([float(okp.sum()), float(out.success.sum()), secs, float(out.iterations[out.success].median()) if
+                             bool(out.success.any()) else -1.0, float(out.evaluations), float(ip.kkt_seconds),
+                             float(xs.numel() * 8 + lam.numel() * 8), float(x0k.size * 8 + pk.size * 8)],
+                            dtype=torch.float64, device=dev)
+    except Exception as exc:  # noqa: BLE001 -- a solver failure must not cost the throughput line
+        mine = torch.tensor([0.0, 0.0, 1e-9, -1.0, 0.0, 0.0, 0.0, 0.0], dtype=torch.float64, device=dev)
+        err = f"{type(exc).__name__}: {exc}"
+    else:
+        err = None
+    if world > 1:
+        allr = torch.empty((world, mine.numel()), dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(allr, mine[None].contiguous())
+    else:
+        allr = mine[None]
+    a = allr.cpu().numpy()
+    conv, slow = float(a[:, 1].sum()), float(a[:, 2].max())
+    return {"workload": f"keep-standing OCPs at the bench size (horizon {HORIZON}, n_x {lay.n_x}, m {lay.m}), one wave of "
+                        f"instances per GPU, stage-wise KKT on the batched LU kernels; host guess in, host solution out",
+            "n_gpus": world, "instances": int(a[:, 0].sum()), "converged": int(conv), "seconds_max_over_ranks": slow,
+            "solves_per_s": conv / slow if slow > 0 else 0.0, "per_rank_solves_per_s": [float(r[1] / r[2]) for r in a],
+            "iterations_median_per_rank": [float(r[3]) for r in a], "batched_evaluations_per_rank": [int(r[4]) for r in a],
+            "seconds_in_kkt_per_rank": [float(r[5]) for r in a], "h2d_bytes": float(a[:, 7].sum()),
+            "d2h_bytes": float(a[:, 6].sum()), "error": err}
+
+
 def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -114,11 +210,16 @@ def run_reference(args):
 
     model = synthetic_ergocub()
     lay = KinoLayout(model, KinoSettings(horizon=HORIZON))
-    n = args.cpu_sample
-    x, p, lam, sigma = kino_batch(lay, model, n, seed=2)
     pool = OraclePool(model, HORIZON)
-    steps = max(1, min(args.steps, 3))
-    warm = max(1, min(args.warmup, 1))
+    # --steps K --warmup W are honoured; each step is a BOUNDED SAMPLE of the workload, sized from a probe so that
+    # the whole run stays within REFERENCE_BUDGET_S seconds (the contract: "ends within a few minutes")
+    steps, warm = max(1, args.steps), max(0, args.warmup)
+    xp, pp, lp, sp = kino_batch(lay, model, 16, seed=3)
+    pool.step(xp, pp, lp, sp)
+    dt_probe, _ = pool.step(xp, pp, lp, sp)
+    rate = 16 / max(dt_probe, 1e-6)  # instances per second on this host
+    n = int(max(min(8, args.cpu_sample), min(args.cpu_sample, REFERENCE_BUDGET_S * rate / (steps + warm))))
+    x, p, lam, sigma = kino_batch(lay, model, n, seed=2)
     for _ in range(warm):
         pool.step(x, p, lam, sigma)
     t = 0.0
@@ -166,6 +267,7 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa = bind_to_gpu_numa_node(local_rank, world)  # before any pinned allocation (first-touch placement)
     if world > 1:
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
     if rank == 0:
@@ -244,6 +346,35 @@ def main():
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
     e2e_value = total_instances * HORIZON / float(e2e_s.item())
     checksum = float(res["f"].sum())
+    e2e_h2d, e2e_d2h = pipe.h2d_bytes, pipe.d2h_bytes
+    del pipe
+    # the same call with the mask IPOPT uses in the reference's own configuration of these planners
+    # (hessian_approximation = limited-memory, main_single_step_flat_ground.py:112): f, grad_f, g, jac_g
+    from hippopt_b200.evaluator import F, G, GRAD_F, JAC_G
+
+    pipe1 = HostPipeline(ev, B, F | GRAD_F | G | JAC_G)
+    pipe1.set_parameters(ph)
+    for _ in range(2):
+        pipe1.run(xh)
+    fence()
+    te = time.perf_counter()
+    for _ in range(e2e_steps):
+        pipe1.run(xh)
+    fence()
+    e2e1_s = torch.tensor([(time.perf_counter() - te) / e2e_steps], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e1_s, op=dist.ReduceOp.MAX)
+    e2e_first_order = {"value": total_instances * HORIZON / float(e2e1_s.item()), "unit": "knot-evals/s (f+grad_f+g+jac_g)",
+                       "h2d_bytes_per_step": pipe1.h2d_bytes, "d2h_bytes_per_step": pipe1.d2h_bytes,
+                       "note": "mask of the reference's own IPOPT configuration (limited-memory Hessian: hess_l is never "
+                               "requested)"}
+    del pipe1
+
+    # ---- row f1 at every world size (second half of BASELINE.json's metric: "solves/s at 1/2/4/8 B200"): every rank
+    # solves its own wave of instances, results are gathered with NCCL
+    solves_all = None
+    if not args.no_cpu_baseline:
+        solves_all = sharded_solves(model, ev, dev, rank, world)
 
     if rank != 0:
         if world > 1:
@@ -256,28 +387,42 @@ def main():
     hbm_peak, hbm_src = measured_peaks()
     bytes_per_knot = lay.kernel_bytes_per_knot()["kinematics"]
     achieved_gbs = bytes_per_knot * knot_evals_per_launch / (kin_ms * 1e-3) / 1e9
-    counts_path = os.path.join(ROOT, "profiles", "algorithmic_counts.json")
-    flops_per_knot = json.load(open(counts_path))["kinematics_kernel_flops"] if os.path.exists(counts_path) else None
+    # fp64 roofline of the same kernel from EXECUTED flops: ncu's predicated-on thread-instruction counters of the
+    # committed capture (profiles/ncu_counters.json, written by tools/ncu_counters.py from the ncu CSV of
+    # `tools/time_kino.py`), not the oracle's tape count -- that one is kept as "reference_work"
     fp64_peak = probe_fp64_tflops()
     roofline_fp64 = None
-    if flops_per_knot:
-        ach = flops_per_knot * knot_evals_per_launch / (kin_ms * 1e-3) / 1e12
-        roofline_fp64 = {"bound": "fp64", "achieved": ach, "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach / fp64_peak,
-                         "peak_source": "measured in this run (hb_probe_fp64_tflops, DFMA chains on all SMs)",
-                         "flops_per_knot_eval": flops_per_knot,
-                         "note": "algorithmic flops = instruction count of the oracle's f/g, forward-mode "
-                                 "Jacobian and forward-over-reverse Hessian tapes (SURVEY.md 8(d))"}
+    cpath = os.path.join(ROOT, "profiles", "ncu_counters.json")
     traffic = None
-    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
-    if os.path.exists(tpath):
-        prof = json.load(open(tpath))
-        traffic = prof.get("kinematics_dram_bytes_per_launch")
-        if roofline_fp64 is not None:
-            # the honest utilisation figure: what ncu measured on the same kernel (committed capture)
-            roofline_fp64["pipe_fp64_active_pct_ncu"] = prof.get("kinematics_fp64_pipe_active_pct")
-            roofline_fp64["note"] += ("; frac can exceed 1: the kernel's closed-form tangents / composite moments "
-                                      "execute fewer fp64 operations than the oracle's tapes count -- "
-                                      "pipe_fp64_active_pct_ncu is the measured utilisation of the fp64 pipe")
+    if os.path.exists(cpath):
+        prof = json.load(open(cpath))
+        kin = prof["kernels"]["kino_kin_kernel<1>"]
+        flops_launch = 2.0 * kin["dfma"] + kin["dadd"] + kin["dmul"]
+        per_knot = flops_launch / prof["knot_evals_per_launch"]
+        ach = per_knot * knot_evals_per_launch / (kin_ms * 1e-3) / 1e12
+        sm_clock = (clocks or {}).get("sm_mhz") or 1965.0
+        n_sm = torch.cuda.get_device_properties(dev).multi_processor_count
+        nominal = n_sm * 64 * 2 * sm_clock * 1e6 / 1e12
+        counts_path = os.path.join(ROOT, "profiles", "algorithmic_counts.json")
+        ref_work = json.load(open(counts_path))["kinematics_kernel_flops"] if os.path.exists(counts_path) else None
+        # an fp64 warp instruction holds its scheduler's issue port for two cycles (64 lanes per SM and clock), every
+        # other one for one: the share of issue cycles the kernel's instruction stream needs
+        issue_cycles = kin["inst_executed"] + kin["inst_fp64"]
+        issue_frac = issue_cycles / (kin["sm_cycles"] * n_sm * 4) if kin.get("sm_cycles") else None
+        roofline_fp64 = {
+            "bound": "fp64", "kernel": "kino_kin_kernel<true>", "achieved": ach, "peak": fp64_peak, "unit": "TFLOP/s",
+            "frac": ach / fp64_peak,
+            "peak_source": "measured in this run (hb_probe_fp64_tflops: 8 independent DFMA chains per thread, all SMs)",
+            "peak_nominal": nominal, "peak_nominal_source": f"{n_sm} SMs x 64 DFMA/clk x 2 x {sm_clock:.0f} MHz",
+            "executed_flops_per_knot_eval": per_knot,
+            "flops_source": prof["source"],
+            "pipe_fp64_active_pct_ncu": kin.get("fp64_pipe_active_pct"), "issue_active_pct_ncu": kin.get("issue_active_pct"),
+            "issue_cycles_needed_frac_ncu": issue_frac,
+            "reference_work_flops_per_knot_eval": ref_work,
+            "note": "executed = 2 DFMA + DADD + DMUL predicated-on thread instructions (ncu) per knot-eval of the "
+                    "committed capture x this run's launch rate; reference_work = operation count of the oracle's "
+                    "(CasADi-style) tapes for the same rows, which the tree algorithm does not execute"}
+        traffic = kin["dram_read"] + kin["dram_write"]
 
     # ---- the other BASELINE configs (device-resident, 10 timed steps each; parity cases, not the headline)
     other = None
@@ -337,8 +482,8 @@ def main():
                     "ms_per_batched_solve": tk * 1e3, "kkt_solves_per_s": nk / tk}
         del kkt, vals
 
-    # ---- row f1: complete solves with the evaluator in the loop (pose finder, then "keep standing" OCPs of the
-    # bench workload's size built from those poses); informational, failures are reported, not hidden
+    # ---- row f1: complete solves with the evaluator in the loop (pose finder here; the "keep standing" OCPs of the
+    # bench workload's size are in sharded_solves); informational, failures are reported, not hidden
     solves = None
     if world == 1 and not args.no_cpu_baseline:
         from hippopt_b200.evaluator import PoseEvaluator
@@ -357,22 +502,9 @@ def main():
             torch.cuda.synchronize(dev)
             t_pose = time.perf_counter() - ts
             okp = po_out.success.cpu().numpy()
-            pk, x0k = standing_problem(lay, model, po_out.values.cpu().numpy()[okp])
-            lbs_, ubs_ = lay.bounds(pk)
-            ip = BatchedInteriorPoint(ev, tol=1e-6, max_iter=150, kkt="stage", delta_c=1e-9, mu_init=1e-3)
-            ts = time.perf_counter()
-            st_out = ip.solve(torch.tensor(x0k, device=dev), torch.tensor(pk, device=dev), lbs_, ubs_)
-            torch.cuda.synchronize(dev)
-            t_ocp = time.perf_counter() - ts
-            n_ok = int(st_out.success.sum())
             solves = {"pose_finder": {"instances": n_s, "converged": int(okp.sum()), "solves_per_s": int(okp.sum()) / t_pose,
                                       "iterations_median": int(po_out.iterations.median())},
-                      "standing_ocp": {"workload": f"keep-standing OCP at the bench size (horizon {HORIZON}, n_x {lay.n_x}, "
-                                                   f"m {lay.m}) from the converged poses, stage-wise KKT",
-                                       "instances": int(okp.sum()), "converged": n_ok, "solves_per_s": n_ok / t_ocp,
-                                       "iterations_median": int(st_out.iterations[st_out.success].median()) if n_ok else None,
-                                       "seconds": t_ocp, "seconds_in_kkt": ip.kkt_seconds,
-                                       "batched_evaluations": st_out.evaluations}}
+                      "standing_ocp": "see solves_sharded (reported at every number of GPUs)"}
             # row f3: set-up of periodic-step plans (3 keyframe pose solves per instance + device interpolation of
             # the guess into the decision vector), hippopt_b200/initial_guess.py
             try:
@@ -446,11 +578,12 @@ def main():
                    "nnz_jac": lay.nnz_j, "nnz_hess": lay.nnz_h, "parallelism": f"instances sharded over {world} GPU(s)",
                    "l2": "two rotating input sets; each step streams ~1 GB of inputs+outputs (>> 126 MB L2)"},
         "clocks": clocks,
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": pipe.h2d_bytes,
-                "d2h_bytes_per_step": pipe.d2h_bytes, "steps": e2e_steps,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": e2e_h2d,
+                "d2h_bytes_per_step": e2e_d2h, "steps": e2e_steps, "numa": numa,
                 "path": "hb_eval_host (C ABI, host pointers): pinned host x/lam/sigma -> device, kernels, all five "
                         "outputs -> pinned host; 128-instance chunks over 3 internal streams",
                 "checksum_f": checksum},
+        "e2e_first_order": e2e_first_order,
         "gpu_launches": launches_per_step * args.steps,
         "kernel_ms_per_step": {k: v / max(n_evals, 1) for k, v in kernel_ms.items()},
         "roofline": {"bound": "hbm", "kernel": "kino_kin_kernel<true>", "achieved": achieved_gbs, "peak": hbm_peak,
@@ -462,6 +595,7 @@ def main():
         "other_configs": other,
         "kkt": kkt_line,
         "solves": solves,
+        "solves_sharded": solves_all,
     }
     print(json.dumps(line))
     if world > 1:

@@ -31,6 +31,16 @@ def test_reference_arm_line():
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     cb = d["cpu_baseline"]
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "4 of the 1024 instances" in cb["sample"]
+    assert d["steps"] == 1 and d["warmup"] == 1
+
+
+def test_reference_arm_honours_steps_and_warmup():
+    """--steps / --warmup are taken as given (round-1 verdict: they were clamped to 3 / 1); the per-step sample is
+    what is bounded."""
+    r = run(["--impl", "reference", "--gpus", "1", "--steps", "4", "--warmup", "2", "--cpu-sample", "4"])
+    assert r.returncode == 0, r.stderr[-2000:]
+    d = json.loads([ln for ln in r.stdout.splitlines() if ln.strip()][0])
+    assert d["steps"] == 4 and d["warmup"] == 2 and "(4 timed steps, 2 warm-up)" in d["cpu_baseline"]["sample"]
 
 
 def test_reference_arm_other_ranks_exit_quietly():
