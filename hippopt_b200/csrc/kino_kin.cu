@@ -764,7 +764,8 @@ template <bool WITH_HESS>
 #ifndef KIN_H_THREADS
 #define KIN_H_THREADS 128
 #endif
-__global__ void __launch_bounds__(WITH_HESS ? KIN_H_THREADS : 128, WITH_HESS ? KIN_H_MIN_BLOCKS : 3) kino_kin_kernel(const __grid_constant__ KinTopo T,
+__global__ void __launch_bounds__(WITH_HESS ? KIN_H_THREADS : 128, WITH_HESS ? KIN_H_MIN_BLOCKS : 3) kino_kin_kernel(
+    const __grid_constant__ KinTopo T,
                                                        const KinoConst* __restrict__ Cp, unsigned mask,
                                                        const double* __restrict__ x, const double* __restrict__ p,
                                                        long p_stride, const double* __restrict__ lam,
