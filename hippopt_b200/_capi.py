@@ -83,6 +83,14 @@ def lib() -> ctypes.CDLL:
     L.hb_pattern_hess.argtypes = [vp, i64p, i64p]
     L.hb_eval.restype = ctypes.c_int
     L.hb_eval.argtypes = [vp, ctypes.c_uint32, vp, vp, ctypes.c_int64, vp, vp, vp, vp, vp, vp, vp, ctypes.c_int64, vp]
+    L.hb_kino_attach_tables.restype = ctypes.c_int
+    L.hb_kino_attach_tables.argtypes = [vp, i64p, i64p, i64p, i64p, i32p, f64p, i32p, f64p]
+    L.hb_bounds.restype = ctypes.c_int
+    L.hb_bounds.argtypes = [vp, f64p, f64p, f64p]
+    L.hb_save.restype = ctypes.c_int
+    L.hb_save.argtypes = [vp, ctypes.c_char_p]
+    L.hb_load.restype = ctypes.c_int
+    L.hb_load.argtypes = [ctypes.c_char_p, ctypes.POINTER(vp)]
     L.hb_eval_cost_terms.restype = ctypes.c_int
     L.hb_eval_cost_terms.argtypes = [vp, vp, vp, ctypes.c_int64, vp, ctypes.c_int64, vp]
     L.hb_debug_sweep_schedule.restype = ctypes.c_int
@@ -126,7 +134,7 @@ EXPORTED_SYMBOLS = [
     "hb_last_launch_count", "hb_last_error", "hb_probe_fp64_tflops", "hb_profile_enable", "hb_profile_read",
     "hb_host_set_parameters", "hb_eval_host", "hb_host_last_traffic", "hb_host_alloc", "hb_host_free",
     "hb_lu_factor_batched", "hb_lu_solve_batched", "hb_set_option", "hb_interpolate_humanoid_states",
-    "hb_eval_cost_terms", "hb_debug_sweep_schedule",
+    "hb_eval_cost_terms", "hb_debug_sweep_schedule", "hb_kino_attach_tables", "hb_bounds", "hb_save", "hb_load",
 ]
 
 

@@ -49,6 +49,12 @@ struct hb_problem_s {
   double* d_p = nullptr;    // parameters of the current solve
   int64_t p_cap = 0, p_stride = -1, p_batch = 0;
   int64_t h2d_bytes = 0, d2h_bytes = 0;
+  // host copies of what the handle was created from (hb_save) and the tables a non-Python caller needs: CCS
+  // patterns of jac_g / hess_l and the affine description of lbg / ubg (hb_kino_attach_tables)
+  std::vector<int32_t> c_icfg, c_jc, c_jk, c_hc, c_hk, c_hk2, lb_idx, ub_idx;
+  std::vector<int16_t> c_hci;
+  std::vector<double> c_dcfg, lb_val, ub_val;
+  std::vector<int64_t> jac_colind, jac_row, hess_colind, hess_row;
 };
 
 
@@ -374,6 +380,14 @@ extern "C" int hb_kino_create(const int32_t* icfg, const double* dcfg, const int
     T.w_yaw = C.w_yaw;
   }
   const size_t N = C.N;
+  h->c_icfg.assign(icfg, icfg + HB_KI_COUNT);
+  h->c_dcfg.assign(dcfg, dcfg + HB_KD_COUNT);
+  h->c_jc.assign(jc_map, jc_map + N * C.n_jc);
+  h->c_jk.assign(jk_map, jk_map + N * C.n_jk);
+  h->c_hci.assign(hc_index, hc_index + 129 * 129);
+  h->c_hc.assign(hc_map, hc_map + N * C.n_hc);
+  h->c_hk.assign(hk_map, hk_map + N * 27 * 57);
+  h->c_hk2.assign(hk2_map, hk2_map + N * 27);
   cudaError_t e = cudaSuccess;
   if (e == cudaSuccess) e = upload(&h->d_jc, jc_map, N * C.n_jc);
   if (e == cudaSuccess) e = upload(&h->d_jk, jk_map, N * C.n_jk);
@@ -482,14 +496,26 @@ extern "C" int hb_dims(hb_handle h, int64_t* n_x, int64_t* n_p, int64_t* m, int6
 
 extern "C" int hb_pattern_jac(hb_handle h, int64_t* colind, int64_t* row) {
   if (!h || !colind || !row) return fail(HB_ERR_INVALID, "hb_pattern_jac: null argument");
-  if (h->kind != KIND_TOY) return fail(HB_ERR_UNSUPPORTED, "hb_pattern_jac: pattern is owned by the layout compiler");
+  if (h->kind != KIND_TOY) {
+    if (h->jac_row.empty())
+      return fail(HB_ERR_UNSUPPORTED, "hb_pattern_jac: no pattern attached to this handle (hb_kino_attach_tables)");
+    std::copy(h->jac_colind.begin(), h->jac_colind.end(), colind);
+    std::copy(h->jac_row.begin(), h->jac_row.end(), row);
+    return HB_OK;
+  }
   hb::toy_pattern_jac(h->toy, colind, row);
   return HB_OK;
 }
 
 extern "C" int hb_pattern_hess(hb_handle h, int64_t* colind, int64_t* row) {
   if (!h || !colind || !row) return fail(HB_ERR_INVALID, "hb_pattern_hess: null argument");
-  if (h->kind != KIND_TOY) return fail(HB_ERR_UNSUPPORTED, "hb_pattern_hess: pattern is owned by the layout compiler");
+  if (h->kind != KIND_TOY) {
+    if (h->hess_row.empty())
+      return fail(HB_ERR_UNSUPPORTED, "hb_pattern_hess: no pattern attached to this handle (hb_kino_attach_tables)");
+    std::copy(h->hess_colind.begin(), h->hess_colind.end(), colind);
+    std::copy(h->hess_row.begin(), h->hess_row.end(), row);
+    return HB_OK;
+  }
   hb::toy_pattern_hess(h->toy, colind, row);
   return HB_OK;
 }
@@ -873,6 +899,105 @@ extern "C" int hb_probe_fp64_tflops(double* tflops, void* stream) {
   cudaEventDestroy(e1);
   cudaFree(buf);
   *tflops = best;
+  return HB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// tables for callers without the Python layout compiler, and (de)serialisation of a handle
+extern "C" int hb_kino_attach_tables(hb_handle h, const int64_t* jac_colind, const int64_t* jac_row,
+                                     const int64_t* hess_colind, const int64_t* hess_row, const int32_t* lb_idx,
+                                     const double* lb_val, const int32_t* ub_idx, const double* ub_val) {
+  if (!h || h->kind != KIND_KINO) return fail(HB_ERR_INVALID, "hb_kino_attach_tables: kinodynamic / pose-finder handle required");
+  if (!jac_colind || !jac_row || !hess_colind || !hess_row || !lb_idx || !lb_val || !ub_idx || !ub_val)
+    return fail(HB_ERR_INVALID, "hb_kino_attach_tables: null argument");
+  const hb::KinoConst& C = h->host;
+  if (jac_colind[C.n_x] != C.nnz_j || hess_colind[C.n_x] != C.nnz_h)
+    return fail(HB_ERR_INVALID, "hb_kino_attach_tables: colind does not end at nnz");
+  for (int r = 0; r < C.m; ++r)
+    if (lb_idx[r] >= C.n_p || ub_idx[r] >= C.n_p) return fail(HB_ERR_INVALID, "hb_kino_attach_tables: parameter index out of range");
+  h->jac_colind.assign(jac_colind, jac_colind + C.n_x + 1);
+  h->jac_row.assign(jac_row, jac_row + C.nnz_j);
+  h->hess_colind.assign(hess_colind, hess_colind + C.n_x + 1);
+  h->hess_row.assign(hess_row, hess_row + C.nnz_h);
+  h->lb_idx.assign(lb_idx, lb_idx + C.m);
+  h->lb_val.assign(lb_val, lb_val + C.m);
+  h->ub_idx.assign(ub_idx, ub_idx + C.m);
+  h->ub_val.assign(ub_val, ub_val + C.m);
+  return HB_OK;
+}
+
+extern "C" int hb_bounds(hb_handle h, const double* p, double* lbg, double* ubg) {
+  if (!h || !p || !lbg || !ubg) return fail(HB_ERR_INVALID, "hb_bounds: null argument");
+  if (h->kind != KIND_KINO || h->lb_idx.empty())
+    return fail(HB_ERR_UNSUPPORTED, "hb_bounds: no bound table attached to this handle (hb_kino_attach_tables)");
+  for (int r = 0; r < h->host.m; ++r) {
+    lbg[r] = h->lb_idx[r] >= 0 ? h->lb_val[r] * p[h->lb_idx[r]] : h->lb_val[r];
+    ubg[r] = h->ub_idx[r] >= 0 ? h->ub_val[r] * p[h->ub_idx[r]] : h->ub_val[r];
+  }
+  return HB_OK;
+}
+
+namespace {
+const uint64_t HB_BLOB_MAGIC = 0x3130424f4c424248ull;  // "HBBLOB01"
+template <class T>
+bool put_vec(FILE* f, const std::vector<T>& v) {
+  const uint64_t n = v.size();
+  return fwrite(&n, sizeof(n), 1, f) == 1 && (n == 0 || fwrite(v.data(), sizeof(T), n, f) == n);
+}
+template <class T>
+bool get_vec(FILE* f, std::vector<T>& v) {
+  uint64_t n = 0;
+  if (fread(&n, sizeof(n), 1, f) != 1 || n > (1ull << 31)) return false;
+  v.resize(n);
+  return n == 0 || fread(v.data(), sizeof(T), n, f) == n;
+}
+}  // namespace
+
+extern "C" int hb_save(hb_handle h, const char* path) {
+  if (!h || !path) return fail(HB_ERR_INVALID, "hb_save: null argument");
+  if (h->kind != KIND_KINO) return fail(HB_ERR_UNSUPPORTED, "hb_save: kinodynamic / pose-finder handles (the toy OCP has hb_toy_create)");
+  FILE* f = fopen(path, "wb");
+  if (!f) return fail(HB_ERR_INVALID, std::string("hb_save: cannot open ") + path);
+  bool ok = fwrite(&HB_BLOB_MAGIC, sizeof(HB_BLOB_MAGIC), 1, f) == 1;
+  ok = ok && put_vec(f, h->c_icfg) && put_vec(f, h->c_dcfg) && put_vec(f, h->c_jc) && put_vec(f, h->c_jk) &&
+       put_vec(f, h->c_hci) && put_vec(f, h->c_hc) && put_vec(f, h->c_hk) && put_vec(f, h->c_hk2) &&
+       put_vec(f, h->jac_colind) && put_vec(f, h->jac_row) && put_vec(f, h->hess_colind) && put_vec(f, h->hess_row) &&
+       put_vec(f, h->lb_idx) && put_vec(f, h->lb_val) && put_vec(f, h->ub_idx) && put_vec(f, h->ub_val);
+  ok = (fclose(f) == 0) && ok;
+  return ok ? HB_OK : fail(HB_ERR_INVALID, std::string("hb_save: write failed: ") + path);
+}
+
+extern "C" int hb_load(const char* path, hb_handle* out) {
+  if (!path || !out) return fail(HB_ERR_INVALID, "hb_load: null argument");
+  FILE* f = fopen(path, "rb");
+  if (!f) return fail(HB_ERR_INVALID, std::string("hb_load: cannot open ") + path);
+  uint64_t magic = 0;
+  std::vector<int32_t> icfg, jc, jk, hc, hk, hk2, lbi, ubi;
+  std::vector<int16_t> hci;
+  std::vector<double> dcfg, lbv, ubv;
+  std::vector<int64_t> jcol, jrow, hcol, hrow;
+  bool ok = fread(&magic, sizeof(magic), 1, f) == 1 && magic == HB_BLOB_MAGIC;
+  ok = ok && get_vec(f, icfg) && get_vec(f, dcfg) && get_vec(f, jc) && get_vec(f, jk) && get_vec(f, hci) && get_vec(f, hc) &&
+       get_vec(f, hk) && get_vec(f, hk2) && get_vec(f, jcol) && get_vec(f, jrow) && get_vec(f, hcol) && get_vec(f, hrow) &&
+       get_vec(f, lbi) && get_vec(f, lbv) && get_vec(f, ubi) && get_vec(f, ubv);
+  fclose(f);
+  if (!ok || icfg.size() != HB_KI_COUNT || dcfg.size() != HB_KD_COUNT || hci.size() != 129 * 129)
+    return fail(HB_ERR_INVALID, std::string("hb_load: not a hippopt_b200 problem file of this library version: ") + path);
+  const size_t N = (size_t)icfg[HB_KI_HORIZON];
+  if (jc.size() != N * (size_t)icfg[HB_KI_N_JC] || jk.size() != N * (size_t)icfg[HB_KI_N_JK] ||
+      hc.size() != N * (size_t)icfg[HB_KI_N_HC] || hk.size() != N * 27 * 57 || hk2.size() != N * 27)
+    return fail(HB_ERR_INVALID, std::string("hb_load: inconsistent table sizes in ") + path);
+  const int rc = hb_kino_create(icfg.data(), dcfg.data(), jc.data(), jk.data(), hci.data(), hc.data(), hk.data(), hk2.data(), out);
+  if (rc != HB_OK) return rc;
+  if (!jrow.empty()) {
+    const int rc2 = hb_kino_attach_tables(*out, jcol.data(), jrow.data(), hcol.data(), hrow.data(), lbi.data(), lbv.data(),
+                                          ubi.data(), ubv.data());
+    if (rc2 != HB_OK) {
+      hb_destroy(*out);
+      *out = nullptr;
+      return rc2;
+    }
+  }
   return HB_OK;
 }
 

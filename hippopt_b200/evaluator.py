@@ -188,6 +188,38 @@ def _i32(a):
     return np.ascontiguousarray(a, dtype=np.int32)
 
 
+def bound_table(lay, seed: int = 0):
+    """(lb_idx, lb_val, ub_idx, ub_val) with lbg[r] = lb_val[r] * p[lb_idx[r]] if lb_idx[r] >= 0 else lb_val[r].
+
+    Every bound of these planners is a constant or +- one parameter (oracle/kinodynamic.py header: canonical forms of
+    Opti), so the table is recovered from `layout.bounds` itself by evaluating it on two random parameter vectors --
+    no second statement of the bound rules -- and verified on a third."""
+    rng = np.random.default_rng(seed)
+    n_p, m = lay.n_p, lay.m
+    p1, p2, p3 = (rng.uniform(1.0, 2.0, (1, n_p)) * rng.choice([-1.0, 1.0], (1, n_p)) for _ in range(3))
+    out = []
+    for side in (0, 1):
+        b1, b2, b3 = (lay.bounds(p)[side][0] for p in (p1, p2, p3))
+        idx = -np.ones(m, dtype=np.int32)
+        val = b1.copy()
+        moving = np.nonzero(b1 != b2)[0]
+        order = np.argsort(np.abs(p1[0]))
+        sorted_abs = np.abs(p1[0])[order]
+        for r in moving:
+            j = int(np.searchsorted(sorted_abs, abs(b1[r])))
+            cands = [order[q] for q in (j - 1, j, j + 1) if 0 <= q < n_p]
+            hit = [c for c in cands if abs(abs(p1[0, c]) - abs(b1[r])) <= 1e-12 * abs(b1[r])]
+            if len(hit) != 1:
+                raise ValueError(f"bound of row {r} is not +- one parameter")
+            idx[r] = hit[0]
+            val[r] = b1[r] / p1[0, hit[0]]
+        chk = np.where(idx >= 0, val * p3[0, np.maximum(idx, 0)], val)
+        if not np.array_equal(chk, b3) or not np.array_equal(np.where(idx >= 0, val * p2[0, np.maximum(idx, 0)], val), b2):
+            raise ValueError("bounds are not affine in single parameters")
+        out += [idx, np.ascontiguousarray(val, dtype=np.float64)]
+    return tuple(out)
+
+
 class KinoEvaluator(_Evaluator):
     """Evaluator of the humanoid kinodynamic OCP
     (`/root/reference/src/hippopt/turnkey_planners/humanoid_kinodynamic/planner.py:27-176`)."""
@@ -270,6 +302,21 @@ class KinoEvaluator(_Evaluator):
         _capi.check(rc, "hb_kino_create")
         self._read_dims()
         assert (self.n_x, self.n_p, self.m) == (lay.n_x, lay.n_p, lay.m)
+        self._attach_tables(lay)
+
+    def _attach_tables(self, lay):
+        """Patterns and the affine description of lbg / ubg go into the handle, so that hb_pattern_*, hb_bounds and a
+        file written by hb_save serve callers that do not have this layout compiler."""
+        li, lv, ui, uv = bound_table(lay)
+        i64p, i32p, f64p = (ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_double))
+        t = [np.ascontiguousarray(a, dtype=np.int64) for a in (lay.jac_colind, lay.jac_row, lay.hess_colind, lay.hess_row)]
+        rc = _capi.lib().hb_kino_attach_tables(self._h, *(a.ctypes.data_as(i64p) for a in t), li.ctypes.data_as(i32p),
+                                               lv.ctypes.data_as(f64p), ui.ctypes.data_as(i32p), uv.ctypes.data_as(f64p))
+        _capi.check(rc, "hb_kino_attach_tables")
+
+    def save(self, path: str) -> None:
+        """Write the handle to a file a non-Python caller opens with hb_load (include/hippopt_b200.h)."""
+        _capi.check(_capi.lib().hb_save(self._h, path.encode()), "hb_save")
 
     def cost_terms(self, x: torch.Tensor, p: torch.Tensor) -> torch.Tensor:
         """[B, N, HB_COST_TERMS] values of the named cost expressions (hb_eval_cost_terms; names: naming.py)."""

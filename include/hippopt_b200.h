@@ -194,10 +194,27 @@ int hb_destroy(hb_handle h);
 int hb_dims(hb_handle h, int64_t* n_x, int64_t* n_p, int64_t* m, int64_t* nnz_j, int64_t* nnz_h);
 
 /* Sparsity of jac_g (m x n_x) and hess_l (n_x x n_x, upper triangle) in compressed-column form,
- * written to HOST arrays colind[n_x+1], row[nnz].  Only available for problems whose layout lives in
- * the library (toy OCP); the kinodynamic pattern is owned by the layout compiler. */
+ * written to HOST arrays colind[n_x+1], row[nnz].  replaces: Function.sparsity_out() of nlp_jac_g / nlp_hess_l [ext].
+ * The toy OCP's layout lives in the library; kinodynamic / pose-finder handles answer once their tables are
+ * attached (hb_kino_attach_tables: done by hippopt_b200.evaluator at creation, or restored by hb_load). */
 int hb_pattern_jac(hb_handle h, int64_t* colind, int64_t* row);
 int hb_pattern_hess(hb_handle h, int64_t* colind, int64_t* row);
+
+/* Tables a caller without the Python layout compiler needs, copied into the handle (HOST pointers):
+ *   CCS patterns of jac_g / hess_l, and lbg / ubg as an affine function of ONE parameter per row:
+ *   lbg[r] = lb_idx[r] >= 0 ? lb_val[r] * p[lb_idx[r]] : lb_val[r]   (same for ubg; +-inf as IEEE infinities)
+ * replaces: opti.lbg / opti.ubg evaluated at the parameter values (opti_solver.py:616-619). */
+int hb_kino_attach_tables(hb_handle h, const int64_t* jac_colind, const int64_t* jac_row, const int64_t* hess_colind,
+                          const int64_t* hess_row, const int32_t* lb_idx, const double* lb_val, const int32_t* ub_idx,
+                          const double* ub_val);
+/* lbg[m], ubg[m] (HOST) for one parameter vector p[n_p] (HOST) */
+int hb_bounds(hb_handle h, const double* p, double* lbg, double* ubg);
+
+/* Serialise a kinodynamic / pose-finder handle (configuration tables, scatter maps, attached tables) to a file and
+ * create a handle from such a file: a C / C++ / Go caller links the library, calls hb_load on a file written once by
+ * the Python layout compiler for its (robot, settings, horizon), and never needs Python at run time. */
+int hb_save(hb_handle h, const char* path);
+int hb_load(const char* path, hb_handle* out);
 
 /* Evaluate the requested NLP functions for `batch` independent instances.
  *   x      device [batch*n_x]          decision vectors

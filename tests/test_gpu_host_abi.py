@@ -3,6 +3,7 @@
 Checked against the device-pointer form hb_eval, which the parity tests pin to the oracle: the host
 pipeline only moves bytes, so its results must be bit-identical whatever the chunking."""
 import ctypes
+import os
 
 import numpy as np
 import pytest
@@ -92,3 +93,41 @@ def test_host_abi_errors_and_pinned_allocator(model, built_library):
     assert np.array_equal(f, ref["f"])
     _capi.check(L.hb_host_free(ptr), "hb_host_free")
     assert L.hb_host_alloc(None, 8) != 0 and L.hb_host_alloc(ctypes.byref(ptr), 0) != 0
+
+
+def test_c_client_without_python(model, built_library, tmp_path):
+    """(b) C-ABI completeness: a plain C program links libhippopt_b200.so, opens a problem file written by hb_save and
+    gets dimensions, CCS patterns, bounds and all five evaluations without any Python-side layout code."""
+    import shutil
+    import subprocess
+
+    from hippopt_b200.evaluator import ALL, KinoEvaluator
+    from hippopt_b200.kino_layout import KinoSettings
+    from hippopt_b200.workloads import kino_batch
+
+    if shutil.which("gcc") is None:
+        pytest.skip("no C compiler on this box")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    ev = KinoEvaluator(model, KinoSettings(horizon=4, final_state_constraint=True))
+    lay = ev.layout
+    x, p, lam, sigma = kino_batch(lay, model, 1, seed=12, noise=0.1)
+    blob, vec, exe = (str(tmp_path / n) for n in ("problem.bin", "vectors.bin", "client"))
+    ev.save(blob)
+    np.concatenate([x[0], p[0], lam[0], sigma]).astype(np.float64).tofile(vec)
+    libdir = os.path.join(root, "hippopt_b200")
+    subprocess.run(["gcc", "-O1", "-I", os.path.join(root, "include"), os.path.join(root, "tests", "c_client", "client.c"),
+                    "-o", exe, "-L", libdir, "-l:libhippopt_b200.so", f"-Wl,-rpath,{libdir}"], check=True)
+    r = subprocess.run([exe, blob, vec], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    got = {ln.split()[0]: ln.split()[1:] for ln in r.stdout.splitlines()}
+    assert [int(v) for v in got["dims"]] == [ev.n_x, ev.n_p, ev.m, ev.nnz_j, ev.nnz_h]
+    assert [int(v) for v in got["pattern"]] == [lay.jac_colind[-1], lay.jac_row[-1], lay.hess_colind[-1], lay.hess_row[-1]]
+    lb, ub = lay.bounds(p)
+    assert int(got["bounds"][0]) == int((lb[0] == ub[0]).sum())
+    assert float(got["bounds"][1]) == pytest.approx(lb[0][np.isfinite(lb[0])].sum(), rel=1e-14)
+    assert float(got["bounds"][2]) == pytest.approx(ub[0][np.isfinite(ub[0])].sum(), rel=1e-14)
+    out = {k: v.cpu().numpy()[0] for k, v in ev.eval(ALL, *(torch.tensor(a, device="cuda:0") for a in (x, p, lam, sigma))).items()}
+    want = [float(out["f"]), float((out["grad_f"] * (np.arange(ev.n_x) % 11 + 1)).sum()),
+            float((out["g"] * (np.arange(ev.m) % 7 + 1)).sum()), float((out["jac"] * (lay.jac_row % 5 + 1)).sum()),
+            float((out["hess"] * (lay.hess_row % 3 + 1)).sum())]
+    assert [float(v) for v in got["values"]] == pytest.approx(want, rel=1e-12)
