@@ -69,6 +69,7 @@ def lib() -> ctypes.CDLL:
     L = ctypes.CDLL(LIB_PATH)
     vp, i32p, i16p, f64p, i64p = (ctypes.c_void_p, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int16),
                                   ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int64))
+    i64 = ctypes.c_int64
     L.hb_kino_create.restype = ctypes.c_int
     L.hb_kino_create.argtypes = [i32p, f64p, i32p, i32p, i16p, i32p, i32p, i32p, ctypes.POINTER(vp)]
     L.hb_toy_create.restype = ctypes.c_int
@@ -91,6 +92,8 @@ def lib() -> ctypes.CDLL:
     L.hb_save.argtypes = [vp, ctypes.c_char_p]
     L.hb_load.restype = ctypes.c_int
     L.hb_load.argtypes = [ctypes.c_char_p, ctypes.POINTER(vp)]
+    L.hb_ccs_group_mul.restype = ctypes.c_int
+    L.hb_ccs_group_mul.argtypes = [vp, vp, vp, vp, vp, vp, vp, i64, i64, i64, i64, vp]
     L.hb_eval_cost_terms.restype = ctypes.c_int
     L.hb_eval_cost_terms.argtypes = [vp, vp, vp, ctypes.c_int64, vp, ctypes.c_int64, vp]
     L.hb_debug_sweep_schedule.restype = ctypes.c_int
@@ -135,6 +138,7 @@ EXPORTED_SYMBOLS = [
     "hb_host_set_parameters", "hb_eval_host", "hb_host_last_traffic", "hb_host_alloc", "hb_host_free",
     "hb_lu_factor_batched", "hb_lu_solve_batched", "hb_set_option", "hb_interpolate_humanoid_states",
     "hb_eval_cost_terms", "hb_debug_sweep_schedule", "hb_kino_attach_tables", "hb_bounds", "hb_save", "hb_load",
+    "hb_ccs_group_mul",
 ]
 
 

@@ -791,6 +791,18 @@ extern "C" int hb_lu_solve_batched(const double* LU, const int32_t* piv, double*
   return HB_OK;
 }
 
+extern "C" int hb_ccs_group_mul(const double* vals, const int32_t* ptr, const int32_t* entry, const int32_t* idx,
+                                const double* w, const double* x, double* y, int64_t n_out, int64_t n_in, int64_t nnz,
+                                int64_t batch, void* stream) {
+  if (!vals || !ptr || !entry || !idx || !x || !y) return fail(HB_ERR_INVALID, "hb_ccs_group_mul: null argument");
+  if (n_out <= 0 || n_in <= 0 || nnz < 0 || batch <= 0) return fail(HB_ERR_INVALID, "hb_ccs_group_mul: bad sizes");
+  const long total = (long)batch * n_out;
+  hb::ccs_group_mul_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      vals, ptr, entry, idx, w, x, y, (int)n_out, (int)n_in, (long)nnz, (long)batch);
+  CUDA_TRY(cudaGetLastError());
+  return HB_OK;
+}
+
 extern "C" int hb_interpolate_humanoid_states(int64_t batch, int64_t n_points, int64_t n_joints, const double* initial,
                                               const double* final_, const int32_t* schedule,
                                               const double* phases_left, int64_t n_phases_left, int64_t stride_left,

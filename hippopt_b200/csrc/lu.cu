@@ -437,3 +437,28 @@ __global__ void __launch_bounds__(LU_THREADS, HB_LU_SOLVE_MIN_BLOCKS) lu_solve_k
 }
 
 }  // namespace hb
+
+// ---------------------------------------------------------------------------------------------------------------
+// Sparse products with the CCS value arrays of jac_g / hess_l for the interior-point driver (ipsolver.SparseOps):
+//   y[b][o] = sum_{q = ptr[o]}^{ptr[o+1]-1} w[q] * vals[b][entry[q]] * x[b][idx[q]]
+// One thread per (instance, output element) walks its entries in a fixed order: no atomics, so every residual of
+// the solver is reproducible run to run (the index_add_ formulation was not: VERDICT round 1).
+namespace hb {
+__global__ void ccs_group_mul_kernel(const double* __restrict__ vals, const int* __restrict__ ptr,
+                                     const int* __restrict__ entry, const int* __restrict__ idx,
+                                     const double* __restrict__ w, const double* __restrict__ x, double* __restrict__ y,
+                                     int n_out, int n_in, long nnz, long batch) {
+  const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= batch * n_out) return;
+  const long b = t / n_out;
+  const int o = (int)(t % n_out);
+  const double* vb = vals + b * nnz;
+  const double* xb = x + b * n_in;
+  double acc = 0.0;
+  for (int q = ptr[o]; q < ptr[o + 1]; ++q) {
+    const double v = vb[entry[q]] * xb[idx[q]];
+    acc += w ? w[q] * v : v;
+  }
+  y[t] = acc;
+}
+}  // namespace hb

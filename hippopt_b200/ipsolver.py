@@ -56,27 +56,67 @@ class BatchedOutput:
 
 class SparseOps:
     """Products with jac_g / hess_l straight from the CCS value arrays the kernels write (one pattern shared by
-    all instances).  `index_add_` accumulates with atomics on CUDA: sums are reproducible to rounding only."""
+    all instances).  On a CUDA device they run through `hb_ccs_group_mul` (one thread per output element, fixed
+    summation order: bit-reproducible); on the CPU (tests with a torch stand-in evaluator) through `index_add_`,
+    which is sequential there."""
 
     def __init__(self, n_x, m, jac_sparsity, hess_sparsity, device):
         colind, row = jac_sparsity
         self.n, self.m = n_x, m
-        self.jr = torch.as_tensor(np.asarray(row), dtype=torch.long, device=device)
-        self.jc = torch.as_tensor(np.repeat(np.arange(n_x), np.diff(np.asarray(colind))), dtype=torch.long, device=device)
+        row, colind = np.asarray(row), np.asarray(colind)
+        col = np.repeat(np.arange(n_x), np.diff(colind))
+        self.jr = torch.as_tensor(row, dtype=torch.long, device=device)
+        self.jc = torch.as_tensor(col, dtype=torch.long, device=device)
         hcolind, hrow = hess_sparsity
-        self.hr = torch.as_tensor(np.asarray(hrow), dtype=torch.long, device=device)
-        self.hc = torch.as_tensor(np.repeat(np.arange(n_x), np.diff(np.asarray(hcolind))), dtype=torch.long, device=device)
+        hrow = np.asarray(hrow)
+        hcol = np.repeat(np.arange(n_x), np.diff(np.asarray(hcolind)))
+        self.hr = torch.as_tensor(hrow, dtype=torch.long, device=device)
+        self.hc = torch.as_tensor(hcol, dtype=torch.long, device=device)
         self.hw = torch.where(self.hr == self.hc, 1.0, 2.0).to(torch.float64)  # upper triangle stored once
+        self.native = torch.device(device).type == "cuda"
+        if self.native:
+            def group(keys, n_out, entry, idx):
+                order = np.argsort(keys, kind="stable")
+                ptr = np.concatenate([[0], np.cumsum(np.bincount(keys, minlength=n_out))])
+                i32 = lambda a: torch.as_tensor(np.ascontiguousarray(a, dtype=np.int32), device=device)  # noqa: E731
+                return i32(ptr), i32(entry[order]), i32(idx[order])
+
+            e = np.arange(len(row))
+            self._by_row = group(row, m, e, col)          # J x
+            self._by_col = group(col, n_x, e, row)        # J^T lam
+            eh = np.arange(len(hrow))
+            off = hrow != hcol                            # H x over the mirrored upper triangle
+            self._hess = group(np.concatenate([hrow, hcol[off]]), n_x, np.concatenate([eh, eh[off]]),
+                               np.concatenate([hcol, hrow[off]]))
+
+    def _mul(self, tables, vals, x, n_out):
+        from . import _capi
+
+        vals, x = vals.contiguous(), x.contiguous()
+        out = torch.empty((vals.shape[0], n_out), dtype=torch.float64, device=vals.device)
+        ptr, entry, idx = tables
+        stream = torch.cuda.current_stream(vals.device).cuda_stream
+        vp = lambda t: __import__("ctypes").c_void_p(t.data_ptr())  # noqa: E731
+        _capi.check(_capi.lib().hb_ccs_group_mul(vp(vals), vp(ptr), vp(entry), vp(idx), None, vp(x), vp(out), n_out,
+                                                 x.shape[1], vals.shape[1], vals.shape[0],
+                                                 __import__("ctypes").c_void_p(stream)), "hb_ccs_group_mul")
+        return out
 
     def J_mul(self, vals, x):
+        if self.native:
+            return self._mul(self._by_row, vals, x, self.m)
         out = torch.zeros((vals.shape[0], self.m), dtype=vals.dtype, device=vals.device)
         return out.index_add_(1, self.jr, vals * x[:, self.jc])
 
     def Jt_mul(self, vals, lam):
+        if self.native:
+            return self._mul(self._by_col, vals, lam, self.n)
         out = torch.zeros((vals.shape[0], self.n), dtype=vals.dtype, device=vals.device)
         return out.index_add_(1, self.jc, vals * lam[:, self.jr])
 
     def W_quad(self, hvals, x):
+        if self.native:
+            return (self._mul(self._hess, hvals, x, self.n) * x).sum(dim=1)
         return (hvals * x[:, self.hr] * x[:, self.hc] * self.hw).sum(dim=1)
 
     def dense_jac(self, vals):

@@ -306,6 +306,14 @@ int hb_lu_factor_batched(double* A, int32_t* piv, int32_t* info, int64_t n, int6
 int hb_lu_solve_batched(const double* LU, const int32_t* piv, double* Bm, int64_t n, int64_t nrhs, int64_t batch,
                         void* stream);
 
+/* Deterministic sparse products with the CCS value arrays the evaluation kernels write, for solvers that keep their
+ * iterates on the device (hippopt_b200.ipsolver): y[b][o] = sum_{q in [ptr[o], ptr[o+1])} w[q] vals[b][entry[q]] x[b][idx[q]]
+ * (w may be NULL = 1).  With (ptr, entry, idx) grouped by row this is jac_g x, by column jac_g^T lam, by row over the
+ * mirrored upper triangle hess_l x.  One thread per output element, fixed summation order (no atomics).
+ * replaces: the sparse products inside IPOPT's residual and step computations [ext]. */
+int hb_ccs_group_mul(const double* vals, const int32_t* ptr, const int32_t* entry, const int32_t* idx, const double* w,
+                     const double* x, double* y, int64_t n_out, int64_t n_in, int64_t nnz, int64_t batch, void* stream);
+
 /* Initial guesses / reference trajectories on the device.
  * replaces: humanoid_state_interpolator (robot_planning/utilities/interpolators.py:396-448) with its callees
  * linear_interpolator (:24-50), quaternion_slerp (:53-77), transform_interpolator (:80-103),

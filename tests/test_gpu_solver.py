@@ -141,6 +141,36 @@ def test_standing_ocp_solves_with_the_stage_kkt(model, built_library, periodic):
     gs = ev.eval(G, res.values, P)["g"].cpu().numpy()[ok]
     assert (np.maximum(lbk[ok] - gs, 0) + np.maximum(gs - ubk[ok], 0)).max() < 1e-5
     assert torch.isfinite(res.cost_value[res.success]).all()
+    # run to run: every product with jac_g / hess_l has a fixed summation order (hb_ccs_group_mul) and the kernels
+    # write every output slot once, so a second solve reproduces the first bit for bit
+    again = BatchedInteriorPoint(ev, tol=1e-6, max_iter=300, kkt="stage", delta_c=1e-9, mu_init=1e-3).solve(
+        torch.tensor(x0, device=dev), P, lbk, ubk)
+    assert torch.equal(again.iterations, res.iterations) and torch.equal(again.values, res.values)
+    assert torch.equal(again.constraint_multipliers, res.constraint_multipliers)
+
+
+def test_sparse_products_match_dense(model, built_library):
+    """hb_ccs_group_mul (J x, J^T lam, x^T H x) against dense matrices built from the same CCS arrays."""
+    from hippopt_b200.evaluator import ALL, KinoEvaluator
+    from hippopt_b200.ipsolver import SparseOps
+    from hippopt_b200.kino_layout import KinoSettings
+    from hippopt_b200.workloads import kino_batch
+
+    dev = torch.device("cuda:0")
+    ev = KinoEvaluator(model, KinoSettings(horizon=3, final_state_constraint=True, periodicity_constraint=True))
+    x, p, lam, sigma = kino_batch(ev.layout, model, 3, seed=6, noise=0.1)
+    out = ev.eval(ALL, *(torch.tensor(a, device=dev) for a in (x, p, lam, sigma)))
+    ops = SparseOps(ev.n_x, ev.m, ev.jac_sparsity(), ev.hess_sparsity(), dev)
+    assert ops.native
+    J, Hm = ops.dense_jac(out["jac"]), ops.dense_hess(out["hess"])
+    g = torch.Generator().manual_seed(1)
+    v = torch.randn((3, ev.n_x), generator=g, dtype=torch.float64).to(dev)
+    w = torch.randn((3, ev.m), generator=g, dtype=torch.float64).to(dev)
+    assert torch.allclose(ops.J_mul(out["jac"], v), torch.bmm(J, v[:, :, None])[:, :, 0], rtol=1e-12, atol=1e-12)
+    assert torch.allclose(ops.Jt_mul(out["jac"], w), torch.bmm(J.transpose(1, 2), w[:, :, None])[:, :, 0], rtol=1e-12, atol=1e-12)
+    q = (v * torch.bmm(Hm, v[:, :, None])[:, :, 0]).sum(1)
+    assert torch.allclose(ops.W_quad(out["hess"], v), q, rtol=1e-12)
+    assert torch.equal(ops.J_mul(out["jac"], v), ops.J_mul(out["jac"], v))
 
 
 def test_b200solver_behind_the_optimization_solver_interface(model, built_library):
