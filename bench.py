@@ -30,6 +30,7 @@ INSTANCES_PER_GPU = 1024
 METRIC = "knot_evals_per_s"
 UNIT = "knot-evals/s (f+grad_f+g+jac_g+hess_l)"
 WORKLOAD = "humanoid_kinodynamic single step flat ground (BASELINE config 3), horizon 30, 1024 instances per GPU"
+PLANS_PER_GPU = 512  # BASELINE config 4: 4096 instances sharded over 8 GPUs
 REFERENCE_BUDGET_S = 150.0  # wall-clock budget of the reference arm's timed + warm-up steps
 
 
@@ -171,6 +172,48 @@ def sharded_solves(model, ev, dev, rank, world):
         err = f"{type(exc).__name__}: {exc}"
     else:
         err = None
+    # ---- BASELINE config 4 AS POSED: periodic walking step plans, 4096 / 8 = 512 instances per GPU, built like
+    # main_periodic_step.py:365-478 (keyframe poses by the pose finder, interpolated guess with the reference's planned
+    # force of 100 N per point, mass-normalised as the planner does) and solved with the options the reference hands
+    # to IPOPT (:111-134), hessian_approximation = limited-memory included
+    plan = torch.zeros(6, dtype=torch.float64, device=dev)
+    perr = None
+    try:
+        from hippopt_b200.evaluator import KinoEvaluator
+        from hippopt_b200.initial_guess import periodic_step_guess
+        from hippopt_b200.kino_layout import KinoSettings
+
+        n_plans = PLANS_PER_GPU
+        ev4 = KinoEvaluator(model, KinoSettings(horizon=HORIZON, final_state_constraint=True, periodicity_constraint=True))
+        Ls = np.random.default_rng(5 + rank).uniform(0.1, 0.3, n_plans)
+        torch.cuda.synchronize(dev)
+        tg = time.perf_counter()
+        gs = periodic_step_guess(model, pev, ev4, Ls, force_z=100.0, mass_normalised=True)
+        torch.cuda.synchronize(dev)
+        t_setup = time.perf_counter() - tg
+        lb4, ub4 = ev4.layout.bounds(gs.parameters)
+        ref_opts = {"tol": 1e-3, "dual_inf_tol": 1000.0, "compl_inf_tol": 1e-2, "constr_viol_tol": 1e-4,
+                    "acceptable_tol": 10, "acceptable_iter": 2, "acceptable_compl_inf_tol": 1000.0,
+                    "acceptable_obj_change_tol": 1e0, "nlp_scaling_method": "gradient-based", "max_iter": 400,
+                    "hessian_approximation": "limited-memory"}
+        ip4 = BatchedInteriorPoint(ev4, kkt="stage", delta_c=1e-9, mu_init=1e-1, ipopt_options=ref_opts)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+        tp = time.perf_counter()
+        r4 = ip4.solve(gs.x0, torch.tensor(gs.parameters, device=dev), lb4, ub4)
+        x4 = r4.values.cpu()
+        torch.cuda.synchronize(dev)
+        t_plan = time.perf_counter() - tp
+        g4 = ev4.eval(4, r4.values, torch.tensor(gs.parameters, device=dev))["g"].cpu().numpy()
+        okk = r4.success.cpu().numpy()
+        viol = float((np.maximum(lb4 - g4, 0) + np.maximum(g4 - ub4, 0))[okk].max()) if okk.any() else float("nan")
+        plan = torch.tensor([float(n_plans), float(okk.sum()), t_plan, float(r4.iterations[r4.success].median()) if okk.any()
+                             else -1.0, viol, t_setup], dtype=torch.float64, device=dev)
+        del ev4, x4
+    except Exception as exc:  # noqa: BLE001
+        perr = f"{type(exc).__name__}: {exc}"
+    mine = torch.cat([mine, plan])
     if world > 1:
         allr = torch.empty((world, mine.numel()), dtype=torch.float64, device=dev)
         dist.all_gather_into_tensor(allr, mine[None].contiguous())
@@ -178,7 +221,16 @@ def sharded_solves(model, ev, dev, rank, world):
         allr = mine[None]
     a = allr.cpu().numpy()
     conv, slow = float(a[:, 1].sum()), float(a[:, 2].max())
-    return {"workload": f"keep-standing OCPs at the bench size (horizon {HORIZON}, n_x {lay.n_x}, m {lay.m}), one wave of "
+    pconv, pslow = float(a[:, 9].sum()), float(a[:, 10].max())
+    periodic = {"workload": f"BASELINE config 4 as posed: periodic walking step plans (step length U(0.1, 0.3) m, horizon {HORIZON}, "
+                            f"final-state and periodicity rows), {PLANS_PER_GPU} per GPU, the reference's guess (100 N per point, "
+                            f"mass-normalised) and IPOPT options (limited-memory Hessian, tol 1e-3, acceptable_tol 10)",
+                "n_gpus": world, "instances": int(a[:, 8].sum()), "converged": int(pconv),
+                "seconds_max_over_ranks": pslow, "solves_per_s": pconv / pslow if pslow > 0 else 0.0,
+                "iterations_median_per_rank": [float(r[11]) for r in a],
+                "constraint_violation_max": float(np.nanmax(a[:, 12])) if np.isfinite(a[:, 12]).any() else None,
+                "setup_seconds_max_over_ranks": float(a[:, 13].max()), "error": perr}
+    return {"periodic_step_plans": periodic, "workload": f"keep-standing OCPs at the bench size (horizon {HORIZON}, n_x {lay.n_x}, m {lay.m}), one wave of "
                         f"instances per GPU, stage-wise KKT on the batched LU kernels; host guess in, host solution out",
             "n_gpus": world, "instances": int(a[:, 0].sum()), "converged": int(conv), "seconds_max_over_ranks": slow,
             "solves_per_s": conv / slow if slow > 0 else 0.0, "per_rank_solves_per_s": [float(r[1] / r[2]) for r in a],
@@ -525,32 +577,6 @@ def main():
                     "workload": f"{n_s} plans of config 4's structure: contact phases, {3 * n_s} keyframe pose solves, guess "
                                 f"interpolated on the device into the decision vectors, parameters",
                     "instances": n_s, "keyframe_triples_converged": int(gs.ok.sum()), "setups_per_s": n_s / t_set}
-                # rows f3 + f1 + f2 on a plan with contact switches: 32 of those plans (planned force g/8 instead of
-                # the reference's 100) solved with the termination / scaling options the
-                # reference hands to IPOPT (main_periodic_step.py:111-134) -- loose on purpose: acceptable_tol = 10
-                n_p = 32
-                g2 = periodic_step_guess(model, pev, pev4, Ls[:n_p], force_z=9.80665 / 8.0)
-                lb4, ub4 = pev4.layout.bounds(g2.parameters)
-                ref_opts = {"tol": 1e-3, "dual_inf_tol": 1000.0, "compl_inf_tol": 1e-2, "constr_viol_tol": 1e-4,
-                            "acceptable_tol": 10, "acceptable_iter": 2, "acceptable_compl_inf_tol": 1000.0,
-                            "acceptable_obj_change_tol": 1e0, "nlp_scaling_method": "gradient-based", "max_iter": 200}
-                ip4 = BatchedInteriorPoint(pev4, kkt="stage", delta_c=1e-9, mu_init=1e-1, ipopt_options=ref_opts)
-                torch.cuda.synchronize(dev)
-                ts = time.perf_counter()
-                try:
-                    r4 = ip4.solve(g2.x0, torch.tensor(g2.parameters, device=dev), lb4, ub4)
-                    n4, a4 = int(r4.success.sum()), int(r4.acceptable.sum())
-                    it4 = int(r4.iterations[r4.success].median()) if n4 else None
-                except Exception as exc:  # noqa: BLE001 -- OptiFailure: nothing converged
-                    n4, a4, it4 = 0, 0, None
-                    solves["periodic_step_ocp_error"] = f"{type(exc).__name__}: {exc}"
-                torch.cuda.synchronize(dev)
-                t4 = time.perf_counter() - ts
-                solves["periodic_step_ocp"] = {
-                    "workload": f"{n_p} periodic-step plans (step length 0.1-0.3 m, horizon {HORIZON}, final-state and "
-                                f"periodicity rows), the reference's IPOPT termination options, <= 200 iterations",
-                    "instances": n_p, "converged": n4, "at_acceptable_level": a4, "iterations_median": it4,
-                    "seconds": t4, "plans_per_s": n4 / t4}
             except Exception as exc:  # noqa: BLE001
                 solves["periodic_step_setup"] = {"error": f"{type(exc).__name__}: {exc}"}
         except Exception as exc:  # noqa: BLE001 -- a solver failure must not cost the throughput line

@@ -104,9 +104,13 @@ class PeriodicStepGuess:
 
 
 def periodic_step_guess(model, pose_evaluator, kino_evaluator, step_length: np.ndarray, tol: float = 1e-8,
-                        max_iter: int = 300, force_z: float = 100.0) -> PeriodicStepGuess:
+                        max_iter: int = 300, force_z: float = 100.0, mass_normalised: bool = False) -> PeriodicStepGuess:
     """main_periodic_step.py:365-478 for a batch of step lengths (see the module docstring).  force_z: the planned
-    contact force of the phases (100 in the reference, although the planner's forces are divided by the mass)."""
+    contact force of the phases, 100 N per point in the reference's main.  The planner divides every force of the
+    guess by the robot's mass before it reaches the NLP (`planner.py:932-980`, `_apply_mass_regularization`, called
+    from `set_initial_guess`): mass_normalised=True does the same, so that force_z = 100 IS the reference's guess."""
+    if mass_normalised:
+        force_z = force_z / float(model.total_mass())
     lay, pl = kino_evaluator.layout, pose_evaluator.layout
     N, po = lay.N, lay.po
     L = np.asarray(step_length, dtype=np.float64).reshape(-1)

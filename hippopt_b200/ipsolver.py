@@ -151,11 +151,88 @@ class DenseKKT:
         if mE and delta_c:
             K[:, n:, n:] = -delta_c * torch.eye(mE, dtype=K.dtype, device=K.device)
         self.K = K
+        multi = rhs_x.dim() == 3  # (B, n, R) right-hand sides: the low-rank (L-BFGS) correction rides along
         rhs = torch.cat([rhs_x, rhs_E], dim=1)
         # a singular instance gets NaN (-> larger shift for THAT instance); the others keep their solution
-        sol, info = torch.linalg.solve_ex(K, rhs)
-        sol = torch.where((info != 0)[:, None], torch.full_like(sol, float("nan")), sol)
+        sol, info = torch.linalg.solve_ex(K, rhs if multi else rhs[:, :, None])
+        sol = torch.where((info != 0)[:, None, None], torch.full_like(sol, float("nan")), sol)
+        if not multi:
+            sol = sol[:, :, 0]
         return sol[:, :n], sol[:, n:]
+
+
+class LimitedMemory:
+    """IPOPT's `hessian_approximation = limited-memory` (the setting of every kinodynamic main of the reference,
+    e.g. main_periodic_step.py:116): the Hessian of the Lagrangian is replaced by an L-BFGS matrix in compact form
+    (Byrd, Nocedal, Schnabel 1994), B = sigma I - U M^-1 U^T with U = [sigma S, Y],
+    M = [[sigma S^T S, L], [L^T, -D]], L / D the strictly lower / diagonal part of S^T Y, one memory per instance.
+    The KKT matrix is then K0 - [U; 0] M^-1 [U; 0]^T with a DIAGONAL Hessian block in K0, and the step comes from
+    one sweep with 1 + 2k right-hand sides (Sherman-Morrison-Woodbury).  Pairs with s^T y <= sqrt(eps) |s| |y| are
+    skipped (IPOPT's limited_memory_update_type = bfgs); sigma = s^T y / s^T s of the newest pair
+    (limited_memory_initialization = scalar1)."""
+
+    def __init__(self, B, n, k, device):
+        self.k = k
+        self.S = torch.zeros((B, n, k), dtype=torch.float64, device=device)
+        self.Y = torch.zeros((B, n, k), dtype=torch.float64, device=device)
+        self.sigma = torch.ones(B, dtype=torch.float64, device=device)
+        self.count = torch.zeros(B, dtype=torch.long, device=device)
+        self.skipped = torch.zeros(B, dtype=torch.long, device=device)
+
+    def update(self, active, s, y):
+        sy, ss, yy = (s * y).sum(1), (s * s).sum(1), (y * y).sum(1)
+        ok = active & (ss > 0) & (sy > 1.4901161193847656e-08 * torch.sqrt(ss * yy))
+        self.skipped = torch.where(active & ~ok, self.skipped + 1, torch.where(ok, torch.zeros_like(self.skipped), self.skipped))
+        # IPOPT resets the memory after limited_memory_max_skipping = 2 consecutive skips
+        reset = self.skipped >= 2
+        self.S = torch.where(reset[:, None, None], torch.zeros_like(self.S), self.S)
+        self.Y = torch.where(reset[:, None, None], torch.zeros_like(self.Y), self.Y)
+        self.count = torch.where(reset, torch.zeros_like(self.count), self.count)
+        self.sigma = torch.where(reset, torch.ones_like(self.sigma), self.sigma)
+        self.skipped = torch.where(reset, torch.zeros_like(self.skipped), self.skipped)
+        S_new = torch.cat([self.S[:, :, 1:], s[:, :, None]], dim=2)
+        Y_new = torch.cat([self.Y[:, :, 1:], y[:, :, None]], dim=2)
+        self.S = torch.where(ok[:, None, None], S_new, self.S)
+        self.Y = torch.where(ok[:, None, None], Y_new, self.Y)
+        self.count = torch.where(ok, torch.clamp(self.count + 1, max=self.k), self.count)
+        self.sigma = torch.where(ok, sy / torch.clamp(ss, min=1e-300), self.sigma)
+
+    def matrices(self, idx):
+        """sigma (b,), U (b, n, 2k), M (b, 2k, 2k) of the instances idx; unused pairs are zero columns with +-1 on M's
+        diagonal."""
+        S, Y, sg, k = self.S[idx], self.Y[idx], self.sigma[idx], self.k
+        U = torch.cat([sg[:, None, None] * S, Y], dim=2)
+        StY = torch.bmm(S.transpose(1, 2), Y)
+        L = torch.tril(StY, diagonal=-1)
+        D = torch.diagonal(StY, dim1=1, dim2=2)
+        M = torch.zeros((S.shape[0], 2 * k, 2 * k), dtype=S.dtype, device=S.device)
+        M[:, :k, :k] = sg[:, None, None] * torch.bmm(S.transpose(1, 2), S)
+        M[:, :k, k:] = L
+        M[:, k:, :k] = L.transpose(1, 2)
+        M[:, k:, k:] = -torch.diag_embed(D)
+        used = torch.arange(k, device=S.device)[None, :] >= (k - self.count[idx])[:, None]  # newest pairs sit at the end
+        pad = torch.cat([(~used).to(S.dtype), -(~used).to(S.dtype)], dim=1)
+        M = M + torch.diag_embed(pad)
+        return sg, U, M
+
+    def apply(self, idx, v):
+        """B v for the instances idx."""
+        sg, U, M = self.matrices(idx)
+        t = torch.linalg.solve(M, torch.bmm(U.transpose(1, 2), v[:, :, None]))
+        return sg[:, None] * v - torch.bmm(U, t)[:, :, 0]
+
+    def kkt_solve(self, backend, idx, zero_h, jv, Sig, delta, dc, rhs_x, rhs_E):
+        sg, U, M = self.matrices(idx)
+        R = U.shape[2]
+        RX = torch.cat([rhs_x[:, :, None], U], dim=2)
+        RE = torch.cat([rhs_E[:, :, None], torch.zeros((rhs_E.shape[0], rhs_E.shape[1], R), dtype=U.dtype, device=U.device)], dim=2)
+        ZX, ZE = backend.solve(zero_h, jv, Sig, sg + delta, dc, RX, RE)
+        G = M - torch.bmm(U.transpose(1, 2), ZX[:, :, 1:])
+        w, info = torch.linalg.solve_ex(G, torch.bmm(U.transpose(1, 2), ZX[:, :, :1]))
+        w = torch.where((info != 0)[:, None, None], torch.full_like(w, float("nan")), w)
+        dx = ZX[:, :, 0] + torch.bmm(ZX[:, :, 1:], w)[:, :, 0]
+        dl = ZE[:, :, 0] + torch.bmm(ZE[:, :, 1:], w)[:, :, 0]
+        return dx, dl
 
 
 class BatchedInteriorPoint:
@@ -202,6 +279,9 @@ class BatchedInteriorPoint:
         self.ws_mult_push = float(o.get("warm_start_mult_bound_push", 1e-3))
         if "mu_init" in o:
             mu_init = float(o["mu_init"])
+        # hessian_approximation = limited-memory (main_periodic_step.py:116): L-BFGS instead of hess_l
+        self.limited_memory = str(o.get("hessian_approximation", "exact")) == "limited-memory"
+        self.lm_history = int(o.get("limited_memory_max_history", 6))
         self.obj_scaling = o.get("nlp_scaling_method", "none") == "gradient-based"
         self.scaling_max_gradient = float(o.get("nlp_scaling_max_gradient", 100.0))
         self.ev = ev
@@ -260,8 +340,10 @@ class BatchedInteriorPoint:
 
         obj_scale = ones  # IPOPT's gradient-based objective scaling (set below); sigma of the Hessian carries it
 
+        first_order = ALL & ~16 if self.limited_memory else ALL  # IPOPT never asks for hess_l with L-BFGS
+
         def evaluate(xx, lam=None, full=True):
-            out = ev.eval(ALL if full else (F | G), xx, p, lam if lam is not None else zeros_m, obj_scale)
+            out = ev.eval(first_order if full else (F | G), xx, p, lam if lam is not None else zeros_m, obj_scale)
             out = {k: v.clone() for k, v in out.items()}
             if self.obj_scaling:
                 out["f"] = out["f"] * obj_scale
@@ -341,7 +423,18 @@ class BatchedInteriorPoint:
             out = evaluate(x, lam)
             n_eval += 1
             fv, grad, g = out["f"], out["grad_f"], out["g"]
-            jv, hv = out["jac"], out["hess"]
+            jv = out["jac"]
+            if self.limited_memory:
+                if it == 0:
+                    lm = LimitedMemory(B, n, self.lm_history, dev)
+                    hv = torch.zeros((B, ev.nnz_h if hasattr(ev, "nnz_h") else len(ev.hess_sparsity()[1])),
+                                     dtype=torch.float64, device=dev)
+                else:  # secant pair of the step just taken, with the CURRENT multipliers on both sides
+                    y_lm = (grad + ops.Jt_mul(jv, lam)) - (grad_prev + ops.Jt_mul(jv_prev, lam))
+                    lm.update(moved_prev, x - x_prev, y_lm)
+                x_prev, grad_prev, jv_prev = x.clone(), grad.clone(), jv.clone()
+            else:
+                hv = out["hess"]
             cE = g[:, iE] - lbE
             cI = g[:, iI] - s
             rd = grad + ops.Jt_mul(jv, lam)
@@ -435,6 +528,8 @@ class BatchedInteriorPoint:
                 # SAME sweep and the first one that passes the test is taken -- the shifts tried and the step
                 # chosen are those of the one-at-a-time loop, only the number of sweeps drops
                 S = max(1, min(4, self.spec_wave // max(1, idx.numel()))) if self.spec_wave else 1
+                if self.limited_memory:
+                    S = 1  # the L-BFGS matrix is positive definite: shifts are the exception, not worth speculating on
                 if S > 1:
                     cand = [delta[idx]]
                     for _ in range(S - 1):
@@ -462,7 +557,12 @@ class BatchedInteriorPoint:
                     if not bool(need.any()):
                         break
                     continue
-                if idx.numel() == B:
+                if self.limited_memory:
+                    sub = lm.kkt_solve(backend, idx, hv[idx], jv[idx], Sig[idx], delta[idx], dc, rhs_x[idx], -cE[idx])
+                    dxt = torch.zeros_like(x)
+                    lamt = torch.zeros_like(lamE)
+                    dxt[idx], lamt[idx] = sub[0], sub[1]
+                elif idx.numel() == B:
                     dxt, lamt = backend.solve(hv, jv, Sig, delta, dc, rhs_x, -cE)
                 else:
                     sub = backend.solve(hv[idx], jv[idx], Sig[idx], delta[idx], dc, rhs_x[idx], -cE[idx])
@@ -479,7 +579,12 @@ class BatchedInteriorPoint:
                     inertia_ok = torch.zeros(B, dtype=torch.bool, device=dev)
                     inertia_ok[idx] = (torch.linalg.eigvalsh(backend.K) < 0).sum(dim=1) == mE
                 else:  # cheap proxy: positive curvature of the barrier Lagrangian along the step
-                    curv = ops.W_quad(hv, dxt) + delta * (dxt * dxt).sum(1) + (Sig * dst * dst).sum(1)
+                    if self.limited_memory:
+                        allidx = torch.arange(B, device=dev)
+                        wq = (dxt * lm.apply(allidx, dxt)).sum(1)
+                    else:
+                        wq = ops.W_quad(hv, dxt)
+                    curv = wq + delta * (dxt * dxt).sum(1) + (Sig * dst * dst).sum(1)
                     inertia_ok = curv > 1e-12 * (dxt * dxt).sum(1)
                 ok = torch.isfinite(dxt).all(dim=1) & torch.isfinite(lamt).all(dim=1) & inertia_ok
                 take = need & ok
@@ -547,6 +652,7 @@ class BatchedInteriorPoint:
                     break
                 alpha = torch.where(accepted, alpha, alpha * 0.5)
             moved = accepted & ~inactive
+            moved_prev = moved.clone()
             # instances whose line search failed get a larger Hessian shift and try again; after max_fail
             # failures in a row an instance is given up (it would otherwise cost 16 evaluations and a KKT
             # solve per iteration until max_iter: there is no restoration phase to send it to)

@@ -251,33 +251,38 @@ class StageKKT:
                                 delta_c, rhs_x[i:i + chunk], rhs_E[i:i + chunk], chunk) for i in range(0, B, chunk)]
             return torch.cat([a for a, _ in parts]), torch.cat([b for _, b in parts])
         nbr = self.n_border
+        multi = rhs_x.dim() == 3  # (B, n_x, R) / (B, m_E, R): several right-hand sides (L-BFGS low-rank correction)
+        if not multi:
+            rhs_x, rhs_E = rhs_x[:, :, None], rhs_E[:, :, None]
+        R0 = rhs_x.shape[2]
         if nbr == 0:
-            DX, DL = self._sweep(hess_vals, jac_vals, sigma_I, delta, delta_c, rhs_x[:, :, None], rhs_E[:, :, None])
-            return DX[:, :, 0], DL[:, :, 0]
+            DX, DL = self._sweep(hess_vals, jac_vals, sigma_I, delta, delta_c, rhs_x, rhs_E)
+            return (DX, DL) if multi else (DX[:, :, 0], DL[:, :, 0])
         dev, dt = hess_vals.device, hess_vals.dtype
         bd = self.border
         pv = jac_vals[:, bd["idx"]]  # (B, nnz of P)
-        RX = torch.zeros((B, self.n_x, 1 + nbr), dtype=dt, device=dev)
-        RX[:, :, 0] = rhs_x
-        RX[:, bd["col"], 1 + bd["row"]] = pv  # P^T
-        RE = torch.zeros((B, self.mE, 1 + nbr), dtype=dt, device=dev)
-        RE[:, :, 0] = rhs_E
-        RE[:, bd["eq"], 0] = 0.0  # border rows are not part of K_bt
+        RX = torch.zeros((B, self.n_x, R0 + nbr), dtype=dt, device=dev)
+        RX[:, :, :R0] = rhs_x
+        RX[:, bd["col"], R0 + bd["row"]] = pv  # P^T
+        RE = torch.zeros((B, self.mE, R0 + nbr), dtype=dt, device=dev)
+        RE[:, :, :R0] = rhs_E
+        RE[:, bd["eq"], :R0] = 0.0  # border rows are not part of K_bt
         DX, DL = self._sweep(hess_vals, jac_vals, sigma_I, delta, delta_c, RX, RE)
-        # P X for X = [y0 | Y] (dx part only: P has no multiplier columns)
-        PX = torch.zeros((B, nbr, 1 + nbr), dtype=dt, device=dev)
+        # P X for X = [y0 | Y] (dx part only: P has no multiplier columns).  Every border row has one entry per
+        # side (x_0 term, x_{N-1} term): at most two additions per element, order-independent
+        PX = torch.zeros((B, nbr, R0 + nbr), dtype=dt, device=dev)
         PX.index_add_(1, bd["row"], pv[:, :, None] * DX[:, bd["col"], :])
-        S = -PX[:, :, 1:] - delta_c * torch.eye(nbr, dtype=dt, device=dev)
+        S = -PX[:, :, R0:] - delta_c * torch.eye(nbr, dtype=dt, device=dev)
         # small (n_border^2) library solve; a singular / non-finite Schur complement (a stage block that failed
         # to factor) gives NaN for that instance, which the caller treats like any failed solve
         S = torch.where(torch.isfinite(S), S, torch.zeros_like(S))
-        lam_p, info = torch.linalg.solve_ex(S, (rhs_E[:, bd["eq"]] - PX[:, :, 0])[:, :, None], check_errors=False)
+        lam_p, info = torch.linalg.solve_ex(S, rhs_E[:, bd["eq"], :] - PX[:, :, :R0], check_errors=False)
         bad = (info != 0) | ~torch.isfinite(PX).all(dim=2).all(dim=1)
         lam_p = torch.where(bad[:, None, None], torch.full_like(lam_p, float("nan")), lam_p)
-        dx = DX[:, :, 0] - torch.bmm(DX[:, :, 1:], lam_p)[:, :, 0]
-        dl = DL[:, :, 0] - torch.bmm(DL[:, :, 1:], lam_p)[:, :, 0]
-        dl[:, bd["eq"]] = lam_p[:, :, 0]
-        return dx, dl
+        dx = DX[:, :, :R0] - torch.bmm(DX[:, :, R0:], lam_p)
+        dl = DL[:, :, :R0] - torch.bmm(DL[:, :, R0:], lam_p)
+        dl[:, bd["eq"], :] = lam_p
+        return (dx, dl) if multi else (dx[:, :, 0], dl[:, :, 0])
 
     def _sweep(self, hess_vals, jac_vals, sigma_I, delta, delta_c, RX, RE):
         """Block-tridiagonal part: K_bt [DX; DL] = [RX; RE] for R right-hand sides (B, n_x | m_E, R)."""

@@ -241,3 +241,38 @@ def test_oracle_cache_over_hb_eval_host(model, built_library):
     assert cache.launches == {"first_order": 1, "hess": 1}
     cache.get("g", x[0] + 1e-3)
     assert cache.launches["first_order"] == 2
+
+
+def test_periodic_step_plans_with_the_references_own_options(model, built_library):
+    """BASELINE config 4 as posed (rows f1 + f2 + f3): periodic walking step plans set up like main_periodic_step.py
+    (keyframe poses, interpolated guess, planned force 100 N per point divided by the mass as the planner does) and
+    solved with the options the reference hands to IPOPT (:111-134) -- hessian_approximation = limited-memory, tol 1e-3,
+    acceptable level -- converge, satisfy the constraints and make the planned step."""
+    from hippopt_b200.evaluator import G, KinoEvaluator, PoseEvaluator
+    from hippopt_b200.initial_guess import periodic_step_guess
+    from hippopt_b200.ipsolver import BatchedInteriorPoint
+    from hippopt_b200.kino_layout import KinoSettings
+
+    dev = torch.device("cuda:0")
+    N, B = 30, 24
+    pev = PoseEvaluator(model)
+    ev = KinoEvaluator(model, KinoSettings(horizon=N, final_state_constraint=True, periodicity_constraint=True))
+    L = np.random.default_rng(5).uniform(0.1, 0.3, B)
+    gs = periodic_step_guess(model, pev, ev, L, force_z=100.0, mass_normalised=True)
+    assert bool(gs.ok.all())
+    lb, ub = ev.layout.bounds(gs.parameters)
+    opts = {"tol": 1e-3, "dual_inf_tol": 1000.0, "compl_inf_tol": 1e-2, "constr_viol_tol": 1e-4, "acceptable_tol": 10,
+            "acceptable_iter": 2, "acceptable_compl_inf_tol": 1000.0, "acceptable_obj_change_tol": 1e0,
+            "nlp_scaling_method": "gradient-based", "max_iter": 400, "hessian_approximation": "limited-memory"}
+    ip = BatchedInteriorPoint(ev, kkt="stage", delta_c=1e-9, mu_init=1e-1, ipopt_options=opts)
+    P = torch.tensor(gs.parameters, device=dev)
+    res = ip.solve(gs.x0, P, lb, ub)
+    ok = res.success.cpu().numpy()
+    assert ok.sum() >= int(0.9 * B), f"{int(ok.sum())} of {B} periodic-step plans converged"
+    assert int(res.iterations[res.success].median()) <= 150
+    g = ev.eval(G, res.values, P)["g"].cpu().numpy()[ok]
+    assert (np.maximum(lb[ok] - g, 0) + np.maximum(g - ub[ok], 0)).max() <= 1e-4  # the reference's constr_viol_tol
+    z = res.values.cpu().numpy()[ok][:, :189 * N].reshape(-1, N, 189)
+    travelled = z[:, -1, 6] - z[:, 0, 6]  # x of the first left contact point, first to last knot
+    assert np.abs(travelled - L[ok]).max() < 5e-3
+    assert z[:, :, 8].max(axis=1).min() > 0.01  # the swing foot leaves the ground

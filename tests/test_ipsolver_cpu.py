@@ -230,3 +230,49 @@ def test_stage_backend_needs_a_stage_structure():
     ip = BatchedInteriorPoint(ev, kkt="stage")
     with pytest.raises(ValueError, match="multiple-shooting layout"):
         ip.solve(torch.zeros((1, 2), dtype=torch.float64), torch.zeros((1, 1), dtype=torch.float64), np.array([0.0]), np.array([0.0]))
+
+
+def test_limited_memory_mode_reaches_the_known_answer():
+    """hessian_approximation = limited-memory (the reference's setting for the kinodynamic planners,
+    main_periodic_step.py:116): hess_l is never requested, the L-BFGS matrix takes its place."""
+    f, g, lb, ub = hs071()
+
+    class NoHessian(TorchEvaluator):
+        def eval(self, mask, x, p, lam, sigma):
+            assert not mask & HESS_L, "limited-memory mode must not ask for hess_l"
+            return super().eval(mask, x, p, lam, sigma)
+
+    ev = NoHessian(f, g, 4, 6)
+    out = BatchedInteriorPoint(ev, tol=1e-8, max_iter=200, ipopt_options={"hessian_approximation": "limited-memory"}).solve(
+        starts(), torch.zeros((3, 1), dtype=torch.float64), lb, ub)
+    assert bool(out.success.all())
+    assert out.values.numpy() == pytest.approx(np.tile(HS071_X, (3, 1)), abs=1e-5)
+    assert out.cost_value.numpy() == pytest.approx(HS071_F, abs=1e-6)
+    assert out.constraint_multipliers[:, :2].numpy() == pytest.approx(np.tile(HS071_LAM, (3, 1)), abs=1e-4)
+
+
+def test_limited_memory_matrix_is_the_bfgs_matrix():
+    """compact representation against the textbook recursive BFGS update started from sigma I"""
+    from hippopt_b200.ipsolver import LimitedMemory
+
+    rng = np.random.default_rng(0)
+    n, k = 7, 4
+    lm = LimitedMemory(1, n, k, "cpu")
+    A = rng.normal(size=(n, n))
+    A = A @ A.T + n * np.eye(n)  # SPD "true" Hessian: y = A s guarantees s^T y > 0
+    pairs = []
+    for _ in range(6):  # more pairs than the history holds: the oldest are dropped
+        s = rng.normal(size=n)
+        y = A @ s
+        lm.update(torch.ones(1, dtype=torch.bool), torch.tensor(s[None]), torch.tensor(y[None]))
+        pairs.append((s, y))
+    pairs = pairs[-k:]
+    sigma = float(lm.sigma[0])
+    assert sigma == pytest.approx(pairs[-1][0] @ pairs[-1][1] / (pairs[-1][0] @ pairs[-1][0]))
+    Bm = sigma * np.eye(n)
+    for s, y in pairs:
+        Bs = Bm @ s
+        Bm = Bm - np.outer(Bs, Bs) / (s @ Bs) + np.outer(y, y) / (y @ s)
+    v = rng.normal(size=(1, n))
+    got = lm.apply(torch.tensor([0]), torch.tensor(v)).numpy()
+    assert got == pytest.approx(v @ Bm.T, rel=1e-10)

@@ -77,6 +77,8 @@ if "-s" in sys.argv:
     ref_opts = {"tol": 1e-3, "dual_inf_tol": 1000.0, "compl_inf_tol": 1e-2, "constr_viol_tol": 1e-4, "acceptable_tol": 10,
                 "acceptable_iter": 2, "acceptable_compl_inf_tol": 1000.0, "acceptable_obj_change_tol": 1e0,
                 "nlp_scaling_method": "gradient-based"} if "--ref-options" in sys.argv else None
+    if "--lbfgs" in sys.argv:  # hessian_approximation = limited-memory, the reference's own setting (:116)
+        ref_opts = dict(ref_opts or {}, hessian_approximation="limited-memory", limited_memory_max_history=arg("--history", 6))
     sol = BatchedInteriorPoint(ev, tol=arg("-t", 1e-6), max_iter=iters, verbose="-v" in sys.argv, kkt="stage",
                                delta_c=1e-9, mu_init=arg("-m", 1e-1), ipopt_options=ref_opts)
     if "--callback" in sys.argv:  # the planner's criterion (humanoid_kinodynamic/planner.py:57-63)
