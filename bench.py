@@ -321,6 +321,7 @@ def main():
     dev = torch.device("cuda", local_rank)
     numa = bind_to_gpu_numa_node(local_rank, world)  # before any pinned allocation (first-touch placement)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG", "WARN")  # keep NCCL's version banner off stdout: ONE JSON line
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
     if rank == 0:
         entry.build()
