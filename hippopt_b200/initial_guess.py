@@ -152,3 +152,64 @@ def periodic_step_guess(model, pose_evaluator, kino_evaluator, step_length: np.n
         p[:, r + po.R_BQV:r + po.R_BQV + 4] = 0.0
         p[:, r + po.R_JR:r + po.R_JR + NJ] = guess[:, k, 79:79 + NJ]
     return PeriodicStepGuess(parameters=p, x0=x0, ok=ok, keyframes=key, pose_iterations=out.iterations)
+
+
+def single_step_problem(model, pose_evaluator, kino_evaluator, step_length: np.ndarray, tol: float = 1e-8,
+                        max_iter: int = 300) -> PeriodicStepGuess:
+    """BASELINE config 3, main_single_step_flat_ground.py:188-356, for a batch of step lengths: the initial state
+    (feet side by side, `compute_initial_state` :188-262) and the final state (right foot one step ahead, CoM half
+    a step ahead, `compute_final_state` :265-338) from 2 B pose-finder solves, and the references of
+    `get_references` (:341-356: contact centroid one step ahead with weights (100, 100, 10), joint regularisation
+    towards the final joints, CoM velocity 0.1 m/s forward), scaled from the main's 0.3 m step to L.
+
+    The main hands IPOPT no initial guess (the planner's default variables); here the guess holds the initial state
+    over the horizon with zero velocities -- the same "standing" start in the layout of the decision vector."""
+    lay, pl = kino_evaluator.layout, pose_evaluator.layout
+    N, po = lay.N, lay.po
+    L = np.asarray(step_length, dtype=np.float64).reshape(-1)
+    B = L.shape[0]
+    dev = torch.device("cuda", torch.cuda.current_device())
+    zero = np.zeros(B)
+
+    def pos(x, y):
+        return np.stack([x, np.full(B, y), zero], axis=1)
+
+    lp = np.concatenate([pos(zero, 0.1), pos(zero, 0.1)])
+    rp = np.concatenate([pos(zero, -0.1), pos(L, -0.1)])
+    xq, pq = pose_problem(pl, model, lp, rp)
+    lb, ub = pose_evaluator.bounds(pq)
+    out = BatchedInteriorPoint(pose_evaluator, tol=tol, max_iter=max_iter).solve(
+        torch.tensor(xq, device=dev), torch.tensor(pq, device=dev), lb, ub)
+    key = state_blocks(out.values).view(2, B, 105)
+    ok = out.success.view(2, B).all(dim=0)
+    k0, k2 = key[0].cpu().numpy(), key[1].cpu().numpy()
+    p = kino_parameters(lay, model, B, np.random.default_rng(0), spread=0.0)
+    n_state = po.ST_COM + 3
+    p[:, po.init:po.init + n_state] = k0
+    p[:, po.final:po.final + n_state] = k2
+    for k in range(N):
+        r = po.refs0 + 55 * k
+        p[:, r + po.R_CW:r + po.R_CW + 3] = [100.0, 100.0, 10.0]
+        p[:, r + po.R_CC] = L
+        p[:, r + po.R_CC + 1:r + po.R_CC + 3] = 0.0
+        p[:, r + po.R_COMV:r + po.R_COMV + 3] = [0.1, 0.0, 0.0]
+        p[:, r + po.R_YAW_L] = p[:, r + po.R_YAW_R] = 0.0
+        p[:, r + po.R_FQ:r + po.R_FQ + 4] = [0.0, 0.0, 0.0, 1.0]
+        p[:, r + po.R_BQ:r + po.R_BQ + 4] = [0.0, 0.0, 0.0, 1.0]
+        p[:, r + po.R_BQV:r + po.R_BQV + 4] = 0.0
+        p[:, r + po.R_JR:r + po.R_JR + NJ] = k2[:, po.ST_S:po.ST_S + NJ]
+    # guess: the initial state at every knot (points p, f; base; joints; CoM), velocities and momentum zero
+    from .kino_layout import COM, F, NZ, P, PB, Q, S
+
+    x0 = np.zeros((B, lay.n_x))
+    for k in range(N):
+        z = x0[:, NZ * k:NZ * (k + 1)]
+        for i in range(NPT):
+            z[:, 15 * i + P:15 * i + P + 3] = k0[:, 9 * i:9 * i + 3]
+            z[:, 15 * i + F:15 * i + F + 3] = k0[:, 9 * i + 3:9 * i + 6]
+        z[:, PB:PB + 3] = k0[:, po.ST_PB:po.ST_PB + 3]
+        z[:, Q:Q + 4] = k0[:, po.ST_Q:po.ST_Q + 4]
+        z[:, S:S + NJ] = k0[:, po.ST_S:po.ST_S + NJ]
+        z[:, COM:COM + 3] = k0[:, po.ST_COM:po.ST_COM + 3]
+    return PeriodicStepGuess(parameters=p, x0=torch.tensor(x0, device=dev), ok=ok,
+                             keyframes=torch.stack([key[0], key[1], key[1]]), pose_iterations=out.iterations)
