@@ -23,9 +23,22 @@ static int fail(int code, const std::string& msg) {
 
 enum { KIND_KINO = 1, KIND_TOY = 2 };
 
+// a handle's tables and scratch live on the device that was current at creation: calls from another current
+// device would launch on the wrong GPU with foreign pointers
+#define CHECK_DEVICE(h, what)                                                                          \
+  do {                                                                                                 \
+    int cur__ = -1;                                                                                    \
+    cudaGetDevice(&cur__);                                                                             \
+    if ((h)->device >= 0 && cur__ != (h)->device)                                                      \
+      return fail(HB_ERR_INVALID, std::string(what) + ": the handle belongs to CUDA device " +         \
+                                      std::to_string((h)->device) + ", the current device is " +       \
+                                      std::to_string(cur__) + " (cudaSetDevice before the call)");      \
+  } while (0)
+
 struct hb_problem_s {
   int kind = 0;
   int launches = 0;
+  int device = -1;  // CUDA device the handle's tables live on (advisor finding, round 1): checked at every call
   // kinodynamic
   hb::KinoConst host{};
   hb::KinoConst* dev = nullptr;
@@ -154,6 +167,7 @@ extern "C" int hb_kino_create(const int32_t* icfg, const double* dcfg, const int
     return fail(HB_ERR_INVALID, "hb_kino_create: null argument");
   hb_problem_s* h = new hb_problem_s();
   h->kind = KIND_KINO;
+  cudaGetDevice(&h->device);
   hb::KinoConst& C = h->host;
   C.N = icfg[HB_KI_HORIZON];
   C.n_x = icfg[HB_KI_N_X];
@@ -449,6 +463,7 @@ extern "C" int hb_toy_create(int32_t horizon, int32_t integrator, double dt, hb_
   if (!out || horizon < 2 || (integrator != 0 && integrator != 1)) return fail(HB_ERR_INVALID, "hb_toy_create: bad argument");
   hb_problem_s* h = new hb_problem_s();
   h->kind = KIND_TOY;
+  cudaGetDevice(&h->device);
   h->toy = hb::toy_create(horizon, integrator, dt);
   if (!h->toy) {
     delete h;
@@ -533,6 +548,7 @@ extern "C" int hb_eval(hb_handle h, uint32_t mask, const double* x, const double
   if ((mask & HB_EVAL_HESS_L) && (!hess_vals || !lam_g || !sigma))
     return fail(HB_ERR_INVALID, "hb_eval: hess_vals, lam_g and sigma are required for HB_EVAL_HESS_L");
   if (!(mask & 31u)) return fail(HB_ERR_INVALID, "hb_eval: empty mask");
+  CHECK_DEVICE(h, "hb_eval");
   cudaStream_t st = (cudaStream_t)stream;
   h->launches = 0;
   if (h->kind == KIND_TOY) {
@@ -1023,6 +1039,7 @@ extern "C" int hb_eval_cost_terms(hb_handle h, const double* x, const double* p,
     return fail(HB_ERR_UNSUPPORTED, "hb_eval_cost_terms: kinodynamic OCP handles only");
   const hb::KinoConst& C = h->host;
   if (p_stride != 0 && p_stride != C.n_p) return fail(HB_ERR_INVALID, "hb_eval_cost_terms: p_stride must be 0 or n_p");
+  CHECK_DEVICE(h, "hb_eval_cost_terms");
   cudaStream_t st = (cudaStream_t)stream;
   const int wpb = 4;
   const long total_warps = (long)batch * C.N;

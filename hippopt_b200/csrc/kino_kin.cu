@@ -799,15 +799,19 @@ __global__ void __launch_bounds__(WITH_HESS ? KIN_H_THREADS : 128, WITH_HESS ? K
   // the forward kinematics instead of being exposed one by one at their points of use
   // (loads first, shared-memory stores last: a store that waits for its load would hold back, in program
   // order, every load behind it)
-  double xr[6];
+  // of the 189 variables of the knot this kernel reads the 24 contact-point positions (FK rows) and the robot block
+  // [Z_VB, NZ): 93 doubles in 4 coalesced requests (the contact kernel owns the rest of the point variables)
+  double xr[4];
+  int xi[4];
 #pragma unroll
-  for (int u = 0; u < 6; ++u) {
-    const int i = lane + 32 * u;
+  for (int u = 0; u < 4; ++u) {
+    xi[u] = u == 0 ? (lane < 24 ? 15 * (lane / 3) + Z_P + lane % 3 : -1) : Z_VB + lane + 32 * (u - 1);
+    if (xi[u] >= NZ) xi[u] = -1;
     xr[u] = 0.0;
-    if (i < NZ) {
-      if (T.zmap_identity) xr[u] = xb[i];
+    if (xi[u] >= 0) {
+      if (T.zmap_identity) xr[u] = xb[xi[u]];
       else {
-        const int zi = C.zmap[i];
+        const int zi = C.zmap[xi[u]];
         if (zi >= 0) xr[u] = xb[zi];
       }
     }
@@ -866,8 +870,8 @@ __global__ void __launch_bounds__(WITH_HESS ? KIN_H_THREADS : 128, WITH_HESS ? K
   }
   const unsigned my_submask = lane < nb ? C.sub_mask[lane] : 0u;
 #pragma unroll
-  for (int u = 0; u < 6; ++u)
-    if (lane + 32 * u < NZ) zs[lane + 32 * u] = xr[u];
+  for (int u = 0; u < 4; ++u)
+    if (xi[u] >= 0) zs[xi[u]] = xr[u];
   if (WITH_HESS) lamk[lane] = lam_reg;
   for (int i = lane; i < 58; i += 32) gbuf[i] = 0.0;
   __syncwarp();
