@@ -1576,8 +1576,11 @@ __global__ void __launch_bounds__(WITH_HESS ? KIN_H_THREADS : 128, WITH_HESS ? K
           const D3 a1 = cross(tPd, hbv), a2 = cross(hbv, tP);  // hb.(dP_r x dPdot_d) = dP_r.a1, hb.(dP_d x dPdot_r) = dPdot_r.a2
           double* col = stg + lane * 57;
           const double sM = -1.0 / M;
+          // velocity rows (vb, qd, sd: 0..29) have dP_r = 0: half the loads and products
+#pragma unroll 5
+          for (int r = 0; r < 30; ++r) col[r] = sM * dot(ld3(xt + 6 * r + 3), a2);
 #pragma unroll 3
-          for (int r = 0; r < 57; ++r) col[r] = sM * (dot(ld3(xt + 6 * r), a1) + dot(ld3(xt + 6 * r + 3), a2));
+          for (int r = 30; r < 57; ++r) col[r] = sM * (dot(ld3(xt + 6 * r), a1) + dot(ld3(xt + 6 * r + 3), a2));
           if (lane >= 4) {  // joint regularisation on (sd_j, s_j), (s_j, s_j)
             col[7 + lane - 4] += em.add_sd;
             col[34 + lane - 4] += em.add_s;
