@@ -1074,3 +1074,218 @@ extern "C" int hb_debug_phase_read(unsigned long long* out64) {
   return HB_OK;
 }
 #endif
+
+// ---------------------------------------------------------------------------------------------
+// CasADi's external-function (codegen) ABI for the five nlpsol oracle functions:
+//   cs.external("hb_nlp_jac_g", "libhippopt_b200.so") loads F, F_n_in, F_n_out, F_sparsity_in / _out, F_work,
+//   F_name_in / _out, F_incref / _decref, F_alloc_mem / _init_mem / _free_mem / _checkout / _release by name [ext].
+// External functions carry no handle, so a problem is BOUND to them per process (hb_external_bind); they then share
+// one host pipeline and an x-keyed cache -- f, grad_f, g and jac_g at the same x cost ONE evaluation, hess_l a second
+// one -- the compiled counterpart of hippopt_b200/plugin.py's OracleCache, without the Python callback in between.
+typedef long long int casadi_int;
+namespace {
+struct ExternalBinding {
+  hb_handle h = nullptr;
+  int64_t n_x = 0, n_p = 0, m = 0, nnz_j = 0, nnz_h = 0;
+  double *x = nullptr, *p = nullptr, *lam = nullptr, *sigma = nullptr;      // pinned staging of the inputs
+  double *f = nullptr, *grad = nullptr, *g = nullptr, *jac = nullptr, *hess = nullptr;  // pinned results
+  bool have_first = false, have_p = false;
+  long evals_first = 0, evals_hess = 0;
+  std::vector<casadi_int> sp_x, sp_p, sp_one, sp_g, sp_jac, sp_hess;
+  std::mutex mu;
+} g_ext;
+
+std::vector<casadi_int> dense_sp(casadi_int n) {
+  std::vector<casadi_int> s = {n, 1, 0, n};
+  for (casadi_int i = 0; i < n; ++i) s.push_back(i);
+  return s;
+}
+std::vector<casadi_int> ccs_sp(casadi_int nrow, casadi_int ncol, const std::vector<int64_t>& colind, const std::vector<int64_t>& row) {
+  std::vector<casadi_int> s = {nrow, ncol};
+  s.insert(s.end(), colind.begin(), colind.end());
+  s.insert(s.end(), row.begin(), row.end());
+  return s;
+}
+void ext_free() {
+  double** bufs[] = {&g_ext.x, &g_ext.p, &g_ext.lam, &g_ext.sigma, &g_ext.f, &g_ext.grad, &g_ext.g, &g_ext.jac, &g_ext.hess};
+  for (double** b : bufs) {
+    if (*b) cudaFreeHost(*b);
+    *b = nullptr;
+  }
+}
+// copies x / p into the staging buffers; returns true when x changed (the first-order cache is then stale)
+int ext_inputs(const double** arg) {
+  const size_t bx = sizeof(double) * g_ext.n_x, bp = sizeof(double) * g_ext.n_p;
+  bool changed = !g_ext.have_first;
+  if (arg[0]) {
+    if (memcmp(g_ext.x, arg[0], bx) != 0) {
+      memcpy(g_ext.x, arg[0], bx);
+      changed = true;
+    }
+  } else {
+    for (int64_t i = 0; i < g_ext.n_x; ++i)
+      if (g_ext.x[i] != 0.0) changed = true;
+    memset(g_ext.x, 0, bx);
+  }
+  bool p_changed = !g_ext.have_p;
+  if (arg[1]) {
+    if (memcmp(g_ext.p, arg[1], bp) != 0) {
+      memcpy(g_ext.p, arg[1], bp);
+      p_changed = true;
+    }
+  } else {
+    memset(g_ext.p, 0, bp);
+  }
+  if (p_changed) {
+    if (hb_host_set_parameters(g_ext.h, g_ext.p, 0, 1) != HB_OK) return -1;
+    g_ext.have_p = true;
+    changed = true;
+  }
+  return changed ? 1 : 0;
+}
+int ext_first_order(const double** arg) {
+  if (!g_ext.h) return fail(HB_ERR_INVALID, "hb_nlp_*: no problem bound (hb_external_bind)");
+  const int ch = ext_inputs(arg);
+  if (ch < 0) return 1;
+  if (ch) {
+    if (hb_eval_host(g_ext.h, HB_EVAL_F | HB_EVAL_GRAD_F | HB_EVAL_G | HB_EVAL_JAC_G, g_ext.x, nullptr, nullptr, g_ext.f,
+                     g_ext.grad, g_ext.g, g_ext.jac, nullptr, 1) != HB_OK)
+      return 1;
+    g_ext.have_first = true;
+    ++g_ext.evals_first;
+  }
+  return 0;
+}
+}  // namespace
+
+extern "C" int hb_external_bind(hb_handle h) {
+  std::lock_guard<std::mutex> lock(g_ext.mu);
+  ext_free();
+  g_ext.h = nullptr;
+  g_ext.have_first = g_ext.have_p = false;
+  g_ext.evals_first = g_ext.evals_hess = 0;
+  if (!h) return HB_OK;  // unbind
+  if (h->kind == KIND_KINO && h->jac_row.empty())
+    return fail(HB_ERR_INVALID, "hb_external_bind: attach the patterns first (hb_kino_attach_tables / hb_load)");
+  hb_dims(h, &g_ext.n_x, &g_ext.n_p, &g_ext.m, &g_ext.nnz_j, &g_ext.nnz_h);
+  std::vector<int64_t> jc(g_ext.n_x + 1), jr(g_ext.nnz_j), hc(g_ext.n_x + 1), hr(g_ext.nnz_h);
+  if (hb_pattern_jac(h, jc.data(), jr.data()) != HB_OK || hb_pattern_hess(h, hc.data(), hr.data()) != HB_OK) return HB_ERR_INVALID;
+  g_ext.sp_x = dense_sp(g_ext.n_x);
+  g_ext.sp_p = dense_sp(g_ext.n_p);
+  g_ext.sp_one = dense_sp(1);
+  g_ext.sp_g = dense_sp(g_ext.m);
+  g_ext.sp_jac = ccs_sp(g_ext.m, g_ext.n_x, jc, jr);
+  g_ext.sp_hess = ccs_sp(g_ext.n_x, g_ext.n_x, hc, hr);
+  struct { double** b; int64_t n; } al[] = {{&g_ext.x, g_ext.n_x}, {&g_ext.p, g_ext.n_p}, {&g_ext.lam, g_ext.m}, {&g_ext.sigma, 1},
+                                            {&g_ext.f, 1}, {&g_ext.grad, g_ext.n_x}, {&g_ext.g, g_ext.m},
+                                            {&g_ext.jac, g_ext.nnz_j}, {&g_ext.hess, g_ext.nnz_h}};
+  for (auto& a : al) {
+    CUDA_TRY(cudaHostAlloc((void**)a.b, sizeof(double) * (size_t)(a.n > 0 ? a.n : 1), cudaHostAllocDefault));
+    memset(*a.b, 0, sizeof(double) * (size_t)(a.n > 0 ? a.n : 1));
+  }
+  g_ext.h = h;
+  return HB_OK;
+}
+
+extern "C" int hb_external_stats(int64_t* first_order_evaluations, int64_t* hessian_evaluations) {
+  if (first_order_evaluations) *first_order_evaluations = g_ext.evals_first;
+  if (hessian_evaluations) *hessian_evaluations = g_ext.evals_hess;
+  return HB_OK;
+}
+
+#define HB_EXT_COMMON(F, NIN, NOUT)                                                                         \
+  extern "C" casadi_int F##_n_in(void) { return NIN; }                                                     \
+  extern "C" casadi_int F##_n_out(void) { return NOUT; }                                                   \
+  extern "C" int F##_work(casadi_int* sz_arg, casadi_int* sz_res, casadi_int* sz_iw, casadi_int* sz_w) {   \
+    if (sz_arg) *sz_arg = NIN;                                                                             \
+    if (sz_res) *sz_res = NOUT;                                                                            \
+    if (sz_iw) *sz_iw = 0;                                                                                 \
+    if (sz_w) *sz_w = 0;                                                                                   \
+    return 0;                                                                                              \
+  }                                                                                                        \
+  extern "C" void F##_incref(void) {}                                                                      \
+  extern "C" void F##_decref(void) {}                                                                      \
+  extern "C" int F##_alloc_mem(void) { return 0; }                                                         \
+  extern "C" int F##_init_mem(int) { return 0; }                                                           \
+  extern "C" void F##_free_mem(int) {}                                                                     \
+  extern "C" int F##_checkout(void) { return 0; }                                                          \
+  extern "C" void F##_release(int) {}
+
+static const char* ext_in_name(casadi_int i) {
+  static const char* n[] = {"x", "p", "lam_f", "lam_g"};
+  return i >= 0 && i < 4 ? n[i] : nullptr;
+}
+
+// ---- nlp_f: (x, p) -> f
+HB_EXT_COMMON(hb_nlp_f, 2, 1)
+extern "C" const char* hb_nlp_f_name_in(casadi_int i) { return i < 2 ? ext_in_name(i) : nullptr; }
+extern "C" const char* hb_nlp_f_name_out(casadi_int i) { return i == 0 ? "f" : nullptr; }
+extern "C" const casadi_int* hb_nlp_f_sparsity_in(casadi_int i) { return i == 0 ? g_ext.sp_x.data() : (i == 1 ? g_ext.sp_p.data() : nullptr); }
+extern "C" const casadi_int* hb_nlp_f_sparsity_out(casadi_int i) { return i == 0 ? g_ext.sp_one.data() : nullptr; }
+extern "C" int hb_nlp_f(const double** arg, double** res, casadi_int*, double*, int) {
+  std::lock_guard<std::mutex> lock(g_ext.mu);
+  if (ext_first_order(arg)) return 1;
+  if (res[0]) res[0][0] = g_ext.f[0];
+  return 0;
+}
+// ---- nlp_g: (x, p) -> g
+HB_EXT_COMMON(hb_nlp_g, 2, 1)
+extern "C" const char* hb_nlp_g_name_in(casadi_int i) { return i < 2 ? ext_in_name(i) : nullptr; }
+extern "C" const char* hb_nlp_g_name_out(casadi_int i) { return i == 0 ? "g" : nullptr; }
+extern "C" const casadi_int* hb_nlp_g_sparsity_in(casadi_int i) { return hb_nlp_f_sparsity_in(i); }
+extern "C" const casadi_int* hb_nlp_g_sparsity_out(casadi_int i) { return i == 0 ? g_ext.sp_g.data() : nullptr; }
+extern "C" int hb_nlp_g(const double** arg, double** res, casadi_int*, double*, int) {
+  std::lock_guard<std::mutex> lock(g_ext.mu);
+  if (ext_first_order(arg)) return 1;
+  if (res[0]) memcpy(res[0], g_ext.g, sizeof(double) * g_ext.m);
+  return 0;
+}
+// ---- nlp_grad_f: (x, p) -> (f, grad_f)
+HB_EXT_COMMON(hb_nlp_grad_f, 2, 2)
+extern "C" const char* hb_nlp_grad_f_name_in(casadi_int i) { return i < 2 ? ext_in_name(i) : nullptr; }
+extern "C" const char* hb_nlp_grad_f_name_out(casadi_int i) { return i == 0 ? "f" : (i == 1 ? "grad_f_x" : nullptr); }
+extern "C" const casadi_int* hb_nlp_grad_f_sparsity_in(casadi_int i) { return hb_nlp_f_sparsity_in(i); }
+extern "C" const casadi_int* hb_nlp_grad_f_sparsity_out(casadi_int i) { return i == 0 ? g_ext.sp_one.data() : (i == 1 ? g_ext.sp_x.data() : nullptr); }
+extern "C" int hb_nlp_grad_f(const double** arg, double** res, casadi_int*, double*, int) {
+  std::lock_guard<std::mutex> lock(g_ext.mu);
+  if (ext_first_order(arg)) return 1;
+  if (res[0]) res[0][0] = g_ext.f[0];
+  if (res[1]) memcpy(res[1], g_ext.grad, sizeof(double) * g_ext.n_x);
+  return 0;
+}
+// ---- nlp_jac_g: (x, p) -> (g, jac_g)
+HB_EXT_COMMON(hb_nlp_jac_g, 2, 2)
+extern "C" const char* hb_nlp_jac_g_name_in(casadi_int i) { return i < 2 ? ext_in_name(i) : nullptr; }
+extern "C" const char* hb_nlp_jac_g_name_out(casadi_int i) { return i == 0 ? "g" : (i == 1 ? "jac_g_x" : nullptr); }
+extern "C" const casadi_int* hb_nlp_jac_g_sparsity_in(casadi_int i) { return hb_nlp_f_sparsity_in(i); }
+extern "C" const casadi_int* hb_nlp_jac_g_sparsity_out(casadi_int i) { return i == 0 ? g_ext.sp_g.data() : (i == 1 ? g_ext.sp_jac.data() : nullptr); }
+extern "C" int hb_nlp_jac_g(const double** arg, double** res, casadi_int*, double*, int) {
+  std::lock_guard<std::mutex> lock(g_ext.mu);
+  if (ext_first_order(arg)) return 1;
+  if (res[0]) memcpy(res[0], g_ext.g, sizeof(double) * g_ext.m);
+  if (res[1]) memcpy(res[1], g_ext.jac, sizeof(double) * g_ext.nnz_j);
+  return 0;
+}
+// ---- nlp_hess_l: (x, p, lam_f, lam_g) -> triu(hess_l)
+HB_EXT_COMMON(hb_nlp_hess_l, 4, 1)
+extern "C" const char* hb_nlp_hess_l_name_in(casadi_int i) { return ext_in_name(i); }
+extern "C" const char* hb_nlp_hess_l_name_out(casadi_int i) { return i == 0 ? "triu_hess_gamma_x_x" : nullptr; }
+extern "C" const casadi_int* hb_nlp_hess_l_sparsity_in(casadi_int i) {
+  return i < 2 ? hb_nlp_f_sparsity_in(i) : (i == 2 ? g_ext.sp_one.data() : (i == 3 ? g_ext.sp_g.data() : nullptr));
+}
+extern "C" const casadi_int* hb_nlp_hess_l_sparsity_out(casadi_int i) { return i == 0 ? g_ext.sp_hess.data() : nullptr; }
+extern "C" int hb_nlp_hess_l(const double** arg, double** res, casadi_int*, double*, int) {
+  std::lock_guard<std::mutex> lock(g_ext.mu);
+  if (!g_ext.h) return fail(HB_ERR_INVALID, "hb_nlp_hess_l: no problem bound (hb_external_bind)");
+  const int ch = ext_inputs(arg);
+  if (ch < 0) return 1;
+  if (ch) g_ext.have_first = false;  // x moved without a first-order call in between: that cache is stale
+  g_ext.sigma[0] = arg[2] ? arg[2][0] : 0.0;
+  if (arg[3]) memcpy(g_ext.lam, arg[3], sizeof(double) * g_ext.m);
+  else memset(g_ext.lam, 0, sizeof(double) * g_ext.m);
+  if (hb_eval_host(g_ext.h, HB_EVAL_HESS_L, g_ext.x, g_ext.lam, g_ext.sigma, nullptr, nullptr, nullptr, nullptr, g_ext.hess, 1) != HB_OK)
+    return 1;
+  ++g_ext.evals_hess;
+  if (res[0]) memcpy(res[0], g_ext.hess, sizeof(double) * g_ext.nnz_h);
+  return 0;
+}

@@ -49,6 +49,9 @@ enum { HSTAGE = 27 * 57 };  // per-warp staging of the Hessian columns (and, bef
 #if HB_FWD_JAC && !HB_KIN_STAGE
 #error "HB_FWD_JAC stages the Jacobian columns: it needs HB_KIN_STAGE"
 #endif
+#ifndef KIN_SCAT
+#define KIN_SCAT 17  // scatter-map loads in flight per lane in the Hessian kernel's two scatters (8: 5.3 k -> see DESIGN.md)
+#endif
 #ifndef HB_SWEEP_PACKED
 #define HB_SWEEP_PACKED 1  // Hessian kernel: (direction, body) tasks packed on the lanes (kin_tangent_sweep_packed)
 #endif
@@ -1430,12 +1433,13 @@ __global__ void __launch_bounds__(WITH_HESS ? KIN_H_THREADS : 128, WITH_HESS ? K
         const int* jmap = C.jk_map + (size_t)k * T.n_jk;
         double* jb = jac + b * T.nnz_j;
         const int n = T.n_jk;
-        for (int eb = lane; eb < n; eb += 256) {  // 8 map loads in flight before the dependent stores
-          int sl[8];
+        // KIN_SCAT map loads in flight before the dependent stores: 927 entries in two trips
+        for (int eb = lane; eb < n; eb += 32 * KIN_SCAT) {
+          int sl[KIN_SCAT];
 #pragma unroll
-          for (int u = 0; u < 8; ++u) sl[u] = (eb + 32 * u) < n ? jmap[eb + 32 * u] : -1;
+          for (int u = 0; u < KIN_SCAT; ++u) sl[u] = (eb + 32 * u) < n ? jmap[eb + 32 * u] : -1;
 #pragma unroll
-          for (int u = 0; u < 8; ++u)
+          for (int u = 0; u < KIN_SCAT; ++u)
             if (sl[u] >= 0) jb[sl[u]] = stg[eb + 32 * u];
         }
       }
@@ -1636,12 +1640,12 @@ __global__ void __launch_bounds__(WITH_HESS ? KIN_H_THREADS : 128, WITH_HESS ? K
     if (em.stage) {
       // scatter the staged columns (27 directions x 57 rows) with coalesced map reads
       const double* st = sm + L.stage;
-      for (int eb = lane; eb < HSTAGE; eb += 256) {
-        int sl[8];
+      for (int eb = lane; eb < HSTAGE; eb += 32 * KIN_SCAT) {  // 1539 entries in three trips
+        int sl[KIN_SCAT];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) sl[u] = (eb + 32 * u) < HSTAGE ? em.map[eb + 32 * u] : -1;
+        for (int u = 0; u < KIN_SCAT; ++u) sl[u] = (eb + 32 * u) < HSTAGE ? em.map[eb + 32 * u] : -1;
 #pragma unroll
-        for (int u = 0; u < 8; ++u)
+        for (int u = 0; u < KIN_SCAT; ++u)
           if (sl[u] >= 0) em.hess[sl[u]] = st[eb + 32 * u];
       }
     }

@@ -487,6 +487,31 @@ class OracleBridge:
         self.solver = cs.nlpsol("solver", inner_solver, nlp, opts)
         return self.solver
 
+    def build_external(self, options_plugin: dict, options_solver: dict, inner_solver: str, library_path: str, handle):
+        """The compiled alternative to the Callbacks: CasADi loads the five oracle functions from the library by name
+        (`casadi.external`, the codegen ABI exported by include/hippopt_b200.h) after the problem has been bound to
+        them (`hb_external_bind`); no Python runs inside IPOPT's iteration.  The external functions work on the full
+        row set, so `detect_simple_bounds` is not applied in this mode (bounds stay rows of g)."""
+        from . import _capi
+
+        cs, lay = self.cs, self.layout
+        _capi.check(_capi.lib().hb_external_bind(handle), "hb_external_bind")
+        self.red = RowReduction(lay, False)
+        ext = {n: cs.external(n, library_path) for n in ("hb_nlp_f", "hb_nlp_g", "hb_nlp_grad_f", "hb_nlp_jac_g", "hb_nlp_hess_l")}
+        x_sym, p_sym = cs.MX.sym("x", lay.n_x), cs.MX.sym("p", lay.n_p)
+        nlp = {"x": x_sym, "p": p_sym, "f": ext["hb_nlp_f"](x_sym, p_sym), "g": ext["hb_nlp_g"](x_sym, p_sym)}
+        opts, _ = split_plugin_options(options_plugin)
+        opts = dict(opts)
+        opts[inner_solver] = dict(options_solver or {})
+        opts.update({"grad_f": ext["hb_nlp_grad_f"], "jac_g": ext["hb_nlp_jac_g"], "hess_lag": ext["hb_nlp_hess_l"],
+                     "calc_lam_p": False})
+        if str((options_solver or {}).get("hessian_approximation", "exact")) == "limited-memory":
+            opts.pop("hess_lag")
+        self.options_passed = opts
+        self._callbacks = list(ext.values())
+        self.solver = cs.nlpsol("solver", inner_solver, nlp, opts)
+        return self.solver
+
     def verify(self, x0, p, f_ref: float, g_ref: np.ndarray, rtol: float = 1e-9) -> None:
         """One evaluation of the kernels at the initial point against Opti's own f and g (same canonical form)."""
         first = self.cache.first_order(np.ascontiguousarray(x0, dtype=np.float64))
@@ -525,6 +550,8 @@ def make_opti_solver(cs, hp, evaluator_factory=None):
         robot_model = None        # hippopt_b200.robot_model.RobotModel of the planner's URDF / joint list
         kino_settings = None      # hippopt_b200.kino_layout.KinoSettings mirroring the planner's Settings
         strict = False            # True: a template mismatch raises instead of falling back to the stock path
+        oracle = "callback"       # "callback": cs.Callback objects (Python inside the iteration, simple bounds reduced);
+        #                           "external": casadi.external on the library's codegen ABI (no Python in the loop)
         last_bridge = None        # for inspection: launches / calls per solve
 
         def _default_factory(self, match: TemplateMatch):
@@ -612,7 +639,13 @@ def make_opti_solver(cs, hp, evaluator_factory=None):
                 LOG.warning("falling back to the stock OptiSolver.solve(): %s", err)
                 return super().solve()
             type(self).last_bridge = self.last_bridge = bridge
-            bridge.build(self._options_plugin, self._options_solver, self._inner_solver)
+            ev = getattr(host_eval, "ev", None)
+            if self.oracle == "external" and ev is not None:
+                from . import _capi
+
+                bridge.build_external(self._options_plugin, self._options_solver, self._inner_solver, _capi.LIB_PATH, ev._h)
+            else:
+                bridge.build(self._options_plugin, self._options_solver, self._inner_solver)
             # the callback criterion needs Opti's iteration callback; the shim keeps IPOPT's own termination
             try:
                 x, cost, lam_g, stats = bridge.run(x0, p, lbg, ubg)

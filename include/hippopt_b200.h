@@ -341,6 +341,94 @@ int hb_interpolate_humanoid_states(int64_t batch, int64_t n_points, int64_t n_jo
                                    int64_t n_phases_right, int64_t stride_right, double* states, double* x,
                                    int64_t x_stride, int64_t knot0, void* stream);
 
+/* CasADi external-function (codegen) ABI [ext] for the five nlpsol oracle functions, exported under the names
+ *   hb_nlp_f (x, p -> f), hb_nlp_g (x, p -> g), hb_nlp_grad_f (x, p -> f, grad_f), hb_nlp_jac_g (x, p -> g, jac_g),
+ *   hb_nlp_hess_l (x, p, lam_f, lam_g -> triu hess_l)
+ * each with F(const double** arg, double** res, casadi_int* iw, double* w, int mem), F_n_in, F_n_out, F_sparsity_in,
+ * F_sparsity_out (compact CCS vectors), F_work, F_name_in, F_name_out, F_incref, F_decref, F_alloc_mem, F_init_mem,
+ * F_free_mem, F_checkout, F_release, so that `casadi.external("hb_nlp_jac_g", "libhippopt_b200.so")` loads them.
+ * replaces: the generated-C oracle functions of `nlpsol`; the alternative to the Python Callback shim.
+ * External functions carry no handle: hb_external_bind(h) binds ONE problem per process (NULL unbinds); they share a host
+ * pipeline and an x-keyed cache (f, grad_f, g, jac_g at one x = one evaluation).  hb_external_stats counts them. */
+int hb_external_bind(hb_handle h);
+int hb_external_stats(int64_t* first_order_evaluations, int64_t* hessian_evaluations);
+typedef long long int hb_casadi_int; /* CasADi's casadi_int */
+int hb_nlp_f(const double** arg, double** res, hb_casadi_int* iw, double* w, int mem);
+hb_casadi_int hb_nlp_f_n_in(void);
+hb_casadi_int hb_nlp_f_n_out(void);
+const hb_casadi_int* hb_nlp_f_sparsity_in(hb_casadi_int i);
+const hb_casadi_int* hb_nlp_f_sparsity_out(hb_casadi_int i);
+int hb_nlp_f_work(hb_casadi_int* sz_arg, hb_casadi_int* sz_res, hb_casadi_int* sz_iw, hb_casadi_int* sz_w);
+const char* hb_nlp_f_name_in(hb_casadi_int i);
+const char* hb_nlp_f_name_out(hb_casadi_int i);
+void hb_nlp_f_incref(void);
+void hb_nlp_f_decref(void);
+int hb_nlp_f_alloc_mem(void);
+int hb_nlp_f_init_mem(int mem);
+void hb_nlp_f_free_mem(int mem);
+int hb_nlp_f_checkout(void);
+void hb_nlp_f_release(int mem);
+int hb_nlp_g(const double** arg, double** res, hb_casadi_int* iw, double* w, int mem);
+hb_casadi_int hb_nlp_g_n_in(void);
+hb_casadi_int hb_nlp_g_n_out(void);
+const hb_casadi_int* hb_nlp_g_sparsity_in(hb_casadi_int i);
+const hb_casadi_int* hb_nlp_g_sparsity_out(hb_casadi_int i);
+int hb_nlp_g_work(hb_casadi_int* sz_arg, hb_casadi_int* sz_res, hb_casadi_int* sz_iw, hb_casadi_int* sz_w);
+const char* hb_nlp_g_name_in(hb_casadi_int i);
+const char* hb_nlp_g_name_out(hb_casadi_int i);
+void hb_nlp_g_incref(void);
+void hb_nlp_g_decref(void);
+int hb_nlp_g_alloc_mem(void);
+int hb_nlp_g_init_mem(int mem);
+void hb_nlp_g_free_mem(int mem);
+int hb_nlp_g_checkout(void);
+void hb_nlp_g_release(int mem);
+int hb_nlp_grad_f(const double** arg, double** res, hb_casadi_int* iw, double* w, int mem);
+hb_casadi_int hb_nlp_grad_f_n_in(void);
+hb_casadi_int hb_nlp_grad_f_n_out(void);
+const hb_casadi_int* hb_nlp_grad_f_sparsity_in(hb_casadi_int i);
+const hb_casadi_int* hb_nlp_grad_f_sparsity_out(hb_casadi_int i);
+int hb_nlp_grad_f_work(hb_casadi_int* sz_arg, hb_casadi_int* sz_res, hb_casadi_int* sz_iw, hb_casadi_int* sz_w);
+const char* hb_nlp_grad_f_name_in(hb_casadi_int i);
+const char* hb_nlp_grad_f_name_out(hb_casadi_int i);
+void hb_nlp_grad_f_incref(void);
+void hb_nlp_grad_f_decref(void);
+int hb_nlp_grad_f_alloc_mem(void);
+int hb_nlp_grad_f_init_mem(int mem);
+void hb_nlp_grad_f_free_mem(int mem);
+int hb_nlp_grad_f_checkout(void);
+void hb_nlp_grad_f_release(int mem);
+int hb_nlp_jac_g(const double** arg, double** res, hb_casadi_int* iw, double* w, int mem);
+hb_casadi_int hb_nlp_jac_g_n_in(void);
+hb_casadi_int hb_nlp_jac_g_n_out(void);
+const hb_casadi_int* hb_nlp_jac_g_sparsity_in(hb_casadi_int i);
+const hb_casadi_int* hb_nlp_jac_g_sparsity_out(hb_casadi_int i);
+int hb_nlp_jac_g_work(hb_casadi_int* sz_arg, hb_casadi_int* sz_res, hb_casadi_int* sz_iw, hb_casadi_int* sz_w);
+const char* hb_nlp_jac_g_name_in(hb_casadi_int i);
+const char* hb_nlp_jac_g_name_out(hb_casadi_int i);
+void hb_nlp_jac_g_incref(void);
+void hb_nlp_jac_g_decref(void);
+int hb_nlp_jac_g_alloc_mem(void);
+int hb_nlp_jac_g_init_mem(int mem);
+void hb_nlp_jac_g_free_mem(int mem);
+int hb_nlp_jac_g_checkout(void);
+void hb_nlp_jac_g_release(int mem);
+int hb_nlp_hess_l(const double** arg, double** res, hb_casadi_int* iw, double* w, int mem);
+hb_casadi_int hb_nlp_hess_l_n_in(void);
+hb_casadi_int hb_nlp_hess_l_n_out(void);
+const hb_casadi_int* hb_nlp_hess_l_sparsity_in(hb_casadi_int i);
+const hb_casadi_int* hb_nlp_hess_l_sparsity_out(hb_casadi_int i);
+int hb_nlp_hess_l_work(hb_casadi_int* sz_arg, hb_casadi_int* sz_res, hb_casadi_int* sz_iw, hb_casadi_int* sz_w);
+const char* hb_nlp_hess_l_name_in(hb_casadi_int i);
+const char* hb_nlp_hess_l_name_out(hb_casadi_int i);
+void hb_nlp_hess_l_incref(void);
+void hb_nlp_hess_l_decref(void);
+int hb_nlp_hess_l_alloc_mem(void);
+int hb_nlp_hess_l_init_mem(int mem);
+void hb_nlp_hess_l_free_mem(int mem);
+int hb_nlp_hess_l_checkout(void);
+void hb_nlp_hess_l_release(int mem);
+
 /* Host-only: the (direction, body) task table of the kinematics kernel's packed tangent sweep for a tree
  * (hippopt_b200/csrc/sweep_schedule.h), for the CPU tests of the scheduler.  parent[nb]; typed: homogeneous rounds.
  *   tasks[32*32]  descriptor of (round, lane), 0 = idle

@@ -131,3 +131,72 @@ def test_c_client_without_python(model, built_library, tmp_path):
             float((out["g"] * (np.arange(ev.m) % 7 + 1)).sum()), float((out["jac"] * (lay.jac_row % 5 + 1)).sum()),
             float((out["hess"] * (lay.hess_row % 3 + 1)).sum())]
     assert [float(v) for v in got["values"]] == pytest.approx(want, rel=1e-12)
+
+
+def test_casadi_external_function_abi(model, built_library):
+    """the CasADi codegen ABI (`casadi.external("hb_nlp_jac_g", "libhippopt_b200.so")`) of the five nlpsol
+    oracle functions, called the way CasADi calls an external function -- arg / res pointer arrays, sparsities as
+    compact CCS vectors, work sizes -- and compared with hb_eval; f, grad_f, g, jac_g at one x cost one evaluation."""
+    from hippopt_b200.evaluator import ALL, KinoEvaluator
+    from hippopt_b200.kino_layout import KinoSettings
+    from hippopt_b200.workloads import kino_batch
+
+    lib = built_library
+    ev = KinoEvaluator(model, KinoSettings(horizon=3, final_state_constraint=True))
+    lay = ev.layout
+    x, p, lam, sigma = kino_batch(lay, model, 1, seed=31, noise=0.1)
+    ref = {k: v.cpu().numpy()[0] for k, v in ev.eval(ALL, *(torch.tensor(a, device="cuda:0") for a in (x, p, lam, sigma))).items()}
+    assert lib.hb_external_bind(ev._h) == 0
+    cint, dp = ctypes.c_longlong, ctypes.POINTER(ctypes.c_double)
+
+    def sparsity(fn, i):
+        f = getattr(lib, fn)
+        f.restype, f.argtypes = ctypes.POINTER(cint), [cint]
+        s = f(i)
+        nrow, ncol = s[0], s[1]
+        colind = [s[2 + j] for j in range(ncol + 1)]
+        rows = [s[2 + ncol + 1 + j] for j in range(colind[-1])]
+        return nrow, ncol, colind, rows
+
+    def call(name, ins, out_sizes):
+        f = getattr(lib, name)
+        f.restype = ctypes.c_int
+        n_in, n_out = getattr(lib, name + "_n_in"), getattr(lib, name + "_n_out")
+        n_in.restype = n_out.restype = cint
+        assert (n_in(), n_out()) == (len(ins), len(out_sizes))
+        sz = [cint() for _ in range(4)]
+        assert getattr(lib, name + "_work")(*[ctypes.byref(v) for v in sz]) == 0 and sz[0].value >= len(ins)
+        arrs = [np.ascontiguousarray(a, dtype=np.float64) for a in ins]
+        outs = [np.full(n, np.nan) for n in out_sizes]
+        arg = (dp * len(arrs))(*[a.ctypes.data_as(dp) for a in arrs])
+        res = (dp * len(outs))(*[o.ctypes.data_as(dp) for o in outs])
+        assert f(arg, res, None, None, 0) == 0, lib.hb_last_error()
+        return outs
+
+    try:
+        assert sparsity("hb_nlp_jac_g_sparsity_out", 1) == (ev.m, ev.n_x, list(lay.jac_colind), list(lay.jac_row))
+        assert sparsity("hb_nlp_hess_l_sparsity_out", 0) == (ev.n_x, ev.n_x, list(lay.hess_colind), list(lay.hess_row))
+        assert sparsity("hb_nlp_f_sparsity_in", 0)[:2] == (ev.n_x, 1) and sparsity("hb_nlp_f_sparsity_in", 1)[:2] == (ev.n_p, 1)
+        nm = lib.hb_nlp_hess_l_name_in
+        nm.restype, nm.argtypes = ctypes.c_char_p, [cint]
+        assert [nm(i) for i in range(4)] == [b"x", b"p", b"lam_f", b"lam_g"]
+        (f,) = call("hb_nlp_f", [x[0], p[0]], [1])
+        f2, grad = call("hb_nlp_grad_f", [x[0], p[0]], [1, ev.n_x])
+        (g,) = call("hb_nlp_g", [x[0], p[0]], [ev.m])
+        g2, jac = call("hb_nlp_jac_g", [x[0], p[0]], [ev.m, ev.nnz_j])
+        (hess,) = call("hb_nlp_hess_l", [x[0], p[0], sigma, lam[0]], [ev.nnz_h])
+        assert f[0] == ref["f"] and f2[0] == ref["f"] and np.array_equal(grad, ref["grad_f"])
+        assert np.array_equal(g, ref["g"]) and np.array_equal(g2, ref["g"]) and np.array_equal(jac, ref["jac"])
+        assert np.array_equal(hess, ref["hess"])
+        n1, n2 = ctypes.c_int64(), ctypes.c_int64()
+        lib.hb_external_stats(ctypes.byref(n1), ctypes.byref(n2))
+        assert (n1.value, n2.value) == (1, 1)  # four first-order calls at one x: ONE evaluation
+        call("hb_nlp_g", [x[0] + 1e-3, p[0]], [ev.m])
+        lib.hb_external_stats(ctypes.byref(n1), ctypes.byref(n2))
+        assert n1.value == 2
+    finally:
+        assert lib.hb_external_bind(None) == 0
+    arg = (dp * 2)(x[0].ctypes.data_as(dp), p[0].ctypes.data_as(dp))
+    res = (dp * 1)(np.zeros(1).ctypes.data_as(dp))
+    lib.hb_nlp_f.restype = ctypes.c_int
+    assert lib.hb_nlp_f(arg, res, None, None, 0) != 0 and b"no problem bound" in lib.hb_last_error()
