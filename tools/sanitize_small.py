@@ -45,4 +45,44 @@ for q in (s0, s1):
 xo = torch.zeros((B, 189 * 12 + 6), dtype=torch.float64, device=d)
 humanoid_state_interpolator(s0, s1, ph, 10, 0.1, x_out=xo, knot0=1)
 torch.cuda.synchronize()
+# round 2: named cost values, deterministic sparse products, the CasADi external-function ABI, one L-BFGS solver iteration
+import ctypes  # noqa: E402
+
+from hippopt_b200 import _capi  # noqa: E402
+from hippopt_b200.ipsolver import BatchedInteriorPoint, SparseOps  # noqa: E402
+
+for st in (KinoSettings(horizon=3), KinoSettings(horizon=2, terrain="smooth_steps", n_terrain_params=10)):
+    ev = KinoEvaluator(model, st)
+    x, p, lam, sigma = kino_batch(ev.layout, model, 3, seed=1, noise=0.1)
+    X, P, L, S = (torch.tensor(a, device=d) for a in (x, p, lam, sigma))
+    ev.cost_terms(X, P)
+    out = ev.eval(ALL, X, P, L, S)
+    ops = SparseOps(ev.n_x, ev.m, ev.jac_sparsity(), ev.hess_sparsity(), d)
+    ops.J_mul(out["jac"], X)
+    ops.Jt_mul(out["jac"], L)
+    ops.W_quad(out["hess"], X)
+    torch.cuda.synchronize()
+ev = KinoEvaluator(model, KinoSettings(horizon=3))
+x, p, lam, sigma = kino_batch(ev.layout, model, 1, seed=2, noise=0.1)
+lib = _capi.lib()
+assert lib.hb_external_bind(ev._h) == 0
+dp = ctypes.POINTER(ctypes.c_double)
+gj = [np.zeros(ev.m), np.zeros(ev.nnz_j)]
+arg = (dp * 2)(x[0].ctypes.data_as(dp), p[0].ctypes.data_as(dp))
+res = (dp * 2)(gj[0].ctypes.data_as(dp), gj[1].ctypes.data_as(dp))
+lib.hb_nlp_jac_g.restype = ctypes.c_int
+assert lib.hb_nlp_jac_g(arg, res, None, None, 0) == 0
+hs = np.zeros(ev.nnz_h)
+arg4 = (dp * 4)(x[0].ctypes.data_as(dp), p[0].ctypes.data_as(dp), sigma.ctypes.data_as(dp), lam[0].ctypes.data_as(dp))
+res1 = (dp * 1)(hs.ctypes.data_as(dp))
+lib.hb_nlp_hess_l.restype = ctypes.c_int
+assert lib.hb_nlp_hess_l(arg4, res1, None, None, 0) == 0
+lib.hb_external_bind(None)
+lb, ub = ev.bounds(p)
+try:
+    BatchedInteriorPoint(ev, kkt="stage", delta_c=1e-9, ipopt_options={"hessian_approximation": "limited-memory", "max_iter": 3,
+                                                                       "tol": 1e-3}).solve(torch.tensor(x, device=d), torch.tensor(p, device=d), lb, ub)
+except Exception as exc:  # noqa: BLE001 -- three iterations do not converge: OptiFailure is the expected outcome
+    print("solver:", type(exc).__name__)
+torch.cuda.synchronize()
 print("sanitize workload done")
