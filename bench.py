@@ -213,15 +213,12 @@ def sharded_solves(model, ev, dev, rank, world):
         del ev4, x4
     except Exception as exc:  # noqa: BLE001
         perr = f"{type(exc).__name__}: {exc}"
-    mine = torch.cat([mine, plan])
-    if world > 1:
-        allr = torch.empty((world, mine.numel()), dtype=torch.float64, device=dev)
-        dist.all_gather_into_tensor(allr, mine[None].contiguous())
-    else:
-        allr = mine[None]
+    from hippopt_b200.sharding import gather_rank_rows, whole_job_rate
+
+    allr = gather_rank_rows(torch.cat([mine, plan]))
     a = allr.cpu().numpy()
-    conv, slow = float(a[:, 1].sum()), float(a[:, 2].max())
-    pconv, pslow = float(a[:, 9].sum()), float(a[:, 10].max())
+    conv, slow, _ = whole_job_rate(allr, 1, 2)
+    pconv, pslow, _ = whole_job_rate(allr, 9, 10)
     periodic = {"workload": f"BASELINE config 4 as posed: periodic walking step plans (step length U(0.1, 0.3) m, horizon {HORIZON}, "
                             f"final-state and periodicity rows), {PLANS_PER_GPU} per GPU, the reference's guess (100 N per point, "
                             f"mass-normalised) and IPOPT options (limited-memory Hessian, tol 1e-3, acceptable_tol 10)",

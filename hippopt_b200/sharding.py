@@ -42,3 +42,22 @@ def gather_instances(local: torch.Tensor, n_instances: int, group=None) -> torch
         a, b = shard_range(n_instances, r, world)
         parts.append(out[r * width: r * width + (b - a)])
     return torch.cat(parts, dim=0)
+
+
+def gather_rank_rows(row: torch.Tensor, group=None) -> torch.Tensor:
+    """All-gather ONE fixed-length row of per-rank scalars (counts, seconds, ...) into (world, len) on every rank."""
+    if not dist.is_available() or not dist.is_initialized():
+        return row[None].clone()
+    world = dist.get_world_size(group)
+    out = torch.empty((world, row.numel()), dtype=row.dtype, device=row.device)
+    dist.all_gather_into_tensor(out, row[None].contiguous(), group=group)
+    return out
+
+
+def whole_job_rate(rows: torch.Tensor, count_col: int, seconds_col: int) -> tuple[float, float, float]:
+    """Whole-job throughput of work sharded over ranks: (units of all ranks, slowest rank's seconds, units per second).
+    The job is finished when its slowest rank is: the rate is the SUM of the units over the MAX of the times -- never a
+    sum of per-rank rates."""
+    units = float(rows[:, count_col].sum())
+    slow = float(rows[:, seconds_col].max())
+    return units, slow, (units / slow if slow > 0 else 0.0)

@@ -7,7 +7,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from hippopt_b200.sharding import gather_instances, shard_range
+from hippopt_b200.sharding import gather_instances, gather_rank_rows, shard_range, whole_job_rate
 
 
 def test_shard_range_partitions_everything():
@@ -36,6 +36,12 @@ def _worker(rank, world, port, n):
         t = torch.tensor([float(rank + 1)], dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         assert t.item() == world
+        # sharded solves (bench.py::sharded_solves): one row of scalars per rank, whole-job rate = sum / slowest
+        row = torch.tensor([100.0 + rank, 90.0 + 5 * rank, 2.0 + rank], dtype=torch.float64)  # instances, converged, seconds
+        rows = gather_rank_rows(row)
+        assert rows.shape == (world, 3) and torch.equal(rows[rank], row)
+        units, slow, rate = whole_job_rate(rows, 1, 2)
+        assert (units, slow) == (90.0 + 95.0, 3.0) and rate == pytest.approx(185.0 / 3.0)
     finally:
         dist.destroy_process_group()
 
@@ -47,3 +53,8 @@ def test_gather_over_gloo_world2(n):
     port = s.getsockname()[1]
     s.close()
     mp.spawn(_worker, args=(2, port, n), nprocs=2, join=True)
+
+
+def test_rank_rows_without_a_process_group():
+    rows = gather_rank_rows(torch.tensor([4.0, 3.0, 0.5], dtype=torch.float64))
+    assert rows.shape == (1, 3) and whole_job_rate(rows, 1, 2) == (3.0, 0.5, 6.0)
