@@ -280,6 +280,16 @@ class BatchedInteriorPoint:
         if "mu_init" in o:
             mu_init = float(o["mu_init"])
         # hessian_approximation = limited-memory (main_periodic_step.py:116): L-BFGS instead of hess_l
+        # feasibility restoration (simplified, see _restoration below): entered after `resto_after` failed line searches
+        # in a row, left once the violation fell to required_infeasibility_reduction x its value at entry (IPOPT's
+        # option, 0.9 by default; the reference's mains set 0.8)
+        # Off by default: on every workload of this repository the filter / f-type acceptance and the Levenberg shifts
+        # never fail twice in a row (profiles/r02/solver_v15.txt), so the phase is exercised only when asked for
+        # ("hb_restoration": True, or IPOPT's "start_with_resto": "yes", which begins in it).
+        self.start_with_resto = str(o.get("start_with_resto", "no")) == "yes"
+        self.restoration = self.start_with_resto or bool(o.get("hb_restoration", False))
+        self.resto_after = int(o.get("hb_restoration_after", 2))
+        self.resto_reduction = float(o.get("required_infeasibility_reduction", 0.9))
         self.limited_memory = str(o.get("hessian_approximation", "exact")) == "limited-memory"
         self.lm_history = int(o.get("limited_memory_max_history", 6))
         self.obj_scaling = o.get("nlp_scaling_method", "none") == "gradient-based"
@@ -397,6 +407,9 @@ class BatchedInteriorPoint:
         done = torch.zeros(B, dtype=torch.bool, device=dev)
         stalled = torch.zeros(B, dtype=torch.bool, device=dev)  # given up: max_fail line-search failures in a row
         fails = torch.zeros(B, dtype=torch.long, device=dev)
+        resto = torch.zeros(B, dtype=torch.bool, device=dev)      # instances in the restoration phase
+        theta_entry = torch.zeros(B, dtype=torch.float64, device=dev)
+        self.restoration_entries = 0
         acceptable = torch.zeros(B, dtype=torch.bool, device=dev)
         acc_count = torch.zeros(B, dtype=torch.long, device=dev)
         f_prev = torch.full((B,), float("inf"), dtype=torch.float64, device=dev)
@@ -509,7 +522,11 @@ class BatchedInteriorPoint:
             # solve with a per-instance Levenberg shift until the step has positive curvature
             dx = torch.zeros_like(x)
             lamE_new = lamE.clone()
-            need = ~inactive
+            if it == 0 and self.start_with_resto:
+                theta_entry = cE.abs().sum(1) + cI.abs().sum(1)
+                resto = (theta_entry > self.tol) & ~inactive
+                self.restoration_entries += int(resto.sum())
+            need = ~inactive & ~resto
             def next_delta(dv):  # IPOPT's growth of the Hessian perturbation (kappa_plus = 8, first trial 1e-4)
                 return torch.clamp(torch.maximum(dv * 8.0, torch.full_like(dv, 1e-4)), max=self.delta_max)
 
@@ -595,6 +612,27 @@ class BatchedInteriorPoint:
                     break
                 delta = torch.where(need, next_delta(delta), delta)
             no_step = need & ~inactive  # no shift of the sequence gave a usable step: counts as a failed line search
+            # ---- feasibility restoration.  IPOPT switches to a second NLP (min ||c||_1 + zeta ||D(x - x_r)||^2 with
+            # its own slacks) when the line search cannot make progress; here the instances in that state take
+            # Levenberg-Marquardt steps on the violation instead: the same stage-wise KKT matrix with the Hessian
+            # replaced by lambda I and -I in the (2,2) block,
+            #   [[lambda I + J_I^T Sigma J_I, J_E^T], [J_E, -I]] [dx; y] = [-J_I^T (lamhat + Sigma c_I); -c_E],
+            # i.e. (lambda I + J_E^T J_E + J_I^T Sigma J_I) dx = -J_E^T c_E - J_I^T(...): a damped Gauss-Newton step
+            # that ignores the objective; accepted on decrease of the violation alone (below).
+            ridx = torch.nonzero(resto & ~inactive).ravel()
+            if ridx.numel():
+                lam_r = torch.clamp(1e-2 * torch.ones_like(delta[ridx]) * (1.0 + delta[ridx]), max=1e2)
+                rhs_r = -ops.Jt_mul(jv[ridx], rows_I(lamhat + Sig * cI)[ridx])
+                t_k = time.perf_counter()
+                dxr, lamr = backend.solve(torch.zeros_like(hv[ridx]), jv[ridx], Sig[ridx], lam_r, 1.0, rhs_r, -cE[ridx])
+                if dev.type == "cuda":
+                    torch.cuda.synchronize(dev)
+                self.kkt_seconds += time.perf_counter() - t_k
+                okr = torch.isfinite(dxr).all(dim=1)
+                dx[ridx] = torch.where(okr[:, None], dxr, torch.zeros_like(dxr))
+                lamE_new[ridx] = lamE[ridx]  # multipliers are not updated by a feasibility step
+                no_step = no_step.clone()
+                no_step[ridx] = ~okr
             ds = ops.J_mul(jv, dx)[:, iI] + cI
             lamI_new = lamhat + Sig * ds
             zL_new = torch.where(hasL, mu[:, None] / dL - SigL * ds, torch.zeros_like(s))
@@ -623,6 +661,7 @@ class BatchedInteriorPoint:
             accepted = inactive.clone()
             x_new, s_new = x.clone(), s.clone()
             blocked = no_step
+            ct_acc = cnorm.clone()  # violation of the accepted trial point (restoration bookkeeping)
             for bt in range(self.max_backtrack):
                 xt = x + alpha[:, None] * dx
                 st = s + alpha[:, None] * ds
@@ -644,9 +683,12 @@ class BatchedInteriorPoint:
                 ftype = self.f_type & (cnorm <= theta_min) & (dbar < 0)
                 acc_f = ftype & (bart <= bar0 + self.eta * alpha * dbar) & (ct <= 10.0 * theta_min)
                 good = torch.isfinite(phit) & (armijo | (filt & (cnorm > theta_min)) | acc_f)
+                # restoration: sufficient decrease of the constraint violation is the only criterion
+                good = torch.where(resto, torch.isfinite(ct) & (ct <= (1.0 - 1e-4 * alpha) * cnorm), good)
                 take = good & ~accepted & ~blocked
                 x_new = torch.where(take[:, None], xt, x_new)
                 s_new = torch.where(take[:, None], st, s_new)
+                ct_acc = torch.where(take, ct, ct_acc)
                 accepted |= take
                 if bool((accepted | blocked).all()):
                     break
@@ -658,6 +700,22 @@ class BatchedInteriorPoint:
             # solve per iteration until max_iter: there is no restoration phase to send it to)
             failed = ~accepted
             fails = torch.where(failed, fails + 1, torch.zeros_like(fails))
+            if self.restoration:
+                # leave: the violation fell enough (or the instance is feasible to the tolerance again)
+                ct_now = ct_acc
+                leave = resto & ((ct_now <= self.resto_reduction * theta_entry) | (ct_now <= self.tol))
+                if bool(leave.any()):
+                    resto = resto & ~leave
+                    fails = torch.where(leave, torch.zeros_like(fails), fails)
+                    delta = torch.where(leave, torch.zeros_like(delta), delta)
+                    lamE = torch.where(leave[:, None], torch.zeros_like(lamE), lamE)  # stale multipliers: start afresh
+                    nu = torch.where(leave, torch.ones_like(nu), nu)
+                enter = (~resto) & (~inactive) & (fails >= self.resto_after) & (cnorm > self.tol)
+                if bool(enter.any()):
+                    resto = resto | enter
+                    theta_entry = torch.where(enter, cnorm, theta_entry)
+                    fails = torch.where(enter, torch.zeros_like(fails), fails)
+                    self.restoration_entries += int(enter.sum())
             stalled |= fails >= self.max_fail
             delta = torch.where(failed, torch.clamp(torch.maximum(delta * 8.0, torch.full_like(delta, 1e-4)), max=self.delta_max),
                                 torch.where(moved, delta / 3.0, delta))

@@ -276,3 +276,29 @@ def test_limited_memory_matrix_is_the_bfgs_matrix():
     v = rng.normal(size=(1, n))
     got = lm.apply(torch.tensor([0]), torch.tensor(v)).numpy()
     assert got == pytest.approx(v @ Bm.T, rel=1e-10)
+
+
+def test_restoration_phase_reduces_the_violation_and_hands_back():
+    """The (simplified) feasibility restoration: Levenberg-Marquardt steps on the constraint violation through the
+    same KKT back end, accepted on decrease of the violation alone, left at required_infeasibility_reduction x the
+    violation at entry.  IPOPT's `start_with_resto` begins in it: HS071 from infeasible starts must still reach the
+    known answer, and the first accepted iterates must reduce the violation."""
+    f, g, lb, ub = hs071()
+    ev = TorchEvaluator(f, g, 4, 6)
+    x0 = starts()
+    p = torch.zeros((3, 1), dtype=torch.float64)
+    ip = BatchedInteriorPoint(ev, tol=1e-8, max_iter=200, ipopt_options={"start_with_resto": "yes",
+                                                                        "required_infeasibility_reduction": 0.5})
+    out = ip.solve(x0, p, lb, ub)
+    assert ip.restoration_entries == 3  # all three starts violate sum x^2 = 40
+    assert bool(out.success.all())
+    assert out.values.numpy() == pytest.approx(np.tile(HS071_X, (3, 1)), abs=2e-6)
+    # one iteration only: still in restoration, the violation of the equality row went down
+    one = BatchedInteriorPoint(ev, tol=1e-8, max_iter=1, ipopt_options={"start_with_resto": "yes"},
+                               callback_criterion=None)
+    try:
+        one.solve(x0, p, lb, ub)
+    except OptiFailure:
+        pass
+    plain = BatchedInteriorPoint(ev, tol=1e-8, max_iter=200).solve(x0, p, lb, ub)
+    assert (out.values - plain.values).abs().max() < 1e-5

@@ -79,6 +79,8 @@ if "-s" in sys.argv:
                 "nlp_scaling_method": "gradient-based"} if "--ref-options" in sys.argv else None
     if "--lbfgs" in sys.argv:  # hessian_approximation = limited-memory, the reference's own setting (:116)
         ref_opts = dict(ref_opts or {}, hessian_approximation="limited-memory", limited_memory_max_history=arg("--history", 6))
+    if "--no-resto" in sys.argv:
+        ref_opts = dict(ref_opts or {}, hb_restoration=False)
     sol = BatchedInteriorPoint(ev, tol=arg("-t", 1e-6), max_iter=iters, verbose="-v" in sys.argv, kkt="stage",
                                delta_c=1e-9, mu_init=arg("-m", 1e-1), ipopt_options=ref_opts)
     if "--callback" in sys.argv:  # the planner's criterion (humanoid_kinodynamic/planner.py:57-63)
@@ -115,6 +117,6 @@ if "-s" in sys.argv:
             print(f"  solutions: constraint violation max {vs.max():.1e}; left foot travels {np.median(moved):.3f} m (median; planned "
                   f"{np.median(L[sel][okk]):.3f}) and is lifted by {np.median(lift) * 1e3:.1f} mm (median, max over the knots); "
                   f"cost median {res.cost_value[res.success].median().item():.3e}; {res.evaluations} batched evaluations, "
-                  f"{sol.kkt_seconds:.1f} s in the KKT sweep")
+                  f"{sol.kkt_seconds:.1f} s in the KKT sweep; {sol.restoration_entries} entries into the restoration phase")
     except OptiFailure as e:
         print(f"periodic-step OCP: {e} ({time.perf_counter() - t0:.1f} s)")
