@@ -62,6 +62,11 @@ struct hb_problem_s {
   double* d_p = nullptr;    // parameters of the current solve
   int64_t p_cap = 0, p_stride = -1, p_batch = 0;
   int64_t h2d_bytes = 0, d2h_bytes = 0;
+  // small batches (a CPU-side IPOPT evaluates ONE instance): the contact kernel runs on an auxiliary stream next to
+  // the kinematics kernel -- a handful of warps leave the GPU empty, so the two kernels' single-warp latencies
+  // (33 us and 47 us) overlap instead of adding up
+  cudaStream_t aux = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   // host copies of what the handle was created from (hb_save) and the tables a non-Python caller needs: CCS
   // patterns of jac_g / hess_l and the affine description of lbg / ubg (hb_kino_attach_tables)
   std::vector<int32_t> c_icfg, c_jc, c_jk, c_hc, c_hk, c_hk2, lb_idx, ub_idx;
@@ -490,6 +495,9 @@ extern "C" int hb_destroy(hb_handle h) {
     if (h->hst[i]) cudaStreamDestroy(h->hst[i]);
   }
   cudaFree(h->d_p);
+  if (h->aux) cudaStreamDestroy(h->aux);
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  if (h->ev_join) cudaEventDestroy(h->ev_join);
   if (h->toy) hb::toy_destroy(h->toy);
   delete h;
   return HB_OK;
@@ -592,6 +600,24 @@ extern "C" int hb_eval(hb_handle h, uint32_t mask, const double* x, const double
     return HB_OK;
   };
   if (mark() != HB_OK) return HB_ERR_CUDA;
+  // fewer warps than one kernel's residency on the whole GPU (8 per SM for the kinematics kernel): run the contact
+  // kernel beside the kinematics kernel.  Not while profiling (the per-kernel events assume one stream).
+  int dev_now = 0;
+  CUDA_TRY(cudaGetDevice(&dev_now));
+  CUDA_TRY(ensure_kernel_attributes(dev_now));
+  static const bool no_overlap_env = getenv("HB_NO_SMALL_BATCH_OVERLAP") != nullptr;
+  const bool overlap = !h->prof && !no_overlap_env && C.kind == 0 && total_warps <= 8L * device_sms[dev_now];
+  cudaStream_t st_contact = st;
+  if (overlap) {
+    if (!h->aux) {
+      CUDA_TRY(cudaStreamCreateWithFlags(&h->aux, cudaStreamNonBlocking));
+      CUDA_TRY(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+      CUDA_TRY(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
+    }
+    CUDA_TRY(cudaEventRecord(h->ev_fork, st));         // inputs on `st` are complete before the fork
+    CUDA_TRY(cudaStreamWaitEvent(h->aux, h->ev_fork, 0));
+    st_contact = h->aux;
+  }
   {
     const size_t smem = (size_t)hb::contact_smem_layout(C.n_hc).total * sizeof(double) * warps_per_block;
     {
@@ -604,15 +630,16 @@ extern "C" int hb_eval(hb_handle h, uint32_t mask, const double* x, const double
                                                                        d_fpart, grad_f, g, jac_vals, hess_vals,
                                                                        (long)batch);
     } else if (C.terrain == 0)
-      hb::kino_contact_kernel<0><<<grid, 32 * warps_per_block, smem, st>>>(h->topo, h->dev, mask, x, p, (long)p_stride,
-                                                                          lam_g, sigma, d_fpart, grad_f, g, jac_vals,
-                                                                          hess_vals, (long)batch);
+      hb::kino_contact_kernel<0><<<grid, 32 * warps_per_block, smem, st_contact>>>(h->topo, h->dev, mask, x, p, (long)p_stride,
+                                                                                  lam_g, sigma, d_fpart, grad_f, g, jac_vals,
+                                                                                  hess_vals, (long)batch);
     else
-      hb::kino_contact_kernel<1><<<grid, 32 * warps_per_block, smem, st>>>(h->topo, h->dev, mask, x, p, (long)p_stride,
-                                                                          lam_g, sigma, d_fpart, grad_f, g, jac_vals,
-                                                                          hess_vals, (long)batch);
+      hb::kino_contact_kernel<1><<<grid, 32 * warps_per_block, smem, st_contact>>>(h->topo, h->dev, mask, x, p, (long)p_stride,
+                                                                                  lam_g, sigma, d_fpart, grad_f, g, jac_vals,
+                                                                                  hess_vals, (long)batch);
     CUDA_TRY(cudaGetLastError());
     h->launches++;
+    if (overlap) CUDA_TRY(cudaEventRecord(h->ev_join, h->aux));
   }
   if (mark() != HB_OK) return HB_ERR_CUDA;
   {
@@ -631,6 +658,8 @@ extern "C" int hb_eval(hb_handle h, uint32_t mask, const double* x, const double
     CUDA_TRY(cudaGetLastError());
     h->launches++;
   }
+  // join: everything after this call on `st` (the f reduction, the caller's copies) sees both kernels' outputs
+  if (overlap) CUDA_TRY(cudaStreamWaitEvent(st, h->ev_join, 0));
   if (mark() != HB_OK) return HB_ERR_CUDA;
   if (mask & HB_EVAL_F) {
     reduce_f_kernel<<<(unsigned)((batch + 127) / 128), 128, 0, st>>>(d_fpart, f, 2 * C.N, (long)batch);
@@ -722,21 +751,43 @@ extern "C" int hb_eval_host(hb_handle h, uint32_t mask, const double* x, const d
       d2h += count * 8;
       return cudaMemcpyAsync(dst, src, (size_t)count * 8, cudaMemcpyDeviceToHost, st);
     };
-    CUDA_TRY(up(d_x, x + lo * n_x, n * n_x));
+    // copies whose source and destination ranges are adjacent on BOTH sides are merged into one transfer: a caller
+    // that keeps x | lam_g | sigma and f | grad_f | g | jac | hess in one pinned block each (HostPipeline does) pays
+    // one copy per direction instead of up to eight -- at one instance per call the fixed cost of a copy (~8 us)
+    // is what the call consists of
+    struct Span {
+      double* dst;
+      const double* src;
+      int64_t count;
+    };
+    auto run = [&](std::vector<Span>& v, bool to_device) -> cudaError_t {
+      size_t i = 0;
+      while (i < v.size()) {
+        Span cur = v[i++];
+        while (i < v.size() && v[i].dst == cur.dst + cur.count && v[i].src == cur.src + cur.count) cur.count += v[i++].count;
+        const cudaError_t e = to_device ? up(cur.dst, cur.src, cur.count) : down(cur.dst, cur.src, cur.count);
+        if (e != cudaSuccess) return e;
+      }
+      return cudaSuccess;
+    };
+    std::vector<Span> in = {{d_x, x + lo * n_x, n * n_x}};
     if (need_l) {
-      CUDA_TRY(up(d_lam, lam_g + lo * m, n * m));
-      CUDA_TRY(up(d_sig, sigma + lo, n));
+      in.push_back({d_lam, lam_g + lo * m, n * m});
+      in.push_back({d_sig, sigma + lo, n});
     }
+    CUDA_TRY(run(in, true));
     const double* pc = h->p_stride == 0 ? h->d_p : h->d_p + lo * n_p;
     const int rc = hb_eval(h, mask, d_x, pc, h->p_stride, need_l ? d_lam : nullptr, need_l ? d_sig : nullptr, d_f, d_gf,
                            d_g, d_j, d_h, n, st);
     if (rc != HB_OK) return rc;
     launches += h->launches;
-    if (mask & HB_EVAL_F) CUDA_TRY(down(f + lo, d_f, n));
-    if (mask & HB_EVAL_GRAD_F) CUDA_TRY(down(grad_f + lo * n_x, d_gf, n * n_x));
-    if (mask & HB_EVAL_G) CUDA_TRY(down(g + lo * m, d_g, n * m));
-    if (mask & HB_EVAL_JAC_G) CUDA_TRY(down(jac_vals + lo * nnz_j, d_j, n * nnz_j));
-    if (need_l) CUDA_TRY(down(hess_vals + lo * nnz_h, d_h, n * nnz_h));
+    std::vector<Span> out;
+    if (mask & HB_EVAL_F) out.push_back({f + lo, d_f, n});
+    if (mask & HB_EVAL_GRAD_F) out.push_back({grad_f + lo * n_x, d_gf, n * n_x});
+    if (mask & HB_EVAL_G) out.push_back({g + lo * m, d_g, n * m});
+    if (mask & HB_EVAL_JAC_G) out.push_back({jac_vals + lo * nnz_j, d_j, n * nnz_j});
+    if (need_l) out.push_back({hess_vals + lo * nnz_h, d_h, n * nnz_h});
+    CUDA_TRY(run(out, false));
   }
   for (int i = 0; i < S; ++i) CUDA_TRY(cudaStreamSynchronize(h->hst[i]));
   h->launches = launches;
@@ -1106,12 +1157,13 @@ std::vector<casadi_int> ccs_sp(casadi_int nrow, casadi_int ncol, const std::vect
   s.insert(s.end(), row.begin(), row.end());
   return s;
 }
+// two pinned blocks in hb_eval_host's slab order -- x | lam_g | sigma and f | grad_f | g | jac | hess -- so that an
+// evaluation is one copy in each direction; p has its own buffer (uploaded only when it changes)
 void ext_free() {
-  double** bufs[] = {&g_ext.x, &g_ext.p, &g_ext.lam, &g_ext.sigma, &g_ext.f, &g_ext.grad, &g_ext.g, &g_ext.jac, &g_ext.hess};
-  for (double** b : bufs) {
-    if (*b) cudaFreeHost(*b);
-    *b = nullptr;
-  }
+  if (g_ext.x) cudaFreeHost(g_ext.x);
+  if (g_ext.f) cudaFreeHost(g_ext.f);
+  if (g_ext.p) cudaFreeHost(g_ext.p);
+  g_ext.x = g_ext.lam = g_ext.sigma = g_ext.f = g_ext.grad = g_ext.g = g_ext.jac = g_ext.hess = g_ext.p = nullptr;
 }
 // copies x / p into the staging buffers; returns true when x changed (the first-order cache is then stale)
 int ext_inputs(const double** arg) {
@@ -1176,13 +1228,19 @@ extern "C" int hb_external_bind(hb_handle h) {
   g_ext.sp_g = dense_sp(g_ext.m);
   g_ext.sp_jac = ccs_sp(g_ext.m, g_ext.n_x, jc, jr);
   g_ext.sp_hess = ccs_sp(g_ext.n_x, g_ext.n_x, hc, hr);
-  struct { double** b; int64_t n; } al[] = {{&g_ext.x, g_ext.n_x}, {&g_ext.p, g_ext.n_p}, {&g_ext.lam, g_ext.m}, {&g_ext.sigma, 1},
-                                            {&g_ext.f, 1}, {&g_ext.grad, g_ext.n_x}, {&g_ext.g, g_ext.m},
-                                            {&g_ext.jac, g_ext.nnz_j}, {&g_ext.hess, g_ext.nnz_h}};
-  for (auto& a : al) {
-    CUDA_TRY(cudaHostAlloc((void**)a.b, sizeof(double) * (size_t)(a.n > 0 ? a.n : 1), cudaHostAllocDefault));
-    memset(*a.b, 0, sizeof(double) * (size_t)(a.n > 0 ? a.n : 1));
-  }
+  const size_t n_in = (size_t)(g_ext.n_x + g_ext.m + 1), n_out = (size_t)(1 + g_ext.n_x + g_ext.m + g_ext.nnz_j + g_ext.nnz_h);
+  CUDA_TRY(cudaHostAlloc((void**)&g_ext.x, sizeof(double) * n_in, cudaHostAllocDefault));
+  CUDA_TRY(cudaHostAlloc((void**)&g_ext.f, sizeof(double) * n_out, cudaHostAllocDefault));
+  CUDA_TRY(cudaHostAlloc((void**)&g_ext.p, sizeof(double) * (size_t)(g_ext.n_p > 0 ? g_ext.n_p : 1), cudaHostAllocDefault));
+  memset(g_ext.x, 0, sizeof(double) * n_in);
+  memset(g_ext.f, 0, sizeof(double) * n_out);
+  memset(g_ext.p, 0, sizeof(double) * (size_t)(g_ext.n_p > 0 ? g_ext.n_p : 1));
+  g_ext.lam = g_ext.x + g_ext.n_x;
+  g_ext.sigma = g_ext.lam + g_ext.m;
+  g_ext.grad = g_ext.f + 1;
+  g_ext.g = g_ext.grad + g_ext.n_x;
+  g_ext.jac = g_ext.g + g_ext.m;
+  g_ext.hess = g_ext.jac + g_ext.nnz_j;
   g_ext.h = h;
   return HB_OK;
 }

@@ -139,7 +139,15 @@ class HostPipeline:
         shapes = {"f": (), "grad_f": (ev.n_x,), "g": (ev.m,), "jac": (ev.nnz_j,), "hess": (ev.nnz_h,)}
         bits = {"f": F, "grad_f": GRAD_F, "g": G, "jac": JAC_G, "hess": HESS_L}
         self.names = [n for n in shapes if mask & bits[n]]
-        self.host_out = {n: self.host_buffer((batch, *shapes[n]), pinned) for n in self.names}
+        # one pinned block in the library's slab order (f | grad_f | g | jac | hess): hb_eval_host merges copies whose
+        # host and device ranges are adjacent, which they are whenever the whole batch is one chunk
+        sizes = {n: batch * int(np.prod(shapes[n], dtype=np.int64)) for n in self.names}
+        block = self.host_buffer((sum(sizes.values()),), pinned)
+        self.host_out, o = {}, 0
+        for n in self.names:
+            self.host_out[n] = block[o:o + sizes[n]].view((batch, *shapes[n]))
+            o += sizes[n]
+        self._block = block
         self.h2d_bytes = self.d2h_bytes = 0
 
     @staticmethod

@@ -169,9 +169,12 @@ class HostEvaluator:
         self.masks = {"f": F, "grad_f": GRAD_F, "g": G, "jac": JAC_G, "hess": HESS_L}
         self.first = HostPipeline(ev, 1, F | GRAD_F | G | JAC_G)
         self.second = HostPipeline(ev, 1, HESS_L)
-        self.x_host = HostPipeline.host_buffer((1, ev.n_x))
-        self.lam_host = HostPipeline.host_buffer((1, ev.m))
-        self.sig_host = HostPipeline.host_buffer((1,))
+        # x | lam_g | sigma in one pinned block: one host-to-device copy per evaluation (hb_eval_host merges adjacent ranges)
+        blk = HostPipeline.host_buffer((ev.n_x + ev.m + 1,))
+        self.x_host = blk[:ev.n_x].view(1, ev.n_x)
+        self.lam_host = blk[ev.n_x:ev.n_x + ev.m].view(1, ev.m)
+        self.sig_host = blk[ev.n_x + ev.m:]
+        self._blk = blk
 
     def set_parameters(self, p: np.ndarray) -> None:
         self.first.set_parameters(self.torch.from_numpy(np.ascontiguousarray(p, dtype=np.float64).ravel()))
