@@ -1,5 +1,6 @@
 // api.cu -- C ABI (include/hippopt_b200.h): handle management, launches, fp64 probe.
 #include <algorithm>
+#include <cstdint>
 #include <cstdio>
 #include <cstring>
 #include <map>
@@ -7,6 +8,7 @@
 #include <vector>
 
 #include "kino_const.cuh"
+#include "contact_jac_desc.h"
 // single translation unit: the kernels are included by hippopt_b200.cu before this file
 
 
@@ -45,6 +47,9 @@ struct hb_problem_s {
   hb::KinTopo topo{};  // warp-uniform tables, passed by value to the kinematics kernel
   int *d_jc = nullptr, *d_jk = nullptr, *d_hc = nullptr, *d_hk = nullptr, *d_hk2 = nullptr, *d_sched = nullptr;
   short* d_hci = nullptr;
+  hb::KnotMaps* d_knot_maps = nullptr;
+  int2* d_jc_list = nullptr;
+  unsigned *d_jk_list = nullptr, *d_hc_list = nullptr, *d_hk_list = nullptr;
   // per-knot cost partial sums, one scratch buffer per stream so that evaluations enqueued on
   // different streams (HostPipeline) do not share scratch
   std::map<cudaStream_t, std::pair<double*, int64_t>> fpart;
@@ -408,18 +413,81 @@ extern "C" int hb_kino_create(const int32_t* icfg, const double* dcfg, const int
   h->c_hk.assign(hk_map, hk_map + N * 27 * 57);
   h->c_hk2.assign(hk2_map, hk2_map + N * 27);
   cudaError_t e = cudaSuccess;
-  if (e == cudaSuccess) e = upload(&h->d_jc, jc_map, N * C.n_jc);
-  if (e == cudaSuccess) e = upload(&h->d_jk, jk_map, N * C.n_jk);
+  {
+    // knot-relative tables (KnotMaps in kino_const.cuh): identical rows are stored once, each with its
+    // destination-sorted list
+    std::vector<hb::KnotMaps> km(N);
+    bool too_wide = false;
+    auto relative = [&](const int32_t* map, size_t n, int hb::KnotMaps::*base, int hb::KnotMaps::*off,
+                        int hb::KnotMaps::*cnt, int** dst_rel, void** dst_list, bool with_desc) {
+      std::vector<int32_t> rel, list, counts, row(n);
+      const size_t words = with_desc ? 2 : 1;
+      for (size_t k = 0; k < N; ++k) {
+        int32_t lo = INT32_MAX;
+        for (size_t i = 0; i < n; ++i)
+          if (map[k * n + i] >= 0 && map[k * n + i] < lo) lo = map[k * n + i];
+        if (lo == INT32_MAX) lo = 0;
+        for (size_t i = 0; i < n; ++i) row[i] = map[k * n + i] >= 0 ? map[k * n + i] - lo : -1;
+        size_t c = 0;
+        for (; c * n < rel.size(); ++c)
+          if (std::equal(row.begin(), row.end(), rel.begin() + c * n)) break;
+        if (c * n == rel.size()) {
+          rel.insert(rel.end(), row.begin(), row.end());
+          std::vector<std::pair<int32_t, int32_t>> order;  // (slot, entry)
+          for (size_t i = 0; i < n; ++i) {
+            if (row[i] < 0) continue;
+            if (with_desc && hb::contact_jac_descriptor((int)i, C.terrain) == hb::JC_SKIP) continue;
+            order.emplace_back(row[i], (int32_t)i);
+          }
+          std::sort(order.begin(), order.end());
+          counts.push_back((int32_t)order.size());
+          for (size_t i = 0; i < n; ++i) {
+            if (i >= order.size()) {
+              for (size_t w = 0; w < words; ++w) list.push_back(-1);
+            } else if (with_desc) {
+              list.push_back(order[i].first);
+              list.push_back(hb::contact_jac_descriptor(order[i].second, C.terrain));
+            } else {
+              too_wide = too_wide || order[i].first >= 65536 || order[i].second >= 65536;
+              list.push_back((int32_t)(((uint32_t)order[i].second << 16) | (uint32_t)order[i].first));
+            }
+          }
+        }
+        km[k].*base = lo;
+        km[k].*off = (int)(c * n);
+        if (cnt) km[k].*cnt = counts[c];
+      }
+      cudaError_t err = upload(dst_rel, rel.data(), rel.size());
+      if (err == cudaSuccess && dst_list) err = upload(reinterpret_cast<int32_t**>(dst_list), list.data(), list.size());
+      return err;
+    };
+    using KM = hb::KnotMaps;
+    if (e == cudaSuccess) e = relative(jc_map, C.n_jc, &KM::jc_base, &KM::jc_off, &KM::jc_cnt, &h->d_jc, (void**)&h->d_jc_list, C.kind == 0);
+    if (e == cudaSuccess) e = relative(jk_map, C.n_jk, &KM::jk_base, &KM::jk_off, &KM::jk_cnt, &h->d_jk, (void**)&h->d_jk_list, false);
+    if (e == cudaSuccess) e = relative(hc_map, C.n_hc, &KM::hc_base, &KM::hc_off, &KM::hc_cnt, &h->d_hc, (void**)&h->d_hc_list, false);
+    if (e == cudaSuccess) e = relative(hk_map, 27 * 57, &KM::hk_base, &KM::hk_off, &KM::hk_cnt, &h->d_hk, (void**)&h->d_hk_list, false);
+    if (e == cudaSuccess) e = relative(hk2_map, 27, &KM::hk2_base, &KM::hk2_off, nullptr, &h->d_hk2, nullptr, false);
+    if (e == cudaSuccess) e = upload(&h->d_knot_maps, km.data(), km.size());
+    if (too_wide) {
+      hb_destroy(h);
+      return fail(HB_ERR_UNSUPPORTED, "hb_kino_create: a knot's columns hold more than 65535 non-zeros (packed scatter lists)");
+    }
+  }
   if (e == cudaSuccess) e = upload(&h->d_hci, hc_index, (size_t)129 * 129);
-  if (e == cudaSuccess) e = upload(&h->d_hc, hc_map, N * C.n_hc);
-  if (e == cudaSuccess) e = upload(&h->d_hk, hk_map, N * 27 * 57);
-  if (e == cudaSuccess) e = upload(&h->d_hk2, hk2_map, N * 27);
   C.jc_map = h->d_jc;
   C.jk_map = h->d_jk;
   C.hc_index = h->d_hci;
   C.hc_map = h->d_hc;
   C.hk_map = h->d_hk;
   C.hk2_map = h->d_hk2;
+  C.knot_maps = h->d_knot_maps;
+  C.jc_list = h->d_jc_list;
+  C.jk_list = h->d_jk_list;
+  C.hc_list = h->d_hc_list;
+  C.hk_list = h->d_hk_list;
+  h->topo.knot_maps = h->d_knot_maps;
+  h->topo.jc_list = h->d_jc_list;
+  h->topo.hc_list = h->d_hc_list;
   h->topo.jc_map = h->d_jc;
   h->topo.hc_index = h->d_hci;
   h->topo.hc_map = h->d_hc;
@@ -486,6 +554,11 @@ extern "C" int hb_destroy(hb_handle h) {
   cudaFree(h->d_hc);
   cudaFree(h->d_hk);
   cudaFree(h->d_hk2);
+  cudaFree(h->d_knot_maps);
+  cudaFree(h->d_jc_list);
+  cudaFree(h->d_jk_list);
+  cudaFree(h->d_hc_list);
+  cudaFree(h->d_hk_list);
   cudaFree(h->d_sched);
   cudaFree(h->dev);
   for (auto& kv : h->fpart) cudaFree(kv.second.first);

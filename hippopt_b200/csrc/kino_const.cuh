@@ -42,6 +42,21 @@ struct BodyC {
   int sib_rank;  // index of this body among the children of its parent (level-wise primal adjoint pass)
 };
 
+// Scatter maps are stored RELATIVE to the first entry of their knot: the columns of one knot are contiguous in
+// both compressed-column patterns, and the positions inside that range are the same for every interior knot, so
+// a horizon needs two or three distinct tables (first / interior / last knot) instead of one per knot.  Every
+// interior warp then reads the SAME few kilobytes (L1-resident) where the per-knot tables were an L2 round trip
+// in front of every batch of scattered stores.  `*_off`: element offset of the knot's table inside the map array;
+// `*_base`: what to add to its entries.
+// Besides the entry-indexed tables (`*_map`: local entry -> slot) every class has a DESTINATION-SORTED list
+// (`*_list`, `*_cnt` valid words at the same offset): word = local entry << 16 | slot for the staged outputs, and
+// {slot, value descriptor} (contact_jac_desc.h) for the contact kernel's Jacobian.  Walking a list in order makes
+// consecutive lanes store to consecutive addresses wherever the pattern has runs (whole point blocks of columns).
+struct alignas(16) KnotMaps {
+  int jc_base, jc_off, jc_cnt, hc_base, hc_off, hc_cnt, pad0, pad1;         // contact kernel (two 16-byte loads)
+  int jk_base, jk_off, jk_cnt, hk_base, hk_off, hk_cnt, hk2_base, hk2_off;  // kinematics kernel
+};
+
 struct KinoConst {
   int N, n_x, n_p, m, nnz_j, nnz_h, n_jc, n_jk, n_hc, terrain, has_final, has_per, h_init;
   int po_desc0, po_mass, po_init, po_final, po_dt, po_gravity, po_kt, po_kbs, po_eps, po_mu, po_max_u, po_max_fd,
@@ -68,6 +83,11 @@ struct KinoConst {
   const int* hc_map;
   const int* hk_map;
   const int* hk2_map;
+  const KnotMaps* knot_maps;
+  const int2* jc_list;
+  const unsigned* jk_list;
+  const unsigned* hc_list;
+  const unsigned* hk_list;
 };
 
 // Warp-uniform part of KinoConst.  It is passed BY VALUE as a __grid_constant__ kernel parameter:
@@ -98,6 +118,9 @@ struct KinTopo {
   const int* jc_map;
   const short* hc_index;
   const int* hc_map;
+  const KnotMaps* knot_maps;
+  const int2* jc_list;
+  const unsigned* hc_list;
   // packed tangent sweep (kino_kin.cu): sched[round * 32 + lane] = task descriptor (see KT_* below)
   const int* sched;
   signed char root_slot[32];  // slot that holds the root totals of direction d after the sweep

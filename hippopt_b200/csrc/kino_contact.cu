@@ -22,6 +22,7 @@
 // through the (variable, variable) -> local entry table hc_index and accumulated per warp in shared
 // memory in a fixed order (deterministic), then scattered once.
 #include "kino_const.cuh"
+#include "contact_jac_desc.h"
 #include "kino_smooth.cuh"
 
 namespace hb {
@@ -163,8 +164,9 @@ __global__ void __launch_bounds__(128, TERRAIN == 0 ? CONTACT_MIN_BLOCKS : 1) ki
   double* gb = g + b * C.m;
   const double* lb = lam + b * C.m;
   const double sg = want_hess ? sigma[b] : 0.0;
-  const int* jmap = C.jc_map + (size_t)k * C.n_jc;
-  double* jb = jac + b * C.nnz_j;
+  const int4 kmaps = *reinterpret_cast<const int4*>(&C.knot_maps[k].jc_base);  // {jc_base, jc_off, jc_cnt, hc_base}
+  const int* jmap = C.jc_map + kmaps.y;
+  double* jb = jac + b * C.nnz_j + kmaps.x;
   auto jput = [&](int e, double v) {
     const int slot = jmap[e];
     if (slot >= 0) jb[slot] = v;
@@ -770,86 +772,37 @@ __global__ void __launch_bounds__(128, TERRAIN == 0 ? CONTACT_MIN_BLOCKS : 1) ki
 
   HB_PHASE(1, 3);  // f, grad_f
   // ------------------------------------------------------------------ Jacobian values
-  // The scatter slots are loaded in batches BEFORE the dependent stores (ncu: 25 % of the kernel's stall
-  // samples sat on `jb[slot] = v` waiting for the map load when each store followed its own load).
+  // Every entry is coefficient x source (contact_jac_desc.h).  The derived sources and the coefficient table go
+  // where the previous knot's variables were (zp is dead after the defect rows), then the knot class's
+  // destination-sorted list is streamed: {slot, descriptor} pairs, coalesced stores, no per-entry branching.
   if (want_jac) {
-    auto pair_bc = [](int pr, int& a, int& bcol, int& c) {
-      // 3x3 skew entry order (0,1),(0,2),(1,0),(1,2),(2,0),(2,1)
-      a = pr >> 1;
-      bcol = a == 0 ? (pr & 1) + 1 : (a == 1 ? ((pr & 1) ? 2 : 0) : (pr & 1));
-      c = 3 - a - bcol;
-    };
-    auto value_c14 = [&](int e) -> double {
-      if (e < 324) {  // C1: linear dynamics
-        const int t = e & 3;
-        return t == 0 ? 1.0 : (t == 2 ? -1.0 : -hdt);
-      }
-      if (e < 417) return (e - 324) < 87 ? 1.0 : -1.0;  // C2: initial conditions
-      if (e < 498) return 1.0;                           // C3: final state
-      if (e < 582) return k == 0 ? 1.0 : -1.0;           //     periodicity
-      const int side = (e - 582) / 132, q = (e - 582) % 132;  // C4: centroidal momentum dynamics
-      if (q < 6) return side == 0 ? 1.0 : -1.0;
-      if (q < 30) return -hdt;
-      int a, bcol, c;
-      if (q < 78) {
-        pair_bc((q - 30) % 6, a, bcol, c);
-        return -hdt * eps3(a, bcol) * zs[15 * ((q - 30) / 6) + Z_F + c];
-      }
-      if (q < 126) {
-        pair_bc((q - 78) % 6, a, bcol, c);
-        return hdt * eps3(a, bcol) * (zs[15 * ((q - 78) / 6) + Z_P + c] - zs[Z_COM + c]);
-      }
-      pair_bc(q - 126, a, bcol, c);
-      return hdt * eps3(a, bcol) * (c == 0 ? fsum.x : (c == 1 ? fsum.y : fsum.z));
-    };
-    auto emit_range = [&](int e0, int e1, auto value) {
-      for (int eb = e0 + lane; eb < e1; eb += 256) {
-        int sl[8];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) sl[u] = (eb + 32 * u) < e1 ? jmap[eb + 32 * u] : -1;
-#pragma unroll
-        for (int u = 0; u < 8; ++u)
-          if (sl[u] >= 0) jb[sl[u]] = value(eb + 32 * u);
-      }
-    };
-    emit_range(0, 846, value_c14);
-    if (TERRAIN == 0 && lane < 8) {
-      const int pb0 = 846 + 29 * lane;
-      const double vals[29] = {1.0, 1.0, 1.0, -tau, -tau, -1.0, -dtau * pu.x, -dtau * pu.y,
-                               -pf.z,                   // dcc wrt v_z
-                               -ppos.z,                 // wrt f_dot_z
-                               -kbs * pf.z - pfd.z,     // wrt p_z
-                               -kbs * ppos.z - pv.z,    // wrt f_z
-                               1.0,                     // height
-                               1.0,                     // normal force
-                               -2.0 * pf.x, -2.0 * pf.y, 2.0 * mu * mu * pf.z,   // friction
-                               1.0, 1.0, 1.0, mass, mass, mass,                   // control bounds
-                               1.0, 1.0, 1.0, -1.0, -1.0, -1.0};                  // FK rows wrt p and pb
-      int sl[29];
-#pragma unroll
-      for (int u = 0; u < 29; ++u) sl[u] = jmap[pb0 + u];
-#pragma unroll
-      for (int u = 0; u < 29; ++u)
-        if (sl[u] >= 0) jb[sl[u]] = vals[u];
+    __syncwarp();
+    if (lane < 8) {
+      zs[JX_TAU + lane] = tau;
+      zs[JX_DTAU_U + 2 * lane] = dtau * pu.x;
+      zs[JX_DTAU_U + 2 * lane + 1] = dtau * pu.y;
+      zs[JX_KF + lane] = kbs * pf.z + pfd.z;
+      zs[JX_KP + lane] = kbs * ppos.z + pv.z;
     }
-    // C6: robot rows with constant entries; the CoM-height row has 1 (planar) or 3 (smooth) entries,
-    // the smooth ones are written by the terrain block above
-    constexpr int NCH = TERRAIN == 0 ? 1 : 3;
-    constexpr int base6 = 846 + (TERRAIN == 0 ? 232 : 464);
-    auto value_c6 = [&](int eg) -> double {
-      const int e = eg - base6;
-      if (e < 3) return 1.0;
-      if (e < 6) return -1.0;
-      if (e < 9) return 1.0;
-      if (e < 12) return mass;
-      if (e < 58 + NCH) return 1.0;
-      return (e - 58 - NCH) < 4 ? 0.25 : -0.25;
-    };
-    if (TERRAIN == 0) {
-      emit_range(base6, base6 + 66 + NCH, value_c6);
-    } else {
-      emit_range(base6, base6 + 12, value_c6);
-      emit_range(base6 + 12 + NCH, base6 + 66 + NCH, value_c6);
+    if (lane < 24) zs[JX_PC + lane] = zs[15 * (lane / 3) + Z_P + lane % 3] - zs[Z_COM + lane % 3];
+    if (lane >= 24 && lane < 27) zs[JX_FSUM + lane - 24] = lane == 24 ? fsum.x : (lane == 25 ? fsum.y : fsum.z);
+    if (lane == 27) zs[JX_ONE] = 1.0;
+    if (lane < JC_COUNT) {  // coefficient table, order of the JC_* codes
+      const double cv = lane == JC_ONE ? 1.0 : lane == JC_MONE ? -1.0 : lane == JC_HDT ? hdt : lane == JC_MHDT ? -hdt
+                      : lane == JC_MASS ? mass : lane == JC_QUARTER ? 0.25 : lane == JC_MQUARTER ? -0.25
+                      : lane == JC_PERIODIC ? (k == 0 ? 1.0 : -1.0) : lane == JC_MTWO ? -2.0 : 2.0 * mu * mu;
+      zs[JX_COEF + lane] = cv;
+    }
+    __syncwarp();
+    const int2* lst = C.jc_list + kmaps.y;
+    const int n = kmaps.z;
+    for (int eb = lane; eb < n; eb += 256) {
+      int2 w[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) w[u] = (eb + 32 * u) < n ? lst[eb + 32 * u] : make_int2(-1, 0);
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        if (w[u].x >= 0) jb[w[u].x] = zs[JX_COEF + (w[u].y >> 16)] * zs[w[u].y & 0xffff];
     }
   }
 
@@ -910,16 +863,18 @@ __global__ void __launch_bounds__(128, TERRAIN == 0 ? CONTACT_MIN_BLOCKS : 1) ki
     }
     HB_PHASE(1, 5);  // Hessian terms
     __syncwarp();
-    const int* hmap = C.hc_map + (size_t)k * C.n_hc;
-    double* hb_ = hess + b * C.nnz_h;
-    const int n_hc = C.n_hc;
-    for (int eb = lane; eb < n_hc; eb += 256) {  // 8 map loads in flight before the dependent stores
-      int sl[8];
+    const int2 hcm_ = *reinterpret_cast<const int2*>(&C.knot_maps[k].hc_off);  // {hc_off, hc_cnt}
+    const int2 hcm = make_int2(kmaps.w, hcm_.x);
+    const unsigned* hlst = C.hc_list + hcm.y;  // destination-sorted: entry << 16 | slot
+    double* hb_ = hess + b * C.nnz_h + hcm.x;
+    const int n_l = hcm_.y;
+    for (int eb = lane; eb < n_l; eb += 256) {  // 8 list loads in flight before the dependent stores
+      unsigned w[8];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) sl[u] = (eb + 32 * u) < n_hc ? hmap[eb + 32 * u] : -1;
+      for (int u = 0; u < 8; ++u) w[u] = (eb + 32 * u) < n_l ? hlst[eb + 32 * u] : 0xffffffffu;
 #pragma unroll
       for (int u = 0; u < 8; ++u)
-        if (sl[u] >= 0) hb_[sl[u]] = hbuf[eb + 32 * u];
+        if (w[u] != 0xffffffffu) hb_[w[u] & 0xffffu] = hbuf[w[u] >> 16];
     }
   }
 }

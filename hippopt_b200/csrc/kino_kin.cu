@@ -1175,8 +1175,9 @@ __global__ void __launch_bounds__(WITH_HESS ? KIN_H_THREADS : 128, WITH_HESS ? K
     }
     JacEmit em;
     em.C = Cp;
-    em.map = C.jk_map + (size_t)k * T.n_jk;
-    em.jac = jac + b * T.nnz_j;
+    const int2 jkm = *reinterpret_cast<const int2*>(&T.knot_maps[k].jk_base);  // {base, table offset}
+    em.map = C.jk_map + jkm.y;
+    em.jac = jac + b * T.nnz_j + jkm.x;
     em.gbuf = gbuf;
     em.lane = lane;
     em.k = k;
@@ -1221,14 +1222,15 @@ __global__ void __launch_bounds__(WITH_HESS ? KIN_H_THREADS : 128, WITH_HESS ? K
     if (em.stage && want_jac) {
       // scatter the staged rows: coalesced map reads, no load->store dependency inside the sweep
       const double* st = sm + L.stage;
-      const int n = T.n_jk;
-      for (int eb = lane; eb < n; eb += 256) {  // 8 map loads in flight before the dependent stores
-        int sl[8];
+      const unsigned* lst = C.jk_list + jkm.y;  // destination-sorted: entry << 16 | slot
+      const int n = T.knot_maps[k].jk_cnt;
+      for (int eb = lane; eb < n; eb += 256) {  // 8 list loads in flight before the dependent stores
+        unsigned w[8];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) sl[u] = (eb + 32 * u) < n ? em.map[eb + 32 * u] : -1;
+        for (int u = 0; u < 8; ++u) w[u] = (eb + 32 * u) < n ? lst[eb + 32 * u] : 0xffffffffu;
 #pragma unroll
         for (int u = 0; u < 8; ++u)
-          if (sl[u] >= 0) em.jac[sl[u]] = st[eb + 32 * u];
+          if (w[u] != 0xffffffffu) em.jac[w[u] & 0xffffu] = st[w[u] >> 16];
       }
       __syncwarp();
     }
@@ -1430,17 +1432,18 @@ __global__ void __launch_bounds__(WITH_HESS ? KIN_H_THREADS : 128, WITH_HESS ? K
       HB_PHASE(0, 6);  // Jacobian columns staged
       __syncwarp();
       if (want_jac) {
-        const int* jmap = C.jk_map + (size_t)k * T.n_jk;
-        double* jb = jac + b * T.nnz_j;
-        const int n = T.n_jk;
-        // KIN_SCAT map loads in flight before the dependent stores: 927 entries in two trips
+        const int4 jkm = *reinterpret_cast<const int4*>(&T.knot_maps[k].jk_base);  // {base, offset, count, -}
+        const unsigned* lst = C.jk_list + jkm.y;  // destination-sorted: entry << 16 | slot
+        double* jb = jac + b * T.nnz_j + jkm.x;
+        const int n = jkm.z;
+        // KIN_SCAT list loads in flight before the dependent stores: <= 927 entries in two trips
         for (int eb = lane; eb < n; eb += 32 * KIN_SCAT) {
-          int sl[KIN_SCAT];
+          unsigned w[KIN_SCAT];
 #pragma unroll
-          for (int u = 0; u < KIN_SCAT; ++u) sl[u] = (eb + 32 * u) < n ? jmap[eb + 32 * u] : -1;
+          for (int u = 0; u < KIN_SCAT; ++u) w[u] = (eb + 32 * u) < n ? lst[eb + 32 * u] : 0xffffffffu;
 #pragma unroll
           for (int u = 0; u < KIN_SCAT; ++u)
-            if (sl[u] >= 0) jb[sl[u]] = stg[eb + 32 * u];
+            if (w[u] != 0xffffffffu) jb[w[u] & 0xffffu] = stg[w[u] >> 16];
         }
       }
       if (want_grad) {
@@ -1515,8 +1518,8 @@ __global__ void __launch_bounds__(WITH_HESS ? KIN_H_THREADS : 128, WITH_HESS ? K
       S.chestN = scale(kappa, mGD);
     }
     HessEmit em;
-    em.map = C.hk_map + (size_t)k * (27 * 57);
-    em.hess = hess + b * T.nnz_h;
+    em.map = C.hk_map + T.knot_maps[k].hk_off;
+    em.hess = hess + b * T.nnz_h + T.knot_maps[k].hk_base;
     em.stage = HB_KIN_STAGE ? sm + L.stage : nullptr;
     em.dirj = dirj;
     em.add_sd = em.add_s = 0.0;
@@ -1640,20 +1643,24 @@ __global__ void __launch_bounds__(WITH_HESS ? KIN_H_THREADS : 128, WITH_HESS ? K
     if (em.stage) {
       // scatter the staged columns (27 directions x 57 rows) with coalesced map reads
       const double* st = sm + L.stage;
-      for (int eb = lane; eb < HSTAGE; eb += 32 * KIN_SCAT) {  // 1539 entries in three trips
-        int sl[KIN_SCAT];
+      const int2 hkl = *reinterpret_cast<const int2*>(&T.knot_maps[k].hk_off);  // {offset, count}
+      const unsigned* lst = C.hk_list + hkl.x;  // destination-sorted: entry << 16 | slot; mirrored pairs are absent
+      const int n = hkl.y;
+      for (int eb = lane; eb < n; eb += 32 * KIN_SCAT) {
+        unsigned w[KIN_SCAT];
 #pragma unroll
-        for (int u = 0; u < KIN_SCAT; ++u) sl[u] = (eb + 32 * u) < HSTAGE ? em.map[eb + 32 * u] : -1;
+        for (int u = 0; u < KIN_SCAT; ++u) w[u] = (eb + 32 * u) < n ? lst[eb + 32 * u] : 0xffffffffu;
 #pragma unroll
         for (int u = 0; u < KIN_SCAT; ++u)
-          if (sl[u] >= 0) em.hess[sl[u]] = st[eb + 32 * u];
+          if (w[u] != 0xffffffffu) em.hess[w[u] & 0xffffu] = st[w[u] >> 16];
       }
     }
     // velocity-diagonal entries (HK2): quaternion-velocity cost, joint regularisation
     if (lane < 27) {
-      const int slot2 = C.hk2_map[(size_t)k * 27 + lane];
+      const int2 hk2m = *reinterpret_cast<const int2*>(&T.knot_maps[k].hk2_base);
+      const int slot2 = C.hk2_map[hk2m.y + lane];
       if (slot2 >= 0)
-        em.hess[slot2] = lane < 4 ? 2.0 * sg * T.w_bqv : sg * T.w_joint * 2.0 * HB_N_JOINTS;
+        (hess + b * T.nnz_h + hk2m.x)[slot2] = lane < 4 ? 2.0 * sg * T.w_bqv : sg * T.w_joint * 2.0 * HB_N_JOINTS;
     }
     HB_PHASE(0, 13);  // Hessian scatter
   }

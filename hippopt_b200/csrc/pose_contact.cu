@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(128) pose_contact_kernel(const KinoConst* __re
   double* gb = g + b * C.m;
   const double* lb = lam + b * C.m;
   const double sg = want_hess ? sigma[b] : 0.0;
-  double* jb = jac + b * C.nnz_j;
+  double* jb = jac + b * C.nnz_j + C.knot_maps[0].jc_base;  // single knot: one knot-relative table
   auto jput = [&](int e, double v) {
     const int slot = C.jc_map[e];
     if (slot >= 0) jb[slot] = v;
@@ -229,7 +229,7 @@ __global__ void __launch_bounds__(128) pose_contact_kernel(const KinoConst* __re
         }
     }
     __syncwarp();
-    double* hb_ = hess + b * C.nnz_h;
+    double* hb_ = hess + b * C.nnz_h + C.knot_maps[0].hc_base;
     for (int e = lane; e < C.n_hc; e += 32) {
       const int slot = C.hc_map[e];
       if (slot >= 0) hb_[slot] = hbuf[e];
