@@ -94,6 +94,9 @@ def lib() -> ctypes.CDLL:
     L.hb_load.argtypes = [ctypes.c_char_p, ctypes.POINTER(vp)]
     L.hb_ccs_group_mul.restype = ctypes.c_int
     L.hb_ccs_group_mul.argtypes = [vp, vp, vp, vp, vp, vp, vp, i64, i64, i64, i64, vp]
+    L.hb_kkt_assemble_stage.restype = ctypes.c_int
+    L.hb_kkt_assemble_stage.argtypes = [i32p, vp, vp, i64, vp, i64, vp, i64, vp, ctypes.c_double, vp, i64, vp, i64, vp, vp,
+                                        vp, i64, vp]
     L.hb_external_bind.restype = ctypes.c_int
     L.hb_external_bind.argtypes = [vp]
     L.hb_external_stats.restype = ctypes.c_int
@@ -142,7 +145,7 @@ EXPORTED_SYMBOLS = [
     "hb_host_set_parameters", "hb_eval_host", "hb_host_last_traffic", "hb_host_alloc", "hb_host_free",
     "hb_lu_factor_batched", "hb_lu_solve_batched", "hb_set_option", "hb_interpolate_humanoid_states",
     "hb_eval_cost_terms", "hb_debug_sweep_schedule", "hb_kino_attach_tables", "hb_bounds", "hb_save", "hb_load",
-    "hb_ccs_group_mul", "hb_external_bind", "hb_external_stats",
+    "hb_ccs_group_mul", "hb_external_bind", "hb_external_stats", "hb_kkt_assemble_stage",
 ] + ['hb_nlp_f', 'hb_nlp_f_n_in', 'hb_nlp_f_n_out', 'hb_nlp_f_sparsity_in', 'hb_nlp_f_sparsity_out', 'hb_nlp_f_work', 'hb_nlp_f_name_in', 'hb_nlp_f_name_out', 'hb_nlp_f_incref', 'hb_nlp_f_decref', 'hb_nlp_f_alloc_mem', 'hb_nlp_f_init_mem', 'hb_nlp_f_free_mem', 'hb_nlp_f_checkout', 'hb_nlp_f_release', 'hb_nlp_g', 'hb_nlp_g_n_in', 'hb_nlp_g_n_out', 'hb_nlp_g_sparsity_in', 'hb_nlp_g_sparsity_out', 'hb_nlp_g_work', 'hb_nlp_g_name_in', 'hb_nlp_g_name_out', 'hb_nlp_g_incref', 'hb_nlp_g_decref', 'hb_nlp_g_alloc_mem', 'hb_nlp_g_init_mem', 'hb_nlp_g_free_mem', 'hb_nlp_g_checkout', 'hb_nlp_g_release', 'hb_nlp_grad_f', 'hb_nlp_grad_f_n_in', 'hb_nlp_grad_f_n_out', 'hb_nlp_grad_f_sparsity_in', 'hb_nlp_grad_f_sparsity_out', 'hb_nlp_grad_f_work', 'hb_nlp_grad_f_name_in', 'hb_nlp_grad_f_name_out', 'hb_nlp_grad_f_incref', 'hb_nlp_grad_f_decref', 'hb_nlp_grad_f_alloc_mem', 'hb_nlp_grad_f_init_mem', 'hb_nlp_grad_f_free_mem', 'hb_nlp_grad_f_checkout', 'hb_nlp_grad_f_release', 'hb_nlp_jac_g', 'hb_nlp_jac_g_n_in', 'hb_nlp_jac_g_n_out', 'hb_nlp_jac_g_sparsity_in', 'hb_nlp_jac_g_sparsity_out', 'hb_nlp_jac_g_work', 'hb_nlp_jac_g_name_in', 'hb_nlp_jac_g_name_out', 'hb_nlp_jac_g_incref', 'hb_nlp_jac_g_decref', 'hb_nlp_jac_g_alloc_mem', 'hb_nlp_jac_g_init_mem', 'hb_nlp_jac_g_free_mem', 'hb_nlp_jac_g_checkout', 'hb_nlp_jac_g_release', 'hb_nlp_hess_l', 'hb_nlp_hess_l_n_in', 'hb_nlp_hess_l_n_out', 'hb_nlp_hess_l_sparsity_in', 'hb_nlp_hess_l_sparsity_out', 'hb_nlp_hess_l_work', 'hb_nlp_hess_l_name_in', 'hb_nlp_hess_l_name_out', 'hb_nlp_hess_l_incref', 'hb_nlp_hess_l_decref', 'hb_nlp_hess_l_alloc_mem', 'hb_nlp_hess_l_init_mem', 'hb_nlp_hess_l_free_mem', 'hb_nlp_hess_l_checkout', 'hb_nlp_hess_l_release']
 
 

@@ -943,6 +943,55 @@ extern "C" int hb_ccs_group_mul(const double* vals, const int32_t* ptr, const in
   return HB_OK;
 }
 
+extern "C" int hb_kkt_assemble_stage(const int32_t* hdr, const int32_t* tab, const double* hess_vals, int64_t nnz_h,
+                                     const double* jac_vals, int64_t nnz_j, const double* sigma_I, int64_t m_I,
+                                     const double* delta, double delta_c, const double* RX, int64_t n_x, const double* RE,
+                                     int64_t m_E, const double* prev_sol, double* D, double* rhs, int64_t batch,
+                                     void* stream) {
+  if (!hdr || !tab || !hess_vals || !jac_vals || !delta || !RX || !RE || !D || !rhs)
+    return fail(HB_ERR_INVALID, "hb_kkt_assemble_stage: null argument");
+  hb::KktStage S;
+  S.nb = hdr[hb::KS_NB];
+  S.nx = hdr[hb::KS_NX];
+  S.nv = hdr[hb::KS_NV];
+  S.ne = hdr[hb::KS_NE];
+  S.R = hdr[hb::KS_R];
+  S.n_cpl = hdr[hb::KS_NCPL];
+  S.n_cpl_next = hdr[hb::KS_NCPL_NEXT];
+  S.n_direct = hdr[hb::KS_NDIRECT];
+  S.n_targets = hdr[hb::KS_NTARGETS];
+  S.n_an = hdr[hb::KS_NAN];
+  const int n_contrib = hdr[hb::KS_NCONTRIB], n_a = hdr[hb::KS_NA];
+  if (batch <= 0 || S.nb <= 0 || S.nx <= 0 || S.nx > S.nb || S.nv < 0 || S.nv > S.nx || S.ne < 0 || S.nx + S.ne > S.nb ||
+      S.R <= 0 || S.n_cpl < 0 || S.n_cpl_next < 0 || S.n_direct < 0 || S.n_targets < 0 || n_contrib < 0 || n_a < 0 ||
+      S.n_an < 0)
+    return fail(HB_ERR_INVALID, "hb_kkt_assemble_stage: inconsistent stage header");
+  if (S.n_targets > 0 && (!sigma_I || m_I <= 0)) return fail(HB_ERR_INVALID, "hb_kkt_assemble_stage: sigma_I missing");
+  if (S.n_cpl > 0 && !prev_sol) return fail(HB_ERR_INVALID, "hb_kkt_assemble_stage: the previous stage's solution is missing");
+  const int32_t* t = tab;  // tables in header order
+  S.direct_val = t, t += S.n_direct;
+  S.direct_pos = t, t += S.n_direct;
+  S.tgt_pos = t, t += S.n_targets;
+  S.tgt_ptr = t, t += S.n_targets + 1;
+  S.tgt_sig = t, t += n_contrib;
+  S.tgt_e1 = t, t += n_contrib;
+  S.tgt_e2 = t, t += n_contrib;
+  S.var = t, t += S.nv;
+  S.eq = t, t += S.ne;
+  S.cpl = t, t += S.n_cpl;
+  S.a_ptr = t, t += S.n_cpl + 1;
+  S.a_val = t, t += n_a;
+  S.a_col = t, t += n_a;
+  S.an_val = t, t += S.n_an;
+  S.an_row = t, t += S.n_an;
+  S.an_col = t;
+  hb::kkt_assemble_kernel<<<(unsigned)batch, 512, 0, (cudaStream_t)stream>>>(S, hess_vals, (long)nnz_h, jac_vals, (long)nnz_j,
+                                                                           sigma_I, (long)m_I, delta, delta_c, RX, (long)n_x,
+                                                                           RE, (long)m_E, prev_sol, D, rhs);
+  CUDA_TRY(cudaGetLastError());
+  return HB_OK;
+}
+
 extern "C" int hb_interpolate_humanoid_states(int64_t batch, int64_t n_points, int64_t n_joints, const double* initial,
                                               const double* final_, const int32_t* schedule,
                                               const double* phases_left, int64_t n_phases_left, int64_t stride_left,

@@ -4,5 +4,6 @@
 #include "pose_contact.cu"
 #include "toy.cu"
 #include "lu.cu"
+#include "kkt_assemble.cu"
 #include "interp.cu"
 #include "api.cu"

@@ -55,11 +55,14 @@ def lu_factor(A: torch.Tensor, symmetric: bool = False):
     return F, piv, info
 
 
-def lu_solve(F: torch.Tensor, piv: torch.Tensor, rhs: torch.Tensor) -> torch.Tensor:
-    """Solve with the factors of ``lu_factor``; rhs (B, n, r) -> solution (B, n, r) (a new tensor)."""
+def lu_solve(F: torch.Tensor, piv: torch.Tensor, rhs: torch.Tensor, inplace: bool = False) -> torch.Tensor:
+    """Solve with the factors of ``lu_factor``; rhs (B, n, r) -> solution (B, n, r) (a new tensor, or `rhs` itself
+    with inplace=True, which needs it contiguous)."""
     if rhs.dim() != 3 or rhs.shape[0] != F.shape[0] or rhs.shape[1] != F.shape[1] or not rhs.is_cuda:
         raise ValueError("lu_solve needs a (B, n, r) CUDA right-hand side matching the factors")
-    X = rhs.contiguous().clone()
+    if inplace and not rhs.is_contiguous():
+        raise ValueError("lu_solve(inplace=True) needs a contiguous right-hand side")
+    X = rhs if inplace else rhs.contiguous().clone()
     st = torch.cuda.current_stream(F.device).cuda_stream
     _capi.check(_capi.lib().hb_lu_solve_batched(_ptr(F), _ptr(piv), _ptr(X), F.shape[1], X.shape[2], F.shape[0],
                                                 ctypes.c_void_p(st)), "hb_lu_solve_batched")
@@ -202,6 +205,54 @@ class StageKKT:
         # 2 B <= 148 (one CTA per SM on a B200) is free; measured: sweeps of 32 / 64 instances 29 / 37 ms against ~50 ms
         # one-sided, but 148 instances 58 ms against 55 ms -- no gain once the pair no longer fits one wave
         self.two_sided_max_batch = 74 if linalg == "hb" else 0
+        # ---- tables of the fused assembly kernel (hb_kkt_assemble_stage), in the order include/hippopt_b200.h lists
+        self.fused = linalg == "hb"  # one launch per stage instead of ~25 torch calls; CUDA tensors only
+        self._stage_np = []
+        for k in range(N):
+            sel = np.nonzero(hst == k)[0]
+            je = np.nonzero(is_eq[jac_row] & (row_stage[jac_row] == k) & (jst == k))[0]
+            direct_val = np.concatenate([sel, sel, ~je, ~je])
+            direct_pos = np.concatenate([hr_l[sel] * nb + hc_l[sel], hc_l[sel] * nb + hr_l[sel],
+                                         (nx + loc_E[jac_row[je]]) * nb + jc_l[je], jc_l[je] * nb + (nx + loc_E[jac_row[je]])])
+            # J_I^T Sigma J_I: ordered pairs of the entries of every inequality row, grouped by destination
+            ji = np.nonzero((~is_eq[jac_row]) & (pos_I[jac_row] >= 0) & (row_stage[jac_row] == k))[0]
+            by_row: dict[int, list] = {}
+            for e in ji:
+                by_row.setdefault(int(jac_row[e]), []).append(int(e))
+            contrib: dict[int, list] = {}
+            for r in sorted(by_row):
+                for e1 in by_row[r]:
+                    for e2 in by_row[r]:
+                        contrib.setdefault(int(jc_l[e1]) * nb + int(jc_l[e2]), []).append((int(pos_I[r]), e1, e2))
+            tgt_pos = np.asarray(sorted(contrib), dtype=np.int64)
+            tgt_ptr = np.zeros(len(tgt_pos) + 1, dtype=np.int64)
+            flat = []
+            for i, pos in enumerate(tgt_pos):
+                flat += contrib[int(pos)]
+                tgt_ptr[i + 1] = len(flat)
+            flat = np.asarray(flat, dtype=np.int64).reshape(-1, 3)
+
+            def coupling_rows(kk):  # (row inside the coupling rows of stage kk, jac_vals index, variable slot of stage kk-1)
+                if kk <= 0 or kk >= N:
+                    return np.zeros((0, 3), dtype=np.int64)
+                ja = np.nonzero(is_eq[jac_row] & (row_stage[jac_row] == kk) & (jst == kk - 1))[0]
+                out = np.stack([loc_C[jac_row[ja]], ja, jc_l[ja]], axis=1)
+                return out[np.lexsort((out[:, 2], out[:, 0]))]
+
+            a = coupling_rows(k)
+            n_cpl = len(self.cpl_local[k])
+            a_ptr = np.zeros(n_cpl + 1, dtype=np.int64)
+            np.add.at(a_ptr, a[:, 0] + 1, 1)
+            a_ptr = np.cumsum(a_ptr)
+            an = coupling_rows(k + 1)
+            var = self.maps[k]["var"].cpu().numpy()
+            eqk = pos_E[self.eq_stage_rows[k]]
+            tables = [direct_val, direct_pos, tgt_pos, tgt_ptr, flat[:, 0], flat[:, 1], flat[:, 2], var, eqk,
+                      nx + self.cpl_local[k], a_ptr, a[:, 1], a[:, 2], an[:, 1], an[:, 0], an[:, 2]]
+            hdr = [nb, nx, len(var), len(eqk), 0, n_cpl, len(self.cpl_local[k + 1]) if k + 1 < N else 0, len(direct_val),
+                   len(tgt_pos), len(flat), len(a), len(an)]
+            self._stage_np.append((hdr, np.concatenate([np.asarray(t, dtype=np.int64).ravel() for t in tables]).astype(np.int32)))
+        self._stage_dev = None
 
     @classmethod
     def for_evaluator(cls, ev, lbg, ubg, device="cpu", linalg: str = "hb"):
@@ -288,6 +339,8 @@ class StageKKT:
         """Block-tridiagonal part: K_bt [DX; DL] = [RX; RE] for R right-hand sides (B, n_x | m_E, R)."""
         if self.two_sided and self._two_sided_ok and hess_vals.shape[0] <= self.two_sided_max_batch:
             return self._sweep_two_sided(hess_vals, jac_vals, sigma_I, delta, delta_c, RX, RE)
+        if self.fused and self.linalg == "hb" and hess_vals.is_cuda:
+            return self._sweep_fused(hess_vals, jac_vals, sigma_I, delta, delta_c, RX, RE)
         B, R = hess_vals.shape[0], RX.shape[2]
         dev, dt = hess_vals.device, hess_vals.dtype
         nx, nb, N = self.nx, self.nb, self.N
@@ -353,6 +406,47 @@ class StageKKT:
             u = Wv[k]
             if k < N - 1 and Zs[k + 1] is not None:
                 u = u - torch.bmm(Zs[k + 1], u_next[:, self.maps[k + 1]["cpl"], :])
+            DX[:, mp["var"], :] = u[:, :mp["n_var"], :]
+            DL[:, mp["eq"], :] = u[:, nx:nx + mp["n_eq"], :]
+            u_next = u
+        return DX, DL
+
+    def _sweep_fused(self, hess_vals, jac_vals, sigma_I, delta, delta_c, RX, RE):
+        """The sweep of `_sweep` with every stage assembled by ONE kernel (csrc/kkt_assemble.cu): block, right-hand
+        sides, J_I^T Sigma J_I and the coupling terms come straight from the CCS value arrays; the stage's solution
+        [w | Z] (B, nb, R + n_cpl_next) is the next stage's input and is kept for the back substitution."""
+        B, R = hess_vals.shape[0], RX.shape[2]
+        dev, dt = hess_vals.device, hess_vals.dtype
+        nx, nb, N = self.nx, self.nb, self.N
+        if self._stage_dev is None or self._stage_dev[0] != dev:
+            self._stage_dev = (dev, [torch.as_tensor(tab, device=dev) for _, tab in self._stage_np])
+        L = _capi.lib()
+        st = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        hv, jv, sg, dl = hess_vals.contiguous(), jac_vals.contiguous(), sigma_I.contiguous(), delta.contiguous()
+        rx, re = RX.contiguous(), RE.contiguous()
+        sols, prev = [], None
+        for k in range(N):
+            hdr, _ = self._stage_np[k]
+            hdr = list(hdr)
+            hdr[4] = R
+            D = torch.empty((B, nb, nb), dtype=dt, device=dev)
+            rhs = torch.empty((B, nb, R + hdr[6]), dtype=dt, device=dev)
+            _capi.check(L.hb_kkt_assemble_stage((ctypes.c_int32 * len(hdr))(*hdr), _ptr(self._stage_dev[1][k]), _ptr(hv),
+                                                hv.shape[1], _ptr(jv), jv.shape[1], _ptr(sg), max(sg.shape[1], 1), _ptr(dl),
+                                                float(delta_c), _ptr(rx), self.n_x, _ptr(re), self.mE,
+                                                _ptr(prev) if (prev is not None and hdr[5]) else None, _ptr(D), _ptr(rhs), B, st),
+                        "hb_kkt_assemble_stage")
+            F, piv, _ = lu_factor(D, symmetric=True)  # in place
+            prev = lu_solve(F, piv, rhs, inplace=True)
+            sols.append(prev)
+        DX = torch.zeros((B, self.n_x, R), dtype=dt, device=dev)
+        DL = torch.zeros((B, self.mE, R), dtype=dt, device=dev)
+        u_next = None
+        for k in range(N - 1, -1, -1):
+            mp = self.maps[k]
+            u = sols[k][:, :, :R]
+            if k < N - 1 and self.maps[k + 1]["n_cpl"]:
+                u = u - torch.bmm(sols[k][:, :, R:], u_next[:, self.maps[k + 1]["cpl"], :])
             DX[:, mp["var"], :] = u[:, :mp["n_var"], :]
             DL[:, mp["eq"], :] = u[:, nx:nx + mp["n_eq"], :]
             u_next = u

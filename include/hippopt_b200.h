@@ -306,6 +306,26 @@ int hb_lu_factor_batched(double* A, int32_t* piv, int32_t* info, int64_t n, int6
 int hb_lu_solve_batched(const double* LU, const int32_t* piv, double* Bm, int64_t n, int64_t nrhs, int64_t batch,
                         void* stream);
 
+/* One stage of the block-tridiagonal KKT sweep (hippopt_b200/kkt.py::StageKKT) assembled in one launch from the CCS
+ * value arrays: the dense symmetric stage block D (batch x nb x nb) = hess_l block + J_I^T Sigma J_I + shifts, with the
+ * stage's equality rows in both triangles and the coupling term A_k S_{k-1}^{-1} A_k^T subtracted, and the right-hand
+ * sides rhs (batch x nb x (R + n_cpl_next), row-major) = [b_k - A_k w_{k-1} | A_{k+1}^T; 0].  hb_lu_factor_batched(D) and
+ * hb_lu_solve_batched(D, rhs) follow; the solution is `prev_sol` of the next stage.
+ *   hdr   HOST   int32[12]: nb, nx (variable slots), nv (live variables), ne (equality rows), R, n_cpl, n_cpl_next,
+ *                n_direct, n_targets, n_contrib, n_a, n_an
+ *   tab   device int32 tables in this order: direct_val[n_direct] (>= 0: hess_vals index, < 0: ~index into jac_vals),
+ *                direct_pos[n_direct]; tgt_pos[n_targets], tgt_ptr[n_targets + 1], tgt_sig / tgt_e1 / tgt_e2[n_contrib]
+ *                (D[tgt_pos] += sum sigma_I[sig] jac[e1] jac[e2]); var[nv], eq[ne] (rows of RX / RE); cpl[n_cpl] (block
+ *                rows of the coupling equations); a_ptr[n_cpl + 1], a_val / a_col[n_a] (A_k by row: jac_vals index,
+ *                variable slot of stage k - 1); an_val / an_row / an_col[n_an] (A_{k+1}: rhs[an_col][R + an_row])
+ *   RX    device [batch][n_x][R], RE device [batch][m_E][R]; prev_sol device [batch][nb][R + n_cpl] or NULL
+ * One CTA per instance; fixed summation order (bit-reproducible).
+ * replaces: the assembly of the KKT matrix inside IPOPT / MUMPS [ext] for the stage ordering of kkt.py. */
+int hb_kkt_assemble_stage(const int32_t* hdr, const int32_t* tab, const double* hess_vals, int64_t nnz_h,
+                          const double* jac_vals, int64_t nnz_j, const double* sigma_I, int64_t m_I, const double* delta,
+                          double delta_c, const double* RX, int64_t n_x, const double* RE, int64_t m_E,
+                          const double* prev_sol, double* D, double* rhs, int64_t batch, void* stream);
+
 /* Deterministic sparse products with the CCS value arrays the evaluation kernels write, for solvers that keep their
  * iterates on the device (hippopt_b200.ipsolver): y[b][o] = sum_{q in [ptr[o], ptr[o+1])} w[q] vals[b][entry[q]] x[b][idx[q]]
  * (w may be NULL = 1).  With (ptr, entry, idx) grouped by row this is jac_g x, by column jac_g^T lam, by row over the

@@ -70,9 +70,12 @@ def test_stage_sweep_on_evaluated_values(model, built_library, periodic):
     g = torch.Generator().manual_seed(1)
     hv, jv = out["hess"].clone(), out["jac"].clone()
     sols = {}
-    for linalg in ("hb", "torch"):
-        kkt, eq, ine = StageKKT.for_evaluator(ev, lb[0], ub[0], device=d, linalg=linalg)
+    for linalg in ("hb", "hb-unfused", "torch"):  # hb: one assembly kernel per stage; hb-unfused: the torch assembly
+        kkt, eq, ine = StageKKT.for_evaluator(ev, lb[0], ub[0], device=d, linalg=linalg.split("-")[0])
+        if linalg == "hb-unfused":
+            kkt.fused = False
         if linalg == "hb":
+            assert kkt.fused
             sig = (torch.rand((B, len(ine)), generator=g, dtype=torch.float64) * 10.0).to(d)
             delta = torch.full((B,), 1e-2, dtype=torch.float64, device=d)
             rx = torch.randn((B, ev.n_x), generator=g, dtype=torch.float64).to(d)
@@ -88,3 +91,16 @@ def test_stage_sweep_on_evaluated_values(model, built_library, periodic):
         assert ((u - ref).abs() / scale).max().item() < 1e-6, name  # cond(K) ~ 1e11: the residual is the sharp check
         res = torch.einsum("bij,bj->bi", K, u) - torch.cat([rx, rE], dim=1)
         assert (res.abs() / scale).max().item() < 1e-12, name
+    # several right-hand sides at once (limited-memory mode), fused path: column c solves K u = rhs[:, :, c]
+    kkt, eq, ine = StageKKT.for_evaluator(ev, lb[0], ub[0], device=d, linalg="hb")
+    RXm = torch.randn((B, ev.n_x, 3), generator=g, dtype=torch.float64).to(d)
+    REm = torch.randn((B, len(eq), 3), generator=g, dtype=torch.float64).to(d)
+    REm[:, torch.as_tensor(kkt.dead_eq, device=d), :] = 0.0
+    dxm, dlm = kkt.solve(hv, jv, sig, delta, 1e-9, RXm, REm)
+    um = torch.cat([dxm, dlm], dim=1)
+    rm = torch.cat([RXm, REm], dim=1)
+    resm = torch.bmm(K, um) - rm
+    assert (resm.abs().amax(dim=(1, 2)) / um.abs().amax(dim=(1, 2))).max().item() < 1e-12
+    # and the sweep is reproducible bit for bit
+    dx2, dl2 = kkt.solve(hv, jv, sig, delta, 1e-9, RXm, REm)
+    assert torch.equal(dx2, dxm) and torch.equal(dl2, dlm)
