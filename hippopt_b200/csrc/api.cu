@@ -106,6 +106,11 @@ static cudaError_t ensure_kernel_attributes(int dev) {
   if ((e = cudaFuncSetAttribute(hb::lu_factor_kernel<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, lu_big)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(hb::lu_factor_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, lu_big)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(hb::lu_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, lu_big)) != cudaSuccess) return e;
+  const int lu_staged = 232448 - 1024 - 2560;
+  if ((e = cudaFuncSetAttribute(hb::lu_solve_staged_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, lu_staged)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(hb::lu_solve_staged_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, lu_staged)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(hb::lu_solve_staged_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, lu_staged)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(hb::lu_solve_staged_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, lu_staged)) != cudaSuccess) return e;
   if ((e = cudaDeviceGetAttribute(&device_sms[dev], cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
   done[dev] = true;
   return cudaSuccess;
@@ -919,12 +924,34 @@ extern "C" int hb_lu_solve_batched(const double* LU, const int32_t* piv, double*
   if (!LU || !piv || !Bm) return fail(HB_ERR_INVALID, "hb_lu_solve_batched: null argument");
   if (n <= 0 || n > 768 || batch <= 0 || nrhs <= 0)
     return fail(HB_ERR_INVALID, "hb_lu_solve_batched: need 0 < n <= 768, batch > 0, nrhs > 0");
-  const size_t smem = (size_t)n * (hb::LU_RC + 1) * sizeof(double);
   {
     int dev = 0;
     CUDA_TRY(cudaGetDevice(&dev));
     CUDA_TRY(ensure_kernel_attributes(dev));
   }
+  static const bool unstaged = getenv("HB_LU_SOLVE_UNSTAGED") != nullptr;  // A/B timing against the round-1 kernel
+  // staged substitution (lu.cu): 24 right-hand sides per CTA while two CTAs fit an SM, else 16 / 8 on one CTA per SM
+  const size_t two_per_sm = (233472 / 2) - 1024 - 2560, one_per_sm = 232448 - 1024 - 2560;  // minus the static arrays
+  int ct = 0;  // 8-column tiles per CTA
+  if (!unstaged) {
+    if (hb::lu_staged_smem((int)n, 4) <= two_per_sm) ct = 4;
+    else if (hb::lu_staged_smem((int)n, 3) <= two_per_sm) ct = 3;
+    else if (hb::lu_staged_smem((int)n, 4) <= one_per_sm) ct = 4;
+    else if (hb::lu_staged_smem((int)n, 3) <= one_per_sm) ct = 3;
+    else if (hb::lu_staged_smem((int)n, 2) <= one_per_sm) ct = 2;
+    else if (hb::lu_staged_smem((int)n, 1) <= one_per_sm) ct = 1;
+  }
+  if (ct > 0) {
+    const size_t smem = hb::lu_staged_smem((int)n, ct);
+    const dim3 grid((unsigned)batch, (unsigned)((nrhs + 8 * ct - 1) / (8 * ct)));
+    if (ct == 4) hb::lu_solve_staged_kernel<4><<<grid, hb::LU_THREADS, smem, (cudaStream_t)stream>>>(LU, piv, Bm, (int)n, (int)nrhs);
+    else if (ct == 3) hb::lu_solve_staged_kernel<3><<<grid, hb::LU_THREADS, smem, (cudaStream_t)stream>>>(LU, piv, Bm, (int)n, (int)nrhs);
+    else if (ct == 2) hb::lu_solve_staged_kernel<2><<<grid, hb::LU_THREADS, smem, (cudaStream_t)stream>>>(LU, piv, Bm, (int)n, (int)nrhs);
+    else hb::lu_solve_staged_kernel<1><<<grid, hb::LU_THREADS, smem, (cudaStream_t)stream>>>(LU, piv, Bm, (int)n, (int)nrhs);
+    CUDA_TRY(cudaGetLastError());
+    return HB_OK;
+  }
+  const size_t smem = (size_t)n * (hb::LU_RC + 1) * sizeof(double);
   const dim3 grid((unsigned)batch, (unsigned)((nrhs + hb::LU_RC - 1) / hb::LU_RC));
   hb::lu_solve_kernel<<<grid, hb::LU_THREADS, smem, (cudaStream_t)stream>>>(LU, piv, Bm, (int)n, (int)nrhs);
   CUDA_TRY(cudaGetLastError());

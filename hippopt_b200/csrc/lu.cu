@@ -31,11 +31,22 @@ constexpr int LU_NB = 16;
 #ifndef HB_LU_PREFETCH
 #define HB_LU_PREFETCH 1  // request the A22 tile before the products: its L2 latency overlaps them
 #endif
+#ifndef HB_LU_DMMA
+#define HB_LU_DMMA 1  // trailing update with mma.sync.m8n8k4.f64 instead of 4 x 4 register tiles of FMAs
+#endif
 #ifndef HB_LU_TR
 #define HB_LU_TR 4  // rows of the trailing-update register tile when one CTA runs per SM (4 or 8)
 #endif
 constexpr int LU_THREADS = HB_LU_THREADS;
 constexpr int LU_MAXN = 768;
+
+// D (8 x 8) = A (8 x 4, row) B (4 x 8, col) + C on the fp64 tensor cores.  Fragments (PTX ISA, mma.m8n8k4 .f64):
+// a: row lane / 4, column lane % 4;  b: row lane % 4, column lane / 4;  c, d: row lane / 4, columns 2 (lane % 4) + {0, 1}.
+__device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
 
 __host__ __device__ inline int lu_ldp(int n) { return (n + 3) & ~3; }
 // dynamic shared memory of the factor kernel: panel + U strip (+ slack: the last vector loads of a tile may
@@ -226,6 +237,56 @@ __global__ void __launch_bounds__(LU_THREADS, MB) lu_factor_kernel(double* __res
     // by 32 so that every A22 access is a coalesced 256-byte row segment; contiguous rows per thread were
     // 20 % slower); per k four shared loads of L21 and two 16-byte broadcast loads of U12 feed 16 FMAs
 #ifndef HB_LU_SKIP_TRAILING  // (timing experiments only: how much of a factorisation is the panel work)
+#if HB_LU_DMMA
+    {
+      // Trailing update on the fp64 tensor cores (round 2): warp tile 32 rows x 16 columns = 4 x 2 m8n8k4 accumulators,
+      // A fragments from L21 (negated), B fragments from the U strip, C fragments read from / written to A22 in place
+      // (a fragment's 8 rows of one column are 64 contiguous bytes).  32 MMAs per 24 shared-memory loads, where the
+      // 4 x 4 register tiles issued 16 multiply-adds per 6 loads.
+      const int lane = tid & 31, w = tid >> 5, g = lane >> 2, t4 = lane & 3;
+      const double* L21 = P + nbw;  // local row i of L21 = panel row nbw + i
+      double* A22 = A + (size_t)(j0 + nbw) * n + j0 + nbw;
+      const int n_rt = (nrem + 31) >> 5, n_ct = (nrem + 15) >> 4;
+      for (int tile = w; tile < n_rt * n_ct; tile += nt / 32) {
+        const int rb = (tile % n_rt) * 32, cb = (tile / n_rt) * 16;
+        double c[4][2][2];
+#pragma unroll
+        for (int bq = 0; bq < 2; ++bq)
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int col = cb + 8 * bq + 2 * t4 + e;
+            const double* cp = A22 + (size_t)col * n + rb + g;
+#pragma unroll
+            for (int a = 0; a < 4; ++a) c[a][bq][e] = (col < nrem && rb + 8 * a + g < nrem) ? cp[8 * a] : 0.0;
+          }
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          const int k = 4 * kk + t4;
+          // rows / columns past nrem read whatever the panel / strip hold (inside the shared-memory block); the
+          // accumulators they feed are never stored
+          double af[4], bf[2];
+#pragma unroll
+          for (int a = 0; a < 4; ++a) af[a] = k < nbw ? -L21[k * ldp + rb + 8 * a + g] : 0.0;
+#pragma unroll
+          for (int bq = 0; bq < 2; ++bq) bf[bq] = k < nbw ? U[k * ldp + cb + 8 * bq + g] : 0.0;
+#pragma unroll
+          for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int bq = 0; bq < 2; ++bq) dmma_m8n8k4(c[a][bq][0], c[a][bq][1], af[a], bf[bq]);
+        }
+#pragma unroll
+        for (int bq = 0; bq < 2; ++bq)
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int col = cb + 8 * bq + 2 * t4 + e;
+            double* cp = A22 + (size_t)col * n + rb + g;
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+              if (col < nrem && rb + 8 * a + g < nrem) cp[8 * a] = c[a][bq][e];
+          }
+      }
+    }
+#else
     {
       constexpr int TR = MB == 1 ? HB_LU_TR : 4;  // rows per thread tile: TR x 4, CTA tile 32 TR rows x 32 columns
       const int tx = tid & 31, ty = tid >> 5;
@@ -284,6 +345,7 @@ __global__ void __launch_bounds__(LU_THREADS, MB) lu_factor_kernel(double* __res
             }
         }
     }
+#endif
 #endif
     __syncthreads();
   }
@@ -428,6 +490,205 @@ __global__ void __launch_bounds__(LU_THREADS, HB_LU_SOLVE_MIN_BLOCKS) lu_solve_k
     }
     __syncthreads();
     lu_rows_update(A, b, n, ldb, j0, nbw, 0, j0, tid);
+    __syncthreads();
+  }
+  for (int e = tid; e < n * nc; e += nt) {
+    const int i = e / nc, c = e - i * nc;
+    Bg[(size_t)i * nrhs + c0 + c] = b[i * ldb + c];
+  }
+}
+
+}  // namespace hb
+
+namespace hb {
+
+// ---------------------------------------------------------------------------------------------------------------
+// Substitution with the panel STAGED in shared memory (round 2).  In lu_solve_kernel every row update waits for L2
+// four times per panel (the factor entries of 4 panel columns are requested, used, then the next 4), and the
+// triangular solve of a panel runs on one warp while the other seven wait: 17 800 cycles per panel step on B200,
+// 15 % of them arithmetic.  Here the 16 factor columns of the step (rows below the panel going forward, above it going
+// back) are copied to shared memory with cp.async WHILE warp 0 applies the interchanges and solves the 16 x 16
+// triangle -- neither depends on the other -- and the diagonal block and pivots of the NEXT step travel with them.
+// The update then reads only shared memory.
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
+  const unsigned sdst = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sdst), "l"(gsrc));
+}
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
+  const unsigned sdst = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sdst), "l"(gsrc));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// stride of a staged column: >= the rows outside a panel, and = 8 mod 16 so that the A-fragment reads of the
+// tensor-core update (4 consecutive k x 8 consecutive rows per warp) hit every bank pair exactly twice
+__host__ __device__ inline int lu_staged_ps(int n) {
+  const int m = n > 8 ? n - 8 : 1;  // rows outside a half panel (LU_SNB = 8 columns)
+  return ((m + 7) & ~15) + 8;
+}
+__host__ __device__ inline size_t lu_staged_smem(int n, int ct) {
+  // right-hand sides b[n][8 ct] + staged half panel P[8][ps]
+  return ((size_t)n * (8 * ct) + (size_t)8 * lu_staged_ps(n) + 2) * sizeof(double);
+}
+
+// CT = 8-column tiles of right-hand sides per CTA (4: 32 columns, two CTAs per SM for the 337-blocks).
+// * The rows outside the panel are updated on the TENSOR CORES: b[rows][:] += (-P) Y with m8n8k4 fp64 MMAs, 8 x fewer
+//   instructions than 4 x 6 register tiles of fused multiply-adds and a third of their shared-memory reads.
+// * With the update that cheap, the triangle of the panel -- one warp, one right-hand side per lane, the other seven
+//   warps waiting -- was 40 % of the kernel (ncu).  The substitution therefore walks HALF panels (LU_SNB = 8 columns:
+//   valid because the factor kernel interchanges LAPACK-style inside a 16-column panel; the panel's 16 interchanges are
+//   applied on its first half): 28 instead of 120 dependent multiply-adds per step, warp 0 takes no part in the staging,
+//   and the reciprocals of U's diagonal are computed one step ahead by an otherwise idle warp (the fp64 divisions of the
+//   backward sweep were the longest dependent chain).
+constexpr int LU_SNB = 8;
+
+template <int CT>
+__global__ void __launch_bounds__(LU_THREADS, 2) lu_solve_staged_kernel(const double* __restrict__ LUall,
+                                                                        const int* __restrict__ pivall,
+                                                                        double* __restrict__ Ball, int n, int nrhs) {
+  constexpr int RC = 8 * CT;
+  constexpr int nt = LU_THREADS;
+  constexpr int ldb = RC;
+  extern __shared__ __align__(16) double lu_sm[];
+  const double* A = LUall + (size_t)blockIdx.x * n * n;
+  const int* piv = pivall + (size_t)blockIdx.x * n;
+  double* Bg = Ball + (size_t)blockIdx.x * n * nrhs;
+  const int c0 = blockIdx.y * RC;
+  const int nc = min(RC, nrhs - c0);
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int ps = lu_staged_ps(n);
+  double* b = lu_sm;                     // b[i * ldb + c]; columns >= nc are zero
+  double* P = lu_sm + (size_t)n * ldb;   // P[k * ps + i] = A[r0 + i, j0 + k]
+  __shared__ double tri[2][LU_SNB][LU_SNB + 1];  // tri[s & 1][k][i] = A[j0 + i, j0 + k] of step s
+  __shared__ double rinv[2][LU_SNB];             // backward steps: 1 / U[j0 + k, j0 + k]
+  __shared__ int s_piv[2][LU_NB];
+  const int S = (n + LU_SNB - 1) / LU_SNB;  // steps 0 .. S-1 forward, S .. 2S-1 backward (half panels aligned from the end)
+  auto panel_of = [&](int s, int& j0, int& nbw) {
+    if (s < S) {
+      j0 = LU_SNB * s;
+      nbw = min(LU_SNB, n - j0);
+    } else {
+      const int j1 = n - LU_SNB * (s - S);
+      j0 = max(0, j1 - LU_SNB);
+      nbw = j1 - j0;
+    }
+  };
+  // diagonal block of step s into buffer s & 1 (threads t0 .. t0 + 63), pivots of a full panel (threads t0 + 64 .. + 79)
+  auto fetch_tri = [&](int s, int t0) {
+    int j0, nbw;
+    panel_of(s, j0, nbw);
+    const int t = tid - t0;
+    if (t >= 0 && t < LU_SNB * LU_SNB) {
+      const int k = t >> 3, i = t & 7;
+      if (k < nbw && i < nbw) cp_async8(&tri[s & 1][k][i], &A[(size_t)(j0 + k) * n + j0 + i]);
+      else tri[s & 1][k][i] = 0.0;
+    }
+    if (s < S && (j0 % LU_NB) == 0 && t >= 64 && t < 64 + LU_NB && j0 + t - 64 < n)
+      cp_async4(&s_piv[s & 1][t - 64], &piv[j0 + t - 64]);
+  };
+  fetch_tri(0, 0);
+  cp_async_commit();
+  for (int e = tid; e < n * RC; e += nt) {
+    const int i = e / RC, c = e - i * RC;
+    b[i * ldb + c] = c < nc ? Bg[(size_t)i * nrhs + c0 + c] : 0.0;
+  }
+  cp_async_wait_all();
+  __syncthreads();
+  for (int s = 0; s < 2 * S; ++s) {
+    int j0, nbw;
+    panel_of(s, j0, nbw);
+    const bool fwd = s < S;
+    const int r0 = fwd ? j0 + nbw : 0, r1 = fwd ? n : j0;
+    const int m = r1 - r0;
+    if (w > 0) {
+      // ---- warps 1..7 stage the step's factor columns and the next step's diagonal block
+      for (int k = 0; k < nbw; ++k) {
+        const double* src = A + (size_t)(j0 + k) * n + r0;
+        double* dst = P + (size_t)k * ps;
+        for (int i = tid - 32; i < m; i += nt - 32) cp_async8(dst + i, src + i);
+      }
+      if (s + 1 < 2 * S) fetch_tri(s + 1, 32);
+      cp_async_commit();
+      cp_async_wait_all();
+    } else if (lane < RC) {
+      // ---- warp 0 meanwhile: interchanges and the triangle of this half panel, one right-hand side per lane
+      const double(*T)[LU_SNB + 1] = tri[s & 1];
+      if (fwd) {
+        if ((j0 % LU_NB) == 0) {
+          const int np = min(LU_NB, n - j0);
+          for (int c = 0; c < np; ++c) {
+            const int r = s_piv[s & 1][c];
+            if (r != j0 + c) {
+              const double t = b[(j0 + c) * ldb + lane];
+              b[(j0 + c) * ldb + lane] = b[r * ldb + lane];
+              b[r * ldb + lane] = t;
+            }
+          }
+        }
+        double y[LU_SNB];
+#pragma unroll
+        for (int k = 0; k < LU_SNB; ++k) y[k] = k < nbw ? b[(j0 + k) * ldb + lane] : 0.0;
+#pragma unroll
+        for (int k = 0; k < LU_SNB; ++k)
+#pragma unroll
+          for (int i = k + 1; i < LU_SNB; ++i) y[i] -= T[k][i] * y[k];  // entries outside the block are zero
+#pragma unroll
+        for (int k = 0; k < LU_SNB; ++k)
+          if (k < nbw) b[(j0 + k) * ldb + lane] = y[k];
+      } else {
+        double xv[LU_SNB];
+#pragma unroll
+        for (int k = 0; k < LU_SNB; ++k) xv[k] = k < nbw ? b[(j0 + k) * ldb + lane] : 0.0;
+#pragma unroll
+        for (int k = LU_SNB - 1; k >= 0; --k)
+          if (k < nbw) {
+            xv[k] = xv[k] * rinv[s & 1][k];
+#pragma unroll
+            for (int i = 0; i < k; ++i) xv[i] -= T[k][i] * xv[k];
+          }
+#pragma unroll
+        for (int k = 0; k < LU_SNB; ++k)
+          if (k < nbw) b[(j0 + k) * ldb + lane] = xv[k];
+      }
+    }
+    __syncthreads();
+    // ---- reciprocals of the next backward step's diagonal (its block landed with this step's copies)
+    if (w == 7 && lane < LU_SNB && s + 1 >= S && s + 1 < 2 * S) {
+      const double d = tri[(s + 1) & 1][lane][lane];
+      rinv[(s + 1) & 1][lane] = 1.0 / d;  // a zero pivot keeps its IEEE consequences (inf / NaN: the caller's failed-solve path)
+    }
+    // ---- rows outside the panel on the tensor cores: an 8-row tile per warp and trip, all CT column tiles
+    {
+      const int g = lane >> 2, t4 = lane & 3;
+      double yb[CT][LU_SNB / 4];  // B fragments: Y[k][col], k = 4 kk + t4, col = 8 ct + g
+#pragma unroll
+      for (int ct = 0; ct < CT; ++ct)
+#pragma unroll
+        for (int kk = 0; kk < LU_SNB / 4; ++kk) {
+          const int k = 4 * kk + t4;
+          yb[ct][kk] = k < nbw ? b[(j0 + k) * ldb + 8 * ct + g] : 0.0;
+        }
+      const int n_rt = (m + 7) >> 3;
+      for (int rt = w; rt < n_rt; rt += nt / 32) {
+        const int i = rt * 8 + g;  // row inside the staged columns
+        const bool valid = i < m;
+        double a[LU_SNB / 4];
+#pragma unroll
+        for (int kk = 0; kk < LU_SNB / 4; ++kk) {
+          const int k = 4 * kk + t4;
+          a[kk] = (valid && k < nbw) ? -P[(size_t)k * ps + i] : 0.0;
+        }
+        double2* crow = reinterpret_cast<double2*>(b + (size_t)(r0 + (valid ? i : 0)) * ldb + 2 * t4);
+#pragma unroll
+        for (int ct = 0; ct < CT; ++ct) {
+          double2 c = crow[4 * ct];
+#pragma unroll
+          for (int kk = 0; kk < LU_SNB / 4; ++kk) dmma_m8n8k4(c.x, c.y, a[kk], yb[ct][kk]);
+          if (valid) crow[4 * ct] = c;
+        }
+      }
+    }
     __syncthreads();
   }
   for (int e = tid; e < n * nc; e += nt) {
