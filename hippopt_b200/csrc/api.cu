@@ -943,11 +943,12 @@ extern "C" int hb_lu_solve_batched(const double* LU, const int32_t* piv, double*
   }
   if (ct > 0) {
     const size_t smem = hb::lu_staged_smem((int)n, ct);
-    const dim3 grid((unsigned)batch, (unsigned)((nrhs + 8 * ct - 1) / (8 * ct)));
-    if (ct == 4) hb::lu_solve_staged_kernel<4><<<grid, hb::LU_THREADS, smem, (cudaStream_t)stream>>>(LU, piv, Bm, (int)n, (int)nrhs);
-    else if (ct == 3) hb::lu_solve_staged_kernel<3><<<grid, hb::LU_THREADS, smem, (cudaStream_t)stream>>>(LU, piv, Bm, (int)n, (int)nrhs);
-    else if (ct == 2) hb::lu_solve_staged_kernel<2><<<grid, hb::LU_THREADS, smem, (cudaStream_t)stream>>>(LU, piv, Bm, (int)n, (int)nrhs);
-    else hb::lu_solve_staged_kernel<1><<<grid, hb::LU_THREADS, smem, (cudaStream_t)stream>>>(LU, piv, Bm, (int)n, (int)nrhs);
+    const int n_chunks = (int)((nrhs + 8 * ct - 1) / (8 * ct));
+    const unsigned grid = (unsigned)(batch * n_chunks);
+    if (ct == 4) hb::lu_solve_staged_kernel<4><<<grid, hb::LU_THREADS, smem, (cudaStream_t)stream>>>(LU, piv, Bm, (int)n, (int)nrhs, n_chunks);
+    else if (ct == 3) hb::lu_solve_staged_kernel<3><<<grid, hb::LU_THREADS, smem, (cudaStream_t)stream>>>(LU, piv, Bm, (int)n, (int)nrhs, n_chunks);
+    else if (ct == 2) hb::lu_solve_staged_kernel<2><<<grid, hb::LU_THREADS, smem, (cudaStream_t)stream>>>(LU, piv, Bm, (int)n, (int)nrhs, n_chunks);
+    else hb::lu_solve_staged_kernel<1><<<grid, hb::LU_THREADS, smem, (cudaStream_t)stream>>>(LU, piv, Bm, (int)n, (int)nrhs, n_chunks);
     CUDA_TRY(cudaGetLastError());
     return HB_OK;
   }

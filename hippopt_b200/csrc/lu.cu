@@ -546,15 +546,18 @@ constexpr int LU_SNB = 8;
 template <int CT>
 __global__ void __launch_bounds__(LU_THREADS, 2) lu_solve_staged_kernel(const double* __restrict__ LUall,
                                                                         const int* __restrict__ pivall,
-                                                                        double* __restrict__ Ball, int n, int nrhs) {
+                                                                        double* __restrict__ Ball, int n, int nrhs, int n_chunks) {
   constexpr int RC = 8 * CT;
   constexpr int nt = LU_THREADS;
   constexpr int ldb = RC;
   extern __shared__ __align__(16) double lu_sm[];
-  const double* A = LUall + (size_t)blockIdx.x * n * n;
-  const int* piv = pivall + (size_t)blockIdx.x * n;
-  double* Bg = Ball + (size_t)blockIdx.x * n * nrhs;
-  const int c0 = blockIdx.y * RC;
+  // the column chunks of one matrix are neighbours in launch order: they run at the same time and share the factor in
+  // L2 (with the matrix index fastest they ran waves apart and each streamed it from DRAM: 943 MB per launch of 296)
+  const size_t mat = blockIdx.x / n_chunks;
+  const double* A = LUall + mat * n * n;
+  const int* piv = pivall + mat * n;
+  double* Bg = Ball + mat * n * nrhs;
+  const int c0 = (blockIdx.x % n_chunks) * RC;
   const int nc = min(RC, nrhs - c0);
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const int ps = lu_staged_ps(n);

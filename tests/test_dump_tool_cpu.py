@@ -64,3 +64,32 @@ def test_dump_has_the_fixture_layout_and_is_picked_up(model, tmp_path):
 def test_main_reports_the_missing_environment(capsys):
     assert _tool().main([]) == 2
     assert "reference environment" in capsys.readouterr().out
+
+
+def test_per_instance_dumps_merge_into_one_fixture():
+    """Stairs fixtures are dumped one planner per instance (the reference bakes the step dimensions into the graph):
+    batched keys stack, patterns must agree."""
+    import importlib.util
+    import os
+
+    import numpy as np
+    import pytest
+
+    spec = importlib.util.spec_from_file_location(
+        "dump_casadi_golden", os.path.join(os.path.dirname(__file__), "..", "tools", "dump_casadi_golden.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+
+    def part(v):
+        return {"x": np.full((1, 3), v), "p": np.full((1, 2), v), "lam": np.zeros((1, 2)), "sigma": np.ones(1),
+                "f": np.array([v]), "grad_f": np.full((1, 3), v), "g": np.zeros((1, 2)), "jac": np.full((1, 4), v),
+                "hess": np.full((1, 5), v), "lbg": np.zeros((1, 2)), "ubg": np.zeros((1, 2)),
+                "jac_colind": np.array([0, 2, 3, 4]), "jac_row": np.array([0, 1, 0, 1]), "sb_m": np.int64(2)}
+
+    out = mod.merge_instances([part(1.0), part(2.0)])
+    assert out["x"].shape == (2, 3) and out["f"].tolist() == [1.0, 2.0] and out["jac"][1, 0] == 2.0
+    assert np.array_equal(out["jac_row"], [0, 1, 0, 1]) and int(out["sb_m"]) == 2
+    bad = part(3.0)
+    bad["jac_row"] = np.array([0, 1, 1, 1])
+    with pytest.raises(ValueError, match="jac_row"):
+        mod.merge_instances([part(1.0), bad])

@@ -2,11 +2,13 @@
 `hippopt` are importable (they are not in the build container, which is why the oracle is "parity unpinned" for the
 kinematic rows).
 
-For every committed fixture tests/golden/kino_*.npz / toy_*.npz the script builds the same problem through the
-reference's own code --
-  kinodynamic: `hippopt.turnkey_planners.humanoid_kinodynamic.planner.Planner(settings)` (planner.py:27-176) on the
-               synthetic ergoCub URDF the tests use (hippopt_b200.robot_model.synthetic_ergocub_urdf),
-  toy        : the OptimalControlProblem of test/test_multiple_shooting.py:210-353 --
+For every committed fixture tests/golden/kino_*.npz the script builds the same problem through the reference's own
+code -- `hippopt.turnkey_planners.humanoid_kinodynamic.planner.Planner(settings)` (planner.py:27-176) on the synthetic
+ergoCub URDF the tests use (hippopt_b200.robot_model.synthetic_ergocub_urdf); planar terrain for configs 3 / 4, and for
+the stairs fixtures (config 5) the sum of two `SmoothTerrain.step` boxes of main_walking_on_stairs.py:18-28, one planner
+per instance because the reference bakes the step dimensions into the graph where this library reads them from ten
+parameters (those ten are stripped from p before the call).  (The toy fixtures toy_*.npz are pinned differently: the
+reference's own test holds their known answers, tests/test_golden_cpu.py.)  It
 takes the fixture's x / p / lam / sigma, evaluates the five nlpsol oracle functions CasADi generates (nlp_f,
 nlp_grad_f, nlp_g, nlp_jac_g, nlp_hess_l) and writes tests/golden/casadi_<fixture>.npz with THE SAME KEYS
 (x, p, lam, sigma, f, grad_f, g, jac, hess, jac_colind, jac_row, hess_colind, hess_row, lbg, ubg + the settings keys).
@@ -84,9 +86,26 @@ def dump_nlp(cs, opti, x, p, lam, sigma, plugin_options=None) -> dict:
     return out
 
 
+def merge_instances(parts: list) -> dict:
+    """Per-instance dumps (one planner each) -> one dump: batched keys are stacked, the patterns must agree."""
+    out = dict(parts[0])
+    if len(parts) == 1:
+        return out
+    batched = ("x", "p", "lam", "sigma", "f", "grad_f", "g", "jac", "hess", "lbg", "ubg")
+    for k, v in parts[0].items():
+        if k in batched:
+            out[k] = np.concatenate([np.asarray(q[k]) for q in parts], axis=0)
+        else:
+            for q in parts[1:]:
+                if not np.array_equal(np.asarray(q[k]), np.asarray(v)):
+                    raise ValueError(f"instances disagree on '{k}': the sparsity pattern depends on the terrain")
+    return out
+
+
 # ------------------------------------------------------------------------------------------------------ planners
-def build_kinodynamic_opti(fixture: dict):
-    """The reference's planner for one fixture -> (casadi module, baked Opti).  Needs the reference environment."""
+def build_kinodynamic_opti(fixture: dict, terrain_params=None):
+    """The reference's planner for one fixture -> (casadi module, baked Opti).  Needs the reference environment.
+    terrain_params: (l, w, height, ox, oy) x 2 of the two smooth steps (one instance of a stairs fixture)."""
     import casadi as cs
     import hippopt as hp
     import hippopt.robot_planning as hp_rp
@@ -114,8 +133,12 @@ def build_kinodynamic_opti(fixture: dict):
     st.integrator = hp.ImplicitTrapezoid
     st.terrain = hp_rp.PlanarTerrain()
     if bool(fixture.get("smooth", False)):
-        raise NotImplementedError("smooth-step fixtures: build TerrainSum of two SmoothTerrain.step as in "
-                                  "main_walking_on_stairs.py:18-28 with the ten terrain parameters as hp.Parameter")
+        if terrain_params is None:
+            raise ValueError("a stairs fixture needs the terrain parameters of one instance")
+        tp = np.asarray(terrain_params, dtype=np.float64).reshape(2, 5)
+        steps = [hp_rp.SmoothTerrain.step(length=float(t[0]), width=float(t[1]), height=float(t[2]),
+                                          position=np.array([t[3], t[4], 0.0])) for t in tp]
+        st.terrain = steps[0] + steps[1]  # TerrainSum (utilities/terrain_sum.py)
     st.desired_frame_quaternion_cost_frame_name = "chest"
     st.final_state_expression_type = hp.ExpressionType.subject_to if bool(fixture["final"]) else hp.ExpressionType.skip
     st.periodicity_expression_type = (hp.ExpressionType.subject_to if bool(fixture["periodicity"])
@@ -156,16 +179,20 @@ def main(argv=None):
         return 2
     for path in sorted(glob.glob(os.path.join(GOLD, args.fixtures))):
         fx = dict(np.load(path))
-        try:
-            cs, opti = build_kinodynamic_opti(fx)
-        except NotImplementedError as err:
-            print(f"skipping {os.path.basename(path)}: {err}")
-            continue
-        if (opti.nx, opti.np, opti.ng) != (fx["x"].shape[1], fx["p"].shape[1], fx["g"].shape[1]):
-            print(f"{os.path.basename(path)}: dimensions differ (Opti {opti.nx}/{opti.np}/{opti.ng}) -- layout mismatch, "
-                  "SURVEY.md Appendix B needs revisiting")
-            return 1
-        out = dump_nlp(cs, opti, fx["x"], fx["p"], fx["lam"], fx["sigma"])
+        smooth = bool(fx.get("smooth", False))
+        n_tp = 10 if smooth else 0
+        parts = []
+        for b in (range(fx["x"].shape[0]) if smooth else [None]):
+            cs, opti = build_kinodynamic_opti(fx, fx["p"][b, -n_tp:] if smooth else None)
+            if (opti.nx, opti.np + n_tp, opti.ng) != (fx["x"].shape[1], fx["p"].shape[1], fx["g"].shape[1]):
+                print(f"{os.path.basename(path)}: dimensions differ (Opti {opti.nx}/{opti.np}/{opti.ng}) -- layout "
+                      "mismatch, SURVEY.md Appendix B needs revisiting")
+                return 1
+            sel = slice(None) if b is None else slice(b, b + 1)
+            p_ref = fx["p"][sel, :fx["p"].shape[1] - n_tp]
+            parts.append(dump_nlp(cs, opti, fx["x"][sel], p_ref, fx["lam"][sel], fx["sigma"][sel]))
+        out = merge_instances(parts)
+        out["p"] = fx["p"]  # the fixture's own parameter vector (with the terrain block), so that the keys line up
         for k in ("horizon", "final", "periodicity", "smooth", "dt"):
             if k in fx:
                 out[k] = fx[k]
