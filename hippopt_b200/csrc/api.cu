@@ -989,10 +989,11 @@ extern "C" int hb_kkt_assemble_stage(const int32_t* hdr, const int32_t* tab, con
   S.n_direct = hdr[hb::KS_NDIRECT];
   S.n_targets = hdr[hb::KS_NTARGETS];
   S.n_an = hdr[hb::KS_NAN];
+  S.nb_prev = hdr[hb::KS_NB_PREV];
   const int n_contrib = hdr[hb::KS_NCONTRIB], n_a = hdr[hb::KS_NA];
   if (batch <= 0 || S.nb <= 0 || S.nx <= 0 || S.nx > S.nb || S.nv < 0 || S.nv > S.nx || S.ne < 0 || S.nx + S.ne > S.nb ||
       S.R <= 0 || S.n_cpl < 0 || S.n_cpl_next < 0 || S.n_direct < 0 || S.n_targets < 0 || n_contrib < 0 || n_a < 0 ||
-      S.n_an < 0)
+      S.n_an < 0 || (S.n_cpl > 0 && S.nb_prev <= 0))
     return fail(HB_ERR_INVALID, "hb_kkt_assemble_stage: inconsistent stage header");
   if (S.n_targets > 0 && (!sigma_I || m_I <= 0)) return fail(HB_ERR_INVALID, "hb_kkt_assemble_stage: sigma_I missing");
   if (S.n_cpl > 0 && !prev_sol) return fail(HB_ERR_INVALID, "hb_kkt_assemble_stage: the previous stage's solution is missing");

@@ -18,11 +18,11 @@
 namespace hb {
 
 enum {  // header of a stage table (host int32 array)
-  KS_NB, KS_NX, KS_NV, KS_NE, KS_R, KS_NCPL, KS_NCPL_NEXT, KS_NDIRECT, KS_NTARGETS, KS_NCONTRIB, KS_NA, KS_NAN, KS_COUNT
+  KS_NB, KS_NX, KS_NV, KS_NE, KS_R, KS_NCPL, KS_NCPL_NEXT, KS_NDIRECT, KS_NTARGETS, KS_NCONTRIB, KS_NA, KS_NAN, KS_NB_PREV, KS_COUNT
 };
 
 struct KktStage {
-  int nb, nx, nv, ne, R, n_cpl, n_cpl_next, n_direct, n_targets, n_an;
+  int nb, nx, nv, ne, R, n_cpl, n_cpl_next, n_direct, n_targets, n_an, nb_prev;
   const int *direct_val, *direct_pos, *tgt_pos, *tgt_ptr, *tgt_sig, *tgt_e1, *tgt_e2, *var, *eq, *cpl, *a_ptr, *a_val,
       *a_col, *an_val, *an_row, *an_col;
 };
@@ -95,7 +95,7 @@ __global__ void __launch_bounds__(512) kkt_assemble_kernel(const KktStage S, con
   if (S.n_cpl > 0 && prev != nullptr) {
     __syncthreads();
     const int Wp = R + S.n_cpl;
-    const double* pb = prev + b * (long)nb * Wp;
+    const double* pb = prev + b * (long)S.nb_prev * Wp;  // the previous stage's block may have another size
     for (int idx = tid; idx < S.n_cpl * Wp; idx += nt) {
       const int r = idx / Wp, t = idx - r * Wp;
       double acc = 0.0;

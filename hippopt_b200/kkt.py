@@ -205,15 +205,23 @@ class StageKKT:
         # 2 B <= 148 (one CTA per SM on a B200) is free; measured: sweeps of 32 / 64 instances 29 / 37 ms against ~50 ms
         # one-sided, but 148 instances 58 ms against 55 ms -- no gain once the pair no longer fits one wave
         self.two_sided_max_batch = 74 if linalg == "hb" else 0
-        # ---- tables of the fused assembly kernel (hb_kkt_assemble_stage), in the order include/hippopt_b200.h lists
+        # ---- tables of the fused assembly kernel (hb_kkt_assemble_stage), in the order include/hippopt_b200.h lists.
+        # The fused sweep sizes every stage block by ITS variables and equality rows (nb_k = n_var_k + n_eq_k) instead
+        # of the padded maximum: with a final-state constraint the last stage has 81 more rows than the others
+        # (config 4: 418 against 331), and a padded block costs (418 / 331)^3 = 2 x the factorisation on 29 of 30 stages.
         self.fused = linalg == "hb"  # one launch per stage instead of ~25 torch calls; CUDA tensors only
         self._stage_np = []
+        self.stage_nx = [len(mp_["var"]) for mp_ in self.maps]
+        self.stage_nb = [self.stage_nx[k] + len(self.eq_stage_rows[k]) for k in range(N)]
         for k in range(N):
+            nxk, nbk = self.stage_nx[k], self.stage_nb[k]
             sel = np.nonzero(hst == k)[0]
             je = np.nonzero(is_eq[jac_row] & (row_stage[jac_row] == k) & (jst == k))[0]
             direct_val = np.concatenate([sel, sel, ~je, ~je])
-            direct_pos = np.concatenate([hr_l[sel] * nb + hc_l[sel], hc_l[sel] * nb + hr_l[sel],
-                                         (nx + loc_E[jac_row[je]]) * nb + jc_l[je], jc_l[je] * nb + (nx + loc_E[jac_row[je]])])
+            direct_pos = np.concatenate([hr_l[sel] * nbk + hc_l[sel], hc_l[sel] * nbk + hr_l[sel],
+                                         (nxk + loc_E[jac_row[je]]) * nbk + jc_l[je], jc_l[je] * nbk + (nxk + loc_E[jac_row[je]])])
+            if len(sel) and max(hr_l[sel].max(), hc_l[sel].max()) >= nxk or len(je) and jc_l[je].max() >= nxk:
+                raise AssertionError("a stage references a variable slot beyond its own variables")
             # J_I^T Sigma J_I: ordered pairs of the entries of every inequality row, grouped by destination
             ji = np.nonzero((~is_eq[jac_row]) & (pos_I[jac_row] >= 0) & (row_stage[jac_row] == k))[0]
             by_row: dict[int, list] = {}
@@ -223,7 +231,7 @@ class StageKKT:
             for r in sorted(by_row):
                 for e1 in by_row[r]:
                     for e2 in by_row[r]:
-                        contrib.setdefault(int(jc_l[e1]) * nb + int(jc_l[e2]), []).append((int(pos_I[r]), e1, e2))
+                        contrib.setdefault(int(jc_l[e1]) * nbk + int(jc_l[e2]), []).append((int(pos_I[r]), e1, e2))
             tgt_pos = np.asarray(sorted(contrib), dtype=np.int64)
             tgt_ptr = np.zeros(len(tgt_pos) + 1, dtype=np.int64)
             flat = []
@@ -248,9 +256,9 @@ class StageKKT:
             var = self.maps[k]["var"].cpu().numpy()
             eqk = pos_E[self.eq_stage_rows[k]]
             tables = [direct_val, direct_pos, tgt_pos, tgt_ptr, flat[:, 0], flat[:, 1], flat[:, 2], var, eqk,
-                      nx + self.cpl_local[k], a_ptr, a[:, 1], a[:, 2], an[:, 1], an[:, 0], an[:, 2]]
-            hdr = [nb, nx, len(var), len(eqk), 0, n_cpl, len(self.cpl_local[k + 1]) if k + 1 < N else 0, len(direct_val),
-                   len(tgt_pos), len(flat), len(a), len(an)]
+                      nxk + self.cpl_local[k], a_ptr, a[:, 1], a[:, 2], an[:, 1], an[:, 0], an[:, 2]]
+            hdr = [nbk, nxk, len(var), len(eqk), 0, n_cpl, len(self.cpl_local[k + 1]) if k + 1 < N else 0, len(direct_val),
+                   len(tgt_pos), len(flat), len(a), len(an), self.stage_nb[k - 1] if k > 0 else 0]
             self._stage_np.append((hdr, np.concatenate([np.asarray(t, dtype=np.int64).ravel() for t in tables]).astype(np.int32)))
         self._stage_dev = None
 
@@ -429,8 +437,9 @@ class StageKKT:
             hdr, _ = self._stage_np[k]
             hdr = list(hdr)
             hdr[4] = R
-            D = torch.empty((B, nb, nb), dtype=dt, device=dev)
-            rhs = torch.empty((B, nb, R + hdr[6]), dtype=dt, device=dev)
+            nbk = hdr[0]
+            D = torch.empty((B, nbk, nbk), dtype=dt, device=dev)
+            rhs = torch.empty((B, nbk, R + hdr[6]), dtype=dt, device=dev)
             _capi.check(L.hb_kkt_assemble_stage((ctypes.c_int32 * len(hdr))(*hdr), _ptr(self._stage_dev[1][k]), _ptr(hv),
                                                 hv.shape[1], _ptr(jv), jv.shape[1], _ptr(sg), max(sg.shape[1], 1), _ptr(dl),
                                                 float(delta_c), _ptr(rx), self.n_x, _ptr(re), self.mE,
@@ -444,13 +453,23 @@ class StageKKT:
         u_next = None
         for k in range(N - 1, -1, -1):
             mp = self.maps[k]
+            nxk = self.stage_nx[k]
             u = sols[k][:, :, :R]
             if k < N - 1 and self.maps[k + 1]["n_cpl"]:
-                u = u - torch.bmm(sols[k][:, :, R:], u_next[:, self.maps[k + 1]["cpl"], :])
-            DX[:, mp["var"], :] = u[:, :mp["n_var"], :]
-            DL[:, mp["eq"], :] = u[:, nx:nx + mp["n_eq"], :]
+                nxn = self.stage_nx[k + 1]
+                cp_next = u_next[:, nxn + self._cpl_local_dev(k + 1, dev), :]
+                u = u - torch.bmm(sols[k][:, :, R:], cp_next)
+            DX[:, mp["var"], :] = u[:, :nxk, :]
+            DL[:, mp["eq"], :] = u[:, nxk:nxk + mp["n_eq"], :]
             u_next = u
         return DX, DL
+
+    def _cpl_local_dev(self, k, dev):
+        cache = self.__dict__.setdefault("_cpl_dev", {})
+        key = (k, str(dev))
+        if key not in cache:
+            cache[key] = torch.as_tensor(np.ascontiguousarray(self.cpl_local[k]), dtype=torch.long, device=dev)
+        return cache[key]
 
     # ------------------------------------------------------------------ two-sided sweep
     def _assemble(self, k, hess_vals, jac_vals, sigma_I, delta, delta_c, RX, RE):

@@ -311,14 +311,14 @@ int hb_lu_solve_batched(const double* LU, const int32_t* piv, double* Bm, int64_
  * stage's equality rows in both triangles and the coupling term A_k S_{k-1}^{-1} A_k^T subtracted, and the right-hand
  * sides rhs (batch x nb x (R + n_cpl_next), row-major) = [b_k - A_k w_{k-1} | A_{k+1}^T; 0].  hb_lu_factor_batched(D) and
  * hb_lu_solve_batched(D, rhs) follow; the solution is `prev_sol` of the next stage.
- *   hdr   HOST   int32[12]: nb, nx (variable slots), nv (live variables), ne (equality rows), R, n_cpl, n_cpl_next,
- *                n_direct, n_targets, n_contrib, n_a, n_an
+ *   hdr   HOST   int32[13]: nb, nx (variable slots), nv (live variables), ne (equality rows), R, n_cpl, n_cpl_next,
+ *                n_direct, n_targets, n_contrib, n_a, n_an, nb_prev (block size of stage k - 1: stages may differ)
  *   tab   device int32 tables in this order: direct_val[n_direct] (>= 0: hess_vals index, < 0: ~index into jac_vals),
  *                direct_pos[n_direct]; tgt_pos[n_targets], tgt_ptr[n_targets + 1], tgt_sig / tgt_e1 / tgt_e2[n_contrib]
  *                (D[tgt_pos] += sum sigma_I[sig] jac[e1] jac[e2]); var[nv], eq[ne] (rows of RX / RE); cpl[n_cpl] (block
  *                rows of the coupling equations); a_ptr[n_cpl + 1], a_val / a_col[n_a] (A_k by row: jac_vals index,
  *                variable slot of stage k - 1); an_val / an_row / an_col[n_an] (A_{k+1}: rhs[an_col][R + an_row])
- *   RX    device [batch][n_x][R], RE device [batch][m_E][R]; prev_sol device [batch][nb][R + n_cpl] or NULL
+ *   RX    device [batch][n_x][R], RE device [batch][m_E][R]; prev_sol device [batch][nb_prev][R + n_cpl] or NULL
  * One CTA per instance; fixed summation order (bit-reproducible).
  * replaces: the assembly of the KKT matrix inside IPOPT / MUMPS [ext] for the stage ordering of kkt.py. */
 int hb_kkt_assemble_stage(const int32_t* hdr, const int32_t* tab, const double* hess_vals, int64_t nnz_h,
