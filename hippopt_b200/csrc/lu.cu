@@ -685,7 +685,7 @@ __global__ void __launch_bounds__(LU_THREADS, 2) lu_solve_staged_kernel(const do
         double2* crow = reinterpret_cast<double2*>(b + (size_t)(r0 + (valid ? i : 0)) * ldb + 2 * t4);
 #pragma unroll
         for (int ct = 0; ct < CT; ++ct) {
-          double2 c = crow[4 * ct];
+          double2 c = valid ? crow[4 * ct] : make_double2(0.0, 0.0);  // rows past the end are neither read nor written
 #pragma unroll
           for (int kk = 0; kk < LU_SNB / 4; ++kk) dmma_m8n8k4(c.x, c.y, a[kk], yb[ct][kk]);
           if (valid) crow[4 * ct] = c;

@@ -33,6 +33,9 @@ lu_solve(Fm, piv, torch.randn(3, 37, 5, dtype=torch.float64, device=d))
 A = torch.randn(2, 337, 337, dtype=torch.float64, device=d)  # the KKT stage-block size: 22 panels, both register variants
 Fm, piv, info = lu_factor(A.clone())
 lu_solve(Fm, piv, torch.randn(2, 337, 40, dtype=torch.float64, device=d))
+A = torch.randn(1, 700, 700, dtype=torch.float64, device=d)  # one CTA per SM in the staged substitution (fewer columns per CTA)
+Fm, piv, info = lu_factor(A.clone())
+lu_solve(Fm, piv, torch.randn(1, 700, 19, dtype=torch.float64, device=d))
 # interpolation kernel: a plan with swings, per-instance phases, both outputs, a warp with fewer than three items
 from hippopt_b200.initial_guess import periodic_step_phases  # noqa: E402
 from hippopt_b200.interpolators import humanoid_state_interpolator  # noqa: E402
