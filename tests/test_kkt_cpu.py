@@ -131,3 +131,79 @@ def test_two_sided_sweep_matches_dense_and_one_sided(model, N, final, periodic):
     # N < 4 (or irregular coupling) falls back to the one-sided sweep
     _, small, _, _ = _setup(model, 3, False)
     assert not small._two_sided_ok
+
+
+def _emulate_assemble(hdr, tab, hv, jv, sig, delta, delta_c, RX, RE, prev):
+    """numpy restatement of csrc/kkt_assemble.cu for ONE instance: what hb_kkt_assemble_stage builds from a stage table."""
+    nb, nx, nv, ne, R, n_cpl, n_cpl_next, n_direct, n_targets, n_contrib, n_a, n_an, nb_prev = hdr
+    parts = [n_direct, n_direct, n_targets, n_targets + 1, n_contrib, n_contrib, n_contrib, nv, ne, n_cpl, n_cpl + 1, n_a, n_a,
+             n_an, n_an, n_an]
+    assert sum(parts) == len(tab)
+    o = np.cumsum([0] + parts)
+    (direct_val, direct_pos, tgt_pos, tgt_ptr, tgt_sig, tgt_e1, tgt_e2, var, eq, cpl, a_ptr, a_val, a_col, an_val, an_row,
+     an_col) = (tab[o[i]:o[i + 1]] for i in range(16))
+    W = R + n_cpl_next
+    D = np.zeros(nb * nb)
+    rhs = np.zeros((nb, W))
+    D[direct_pos] = np.where(direct_val >= 0, hv[np.maximum(direct_val, 0)], jv[np.maximum(~direct_val, 0)])
+    rhs[:nv, :R] = RX[var]
+    rhs[nx:nx + ne, :R] = RE[eq]
+    rhs[an_col, R + an_row] = jv[an_val]
+    for t in range(n_targets):
+        q = slice(tgt_ptr[t], tgt_ptr[t + 1])
+        D[tgt_pos[t]] += np.sum(sig[tgt_sig[q]] * jv[tgt_e1[q]] * jv[tgt_e2[q]])
+    D = D.reshape(nb, nb)
+    i = np.arange(nb)
+    D[i, i] += np.where(i < nv, delta, np.where(i < nx, 1.0, np.where(i < nx + ne, -delta_c, 1.0)))
+    if n_cpl and prev is not None:
+        assert prev.shape == (nb_prev, R + n_cpl)
+        for r in range(n_cpl):
+            q = slice(a_ptr[r], a_ptr[r + 1])
+            acc = jv[a_val[q]] @ prev[a_col[q], :]
+            rhs[cpl[r], :R] -= acc[:R]
+            D[cpl[r], cpl] -= acc[R:]
+    return D, rhs
+
+
+@pytest.mark.parametrize("N,final", [(3, False), (3, True)])
+def test_fused_stage_tables_match_the_torch_assembly(model, N, final):
+    """The tables hb_kkt_assemble_stage consumes (per-stage block sizes, value entries, J_I^T Sigma J_I contribution lists,
+    coupling rows) against the torch assembly of the unfused sweep, through a numpy restatement of the kernel."""
+    lay, kkt, eq, ine = _setup(model, N, final)
+    g = torch.Generator().manual_seed(7)
+    hv = torch.randn((1, lay.nnz_h), generator=g, dtype=torch.float64)
+    jv = torch.randn((1, lay.nnz_j), generator=g, dtype=torch.float64)
+    sig = torch.rand((1, len(ine)), generator=g, dtype=torch.float64) * 3.0
+    delta = torch.tensor([0.7], dtype=torch.float64)
+    R = 2
+    RX = torch.randn((1, lay.n_x, R), generator=g, dtype=torch.float64)
+    RE = torch.randn((1, len(eq), R), generator=g, dtype=torch.float64)
+    nx = kkt.nx
+    assert kkt.stage_nb == [kkt.stage_nx[k] + len(kkt.eq_stage_rows[k]) for k in range(N)]
+    assert max(kkt.stage_nb) <= kkt.nb and (not final or kkt.stage_nb[-1] > kkt.stage_nb[1])
+    for k in range(N):
+        hdr, tab = kkt._stage_np[k]
+        hdr = list(hdr)
+        hdr[4] = R
+        nbk, nxk, ne = hdr[0], hdr[1], hdr[3]
+        n_cpl = hdr[5]
+        prev = None
+        if n_cpl:
+            prev = np.random.default_rng(k).standard_normal((hdr[12], R + n_cpl))
+        D, rhs = _emulate_assemble(hdr, tab.astype(np.int64), hv[0].numpy(), jv[0].numpy(), sig[0].numpy(), 0.7, 1e-6,
+                                   RX[0].numpy(), RE[0].numpy(), prev)
+        Dt, bt = kkt._assemble(k, hv, jv, sig, delta, 1e-6, RX, RE)
+        Dt, bt = Dt[0].numpy().copy(), bt[0].numpy().copy()
+        idx = np.concatenate([np.arange(nxk), nx + np.arange(ne)])  # the stage's own slots inside the padded block
+        if n_cpl:
+            A = kkt._coupling(k, jv)[0].numpy()                       # (n_cpl, nx) on the padded slots of stage k - 1
+            nx_prev = kkt.stage_nx[k - 1]
+            assert np.all(A[:, nx_prev:] == 0.0)
+            cp = nx + kkt.cpl_local[k]
+            Dt[np.ix_(cp, cp)] -= A[:, :nx_prev] @ prev[:nx_prev, R:]
+            bt[cp, :] -= A[:, :nx_prev] @ prev[:nx_prev, :R]
+        assert np.allclose(D, Dt[np.ix_(idx, idx)], rtol=1e-13, atol=1e-13)
+        assert np.allclose(rhs[:, :R], bt[idx], rtol=1e-13, atol=1e-13)
+        if k + 1 < N:  # appended columns: A_{k+1}^T on this stage's variable rows
+            An = kkt._coupling(k + 1, jv)[0].numpy()
+            assert np.allclose(rhs[:nxk, R:], An[:, :nxk].T) and np.all(rhs[nxk:, R:] == 0.0)
