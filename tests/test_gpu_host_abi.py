@@ -200,3 +200,34 @@ def test_casadi_external_function_abi(model, built_library):
     res = (dp * 1)(np.zeros(1).ctypes.data_as(dp))
     lib.hb_nlp_f.restype = ctypes.c_int
     assert lib.hb_nlp_f(arg, res, None, None, 0) != 0 and b"no problem bound" in lib.hb_last_error()
+
+
+def test_repeated_single_chunk_calls_replay_a_graph(model, built_library):
+    """What a CPU-side IPOPT does: the same pinned buffers, new contents, call after call.  From the third call on
+    hb_eval_host replays a captured CUDA graph; every call must return what a plain device evaluation returns, also after
+    the parameters or the mask change."""
+    from hippopt_b200.evaluator import ALL, F, G, GRAD_F, JAC_G, HostPipeline, KinoEvaluator
+    from hippopt_b200.kino_layout import KinoSettings
+    from hippopt_b200.workloads import kino_batch
+
+    ev = KinoEvaluator(model, KinoSettings(horizon=3))
+    B = 2
+    pipe = HostPipeline(ev, B, ALL)
+    first = HostPipeline(ev, B, F | GRAD_F | G | JAC_G)
+    xh, lh, sh = (HostPipeline.host_buffer(s) for s in ((B, ev.n_x), (B, ev.m), (B,)))
+    for it in range(6):
+        x, p, lam, sigma = kino_batch(ev.layout, model, B, seed=20 + it, noise=0.1)
+        if it in (0, 4):  # new parameters mid-sequence (same size: the graphs stay valid, the values are read from d_p)
+            pipe.set_parameters(torch.from_numpy(np.ascontiguousarray(p)))
+            p_now = p
+        xh.copy_(torch.from_numpy(x))
+        lh.copy_(torch.from_numpy(lam))
+        sh.copy_(torch.from_numpy(sigma))
+        ref = _device_eval(ev, ALL, x, p_now, lam, sigma)
+        out = pipe.run(xh, lh, sh)
+        for k in ref:
+            assert np.array_equal(out[k].numpy(), ref[k]), (it, k)
+        out1 = first.run(xh)  # the other mask, interleaved: its own graph
+        for k in ("f", "grad_f", "g", "jac"):
+            assert np.array_equal(out1[k].numpy(), ref[k]), (it, k)
+        assert ev.last_launch_count() == 3
