@@ -764,6 +764,13 @@ template <bool WITH_HESS>
 #ifndef KIN_H_MIN_BLOCKS
 #define KIN_H_MIN_BLOCKS 2
 #endif
+#ifndef HB_KIN_JAC_LIST
+#define HB_KIN_JAC_LIST 1  // Jacobian scatter through the destination-sorted list (measured 1.145 ms against 1.162 ms in entry order)
+#endif
+#ifndef HB_KIN_HESS_LIST
+#define HB_KIN_HESS_LIST 0  // 1: Hessian scatter through the destination-sorted list.  Measured: 1.161 ms against 1.145 ms in
+                            // entry order -- the staged columns are read conflict-free in entry order, in destination order not
+#endif
 #ifndef KIN_H_THREADS
 #define KIN_H_THREADS 128
 #endif
@@ -1433,8 +1440,9 @@ __global__ void __launch_bounds__(WITH_HESS ? KIN_H_THREADS : 128, WITH_HESS ? K
       __syncwarp();
       if (want_jac) {
         const int4 jkm = *reinterpret_cast<const int4*>(&T.knot_maps[k].jk_base);  // {base, offset, count, -}
-        const unsigned* lst = C.jk_list + jkm.y;  // destination-sorted: entry << 16 | slot
         double* jb = jac + b * T.nnz_j + jkm.x;
+#if HB_KIN_JAC_LIST
+        const unsigned* lst = C.jk_list + jkm.y;  // destination-sorted: entry << 16 | slot
         const int n = jkm.z;
         // KIN_SCAT list loads in flight before the dependent stores: <= 927 entries in two trips
         for (int eb = lane; eb < n; eb += 32 * KIN_SCAT) {
@@ -1445,6 +1453,18 @@ __global__ void __launch_bounds__(WITH_HESS ? KIN_H_THREADS : 128, WITH_HESS ? K
           for (int u = 0; u < KIN_SCAT; ++u)
             if (w[u] != 0xffffffffu) jb[w[u] & 0xffffu] = stg[w[u] >> 16];
         }
+#else
+        const int* jmap = C.jk_map + jkm.y;
+        const int n = T.n_jk;
+        for (int eb = lane; eb < n; eb += 32 * KIN_SCAT) {  // entry order: 927 entries in two trips
+          int sl[KIN_SCAT];
+#pragma unroll
+          for (int u = 0; u < KIN_SCAT; ++u) sl[u] = (eb + 32 * u) < n ? jmap[eb + 32 * u] : -1;
+#pragma unroll
+          for (int u = 0; u < KIN_SCAT; ++u)
+            if (sl[u] >= 0) jb[sl[u]] = stg[eb + 32 * u];
+        }
+#endif
       }
       if (want_grad) {
         // gbuf order vb3 qd4 q4 sd23 s23 -> x offsets
@@ -1643,6 +1663,7 @@ __global__ void __launch_bounds__(WITH_HESS ? KIN_H_THREADS : 128, WITH_HESS ? K
     if (em.stage) {
       // scatter the staged columns (27 directions x 57 rows) with coalesced map reads
       const double* st = sm + L.stage;
+#if HB_KIN_HESS_LIST
       const int2 hkl = *reinterpret_cast<const int2*>(&T.knot_maps[k].hk_off);  // {offset, count}
       const unsigned* lst = C.hk_list + hkl.x;  // destination-sorted: entry << 16 | slot; mirrored pairs are absent
       const int n = hkl.y;
@@ -1654,6 +1675,16 @@ __global__ void __launch_bounds__(WITH_HESS ? KIN_H_THREADS : 128, WITH_HESS ? K
         for (int u = 0; u < KIN_SCAT; ++u)
           if (w[u] != 0xffffffffu) em.hess[w[u] & 0xffffu] = st[w[u] >> 16];
       }
+#else
+      for (int eb = lane; eb < HSTAGE; eb += 32 * KIN_SCAT) {  // entry order: 1539 entries in three trips
+        int sl[KIN_SCAT];
+#pragma unroll
+        for (int u = 0; u < KIN_SCAT; ++u) sl[u] = (eb + 32 * u) < HSTAGE ? em.map[eb + 32 * u] : -1;
+#pragma unroll
+        for (int u = 0; u < KIN_SCAT; ++u)
+          if (sl[u] >= 0) em.hess[sl[u]] = st[eb + 32 * u];
+      }
+#endif
     }
     // velocity-diagonal entries (HK2): quaternion-velocity cost, joint regularisation
     if (lane < 27) {
