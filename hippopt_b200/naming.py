@@ -66,6 +66,8 @@ def _full_name(base: str, kind: str, k: int) -> str:
 
 def constraint_rows(layout) -> dict[str, np.ndarray]:
     """name -> rows of g (and of lam_g), in the reference's `subject_to` order (= increasing row index)."""
+    if is_pose_layout(layout):
+        return _pose_constraint_rows(layout)
     out: dict[str, np.ndarray] = {}
     fams = [(f"pt{i}.{fam}", base.format(pt=point_symbol(i)), kind) for i in range(NPT)
             for fam, base, kind in _POINT_FAMILIES]
@@ -117,3 +119,94 @@ def constraint_multipliers(layout, lam_g: np.ndarray) -> dict[str, np.ndarray]:
     """One instance's lam_g -> {name: multipliers} (`OptiSolver.get_constraint_multipliers`)."""
     lam_g = np.asarray(lam_g).ravel()
     return {name: lam_g[rows].copy() for name, rows in constraint_rows(layout).items()}
+
+
+# ------------------------------------------------------------------------------------------------ pose finder
+# The static pose finder (`turnkey_planners/humanoid_pose_finder/planner.py`) is a plain `hp.Problem`: names carry no
+# "[k]" suffix, and its variables live under `state` (`Variables.state: HumanoidState`, planner.py:226-229).
+def pose_point_symbol(i: int) -> str:
+    return f"state.contact_points.{'left' if i < 4 else 'right'}[{i % 4}]"
+
+
+_POSE_POINT_FAMILIES = [("complementarity", "{pt}.p_complementarity"), ("height", "{pt}.p_height"),
+                        ("normal", "{pt}.f_normal"), ("friction", "{pt}.f_friction"),
+                        ("fk", "{pt}.p_kinematics_consistency")]
+_POSE_ROBOT_FAMILIES = [("unit_quat", "unitary_quaternion"), ("com_kin", "com_kinematics_consistency"),
+                        ("balance", "centroidal_momentum_dynamics"), ("s_bounds", "joint_position_bounds")]
+
+
+def is_pose_layout(layout) -> bool:
+    return getattr(layout, "N", None) == 1 and "balance" in getattr(layout, "fam", {})
+
+
+def _pose_constraint_rows(layout) -> dict[str, np.ndarray]:
+    out = {}
+    for i in range(NPT):
+        for fam, base in _POSE_POINT_FAMILIES:
+            first, rows, _, _ = layout.fam[f"pt{i}.{fam}"]
+            out[base.format(pt=pose_point_symbol(i))] = np.arange(first, first + rows)
+    for fam, base in _POSE_ROBOT_FAMILIES:
+        first, rows, _, _ = layout.fam[fam]
+        out[base] = np.arange(first, first + rows)
+    return dict(sorted(out.items(), key=lambda kv: kv[1][0]))
+
+
+def _rot_from_quat(q):
+    """R = I + 2 w [v]x + 2 [v]x^2 of an xyzw quaternion (as given: callers normalise where the planner does)."""
+    v, w = q[:3], q[3]
+    S = np.array([[0.0, -v[2], v[1]], [v[2], 0.0, -v[0]], [-v[1], v[0], 0.0]])
+    return np.eye(3) + 2.0 * w * S + 2.0 * S @ S
+
+
+def _frame_rotation(model, frame: str, qn, s):
+    """Orientation of a frame in the inertial frame: base rotation, then joint_rot @ Rodrigues(axis, s) down the chain."""
+    body, R_f, _ = model.frames[frame]
+    R = _rot_from_quat(qn)
+    for b in model.chain_to_root(body):
+        a = model.joint_axis[b]
+        K = np.array([[0.0, -a[2], a[1]], [a[2], 0.0, -a[0]], [-a[1], a[0], 0.0]])
+        th = s[b - 1]
+        R = R @ model.joint_rot[b] @ (np.eye(3) + np.sin(th) * K + (1.0 - np.cos(th)) * K @ K)
+    return R @ R_f
+
+
+def pose_cost_values(layout, model, x, p) -> dict[str, float]:
+    """Values of the pose finder's named costs at one solution, in the order the planner records them
+    (planner.py:523-594, 751-788): `OptiSolver.get_cost_values()` of that problem.  Evaluated on the host from the
+    solution (a report made once per solve, not part of the evaluation path); their sum is the objective the kernels
+    return."""
+    from .pose_layout import XCOM, XQ, XS  # local: naming has no other dependency on the layouts
+
+    x, p = np.asarray(x, dtype=np.float64).ravel(), np.asarray(p, dtype=np.float64).ravel()
+    st, po = layout.st, layout.po
+    q, s, com = x[XQ:XQ + 4], x[XS:XS + len(model.joint_names)], x[XCOM:XCOM + 3]
+    ref = p[po.ref:po.ref + 105]
+    qd, s_ref, com_ref = ref[po.ST_Q:po.ST_Q + 4], ref[po.ST_S:po.ST_S + len(s)], ref[po.ST_COM:po.ST_COM + 3]
+    out: dict[str, float] = {}
+    # base quaternion: (qd^-1 (x) q) - identity, xyzw Hamilton product with the conjugate of qd (quaternion.py:54-85)
+    a = np.array([-qd[0], -qd[1], -qd[2], qd[3]])
+    av, aw, bv, bw = a[:3], a[3], q[:3], q[3]
+    e = np.concatenate([aw * bv + bw * av + np.cross(av, bv), [aw * bw - av @ bv - 1.0]])
+    out["base_quaternion_error"] = st.base_quaternion_cost_multiplier * float(e @ e)
+    # frame orientation: (trace(R_frame R(q_desired)^T) - 3)^2 with the normalised base quaternion (kinematics.py:444-448)
+    fq = p[po.ref_fq:po.ref_fq + 4]
+    E = _frame_rotation(model, st.frame_quaternion_cost_frame, q / np.linalg.norm(q), s) @ _rot_from_quat(fq).T
+    out["frame_rotation_error"] = st.desired_frame_quaternion_cost_multiplier * float((np.trace(E) - 3.0) ** 2)
+    out["com_position_error"] = st.com_regularization_cost_multiplier * float((com - com_ref) @ (com - com_ref))
+    es = s - s_ref
+    out["joint_positions_error"] = st.joint_regularization_cost_multiplier * float(
+        es @ (np.asarray(st.joint_regularization_cost_weights) * es))
+    for foot in range(2):
+        pts = [4 * foot + i for i in range(4)]
+        forces = [x[6 * i + 3:6 * i + 6] for i in pts]
+        mean = 0.25 * (forces[0] + forces[1] + forces[2] + forces[3])
+        for i, f in zip(pts, forces):
+            out[f"{pose_point_symbol(i)}.f_average_regularization"] = (
+                st.average_force_regularization_cost_multiplier * float((f - mean) @ (f - mean)))
+        for i, f in zip(pts, forces):
+            pt = pose_point_symbol(i)
+            dp = x[6 * i:6 * i + 3] - ref[9 * i:9 * i + 3]
+            df = f - ref[9 * i + 3:9 * i + 6]
+            out[f"{pt}.p_regularization"] = st.point_position_regularization_cost_multiplier * float(dp @ dp)
+            out[f"{pt}.f_regularization"] = st.force_regularization_cost_multiplier * float(df @ df)
+    return out

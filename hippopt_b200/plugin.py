@@ -385,14 +385,21 @@ class B200Solver:
         out = ip.solve(x0, p, lbg, ubg, lam0=self._guess.get("lam_g"))  # raises OptiFailure like opti_solver.py:520
         self._last_output = out
         x = out.values.contiguous()
-        terms = ev.cost_terms(x, p).cpu().numpy() if hasattr(ev, "cost_terms") else None
+        pose = naming.is_pose_layout(lay)
+        terms = ev.cost_terms(x, p).cpu().numpy() if (hasattr(ev, "cost_terms") and not pose) else None
         xs, lam = x.cpu().numpy(), out.constraint_multipliers.cpu().numpy()
         self._output_cost = out.cost_value.cpu().numpy()
         from . import solution
 
         self._output_solution = [solution.values_dict(lay, xs[b], self._guess["p"][b]) for b in range(self._batch)]
-        self._cost_values = ([naming.cost_values(lay, terms[b]) for b in range(self._batch)] if terms is not None else
-                             [{} for _ in range(self._batch)])
+        if terms is not None:
+            self._cost_values = [naming.cost_values(lay, terms[b]) for b in range(self._batch)]
+        elif pose:  # the pose finder's 28 named costs, from the solution on the host
+            model = self._model if self._model is not None else getattr(lay, "model", None)
+            self._cost_values = [naming.pose_cost_values(lay, model, xs[b], self._guess["p"][b])
+                                 for b in range(self._batch)]
+        else:
+            self._cost_values = [{} for _ in range(self._batch)]
         self._constraint_values = [naming.constraint_multipliers(lay, lam[b]) for b in range(self._batch)]
         self._solution_vectors = {"x": xs, "lam_g": lam, "p": self._guess["p"]}
 

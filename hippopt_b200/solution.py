@@ -48,9 +48,40 @@ def _state_block(blk):
             "com": blk[102:105].copy()}
 
 
+def pose_values_dict(layout, x: np.ndarray, p: np.ndarray) -> dict:
+    """The pose finder's `Variables` tree (`humanoid_pose_finder/planner.py:226-300`): `state` (a HumanoidState: contact
+    points with p, f and descriptor, base pose, joints, com) from x, the parameters and `references` from p
+    (SURVEY.md Appendix B.4)."""
+    x, p = np.asarray(x, dtype=np.float64).ravel(), np.asarray(p, dtype=np.float64).ravel()
+    assert x.shape == (layout.n_x,) and p.shape == (layout.n_p,)
+    po = layout.po
+    desc = p[po.desc0:po.desc0 + 24].reshape(NPT, 3)
+    pts = [{"p": x[6 * i:6 * i + 3].copy(), "f": x[6 * i + 3:6 * i + 6].copy(),
+            "descriptor": {"position_in_foot_frame": desc[i].copy()}} for i in range(NPT)]
+    state = {"contact_points": {"left": pts[:4], "right": pts[4:]},
+             "kinematics": {"base": {"position": x[48:51].copy(), "quaternion_xyzw": x[51:55].copy()},
+                            "joints": {"positions": x[55:55 + NJ].copy()}},
+             "com": x[78:81].copy()}
+    return {
+        "state": state, "mass": p[po.mass], "parametric_link_length_multipliers": p[po.plm],
+        "parametric_link_densities": p[po.pld], "gravity": p[po.gravity:po.gravity + 6].copy(),
+        "references": {"state": _state_block(p[po.ref:po.ref + 105]),
+                       "frame_quaternion_xyzw": p[po.ref_fq:po.ref_fq + 4].copy(),
+                       "left_hand_position": p[po.ref_lhand:po.ref_lhand + 3].copy(),
+                       "right_hand_position": p[po.ref_rhand:po.ref_rhand + 3].copy()},
+        "relaxed_complementarity_epsilon": p[po.eps], "static_friction": p[po.mu],
+        "maximum_joint_positions": p[po.max_s:po.max_s + NJ].copy(),
+        "minimum_joint_positions": p[po.min_s:po.min_s + NJ].copy(),
+        "left_hand_position_in_frame": p[po.lhand_in_frame:po.lhand_in_frame + 3].copy(),
+        "right_hand_position_in_frame": p[po.rhand_in_frame:po.rhand_in_frame + 3].copy(),
+    }
+
+
 def values_dict(layout, x: np.ndarray, p: np.ndarray) -> dict:
     """`output.values.to_dict(flatten=False)`: the `Variables` tree (variables.py:254-301) as nested dicts / lists,
     variables taken from x and parameters from p."""
+    if naming.is_pose_layout(layout):
+        return pose_values_dict(layout, x, p)
     x, p = np.asarray(x, dtype=np.float64).ravel(), np.asarray(p, dtype=np.float64).ravel()
     assert x.shape == (layout.n_x,) and p.shape == (layout.n_p,)
     po = layout.po

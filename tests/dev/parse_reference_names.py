@@ -1,15 +1,21 @@
-"""Extract the expression names the reference's kinodynamic planner passes as `name=` arguments
-(/root/reference/src/hippopt/turnkey_planners/humanoid_kinodynamic/planner.py) and how each is added
-(add_dynamics / add_expression_to_horizon / add_expression, and minimize vs subject_to where the call says so).
-Run in the build container (the reference is not on the GPU box): writes tests/golden/reference_expression_names.json.
+"""Extract the expression names the reference's planners pass as `name=` arguments and how each is added
+(add_dynamics / add_expression_to_horizon / add_expression / add_constraint / add_cost, and minimize vs subject_to where
+the call says so):
+  /root/reference/src/hippopt/turnkey_planners/humanoid_kinodynamic/planner.py -> tests/golden/reference_expression_names.json
+  /root/reference/src/hippopt/turnkey_planners/humanoid_pose_finder/planner.py -> tests/golden/reference_pose_expression_names.json
+Run in the build container (the reference is not on the GPU box).
 """
 import ast
 import json
 import os
 import sys
 
-REF = "/root/reference/src/hippopt/turnkey_planners/humanoid_kinodynamic/planner.py"
-OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "golden", "reference_expression_names.json")
+GOLD = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "golden")
+JOBS = [("/root/reference/src/hippopt/turnkey_planners/humanoid_kinodynamic/planner.py",
+         os.path.join(GOLD, "reference_expression_names.json")),
+        ("/root/reference/src/hippopt/turnkey_planners/humanoid_pose_finder/planner.py",
+         os.path.join(GOLD, "reference_pose_expression_names.json"))]
+CALLS = ("add_dynamics", "add_expression_to_horizon", "add_expression", "add_constraint", "add_cost")
 
 
 def render(node) -> str:
@@ -27,13 +33,13 @@ def render(node) -> str:
     return ast.unparse(node)
 
 
-def main():
+def parse(REF, OUT):
     tree = ast.parse(open(REF).read())
     out = []
     for node in ast.walk(tree):
         if not (isinstance(node, ast.Call) and isinstance(node.func, ast.Attribute)):
             continue
-        if node.func.attr not in ("add_dynamics", "add_expression_to_horizon", "add_expression"):
+        if node.func.attr not in CALLS:
             continue
         kw = {k.arg: k.value for k in node.keywords}
         if "name" not in kw:
@@ -45,6 +51,11 @@ def main():
     out.sort(key=lambda d: d["line"])
     json.dump({"source": REF, "expressions": out}, open(OUT, "w"), indent=1)
     print(f"{len(out)} named expressions -> {OUT}")
+
+
+def main():
+    for ref, out in JOBS:
+        parse(ref, out)
 
 
 if __name__ == "__main__":

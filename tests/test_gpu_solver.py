@@ -276,3 +276,32 @@ def test_periodic_step_plans_with_the_references_own_options(model, built_librar
     travelled = z[:, -1, 6] - z[:, 0, 6]  # x of the first left contact point, first to last knot
     assert np.abs(travelled - L[ok]).max() < 5e-3
     assert z[:, :, 8].max(axis=1).min() > 0.01  # the swing foot leaves the ground
+
+
+def test_b200solver_on_the_pose_finder_template(model, built_library):
+    """Config 2 behind the same 16-method interface: a batch of static pose problems, per-name cost values (the 28 named
+    costs of humanoid_pose_finder/planner.py add up to the objective), multipliers per named constraint, the `state` tree."""
+    from hippopt_b200 import naming, plugin
+    from hippopt_b200.evaluator import F, PoseEvaluator
+    from hippopt_b200.workloads import pose_batch
+
+    dev = torch.device("cuda:0")
+    pev = PoseEvaluator(model)
+    B = 6
+    x, p, _, _ = pose_batch(pev.layout, model, B, seed=5, noise=0.02)
+    s = plugin.B200Solver(model=model, batch=B, evaluator=pev, kkt="dense", options_solver={"tol": 1e-8, "max_iter": 300})
+    s.generate_optimization_objects({"x": x, "p": p})
+    s.register_problem("pose")
+    s.solve()
+    vals, costs, mult = s.get_values(), s.get_cost_values(), s.get_constraint_multipliers()
+    vec = s.get_solution_vectors()
+    f = pev.eval(F, torch.tensor(vec["x"], device=dev), torch.tensor(p, device=dev))["f"].cpu().numpy()
+    assert s.get_cost_value() == pytest.approx(f, rel=1e-12)
+    rows = naming.constraint_rows(pev.layout)
+    for b in range(B):
+        assert len(costs[b]) == 28 and sum(costs[b].values()) == pytest.approx(f[b], rel=1e-11)
+        assert "state.contact_points.right[3].f_regularization" in costs[b] and "frame_rotation_error" in costs[b]
+        assert set(mult[b]) == set(rows) and "centroidal_momentum_dynamics" in mult[b]
+        assert np.array_equal(mult[b]["joint_position_bounds"], vec["lam_g"][b][rows["joint_position_bounds"]])
+        assert np.array_equal(vals[b]["state"]["kinematics"]["joints"]["positions"], vec["x"][b, 55:78])
+        assert np.array_equal(vals[b]["references"]["state"]["com"], p[b, pev.layout.po.ref + 102:pev.layout.po.ref + 105])

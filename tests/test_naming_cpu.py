@@ -122,3 +122,54 @@ def test_output_to_dict_and_mat_file(model, tmp_path):
     assert np.allclose(back["output"]["constraint_multipliers"]["final_state_expression"],
                        lam[0][naming.constraint_rows(lay)["final_state_expression"]])
     assert back["output"]["cost_values"]["joint_positions_error_2"] == terms[2, H["HB_CT_JOINTS"]]
+
+
+# ------------------------------------------------------------------------------------------------ pose finder
+POSE_GOLD = os.path.join(os.path.dirname(__file__), "golden", "reference_pose_expression_names.json")
+
+
+def test_pose_finder_names_match_the_reference_planner(model):
+    """Static pose finder (config 2): a plain hp.Problem -- names carry no [k] suffix and live under `state.`; every
+    name= argument of humanoid_pose_finder/planner.py that the default settings use is present exactly once per point."""
+    from hippopt_b200.pose_layout import PoseLayout
+    from hippopt_b200.workloads import pose_batch
+
+    reference = {e["name"]: e for e in json.load(open(POSE_GOLD))["expressions"]}
+    lay = PoseLayout(model)
+    x, p, _, _ = pose_batch(lay, model, 1, seed=3)
+    cons = naming.constraint_rows(lay)
+    costs = naming.pose_cost_values(lay, model, x[0], p[0])
+    assert sorted(np.concatenate(list(cons.values())).tolist()) == list(range(lay.m))  # every row of g has a name
+    seen: dict[str, int] = {}
+    for full in list(cons) + list(costs):
+        assert "[" not in full.replace("left[", "").replace("right[", ""), full  # no horizon index
+        base = re.sub(r"^state\.contact_points\.(left|right)\[\d\]\.", "<point>.", full)
+        assert base in reference, f"{full}: {base} is not a name= argument of the reference pose finder"
+        ref = reference[base]
+        if ref["call"] == "add_cost":
+            assert full in costs, full
+        elif ref["call"] == "add_constraint":
+            assert full in cons, full
+        seen[base] = seen.get(base, 0) + 1
+    # hands are skipped by the defaults of planner.py:79-92 (ExpressionType.skip); everything else is used
+    assert set(seen) == set(reference) - {"left_hand_position_error", "right_hand_position_error"}
+    for base, n in seen.items():
+        assert n == (8 if base.startswith("<point>.") else 1), base
+
+
+def test_pose_finder_named_costs_against_oracle(model):
+    """`get_cost_values()` of the pose finder: the 28 named costs in recording order against the oracle's per-application
+    values, and their sum against f."""
+    from hippopt_b200.pose_layout import PoseLayout
+    from hippopt_b200.workloads import pose_batch
+    from oracle import pose_finder as pf
+
+    lay = PoseLayout(model)
+    x, p, _, _ = pose_batch(lay, model, 4, seed=9)
+    nlp, _ = pf.build(model)
+    terms, f = nlp.eval_cost_terms(x, p), nlp.eval_f(x, p)
+    for b in range(4):
+        vals = np.array(list(naming.pose_cost_values(lay, model, x[b], p[b]).values()))
+        assert vals.shape == (28,)
+        assert np.abs(vals - terms[b]).max() <= 1e-12 * np.abs(terms[b]).max()
+        assert abs(vals.sum() - f[b]) <= 1e-12 * abs(f[b])
