@@ -68,6 +68,8 @@ def constraint_rows(layout) -> dict[str, np.ndarray]:
     """name -> rows of g (and of lam_g), in the reference's `subject_to` order (= increasing row index)."""
     if is_pose_layout(layout):
         return _pose_constraint_rows(layout)
+    if not hasattr(layout, "fam"):  # a template without a name table (toy OCP): one anonymous block
+        return {"g": np.arange(layout.m)}
     out: dict[str, np.ndarray] = {}
     fams = [(f"pt{i}.{fam}", base.format(pt=point_symbol(i)), kind) for i in range(NPT)
             for fam, base, kind in _POINT_FAMILIES]
@@ -98,6 +100,21 @@ def _cost_table():
           (H["HB_CT_FRAME_QUAT"], "frame_quaternion_error", 1), (H["HB_CT_BASE_QUAT"], "base_quaternion_error", 1),
           (H["HB_CT_BASE_QUAT_VEL"], "base_quaternion_velocity_error", 0), (H["HB_CT_JOINTS"], "joint_positions_error", 1)]
     return t
+
+
+def cost_names(layout) -> list[str]:
+    """Names of the template's cost expressions, in recording order."""
+    if is_pose_layout(layout):
+        names = ["base_quaternion_error", "frame_rotation_error", "com_position_error", "joint_positions_error"]
+        for foot in range(2):
+            pts = [pose_point_symbol(4 * foot + i) for i in range(4)]
+            names += [f"{pt}.f_average_regularization" for pt in pts]
+            for pt in pts:
+                names += [f"{pt}.p_regularization", f"{pt}.f_regularization"]
+        return names
+    if not hasattr(layout, "fam"):
+        return []
+    return list(cost_slots(layout))
 
 
 def cost_slots(layout) -> dict[str, tuple[int, int]]:

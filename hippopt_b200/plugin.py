@@ -236,6 +236,14 @@ class TemplateExpression:
         return self.name
 
 
+class _FlatLayout:
+    """Sizes and bounds of an evaluator that has no layout object of its own."""
+
+    def __init__(self, ev):
+        self.n_x, self.n_p, self.m = ev.n_x, ev.n_p, ev.m
+        self.bounds = ev.bounds
+
+
 class B200Solver:
     """casadi-free `OptimizationSolver` over a template problem, B instances at once (module docstring)."""
 
@@ -271,7 +279,9 @@ class B200Solver:
 
     def _layout(self):
         if self._ev is not None:
-            return self._ev.layout
+            if hasattr(self._ev, "layout"):
+                return self._ev.layout
+            return _FlatLayout(self._ev)  # templates without a field / name table (toy OCP)
         from .kino_layout import KinoLayout
 
         if self._model is None:
@@ -287,7 +297,7 @@ class B200Solver:
             raise ValueError("The input structure is neither an optimization object nor a list.")
         self._objects_structure = copy.deepcopy(input_structure)
         self._objects = {"x": np.arange(lay.n_x), "p": np.arange(lay.n_p),
-                         "constraints": naming.constraint_rows(lay), "costs": naming.cost_slots(lay)}
+                         "constraints": naming.constraint_rows(lay), "costs": naming.cost_names(lay)}
         for name in self._objects["constraints"]:
             self._constraint_expressions[name] = TemplateExpression(name, "constraint")
         for name in self._objects["costs"]:

@@ -82,6 +82,8 @@ def values_dict(layout, x: np.ndarray, p: np.ndarray) -> dict:
     variables taken from x and parameters from p."""
     if naming.is_pose_layout(layout):
         return pose_values_dict(layout, x, p)
+    if not hasattr(layout, "po"):  # a template without a field table (toy OCP): the flat vectors
+        return {"x": np.asarray(x, dtype=np.float64).copy(), "p": np.asarray(p, dtype=np.float64).copy()}
     x, p = np.asarray(x, dtype=np.float64).ravel(), np.asarray(p, dtype=np.float64).ravel()
     assert x.shape == (layout.n_x,) and p.shape == (layout.n_p,)
     po = layout.po

@@ -305,3 +305,24 @@ def test_b200solver_on_the_pose_finder_template(model, built_library):
         assert np.array_equal(mult[b]["joint_position_bounds"], vec["lam_g"][b][rows["joint_position_bounds"]])
         assert np.array_equal(vals[b]["state"]["kinematics"]["joints"]["positions"], vec["x"][b, 55:78])
         assert np.array_equal(vals[b]["references"]["state"]["com"], p[b, pev.layout.po.ref + 102:pev.layout.po.ref + 105])
+
+
+def test_b200solver_on_the_toy_template(built_library):
+    """Config 1 (the mass-falling OCP of the reference's own test) behind the 16-method interface: no name table, so the
+    values are the flat vectors and the multipliers one block; the solution is the test's closed form."""
+    from hippopt_b200 import plugin
+    from hippopt_b200.evaluator import ToyEvaluator
+    from oracle import toy
+
+    N, dt, B = 100, 0.01, 3
+    ev = ToyEvaluator(N, "euler", dt)
+    p = np.tile([-9.81, 1.0, 0.0], (B, 1))
+    s = plugin.B200Solver(batch=B, evaluator=ev, kkt="dense", options_solver={"tol": 1e-8})
+    s.generate_optimization_objects({"x": np.zeros((B, ev.n_x)), "p": p})
+    s.register_problem("mass_falling")
+    s.solve()
+    exact = toy.closed_form_solution(N, dt, -9.81, 1.0, 0.0)
+    for b in range(B):
+        assert np.abs(s.get_values()[b]["x"] - exact).max() < 1e-7
+        assert s.get_cost_values()[b] == {} and list(s.get_constraint_multipliers()[b]) == ["g"]
+    assert s.get_cost_value() == pytest.approx(3 * (98 * 25.0 + 36.0) * np.ones(B), rel=1e-8)
