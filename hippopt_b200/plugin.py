@@ -413,6 +413,24 @@ class B200Solver:
         self._constraint_values = [naming.constraint_multipliers(lay, lam[b]) for b in range(self._batch)]
         self._solution_vectors = {"x": xs, "lam_g": lam, "p": self._guess["p"]}
 
+    def get_solution_sensitivity(self, param_idx, delta: float = 0.0, delta_c: float = 0.0):
+        """d x* / d p[:, param_idx] of the last solve, (B, n_x, k): the counterpart of differentiating the reference's
+        `OptiSolver.to_function(...)` (opti_solver.py:597-638, main_sensitivity.py:213-247) -- one more KKT solve with a
+        right-hand side per parameter (hippopt_b200/sensitivity.py)."""
+        import torch
+
+        from .sensitivity import solution_sensitivity
+
+        if self._output_solution is None:
+            raise SolutionNotAvailableException
+        ev, lay = self._evaluator(), self._layout()
+        dev = torch.device(self._device)
+        sv = self._solution_vectors
+        dx, _, _ = solution_sensitivity(ev, torch.as_tensor(sv["x"], device=dev), torch.as_tensor(sv["lam_g"], device=dev),
+                                        torch.as_tensor(sv["p"], device=dev), lay.bounds, param_idx, kkt=self._kkt,
+                                        delta=delta, delta_c=delta_c)
+        return dx.cpu().numpy()
+
     def get_values(self):
         if self._output_solution is None:
             raise SolutionNotAvailableException

@@ -326,3 +326,77 @@ def test_b200solver_on_the_toy_template(built_library):
         assert np.abs(s.get_values()[b]["x"] - exact).max() < 1e-7
         assert s.get_cost_values()[b] == {} and list(s.get_constraint_multipliers()[b]) == ["g"]
     assert s.get_cost_value() == pytest.approx(3 * (98 * 25.0 + 36.0) * np.ones(B), rel=1e-8)
+
+
+def test_solution_sensitivity_on_the_pose_finder(model, built_library):
+    """Row f4, the `to_function` path: d(solution) / d(parameter) from one more KKT solve against central differences of
+    complete re-solves, for a reference (desired CoM height), a physical parameter (friction) and a joint reference."""
+    from hippopt_b200 import plugin
+    from hippopt_b200.evaluator import PoseEvaluator
+    from hippopt_b200.workloads import pose_batch
+
+    pev = PoseEvaluator(model)
+    po = pev.layout.po
+    B = 4
+    x, p, _, _ = pose_batch(pev.layout, model, B, seed=6, noise=0.02)
+    opts = {"tol": 1e-9, "max_iter": 400}
+
+    def solved(pp, guess=None):
+        s = plugin.B200Solver(model=model, batch=B, evaluator=pev, kkt="dense", options_solver=opts)
+        s.generate_optimization_objects({"x": x if guess is None else guess, "p": pp})
+        s.solve()
+        return s, s._last_output.success.cpu().numpy()
+
+    s0, ok = solved(p)
+    xs = s0.get_solution_vectors()["x"]
+    idx = [po.ref + 104, po.mu, po.ref + 79 + 14]  # desired CoM height, static friction, a knee reference
+    dx = s0.get_solution_sensitivity(idx)
+    assert dx.shape == (B, pev.n_x, 3)
+    for c, j in enumerate(idx):
+        h = 1e-3 * max(1.0, abs(p[0, j]))  # the re-solves are exact to ~1e-9: a smaller step would amplify that noise
+        pp, pm = p.copy(), p.copy()
+        pp[:, j] += h
+        pm[:, j] -= h
+        (sp, okp), (sm, okm) = solved(pp, xs), solved(pm, xs)
+        use = ok & okp & okm
+        assert use.sum() >= B - 1
+        fd = (sp.get_solution_vectors()["x"] - sm.get_solution_vectors()["x"])[use] / (2 * h)
+        scale = max(np.abs(fd).max(), 1e-3)
+        assert np.abs(dx[use][:, :, c] - fd).max() <= 5e-3 * scale, (c, np.abs(dx[use][:, :, c] - fd).max(), scale)
+    assert np.abs(dx[ok][:, :, 0]).max() > 1e-2  # the pose does move with the desired CoM height
+
+
+def test_solution_sensitivity_stage_backend_matches_dense(model, built_library):
+    """The same derivative through the block-tridiagonal sweep (kkt='stage': fused assembly, several right-hand sides)
+    and through one dense solve per instance, on standing OCPs of the kinodynamic planner."""
+    from hippopt_b200 import plugin
+    from hippopt_b200.evaluator import KinoEvaluator, PoseEvaluator
+    from hippopt_b200.ipsolver import BatchedInteriorPoint
+    from hippopt_b200.kino_layout import KinoSettings
+    from hippopt_b200.sensitivity import solution_sensitivity
+    from hippopt_b200.workloads import pose_batch, standing_problem
+
+    dev = torch.device("cuda:0")
+    pev = PoseEvaluator(model)
+    x, p, _, _ = pose_batch(pev.layout, model, 6, seed=4, noise=0.02)
+    lb, ub = pev.bounds(p)
+    pose = BatchedInteriorPoint(pev, tol=1e-8, max_iter=300).solve(torch.tensor(x, device=dev), torch.tensor(p, device=dev), lb, ub)
+    pose = pose.values.cpu().numpy()[pose.success.cpu().numpy()][:3]
+    st = KinoSettings(horizon=4)
+    ev = KinoEvaluator(model, st)
+    pk, x0 = standing_problem(ev.layout, model, pose)
+    s = plugin.B200Solver(model=model, settings=st, batch=pose.shape[0], evaluator=ev,
+                          options_solver={"tol": 1e-7, "max_iter": 300, "mu_init": 1e-3})
+    s.generate_optimization_objects({"x": x0, "p": pk})
+    s.solve()
+    sv = s.get_solution_vectors()
+    po = ev.layout.po
+    idx = [po.dt, po.mu, po.refs0 + 55 * 2 + po.R_JR + 3]  # time step, friction, a joint reference of knot 2
+    args = [torch.as_tensor(sv[k], device=dev) for k in ("x", "lam_g", "p")]
+    # the standing OCP has redundant equality rows and directions its objective barely sees: both systems carry the
+    # solver's own kind of regularisation (Hessian shift, -delta_c on the multiplier block)
+    d_stage, _, _ = solution_sensitivity(ev, *args, ev.layout.bounds, idx, kkt="stage", delta=1e-4, delta_c=1e-8)
+    d_dense, _, _ = solution_sensitivity(ev, *args, ev.layout.bounds, idx, kkt="dense", delta=1e-4, delta_c=1e-8)
+    scale = d_dense.abs().amax(dim=(1, 2), keepdim=True).clamp(min=1e-6)
+    assert torch.isfinite(d_stage).all() and float(scale.max()) < 1e6
+    assert ((d_stage - d_dense).abs() / scale).max().item() < 1e-5
