@@ -263,7 +263,13 @@ int hb_eval_cost_terms(hb_handle h, const double* x, const double* p, int64_t p_
  * opti_solver.py:296-344), so they are uploaded once with hb_host_set_parameters:
  *   p host [batch*n_p] (p_stride = n_p) or [n_p] (p_stride = 0, shared by every instance).
  * hb_eval_host fails with HB_ERR_INVALID if no parameters were set or `batch` exceeds the batch they
- * were set for (p_stride = n_p). */
+ * were set for (p_stride = n_p).
+ *
+ * A call that fits one chunk (batch <= 128) and repeats with the same mask and the same PINNED host pointers -- one
+ * instance per call, every iterate, is what a CPU-side IPOPT does -- is captured as a CUDA graph on its second
+ * occurrence and replayed from then on (copies, kernels and their events as one launch; up to 8 such call shapes per
+ * handle; HB_NO_HOST_GRAPH=1 in the environment turns it off).  The host buffers of such a call must stay allocated
+ * (and pinned) for as long as they are passed with that handle; new parameters of another size drop the graphs. */
 int hb_host_set_parameters(hb_handle h, const double* p, int64_t p_stride, int64_t batch);
 int hb_eval_host(hb_handle h, uint32_t mask, const double* x, const double* lam_g, const double* sigma,
                  double* f, double* grad_f, double* g, double* jac_vals, double* hess_vals, int64_t batch);
