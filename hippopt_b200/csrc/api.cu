@@ -47,6 +47,7 @@ struct hb_problem_s {
   hb::KinTopo topo{};  // warp-uniform tables, passed by value to the kinematics kernel
   int *d_jc = nullptr, *d_jk = nullptr, *d_hc = nullptr, *d_hk = nullptr, *d_hk2 = nullptr, *d_sched = nullptr;
   short* d_hci = nullptr;
+  short* d_hc_pt = nullptr;
   hb::KnotMaps* d_knot_maps = nullptr;
   int2* d_jc_list = nullptr;
   unsigned *d_jk_list = nullptr, *d_hc_list = nullptr, *d_hk_list = nullptr;
@@ -498,6 +499,39 @@ extern "C" int hb_kino_create(const int32_t* icfg, const double* dcfg, const int
     }
   }
   if (e == cudaSuccess) e = upload(&h->d_hci, hc_index, (size_t)129 * 129);
+  if (e == cudaSuccess) {
+    // per-point Hessian terms of the planar contact kernel, in the order kino_contact.cu lists them: 11 complementarity /
+    // friction / swing terms, 6 control regularisations, 12 momentum cross terms -> 29 local entries per point, padded to 32
+    std::vector<int16_t> pt(8 * 32, -1);
+    enum { V = 0, FD = 3, P = 6, F = 9, U = 12, COM = 120, NV = 129 };
+    for (int i = 0; i < 8; ++i) {
+      const int o = 15 * i;
+      int n = 0;
+      auto term = [&](int vi, int vj) { pt[32 * i + n++] = hc_index[vi * NV + vj]; };
+      term(o + P + 2, o + P + 2);
+      term(o + P + 2, o + U);
+      term(o + P + 2, o + U + 1);
+      term(o + P + 2, o + F + 2);
+      term(o + V + 2, o + F + 2);
+      term(o + FD + 2, o + P + 2);
+      term(o + V, o + V);
+      term(o + V + 1, o + V + 1);
+      term(o + F, o + F);
+      term(o + F + 1, o + F + 1);
+      term(o + F + 2, o + F + 2);
+      for (int c = 0; c < 3; ++c) {
+        term(o + U + c, o + U + c);
+        term(o + FD + c, o + FD + c);
+      }
+      for (int a = 0; a < 3; ++a)
+        for (int bb = 0; bb < 3; ++bb) {
+          if (a == bb) continue;
+          term(o + P + a, o + F + bb);
+          term(COM + a, o + F + bb);
+        }
+    }
+    e = upload(&h->d_hc_pt, pt.data(), pt.size());
+  }
   C.jc_map = h->d_jc;
   C.jk_map = h->d_jk;
   C.hc_index = h->d_hci;
@@ -514,6 +548,7 @@ extern "C" int hb_kino_create(const int32_t* icfg, const double* dcfg, const int
   h->topo.hc_list = h->d_hc_list;
   h->topo.jc_map = h->d_jc;
   h->topo.hc_index = h->d_hci;
+  h->topo.hc_pt = h->d_hc_pt;
   h->topo.hc_map = h->d_hc;
   {
     // 4 warps per CTA; the kinematics kernels keep one branch accumulator per body whose children do not
@@ -575,6 +610,7 @@ extern "C" int hb_destroy(hb_handle h) {
   cudaFree(h->d_jc);
   cudaFree(h->d_jk);
   cudaFree(h->d_hci);
+  cudaFree(h->d_hc_pt);
   cudaFree(h->d_hc);
   cudaFree(h->d_hk);
   cudaFree(h->d_hk2);

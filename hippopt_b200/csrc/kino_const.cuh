@@ -121,6 +121,8 @@ struct KinTopo {
   const KnotMaps* knot_maps;
   const int2* jc_list;
   const unsigned* hc_list;
+  // planar terrain: local Hessian entry of the 29 per-point terms of contact point i (kino_contact.cu), 32 shorts per point
+  const short* hc_pt;
   // packed tangent sweep (kino_kin.cu): sched[round * 32 + lane] = task descriptor (see KT_* below)
   const int* sched;
   signed char root_slot[32];  // slot that holds the root totals of direction d after the sweep
